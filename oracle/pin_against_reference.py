@@ -1,0 +1,221 @@
+"""Pin the oracle against the reference itself, and write the golden fixtures.
+
+Runs ONLY in the build container (needs /root/reference).  For each scenario it steps the
+unmodified reference `T1DHStandEnv` (CPU, fake gym, pooled RNG) and the oracle side by side
+on identical synthetic simulator tensors and requires BIT-EQUAL results on every output and
+on the persistent state after every step.  With `--write` it stores the inputs and the
+reference's outputs of the small scenarios under tests/golden/ (the reference cannot travel
+to the GPU box; the fixtures can).
+
+    python oracle/pin_against_reference.py            # check only
+    python oracle/pin_against_reference.py --write    # check + regenerate tests/golden/*.npz
+"""
+import argparse
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import t1_oracle as O                                        # noqa: E402
+from oracle.reference_driver import ReferenceDriver, adopt_reference_state  # noqa: E402
+from ti5_isaacgym_b200.sim.synthetic import fill_synthetic_state, synthetic_actions  # noqa: E402
+
+STATE_KEYS = ("torques actions last_actions last_last_actions last_dof_vel last_root_vel commands feet_air_time "
+              "feet_height last_contacts contact_filt base_quat base_lin_vel base_ang_vel projected_gravity "
+              "base_euler_xyz feet_euler_xyz ext_forces ext_torques rand_push_force rand_push_torque ref_dof_pos "
+              "gait_time gait_start torque_multi motor_offsets randomized_p_gains randomized_d_gains "
+              "randomized_joint_coulomb randomized_joint_viscous joint_armatures lag_buffer dof_lag_buffer "
+              "imu_lag_buffer lag_timestep dof_lag_timestep imu_lag_timestep episode_length_buf phase_length_buf "
+              "rew_buf reset_buf time_out_buf env_origins").split()
+
+
+def robot_from_env(env):
+    """Robot constants as the reference derived them from the URDF via the fake gym."""
+    props = env.gym.asset.dof_props
+    return SimpleNamespace(
+        dof_names=list(env.dof_names), body_names=list(env.gym.asset.body_names), num_dof=env.num_dof,
+        num_bodies=env.num_bodies, feet_indices=env.feet_indices.tolist(), knee_indices=env.knee_indices.tolist(),
+        penalised_contact_indices=env.penalised_contact_indices.tolist(),
+        termination_contact_indices=env.termination_contact_indices.tolist(),
+        dof_effort=[float(x) for x in props["effort"]], dof_velocity=[float(x) for x in props["velocity"]],
+        dof_lower=[float(x) for x in props["lower"]], dof_upper=[float(x) for x in props["upper"]])
+
+
+def same(a, b):
+    if isinstance(a, (int, float, bool)) or isinstance(b, (int, float, bool)):
+        return a == b
+    return a.shape == b.shape and a.dtype == b.dtype and torch.equal(a, b)
+
+
+def snapshot_state(S, C):
+    """All persistent state of an oracle state as a flat dict of tensors."""
+    out = {k: getattr(S, k).clone() for k in STATE_KEYS}
+    out["last_feet_z"] = torch.zeros(S.N, 2) if isinstance(S.last_feet_z, int) else S.last_feet_z.clone()
+    out["obs_history"], out["critic_history"] = S.obs_history.clone(), S.critic_history.clone()
+    out["episode_sums"] = torch.stack([S.episode_sums[k] for k in C.reward_names], 0)
+    out["env_frictions"], out["body_mass"] = S.env_frictions.clone(), S.body_mass.clone()
+    out["counters"] = torch.tensor([S.common_step_counter, int(S.is_first_add_force), int(S.is_first_push)])
+    out["command_ranges"] = torch.tensor([S.command_ranges[k] for k in ("lin_vel_x", "lin_vel_y", "ang_vel_yaw")],
+                                         dtype=torch.float64)
+    if hasattr(S, "terrain_levels"):
+        out["terrain_levels"], out["terrain_types"] = S.terrain_levels.clone(), S.terrain_types.clone()
+    return out
+
+
+SCENARIOS = {
+    # name: (num_envs, steps, mesh_type, cfg edits, base-contact rate, forced events)
+    "plane_default": dict(N=16, steps=28, mesh="plane"),
+    "plane_events": dict(N=24, steps=40, mesh="plane", contact_rate=0.05, events=True),
+    "trimesh_heights_push": dict(N=16, steps=24, mesh="trimesh", contact_rate=0.05, events=True,
+                                 edit=lambda c: (setattr(c.terrain, "measure_heights", True),
+                                                 setattr(c.env, "num_privileged_obs", 3 * (73 + 187)),
+                                                 setattr(c.domain_rand, "push_robots", True))),
+    "big_plane": dict(N=512, steps=12, mesh="plane", contact_rate=0.03, events=True, golden=False),
+}
+
+
+def run_scenario(name, spec, write_dir=None, verbose=True):
+    N, steps = spec["N"], spec["steps"]
+    drv = ReferenceDriver(N, mesh_type=spec["mesh"], cfg_edit=spec.get("edit"), seed=11)
+    env = drv.env
+    terrain = None
+    heights = None
+    if spec["mesh"] == "trimesh":
+        terrain = SimpleNamespace(env_length=env.terrain.env_length, max_level=env.max_terrain_level,
+                                  origins=env.terrain_origins)
+        heights = env.height_samples
+    C = O.make_consts(drv.cfg, drv.cfg.sim.dt, robot_from_env(env), terrain=terrain)
+    gen = torch.Generator().manual_seed(1234)
+    # the reference's own reset() (construction-time state is already random)
+    fill_synthetic_state(drv.sim, env.env_origins, gen)
+    pools = O.draw_pools(C, N, gen)
+    with drv.pooled_rng(pools):
+        env.reset()
+    # spread episode phases so that stand phases, gait switches and time-outs all occur (8d)
+    env.episode_length_buf[:] = torch.randint(1, 2000, (N,), generator=gen)
+    if spec.get("events"):
+        env.episode_length_buf[0] = 2398                  # time-out at the 3rd step
+        env.episode_length_buf[1] = int(env.gait_time[1, 1]) - 2       # gait switch to "stand"
+        env.episode_length_buf[2] = int(env.gait_time[2, 2]) - 3       # and back to walking
+        env.phase_length_buf[:] = env.episode_length_buf
+        env.common_step_counter = 2397                    # command-curriculum check at step 3, ext-force window
+    S = adopt_reference_state(O.new_state(C, N), env)
+    state0 = snapshot_state(S, C)
+    if terrain is not None:
+        state0["terrain_origins"] = terrain.origins.clone()
+        state0["terrain_env_length"] = torch.tensor(float(terrain.env_length))
+    rec = dict(inputs=[], outputs=[])
+    cov = dict(time_outs=0, stand_env_steps=0, ext_force_steps=0, push_steps=0, curriculum_changes=0, gait_switches=0)
+    for t in range(steps):
+        fill_synthetic_state(drv.sim, env.env_origins, gen, base_contact_rate=spec.get("contact_rate", 0.01))
+        sim0 = {k: getattr(drv.sim, k).clone() for k in ("root_states", "dof_state", "contact_forces", "rigid_state")}
+        actions = synthetic_actions(N, gen, "cpu")
+        pools = O.draw_pools(C, N, gen)
+        # oracle on a private copy of the simulator tensors
+        osim = SimpleNamespace(**{k: v.clone() for k, v in sim0.items()})
+        o_obs, o_priv, o_rew, o_reset, o_extras = O.step(C, S, osim, actions, pools, terrain=terrain, height_samples=heights)
+        r_obs, r_priv, r_rew, r_reset, r_extras = drv.step(actions, pools)
+        bad = []
+        for key, a, b in (("obs", o_obs, r_obs), ("priv", o_priv, r_priv), ("rew", o_rew, r_rew), ("reset", o_reset, r_reset)):
+            if not same(a, b):
+                bad.append(key)
+        for key in STATE_KEYS:
+            if not same(getattr(S, key), getattr(env, key)):
+                bad.append(key)
+        if not same(S.last_feet_z, env.last_feet_z):
+            bad.append("last_feet_z")
+        for key in env.episode_sums:
+            if not same(S.episode_sums[key], env.episode_sums[key]):
+                bad.append("episode_sums." + key)
+        for key in ("root_states", "dof_state"):
+            if not same(getattr(osim, key), getattr(drv.sim, key)):
+                bad.append("sim." + key)
+        if not same(torch.stack(list(env.obs_history), 0), S.obs_history):
+            bad.append("obs_history")
+        if not same(torch.stack(list(env.critic_history), 0), S.critic_history):
+            bad.append("critic_history")
+        if "episode" in r_extras:
+            for k, v in r_extras["episode"].items():
+                ov = o_extras["episode"][k]
+                if not (same(v, ov) if torch.is_tensor(v) else v == ov):
+                    bad.append("extras." + k)
+            if not same(r_extras["time_outs"], o_extras["time_outs"]):
+                bad.append("extras.time_outs")
+        if S.command_ranges != {k: list(v) for k, v in env.command_ranges.items()}:
+            bad.append("command_ranges")
+        if not isinstance(S.measured_heights, int) and not same(S.measured_heights, env.measured_heights):
+            bad.append("measured_heights")
+        cov["time_outs"] += int(env.time_out_buf.sum())
+        cov["stand_env_steps"] += int(O.stand_command(C, S).sum())
+        cov["ext_force_steps"] += int(bool(env.ext_forces.abs().sum() > 0))
+        cov["push_steps"] += int(bool(env.rand_push_force.abs().sum() > 0))
+        cov["curriculum_changes"] += int(env.command_ranges["lin_vel_x"][1] != 0.5 and cov["curriculum_changes"] == 0)
+        cov["gait_switches"] += int(((env.episode_length_buf.unsqueeze(1) == env.gait_time[:, 1:]).any(1)).sum())
+        if bad:
+            raise SystemExit(f"[{name}] step {t}: oracle != reference on {bad}")
+        rec["inputs"].append(dict(sim0, actions=actions, **{"rng_" + k: v for k, v in pools.items()}))
+        rec["outputs"].append(dict(
+            obs_new=r_obs[:, -C.cfg.env.num_single_obs:].clone(), priv_new=r_priv[:, -S.critic_history.shape[2]:].clone(),
+            rew=r_rew.clone(), reset=r_reset.clone(), time_out=env.time_out_buf.clone(), torques=env.torques.clone(),
+            commands=env.commands.clone(), contact_filt=env.contact_filt.clone(), feet_air_time=env.feet_air_time.clone(),
+            ref_dof_pos=env.ref_dof_pos.clone(), root_after=drv.sim.root_states.clone(), dof_after=drv.sim.dof_state.clone(),
+            episode_sums=torch.stack([env.episode_sums[k] for k in C.reward_names], 0),
+            reward_terms=torch.stack([S.reward_terms[k] for k in C.reward_names], 0),
+            n_reset=torch.tensor(int(r_reset.sum()))))
+    n_resets = sum(int(o["n_reset"]) for o in rec["outputs"])
+    if verbose:
+        print(f"[{name}] N={N} steps={steps}: oracle == reference bit-for-bit "
+              f"(resets={n_resets}, coverage={cov}, obs checksum={float(r_obs.double().sum()):.6f})")
+    if write_dir is not None and spec.get("golden", True):
+        flat = {f"state0.{k}": v.numpy() for k, v in state0.items()}
+        for t, (i, o) in enumerate(zip(rec["inputs"], rec["outputs"])):
+            for k, v in i.items():
+                flat[f"in{t:03d}.{k}"] = v.numpy()
+            for k, v in o.items():
+                flat[f"out{t:03d}.{k}"] = v.numpy()
+        flat["final.obs"] = r_obs.numpy()
+        flat["final.priv"] = r_priv.numpy()
+        np.savez_compressed(os.path.join(write_dir, f"t1_step_{name}.npz"), **flat)
+    return rec
+
+
+def pin_gae(write_dir=None):
+    """GAE: `RolloutStorage.compute_returns` (rollout_storage.py:97-119) vs the oracle."""
+    from oracle.reference_driver import import_reference
+    import_reference()
+    from humanoid.algo.ppo.rollout_storage import RolloutStorage
+    g = torch.Generator().manual_seed(99)
+    for T, N in ((24, 64), (24, 4096), (5, 7)):
+        st = RolloutStorage(N, T, [4], [4], [2])
+        st.rewards[:] = torch.randn(T, N, 1, generator=g)
+        st.values[:] = torch.randn(T, N, 1, generator=g)
+        st.dones[:] = (torch.rand(T, N, 1, generator=g) < 0.02).byte()
+        last = torch.randn(N, 1, generator=g)
+        st.compute_returns(last, 0.994, 0.9)
+        ret, adv = O.gae_returns(st.rewards, st.values, st.dones, last, 0.994, 0.9)
+        if not (torch.equal(ret, st.returns) and torch.equal(adv, st.advantages)):
+            raise SystemExit(f"GAE oracle != reference at T={T} N={N}")
+        if write_dir is not None and N == 64:
+            np.savez_compressed(os.path.join(write_dir, "gae_T24_N64.npz"), rewards=st.rewards.numpy(),
+                                values=st.values.numpy(), dones=st.dones.numpy(), last_values=last.numpy(),
+                                returns=st.returns.numpy(), advantages=st.advantages.numpy(),
+                                gamma=np.float64(0.994), lam=np.float64(0.9))
+    print("[gae] oracle == reference bit-for-bit")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--write", action="store_true")
+    ap.add_argument("--only", default=None)
+    a = ap.parse_args()
+    out = os.path.join(ROOT, "tests", "golden") if a.write else None
+    for nm, sp in SCENARIOS.items():
+        if a.only is None or a.only == nm:
+            run_scenario(nm, sp, out)
+    if a.only is None:
+        pin_gae(out)

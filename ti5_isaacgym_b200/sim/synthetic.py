@@ -1,0 +1,89 @@
+"""Synthetic simulator state with the Isaac Gym tensor-API layout.
+
+The only PhysX interaction of the hot path is the gym tensor API (lower
+boundary): four AoS tensors that PhysX refreshes in place.  Where Isaac Gym is absent
+(this repo's tests and benchmarks) the same tensors are filled with the seeded
+near-nominal distribution of SURVEY.md 8(d), so the reference, the oracle and the CUDA
+kernels all see identical inputs.
+
+    root_states    (N, 13)      pos3 | quat_xyzw4 | lin_vel3 | ang_vel3     (lr:137)
+    dof_state      (N*D, 2)     interleaved (pos, vel) per DOF              (lr:138-143)
+    contact_forces (N*NB, 3)    net contact force per body                  (lr:151)
+    rigid_state    (N*NB, 13)   pos3 | quat4 | lin_vel3 | ang_vel3 per body (lr:154)
+"""
+from types import SimpleNamespace
+
+import torch
+
+D, NB = 12, 13
+FEET, KNEES = (6, 12), (4, 10)
+_DEFAULT_POSE = (0.0, 0.0, -0.3, 0.6, -0.3, 0.0) * 2
+
+
+def alloc_sim_tensors(num_envs, device):
+    """Zeroed gym tensors (identity quaternions), as `acquire_*_tensor` would hand out."""
+    z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
+    sim = SimpleNamespace(root_states=z(num_envs, 13), dof_state=z(num_envs * D, 2),
+                          contact_forces=z(num_envs * NB, 3), rigid_state=z(num_envs * NB, 13))
+    sim.root_states[:, 6] = 1.0
+    sim.rigid_state[:, 6] = 1.0
+    return sim
+
+
+def _unit_quat(n, gen, device):
+    q = torch.cat((0.03 * torch.randn(n, 3, generator=gen, device=device), torch.ones(n, 1, device=device)), 1)
+    return q / q.norm(dim=1, keepdim=True)
+
+
+def fill_synthetic_state(sim, env_origins, gen, base_contact_rate=0.01, device=None):
+    """Overwrite the four gym tensors in place with one draw of the 8(d) distribution.
+    `gen` is a torch.Generator living on the same device as the tensors it draws for
+    (CPU generator + CPU tensors for the parity fixtures; CUDA for throughput runs)."""
+    N = sim.root_states.shape[0]
+    dev = sim.root_states.device if device is None else device
+    rn = lambda *s: torch.randn(*s, generator=gen, device=dev)
+    ru = lambda *s: torch.rand(*s, generator=gen, device=dev)
+    tgt = sim.root_states.device
+    default = torch.tensor(_DEFAULT_POSE, device=dev)
+
+    dof = torch.stack((default + 0.05 * rn(N, D), 0.5 * rn(N, D)), dim=-1)
+    root = torch.empty(N, 13, device=dev)
+    root[:, 0:3] = env_origins.to(dev) + 0.1 * rn(N, 3)
+    root[:, 2] = 0.96 + 0.02 * rn(N)
+    root[:, 3:7] = _unit_quat(N, gen, dev)
+    root[:, 7:13] = 0.3 * rn(N, 6)
+
+    contact = torch.zeros(N, NB, 3, device=dev)
+    in_contact = ru(N, 2) < 0.6
+    f = torch.cat((20.0 * rn(N, 2, 2), (50.0 + 400.0 * ru(N, 2)).unsqueeze(-1)), dim=-1)
+    f[..., 2] = torch.where(ru(N, 2) < 0.02, torch.full_like(f[..., 2], 700.0), f[..., 2])
+    contact[:, list(FEET)] = f * in_contact.unsqueeze(-1)
+    r = ru(N)
+    contact[:, 0, 2] = torch.where(r < base_contact_rate, torch.full_like(r, 30.0), contact[:, 0, 2])
+    contact[:, 0, 0] = torch.where((r >= base_contact_rate) & (r < base_contact_rate + 0.01),
+                                   torch.full_like(r, 0.5), contact[:, 0, 0])
+
+    rigid = torch.empty(N, NB, 13, device=dev)
+    rigid[:, :, 0:3] = root[:, None, 0:3] + 0.05 * rn(N, NB, 3)
+    for pair, half in ((FEET, 0.15), (KNEES, 0.12)):
+        rigid[:, pair[0], 1] = root[:, 1] + half + 0.01 * rn(N)
+        rigid[:, pair[1], 1] = root[:, 1] - half + 0.01 * rn(N)
+    rigid[:, list(FEET), 2] = 0.05 + 0.04 * ru(N, 2) * (~in_contact)
+    rigid[:, :, 3:7] = _unit_quat(N * NB, gen, dev).view(N, NB, 4)
+    rigid[:, :, 7:13] = 0.3 * rn(N, NB, 6)
+
+    sim.dof_state.copy_(dof.view(N * D, 2).to(tgt))
+    sim.root_states.copy_(root.to(tgt))
+    sim.contact_forces.copy_(contact.view(N * NB, 3).to(tgt))
+    sim.rigid_state.copy_(rigid.view(N * NB, 13).to(tgt))
+    return sim
+
+
+def synthetic_actions(num_envs, gen, device):
+    return 0.3 * torch.randn(num_envs, D, generator=gen, device=device)
+
+
+def synthetic_height_field(rows=2100, cols=2100, seed=7, device="cpu"):
+    """int16 height samples standing in for `Terrain.heightsamples` (lr:1237)."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(-20, 60, (rows, cols), generator=g, dtype=torch.int16).to(device)
