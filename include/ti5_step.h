@@ -1,0 +1,320 @@
+/*
+ * ti5_step.h — C ABI of libti5step.so: the per-step vectorised environment math of the
+ * `t1_dh_stand` task (Robotics-Engineer-khy/ti5_isaacgym) as sm_100a CUDA kernels.
+ *
+ * The reference has no FFI: its "operator API" is the Python `LeggedRobot` / `T1DHStandEnv`
+ * methods.  Each entry point below replaces the torch-op chain of the method(s) cited next to
+ * it ("lr" = humanoid/envs/base/legged_robot.py, "t1" = humanoid/envs/t1/t1_dh_stand_env.py,
+ * "rs" = humanoid/algo/ppo/rollout_storage.py).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned (torch) memory, borrowed for the
+ *     call; the library allocates nothing and keeps no pointers;
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous on it;
+ *   - return value 0 = OK, otherwise a negative TI5_E* code; ti5_last_error() describes it;
+ *     nothing throws across the ABI; there is NO CPU fallback;
+ *   - one policy step is the call sequence
+ *         ti5_begin_step
+ *         DEC x { ti5_torque_substep ; <simulate> ; ti5_lag_push }      (or the fused ti5_substep)
+ *         [ti5_sample_heights] ; ti5_post_physics ; ti5_reset_observe ; [ti5_materialize_obs]
+ *     and all per-step counters live in device memory (Ti5Globals), so the sequence can be
+ *     captured once into a CUDA graph and replayed.
+ */
+#ifndef TI5_STEP_H
+#define TI5_STEP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TI5_ABI_VERSION 3
+
+#define TI5_NUM_DOF 12      /* leg_l1..l6, leg_r1..r6 */
+#define TI5_NUM_BODIES 13   /* base_link + 12 leg links after collapse_fixed_joints */
+#define TI5_NUM_TERMS 28    /* every _reward_* the task defines, alphabetical (see ti5_reward_name) */
+#define TI5_MAX_GAITS 4
+#define TI5_MAX_WINDOWS 8   /* entries of push_duration / add_duration */
+#define TI5_LOG_ROWS 64     /* ring of per-step `extras["episode"]` snapshots */
+#define TI5_LOG_COLS 32     /* TI5_NUM_TERMS means + terrain_level + max_command_x + n_reset + spare */
+
+/* error codes */
+#define TI5_OK 0
+#define TI5_EINVAL (-1)
+#define TI5_ECUDA (-2)
+
+/* Ti5Params.flags: the cfg booleans the kernels branch on (t1_cfg domain_rand / terrain / noise) */
+enum {
+  TI5_F_ADD_LAG = 1 << 0,            /* domain_rand.add_lag */
+  TI5_F_ADD_DOF_LAG = 1 << 1,        /* domain_rand.add_dof_lag */
+  TI5_F_ADD_IMU_LAG = 1 << 2,        /* domain_rand.add_imu_lag */
+  TI5_F_RAND_GAINS = 1 << 3,         /* randomize_gains */
+  TI5_F_RAND_COULOMB = 1 << 4,       /* randomize_coulomb_friction */
+  TI5_F_RAND_TORQUE = 1 << 5,        /* randomize_torque */
+  TI5_F_RAND_MOTOR_OFFSET = 1 << 6,  /* randomize_motor_offset */
+  TI5_F_RAND_ARMATURE = 1 << 7,      /* randomize_joint_armature(_each_joint) */
+  TI5_F_ADD_NOISE = 1 << 8,          /* noise.add_noise */
+  TI5_F_MEASURE_HEIGHTS = 1 << 9,    /* terrain.measure_heights */
+  TI5_F_PUSH_ROBOTS = 1 << 10,       /* domain_rand.push_robots */
+  TI5_F_ADD_EXT_FORCE = 1 << 11,     /* domain_rand.add_ext_force */
+  TI5_F_ONLY_POSITIVE = 1 << 12,     /* rewards.only_positive_rewards */
+  TI5_F_CUSTOM_ORIGINS = 1 << 13,    /* mesh_type in {heightfield, trimesh} */
+  TI5_F_TERRAIN_CURRICULUM = 1 << 14,
+  TI5_F_COMMAND_CURRICULUM = 1 << 15,
+  TI5_F_TRIMESH = 1 << 16,           /* log terrain_level in extras */
+  TI5_F_RAND_LAG_STEPS = 1 << 17,    /* randomize_lag_timesteps */
+  TI5_F_RAND_DOF_LAG_STEPS = 1 << 18,
+  TI5_F_RAND_IMU_LAG_STEPS = 1 << 19,
+  TI5_F_PLANE = 1 << 20              /* heights are identically zero on a plane (lr:1564) */
+};
+
+/* gait kinds of cfg.commands.gait (t1:138-177) */
+enum { TI5_GAIT_STAND = 0, TI5_GAIT_WALK_SAGITTAL = 1, TI5_GAIT_WALK_LATERAL = 2, TI5_GAIT_ROTATE = 3,
+       TI5_GAIT_WALK_OMNI = 4 };
+
+/* phases of ti5_substep / ti5_reset_observe (bit masks) */
+enum { TI5_SUB_PUSH = 1, TI5_SUB_TORQUE = 2 };
+enum { TI5_RO_RESET = 1, TI5_RO_OBSERVE = 2 };
+
+/* how `tensor / python_scalar` is rounded: torch-CPU divides, torch-CUDA multiplies by the
+ * reciprocal (ATen div_true_kernel_cuda); the reference therefore differs by device. */
+enum { TI5_DIV_IEEE = 0, TI5_DIV_RECIPROCAL = 1 };
+
+/* randomness: uniforms supplied by the caller (parity mode) or Philox4x32-10 in-kernel */
+enum { TI5_RNG_POOLS = 0, TI5_RNG_PHILOX = 1 };
+
+/* ---- scalars derived once from the config (lr:94-113, 212-249, 352-384; t1:326-357) ---------- */
+typedef struct Ti5Params {
+  int32_t num_envs;
+  int32_t frame_stack;     /* H: long observation history (66) */
+  int32_t c_frame_stack;   /* CH: critic frame stack (3) */
+  int32_t num_single_obs;  /* K = 47 */
+  int32_t priv_frame;      /* P = 73, or 73 + num_height_points with measure_heights */
+  int32_t decimation;      /* DEC = 10 */
+  int32_t lag_len;         /* lag_timesteps_range[1] + 1 = 31 */
+  int32_t dof_lag_len;     /* 31 */
+  int32_t imu_lag_len;     /* 11 */
+  int32_t flags;           /* TI5_F_* */
+  int32_t div_mode;        /* TI5_DIV_* */
+  int32_t rng_mode;        /* TI5_RNG_* */
+  int32_t env_block;       /* threads (= envs) per CTA of the per-env kernels: 32, 64 or 128 */
+  int32_t num_gaits;
+  int32_t gait_kind[TI5_MAX_GAITS];
+  int32_t num_height_points;
+  int32_t height_rows, height_cols;
+  int32_t feet[2], knees[2];
+  int32_t term_body, pen_body;            /* termination / penalised contact body (base_link) */
+  int32_t lag_range[3][2];                /* action / dof / imu lag index ranges */
+  int32_t n_push_dur, n_add_dur;
+  int32_t terrain_rows, terrain_cols, max_terrain_level;
+  uint32_t term_mask;                     /* bit i set = reward term i has a non-zero scale */
+  uint32_t _pad0;
+  int64_t max_episode_length;             /* ceil(episode_length_s / dt) = 2400 */
+  int64_t push_interval, ext_force_interval, push_update_step, add_update_step;
+  uint64_t seed;                          /* Philox key */
+
+  float dt;                 /* decimation * sim dt (Python double, rounded to fp32 where torch does) */
+  float cycle_time, action_scale, clip_actions, clip_obs, stand_threshold;
+  float max_episode_length_s;
+  float default_dof_pos[TI5_NUM_DOF], p_gains[TI5_NUM_DOF], d_gains[TI5_NUM_DOF];
+  float torque_limits[TI5_NUM_DOF], dof_vel_limits[TI5_NUM_DOF];
+  float reward_scale[TI5_NUM_TERMS];      /* float32(scale * dt), alphabetical term order */
+  float noise_vec[64];                    /* noise_scale_vec (K entries) */
+  float noise_level;
+  float obs_lin_vel, obs_ang_vel, obs_dof_pos, obs_dof_vel, obs_quat, obs_height;
+  float cmd_scale[3];
+  float base_init_state[13];
+  /* reward constants (t1_cfg:360-381) */
+  float base_height_target, foot_min_dist, foot_max_dist, knee_min_dist, knee_max_dist;
+  float target_joint_pos_scale, target_joint_pos_scale2 /* float32(2 * scale) */, target_feet_height, target_feet_height_max, tracking_sigma;
+  float max_contact_force, soft_dof_vel_limit;
+  /* uniform -> value maps, stored as (hi - lo, lo) computed in double then rounded (torch_rand_float) */
+  float torque_multi_w, torque_multi_lo;
+  float motor_offset_w, motor_offset_lo;
+  float kp_mult_w, kp_mult_lo, kd_mult_w, kd_mult_lo;
+  float coulomb_w, coulomb_lo, viscous_w, viscous_lo;
+  float armature_w[TI5_NUM_DOF], armature_lo[TI5_NUM_DOF];
+  float dof_reset_w, dof_reset_lo;                 /* U(-0.1, 0.1), lr:1084 */
+  float root_xy_w, root_xy_lo;                     /* lr:1105-1108 */
+  float gait_time_w[TI5_MAX_GAITS], gait_time_lo[TI5_MAX_GAITS];
+  float push_vel_w, push_vel_lo, push_ang_w, push_ang_lo;
+  float ext_f_w[3], ext_f_lo[3], ext_t_w, ext_t_lo;
+  float ext_force_div, ext_torque_div;             /* ext_force_max_x + 0.1, ext_torque_max + 0.1 */
+  float border_size, horizontal_scale, vertical_scale, terrain_env_length;
+  double push_duration[TI5_MAX_WINDOWS], add_duration[TI5_MAX_WINDOWS];   /* duration / dt, in steps (double) */
+  double cmd_curriculum_max;                       /* commands.max_curriculum */
+  double tracking_lin_vel_scale;                   /* reward_scales["tracking_lin_vel"] (double) */
+} Ti5Params;
+
+/* ---- device-resident counters and curriculum state (single instance per env object) -------- */
+typedef struct Ti5Globals {
+  int64_t step_index;          /* policy steps begun so far (ti5_begin_step increments) */
+  int64_t common_step_offset;  /* common_step_counter = step_index + common_step_offset */
+  int32_t n_reset;             /* envs reset in the current step (lr:490) */
+  int32_t tickets[4];          /* last-CTA-done counters of the per-env kernels */
+  int32_t is_first_add_force;  /* lr:90, t1:205-215 */
+  double cmd_range[3][2];      /* lin_vel_x, lin_vel_y, ang_vel_yaw ranges (curriculum mutates [0]) */
+} Ti5Globals;
+
+/* ---- device buffers.  (N,k) means row-major per-env rows.  See DESIGN.md for the layout ---- */
+typedef struct Ti5Buffers {
+  Ti5Globals* globals;
+  /* gym tensor API, AoS (lr:137-154) */
+  float* root_states;      /* (N,13) */
+  float* dof_state;        /* (N,12,2) */
+  float* contact_forces;   /* (N,13,3) */
+  float* rigid_state;      /* (N,13,13) */
+  /* actuation */
+  float* actions;          /* (N,12) clipped actions of this step */
+  float* torques;          /* (N,12) */
+  float* torque_multi;     /* (N,12) */
+  float* p_gains_r;        /* (N,12) randomized_p_gains */
+  float* d_gains_r;        /* (N,12) */
+  float* motor_offsets;    /* (N,12) */
+  float* coulomb;          /* (N,12) randomized_joint_coulomb */
+  float* viscous;          /* (N,12) randomized_joint_viscous */
+  float* joint_armatures;  /* (N,12) */
+  /* lag rings, slot-major: (len, N, width); slot of push j is j % len */
+  float* act_ring;         /* (lag_len, N, 12) */
+  float* dof_ring;         /* (dof_lag_len, N, 24) = cat(q, qd) */
+  float* imu_ring;         /* (imu_lag_len, N, 6) = cat(base_ang_vel, euler) */
+  int32_t* lag_timestep;   /* (N,3): action / dof / imu lag index */
+  int64_t* ring_stamp;     /* (N): pushes older than this index read as zero (reset) */
+  /* previous-step state */
+  float* last_actions;     /* (N,12) */
+  float* last_last_actions;
+  float* last_dof_vel;     /* (N,12) */
+  float* last_root_vel;    /* (N,6) */
+  /* commands and gait schedule */
+  float* commands;         /* (N,4) */
+  int64_t* episode_length_buf;  /* (N) */
+  int64_t* phase_length_buf;    /* (N) */
+  int32_t* gait_time;      /* (N,num_gaits) */
+  float* gait_start;       /* (N) */
+  /* feet bookkeeping (t1:642-657, 793-814) */
+  float* feet_air_time;    /* (N,2) */
+  float* feet_height;      /* (N,2) */
+  float* last_feet_z;      /* (N,2) */
+  uint8_t* last_contacts;  /* (N,2) bool */
+  uint8_t* contact_filt;   /* (N,2) bool */
+  /* derived base state (lr:475-481) */
+  float* base_quat;        /* (N,4) */
+  float* base_lin_vel;     /* (N,3) */
+  float* base_ang_vel;     /* (N,3) */
+  float* projected_gravity;/* (N,3) */
+  float* base_euler_xyz;   /* (N,3) */
+  float* feet_euler_xyz;   /* (N,2,3) */
+  float* ref_dof_pos;      /* (N,12) */
+  float* ref_action;       /* (N,12) */
+  /* disturbances */
+  float* ext_forces;       /* (N,3) */
+  float* ext_torques;      /* (N,3) */
+  float* rand_push_force;  /* (N,3) */
+  float* rand_push_torque; /* (N,3) */
+  float* applied_force;    /* (N,3) force handed to apply_rigid_body_force_tensors for body 0 */
+  float* applied_torque;   /* (N,3) */
+  float* env_frictions;    /* (N) */
+  float* body_mass;        /* (N) */
+  /* terrain */
+  float* env_origins;      /* (N,3) */
+  int64_t* terrain_levels; /* (N) */
+  int64_t* terrain_types;  /* (N) */
+  float* terrain_origins;  /* (terrain_rows, terrain_cols, 3) */
+  int16_t* height_samples; /* (height_rows, height_cols) */
+  float* height_points;    /* (num_height_points, 2) base-frame scan grid (lr:1535-1549) */
+  float* measured_heights; /* (N, num_height_points) */
+  /* outputs */
+  float* rew_buf;          /* (N) */
+  uint8_t* reset_buf;      /* (N) bool */
+  uint8_t* time_out_buf;   /* (N) bool */
+  uint8_t* time_outs_latched; /* (N) bool: extras["time_outs"] (only rewritten on steps with a reset) */
+  float* episode_sums;     /* (TI5_NUM_TERMS, N) */
+  float* reward_terms;     /* (TI5_NUM_TERMS, N) scaled per-term rewards of this step, or NULL */
+  int32_t* reset_ids;      /* (N) ascending ids of the envs reset this step */
+  int32_t* block_counts;   /* scratch: (ceil(N/32) + 1) */
+  float* block_sums;       /* scratch: (ceil(N/32), TI5_LOG_COLS) */
+  float* extras_log;       /* (TI5_LOG_ROWS, TI5_LOG_COLS) */
+  /* observation histories: mirrored rings (N, 2H, K) and (N, 2CH, P) */
+  float* obs_ring;
+  float* priv_ring;
+  float* obs_out;          /* optional contiguous (N, H*K) for ti5_materialize_obs */
+  float* priv_out;         /* optional contiguous (N, CH*P) */
+} Ti5Buffers;
+
+/* ---- caller-supplied uniforms of one step (TI5_RNG_POOLS).  All fp32 U[0,1) unless noted --- */
+typedef struct Ti5Rng {
+  const float* torque;        /* (DEC, N, 12)  lr:1071 */
+  const float* cmd;           /* (2, 3, N, 3)  t1:126-177: [0] callback pass, [1] pass inside reset_idx */
+  const float* push;          /* (N,5)   t1:223-226 */
+  const float* ext;           /* (N,6)   t1:237-241 */
+  const float* dofs;          /* (N,12)  lr:1084 */
+  const float* root_xy;       /* (N,2)   lr:1105-1108 */
+  const float* dr;            /* (N,7,12) lr:735-783 */
+  const float* gait_time;     /* (N,3)   t1:116 */
+  const float* noise;         /* (N,K)   t1:472 */
+  const int64_t* lag_idx;     /* (N,3)   lr:608-629 integers already in range */
+  const int64_t* gait_start;  /* (N)     t1:523 integers in {0,1} */
+  const int64_t* terrain_level; /* (N)   lr:1156 integers in [0, max_terrain_level) */
+} Ti5Rng;
+
+/* ---- entry points ------------------------------------------------------------------------- */
+
+int ti5_version(void);
+const char* ti5_last_error(void);
+/* sizeof(Ti5Params), sizeof(Ti5Buffers), sizeof(Ti5Rng), sizeof(Ti5Globals): lets a binding check its mirror */
+int ti5_struct_sizes(int32_t out[4]);
+const char* ti5_reward_name(int term);
+
+/* lr:393-394  `self.actions = clip(actions, +-clip_actions)`; also advances Ti5Globals.step_index */
+int ti5_begin_step(const Ti5Params* p, const Ti5Buffers* b, const float* actions_in, void* stream);
+
+/* lr:1019-1074 `_compute_torques` for substep `k` in [0, DEC) */
+int ti5_torque_substep(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, int k, void* stream);
+/* lr:412-434 DOF- and IMU-lag push after the simulator substep `k` */
+int ti5_lag_push(const Ti5Params* p, const Ti5Buffers* b, int k, void* stream);
+/* fused: [push of substep k-1] + [torque of substep k] in one launch (phases = TI5_SUB_*) */
+int ti5_substep(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, int k, int phases, void* stream);
+
+/* lr:1551-1587 `_get_heights` (+ utils/math.py:8-12 quat_apply_yaw) */
+int ti5_sample_heights(const Ti5Params* p, const Ti5Buffers* b, void* stream);
+
+/* lr:458-489 + t1:179-215 + lr:509-517 + lr:654-680 + t1:572-946: counters, derived base state,
+ * command schedule, push / external-force windows, termination, the reward sum, and the
+ * compaction bookkeeping (n_reset, per-CTA offsets, episode statistics, command curriculum).
+ * `push_last` != 0 fuses the lag push of the last substep into the same launch. */
+int ti5_post_physics(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, int push_last, void* stream);
+
+/* The same bookkeeping for an explicit `reset_idx(env_ids)` (lr:450-455 `reset()`): the caller wrote the
+ * mask into reset_buf; follow with ti5_reset_scatter. */
+int ti5_reset_bookkeeping(const Ti5Params* p, const Ti5Buffers* b, void* stream);
+
+/* lr:490 `reset_buf.nonzero()`: stand-alone ascending compaction of any (N) bool mask */
+int ti5_compact_resets(const uint8_t* mask, int32_t n, int32_t* ids_out, int32_t* count_out,
+                       int32_t* scratch /* ceil(n/1024)+1 ints */, void* stream);
+
+/* t1:483-559 `reset_idx` for the flagged envs and t1:368-481 `compute_observations` + lr:496-499
+ * `last_*` copies, in one launch (phases = TI5_RO_*).  Must follow ti5_post_physics. */
+int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, int phases, void* stream);
+int ti5_reset_scatter(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, void* stream);
+int ti5_observations(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, void* stream);
+
+/* lr:441-446: copy the current history windows into contiguous (N,H*K) / (N,CH*P) tensors */
+int ti5_materialize_obs(const Ti5Params* p, const Ti5Buffers* b, void* stream);
+
+/* rs:97-119 `RolloutStorage.compute_returns`: reverse GAE scan over (T,N) + advantage
+ * normalisation with the unbiased std.  `stats` is scratch for the Welford partials:
+ * 3 doubles per CTA + 4 (count, mean, M2 of the whole batch, written by ti5_gae_scan and
+ * read by ti5_gae_normalize, so a multi-GPU caller can all-reduce them in between). */
+int ti5_gae_scan(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
+                 float* returns, float* advantages, int32_t T, int32_t N, float gamma, float lam,
+                 double* stats, int32_t* ticket, void* stream);
+int ti5_gae_normalize(float* advantages, int32_t T, int32_t N, const double* stats, void* stream);
+int ti5_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
+            float* returns, float* advantages, int32_t T, int32_t N, float gamma, float lam,
+            double* stats, int32_t* ticket, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TI5_STEP_H */

@@ -31,25 +31,12 @@ def import_reference():
     return envs
 
 
-class FakeTerrain:
-    """Stand-in for `humanoid.utils.terrain.Terrain` (one-time CPU set-up, out of scope):
-    a random int16 height field of the real shape plus the platform-origin table."""
-
-    def __init__(self, cfg, num_robots):
-        self.cfg = cfg
-        self.env_length, self.env_width = cfg.terrain_length, cfg.terrain_width
-        px = int(cfg.terrain_length / cfg.horizontal_scale)
-        border = int(cfg.border_size / cfg.horizontal_scale)
-        self.tot_rows = int(cfg.num_rows * px) + 2 * border
-        self.tot_cols = int(cfg.num_cols * int(cfg.terrain_width / cfg.horizontal_scale)) + 2 * border
-        g = torch.Generator().manual_seed(7)
-        self.heightsamples = torch.randint(-20, 60, (self.tot_rows, self.tot_cols), generator=g,
-                                           dtype=torch.int16).numpy()
-        self.vertices = np.zeros((3, 3), dtype=np.float32)
-        self.triangles = np.zeros((1, 3), dtype=np.uint32)
-        i, j = np.meshgrid(np.arange(cfg.num_rows), np.arange(cfg.num_cols), indexing="ij")
-        self.env_origins = np.stack(((i + 0.5) * self.env_length, (j + 0.5) * self.env_width,
-                                     0.01 * ((i * 7 + j * 3) % 11)), axis=-1).astype(np.float64)
+def _fake_terrain_class():
+    """The reference builds `Terrain(cfg.terrain, num_envs)` from isaacgym.terrain_utils (absent);
+    both sides use the product's synthetic stand-in so they see the same height field."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from ti5_isaacgym_b200.sim.synthetic import SyntheticTerrain
+    return SyntheticTerrain
 
 
 # site tables: (function name, line) -> how to serve the draw
@@ -84,8 +71,7 @@ class ReferenceDriver:
         import humanoid.envs.t1.t1_dh_stand_env as t1_mod
         import humanoid.envs.base.legged_robot as lr_mod
         self.t1_mod, self.lr_mod = t1_mod, lr_mod
-        t1_mod.Terrain = FakeTerrain
-        lr_mod.Terrain = FakeTerrain
+        t1_mod.Terrain = lr_mod.Terrain = _fake_terrain_class()
         cfg = envs.DHT1StandCfg()
         cfg.env.num_envs = num_envs
         cfg.terrain.mesh_type = mesh_type

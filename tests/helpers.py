@@ -1,0 +1,97 @@
+"""Shared test plumbing: golden-fixture access, env construction in parity mode, comparisons."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SIM_KEYS = ("root_states", "dof_state", "contact_forces", "rigid_state")
+RTOL, ATOL = 1e-5, 2e-6      # north_star: <= 1e-5 relative on floats; atol covers values near zero
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, f"t1_step_{name}.npz"))
+    steps = sorted({k.split(".")[0] for k in z.files if k.startswith("in")})
+    state0 = {k[len("state0."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("state0.")}
+    inputs, outputs = [], []
+    for s in steps:
+        inputs.append({k.split(".", 1)[1]: torch.from_numpy(z[k]) for k in z.files if k.startswith(s + ".")})
+        o = "out" + s[2:]
+        outputs.append({k.split(".", 1)[1]: torch.from_numpy(z[k]) for k in z.files if k.startswith(o + ".")})
+    final = {k[len("final."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("final.")}
+    return state0, inputs, outputs, final
+
+
+def scenario_cfg(name, num_envs):
+    """The product config edited like oracle/pin_against_reference.py SCENARIOS."""
+    from ti5_isaacgym_b200.envs import DHT1StandCfg
+    cfg = DHT1StandCfg()
+    cfg.env.num_envs = num_envs
+    cfg.terrain.mesh_type = "trimesh" if name.startswith("trimesh") else "plane"
+    if name == "trimesh_heights_push":
+        cfg.terrain.measure_heights = True
+        cfg.env.num_privileged_obs = 3 * (73 + 187)
+        cfg.domain_rand.push_robots = True
+    return cfg
+
+
+def make_env(cfg, rng_mode="pools", div_mode="ieee", **kw):
+    from ti5_isaacgym_b200.envs import T1DHStandEnv
+    from ti5_isaacgym_b200.sim.synthetic import SimParams
+    return T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, "cuda:0", True, rng_mode=rng_mode, div_mode=div_mode,
+                        use_cuda_graph=False, **kw)
+
+
+def pools_of(inp):
+    return {k[4:]: v for k, v in inp.items() if k.startswith("rng_")}
+
+
+def set_sim(env, inp):
+    env.root_states.copy_(inp["root_states"].to(env.device))
+    env.dof_state.copy_(inp["dof_state"].to(env.device))
+    env.contact_forces.copy_(inp["contact_forces"].view_as(env.contact_forces).to(env.device))
+    env.rigid_state.copy_(inp["rigid_state"].view_as(env.rigid_state).to(env.device))
+
+
+def close(a, b, what, rtol=RTOL, atol=ATOL):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    bad = err > tol
+    assert not bad.any(), (f"{what}: {int(bad.sum())} of {bad.numel()} beyond rtol={rtol} atol={atol}; "
+                           f"worst |err|={float(err.max()):.3e} at {np.unravel_index(int(err.argmax()), a.shape)} "
+                           f"(got {float(a.flatten()[err.argmax()]):.8g}, want {float(b.flatten()[err.argmax()]):.8g})")
+
+
+def exact(a, b, what):
+    a, b = a.detach().cpu(), b.detach().cpu()
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    assert torch.equal(a.to(b.dtype), b), f"{what}: {int((a.to(b.dtype) != b).sum())} of {b.numel()} entries differ"
+
+
+def oracle_robot():
+    from ti5_isaacgym_b200.envs.t1.t1_robot import robot_constants
+    return robot_constants
+
+
+def state_from_oracle(S, C):
+    """Flat reference-named state dict of an oracle state (same keys as the golden `state0.*`)."""
+    keys = ("torques actions last_actions last_last_actions last_dof_vel last_root_vel commands feet_air_time "
+            "feet_height last_contacts contact_filt base_quat base_lin_vel base_ang_vel projected_gravity "
+            "base_euler_xyz feet_euler_xyz ext_forces ext_torques rand_push_force rand_push_torque ref_dof_pos "
+            "gait_time gait_start torque_multi motor_offsets randomized_p_gains randomized_d_gains "
+            "randomized_joint_coulomb randomized_joint_viscous joint_armatures lag_buffer dof_lag_buffer "
+            "imu_lag_buffer lag_timestep dof_lag_timestep imu_lag_timestep episode_length_buf phase_length_buf "
+            "rew_buf reset_buf time_out_buf env_origins env_frictions body_mass").split()
+    out = {k: getattr(S, k).clone() for k in keys}
+    out["last_feet_z"] = torch.zeros(S.N, 2) if isinstance(S.last_feet_z, int) else S.last_feet_z.clone()
+    out["obs_history"], out["critic_history"] = S.obs_history.clone(), S.critic_history.clone()
+    out["episode_sums"] = torch.stack([S.episode_sums[k] for k in C.reward_names], 0)
+    out["counters"] = torch.tensor([S.common_step_counter, int(S.is_first_add_force), int(S.is_first_push)])
+    out["command_ranges"] = torch.tensor([S.command_ranges[k] for k in ("lin_vel_x", "lin_vel_y", "ang_vel_yaw")],
+                                         dtype=torch.float64)
+    if hasattr(S, "terrain_levels"):
+        out["terrain_levels"], out["terrain_types"] = S.terrain_levels.clone(), S.terrain_types.clone()
+    return out

@@ -1,0 +1,184 @@
+// Device-side helpers shared by the ti5 step kernels (sm_100a).
+//
+// Arithmetic follows the reference's torch fp32 op chains one rounding at a time: the
+// library is built with -fmad=false so that a*b+c rounds twice like two eager torch ops,
+// libdevice sinf/cosf/expf/atan2f/asinf/sqrtf are the functions torch's CUDA kernels call,
+// and `tensor / python_scalar` is rounded the way the reference's device does (div_mode).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ti5_step.h"
+
+namespace ti5 {
+
+constexpr int D = TI5_NUM_DOF;
+constexpr int NB = TI5_NUM_BODIES;
+constexpr int RB = 13;  // floats per rigid-body / root state row
+
+// `2 * torch.pi` and `np.pi` as torch rounds them when they meet an fp32 tensor
+constexpr float TWO_PI_F = 6.283185307179586f;
+constexpr float PI_F = 3.141592653589793f;
+constexpr float HALF_PI_F = 1.5707963267948966f;
+
+// reward term indices: alphabetical order of every `_reward_*` of the task (t1:576-946),
+// which is the order `dir()` yields and the reference sums in (appendix A1)
+enum Term {
+  T_ACTION_SMOOTHNESS = 0, T_BASE_ACC, T_BASE_HEIGHT, T_COLLISION, T_DEFAULT_JOINT_POS, T_DOF_ACC, T_DOF_VEL,
+  T_DOF_VEL_LIMITS, T_FEET_AIR_TIME, T_FEET_CLEARANCE, T_FEET_CONTACT_FORCES, T_FEET_CONTACT_NUMBER,
+  T_FEET_DISTANCE, T_FEET_ROTATION, T_FEET_STUMBLE, T_FOOT_SLIP, T_JOINT_POS, T_KNEE_DISTANCE, T_LOW_SPEED,
+  T_ORIENTATION, T_STAND_STILL, T_STAND_SYSMETRY, T_TERMINATION, T_TORQUES, T_TRACK_VEL_HARD,
+  T_TRACKING_ANG_VEL, T_TRACKING_LIN_VEL, T_VEL_MISMATCH_EXP
+};
+static_assert(T_VEL_MISMATCH_EXP == TI5_NUM_TERMS - 1, "term table out of sync with TI5_NUM_TERMS");
+
+// extras_log columns after the TI5_NUM_TERMS episode means
+constexpr int LOG_TERRAIN_LEVEL = TI5_NUM_TERMS;
+constexpr int LOG_MAX_COMMAND_X = TI5_NUM_TERMS + 1;
+constexpr int LOG_N_RESET = TI5_NUM_TERMS + 2;
+
+// ---------------------------------------------------------------------------------------------
+// scalar helpers
+// ---------------------------------------------------------------------------------------------
+
+// tensor / python scalar (see TI5_DIV_*)
+__device__ __forceinline__ float sdiv(float x, float c, int mode) {
+  return mode == TI5_DIV_RECIPROCAL ? x * (1.0f / c) : x / c;
+}
+
+// torch.remainder for floats (python-style modulo)
+__device__ __forceinline__ float py_mod(float a, float b) {
+  float m = fmodf(a, b);
+  if (m != 0.0f && ((b < 0.0f) != (m < 0.0f))) m += b;
+  return m;
+}
+
+// torch.clip / clamp: min(max(x, lo), hi) with NaN passed through
+__device__ __forceinline__ float clampf(float x, float lo, float hi) {
+  return x < lo ? lo : (x > hi ? hi : x);
+}
+
+__device__ __forceinline__ float signf(float x) { return (float)((x > 0.0f) - (x < 0.0f)); }
+
+// torch_rand_float(lo, hi): (hi - lo) * u + lo with the width rounded once (host) to fp32
+__device__ __forceinline__ float affine(float w, float lo, float u) { return w * u + lo; }
+
+struct V3 {
+  float x, y, z;
+};
+
+// isaacgym.torch_utils.quat_rotate_inverse, q = (x, y, z, w)
+__device__ __forceinline__ V3 quat_rotate_inverse(const float q[4], V3 v) {
+  const float qw = q[3];
+  const float s = 2.0f * (qw * qw) - 1.0f;
+  const float cx = q[1] * v.z - q[2] * v.y;
+  const float cy = q[2] * v.x - q[0] * v.z;
+  const float cz = q[0] * v.y - q[1] * v.x;
+  const float dot = q[0] * v.x + q[1] * v.y + q[2] * v.z;
+  V3 o;
+  o.x = (v.x * s - cx * qw * 2.0f) + q[0] * dot * 2.0f;
+  o.y = (v.y * s - cy * qw * 2.0f) + q[1] * dot * 2.0f;
+  o.z = (v.z * s - cz * qw * 2.0f) + q[2] * dot * 2.0f;
+  return o;
+}
+
+// lr:27-53 get_euler_xyz_tensor: one wrapped angle (which = 0 roll, 1 pitch, 2 yaw)
+__device__ __forceinline__ float wrap_angle(float a) {
+  a = py_mod(a, TWO_PI_F);
+  if (a > PI_F) a -= TWO_PI_F;
+  return a;
+}
+__device__ __forceinline__ float euler_roll(const float q[4]) {
+  const float x = q[0], y = q[1], z = q[2], w = q[3];
+  return wrap_angle(atan2f(2.0f * (w * x + y * z), ((w * w - x * x) - y * y) + z * z));
+}
+__device__ __forceinline__ float euler_pitch(const float q[4]) {
+  const float x = q[0], y = q[1], z = q[2], w = q[3];
+  const float sinp = 2.0f * (w * y - z * x);
+  const float pitch = fabsf(sinp) >= 1.0f ? fabsf(HALF_PI_F) * signf(sinp) : asinf(sinp);
+  return wrap_angle(pitch);
+}
+__device__ __forceinline__ float euler_yaw(const float q[4]) {
+  const float x = q[0], y = q[1], z = q[2], w = q[3];
+  return wrap_angle(atan2f(2.0f * (w * z + x * y), ((w * w + x * x) - y * y) - z * z));
+}
+__device__ __forceinline__ void euler_xyz(const float q[4], float e[3]) {
+  e[0] = euler_roll(q);
+  e[1] = euler_pitch(q);
+  e[2] = euler_yaw(q);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (throughput mode).  One call yields four 32-bit words for the counter
+// (idx, site, step) under the key `seed`; words -> U[0,1) with 24 random bits.
+// ---------------------------------------------------------------------------------------------
+enum RngSite { S_TORQUE = 0, S_CMD = 16, S_PUSH = 24, S_EXT, S_DOFS, S_ROOT, S_DR, S_GAIT_TIME, S_NOISE, S_LAG,
+               S_GAIT_START, S_TERRAIN };
+
+__device__ __forceinline__ uint4 philox4(uint64_t seed, uint64_t step, uint32_t site, uint32_t idx) {
+  uint32_t c0 = idx, c1 = site, c2 = (uint32_t)step, c3 = (uint32_t)(step >> 32);
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
+__device__ __forceinline__ float philox_u(uint64_t seed, uint64_t step, uint32_t site, uint32_t idx) {
+  const uint4 r = philox4(seed, step, site, idx >> 2);
+  const uint32_t lane = idx & 3u;
+  return u01(lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w);
+}
+
+// ---------------------------------------------------------------------------------------------
+// vector loads of per-env rows
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load12(const float* __restrict__ base, int e, float v[12]) {
+  const float4* p = reinterpret_cast<const float4*>(base + (size_t)e * 12);
+  const float4 a = p[0], b = p[1], c = p[2];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
+}
+__device__ __forceinline__ void store12(float* __restrict__ base, int e, const float v[12]) {
+  float4* p = reinterpret_cast<float4*>(base + (size_t)e * 12);
+  p[0] = make_float4(v[0], v[1], v[2], v[3]);
+  p[1] = make_float4(v[4], v[5], v[6], v[7]);
+  p[2] = make_float4(v[8], v[9], v[10], v[11]);
+}
+
+// ring slot of push index j (j >= 0)
+__device__ __forceinline__ int ring_slot(int64_t j, int len) { return (int)(j % len); }
+
+// block-wide exclusive scan helper result for compaction
+struct BlockRank {
+  int rank;   // exclusive rank of this thread's flag within the CTA
+  int total;  // flags set in the CTA
+};
+__device__ __forceinline__ BlockRank block_rank(bool flag, int* s_warp /* >= 32 ints */) {
+  const unsigned bal = __ballot_sync(0xffffffffu, flag);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  if (lane == 0) s_warp[warp] = __popc(bal);
+  __syncthreads();
+  int before = 0, total = 0;
+  for (int w = 0; w < nwarp; ++w) {
+    const int c = s_warp[w];
+    if (w < warp) before += c;
+    total += c;
+  }
+  __syncthreads();
+  BlockRank r;
+  r.rank = before + __popc(bal & ((1u << lane) - 1u));
+  r.total = total;
+  return r;
+}
+
+}  // namespace ti5

@@ -1,0 +1,110 @@
+// Generalised advantage estimation: rs:97-119 `RolloutStorage.compute_returns`.
+// Scan kernel: one thread per env walks the T steps backwards; every (T,N) array is read
+// and written coalesced along N.  The batch statistics for the advantage normalisation
+// (mean, unbiased std over all T*N values) are accumulated in double as (count, sum, sum of
+// squares): per-CTA partials, then the last CTA to finish folds them into stats[0..2].
+// The normalisation is a second, purely streaming kernel, so a multi-GPU caller can
+// all-reduce the three doubles in between.
+#include "ti5_device.cuh"
+#include "ti5_host.h"
+
+namespace ti5 {
+
+constexpr int GB = 128;
+
+__global__ void __launch_bounds__(GB)
+gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const uint8_t* __restrict__ dones,
+                const float* __restrict__ last_values, float* __restrict__ returns, float* __restrict__ advantages,
+                int T, int N, float gamma, float lam, double* stats, int* ticket) {
+  __shared__ double s_sum[GB / 32], s_sq[GB / 32];
+  __shared__ bool s_last;
+  const int n = blockIdx.x * GB + threadIdx.x;
+  double sum = 0.0, sq = 0.0;
+  if (n < N) {
+    float adv = 0.0f;
+    float nxt = last_values[n];
+    for (int t = T - 1; t >= 0; --t) {
+      const size_t i = (size_t)t * N + n;
+      const float v = values[i];
+      const float alive = 1.0f - (float)dones[i];
+      const float delta = (rewards[i] + (alive * gamma) * nxt) - v;
+      adv = delta + ((alive * gamma) * lam) * adv;
+      const float ret = adv + v;
+      returns[i] = ret;
+      const float a = ret - v;
+      advantages[i] = a;
+      sum += (double)a;
+      sq += (double)a * (double)a;
+      nxt = v;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_sum[warp] = sum; s_sq[warp] = sq; }
+  __syncthreads();
+  double* part = stats + 4;
+  if (threadIdx.x == 0) {
+    double a = 0.0, c = 0.0;
+    for (int w = 0; w < GB / 32; ++w) { a += s_sum[w]; c += s_sq[w]; }
+    part[2 * blockIdx.x] = a;
+    part[2 * blockIdx.x + 1] = c;
+    __threadfence();
+    s_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double a = 0.0, c = 0.0;
+    for (int i = 0; i < (int)gridDim.x; ++i) {
+      a += ((volatile double*)part)[2 * i];
+      c += ((volatile double*)part)[2 * i + 1];
+    }
+    stats[0] = (double)T * (double)N;
+    stats[1] = a;
+    stats[2] = c;
+    *ticket = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) gae_normalize_kernel(float* __restrict__ advantages, size_t total,
+                                                            const double* __restrict__ stats) {
+  const double cnt = stats[0], sum = stats[1], sq = stats[2];
+  const double mean = sum / cnt;
+  const double var = (sq - sum * mean) / (cnt - 1.0);      // unbiased (torch.std default, appendix A27)
+  const float mean_f = (float)mean;
+  const float denom = (float)sqrt(var > 0.0 ? var : 0.0) + 1e-8f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
+    advantages[i] = (advantages[i] - mean_f) / denom;
+}
+
+}  // namespace ti5
+
+extern "C" int ti5_gae_scan(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
+                            float* returns, float* advantages, int32_t T, int32_t N, float gamma, float lam,
+                            double* stats, int32_t* ticket, void* stream) {
+  TI5_CHECK_ARGS(rewards && values && dones && last_values && returns && advantages && stats && ticket && T > 0 && N > 0);
+  const int blocks = (N + ti5::GB - 1) / ti5::GB;
+  ti5::gae_scan_kernel<<<blocks, ti5::GB, 0, (cudaStream_t)stream>>>(rewards, values, dones, last_values, returns,
+                                                                      advantages, T, N, gamma, lam, stats, ticket);
+  return ti5_check_launch("ti5_gae_scan");
+}
+
+extern "C" int ti5_gae_normalize(float* advantages, int32_t T, int32_t N, const double* stats, void* stream) {
+  TI5_CHECK_ARGS(advantages && stats && T > 0 && N > 0);
+  const size_t total = (size_t)T * N;
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  ti5::gae_normalize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(advantages, total, stats);
+  return ti5_check_launch("ti5_gae_normalize");
+}
+
+extern "C" int ti5_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
+                       float* returns, float* advantages, int32_t T, int32_t N, float gamma, float lam, double* stats,
+                       int32_t* ticket, void* stream) {
+  const int rc = ti5_gae_scan(rewards, values, dones, last_values, returns, advantages, T, N, gamma, lam, stats, ticket, stream);
+  return rc != TI5_OK ? rc : ti5_gae_normalize(advantages, T, N, stats, stream);
+}

@@ -1,0 +1,497 @@
+// Post-physics phase, part 2: reset scatter for the envs flagged by ti5_post_physics, then the
+// observation frames, the history rings and the `last_*` copies.  One thread per env; frames
+// are staged in shared memory so the ring rows are written as contiguous 188 B / 292 B runs.
+//
+// Replaces t1:483-559 (T1 reset_idx with lr:604-651 randomize_lag_props, lr:732-783
+// randomize_dof_props, lr:1076-1120 _reset_dofs/_reset_root_states, lr:1138-1158 terrain
+// curriculum, t1:109-124 generate_gait_time), t1:368-481 (compute_observations with t1:250-274
+// compute_ref_state), lr:496-499 (last_* copies) and lr:441-446 (observation clip).
+//
+// History layout: the reference keeps a deque of H (N,47) tensors and re-stacks it into a fresh
+// (N, H*47) tensor every step (12.4 KB/env written, then clipped again).  Here the history is a
+// mirrored ring (N, 2H, K): step s writes its frame at slots s%H and s%H+H, so the H most recent
+// frames, oldest first, are always the contiguous run starting at slot s%H+1 of each env row —
+// the caller returns that run as a strided view and nothing is re-stacked.  Frames are clipped to
+// +-clip_obs on the way in: clip(stack(f)) == stack(clip(f)), and nothing else reads the ring.
+#include "ti5_device.cuh"
+#include "ti5_host.h"
+
+namespace ti5 {
+
+struct ObsRng {
+  const Ti5Params& p;
+  const Ti5Rng& r;
+  uint64_t step;
+  bool philox;
+  __device__ __forceinline__ float dofs(int e, int d) const {
+    return philox ? philox_u(p.seed, step, S_DOFS, e * D + d) : r.dofs[(size_t)e * D + d];
+  }
+  __device__ __forceinline__ float root_xy(int e, int c) const {
+    return philox ? philox_u(p.seed, step, S_ROOT, e * 2 + c) : r.root_xy[(size_t)e * 2 + c];
+  }
+  __device__ __forceinline__ float dr(int e, int row, int d) const {
+    return philox ? philox_u(p.seed, step, S_DR + 0, (e * 7 + row) * D + d) : r.dr[((size_t)e * 7 + row) * D + d];
+  }
+  __device__ __forceinline__ float gait_time(int e, int gi) const {
+    return philox ? philox_u(p.seed, step, S_GAIT_TIME, e * TI5_MAX_GAITS + gi) : r.gait_time[(size_t)e * p.num_gaits + gi];
+  }
+  __device__ __forceinline__ float cmd(int pass, int gi, int e, int c, int N) const {
+    return philox ? philox_u(p.seed, step, S_CMD + 4 * pass + gi, e * 3 + c)
+                  : r.cmd[((size_t)(pass * p.num_gaits + gi) * N + e) * 3 + c];
+  }
+  __device__ __forceinline__ float noise(int e, int k) const {
+    return philox ? philox_u(p.seed, step, S_NOISE, e * 64 + k) : r.noise[(size_t)e * p.num_single_obs + k];
+  }
+  __device__ __forceinline__ int lag_idx(int e, int which) const {
+    if (!philox) return (int)r.lag_idx[(size_t)e * 3 + which];
+    const int lo = p.lag_range[which][0], hi = p.lag_range[which][1];
+    int v = lo + (int)(philox_u(p.seed, step, S_LAG, e * 3 + which) * (float)(hi - lo + 1));
+    return v > hi ? hi : v;
+  }
+  __device__ __forceinline__ float gait_start(int e) const {
+    if (!philox) return (float)r.gait_start[e] * 0.5f;
+    return philox_u(p.seed, step, S_GAIT_START, e) < 0.5f ? 0.0f : 0.5f;
+  }
+  __device__ __forceinline__ int64_t terrain_level(int e) const {
+    if (!philox) return r.terrain_level[e] % p.max_terrain_level;
+    int64_t v = (int64_t)(philox_u(p.seed, step, S_TERRAIN, e) * (float)p.max_terrain_level);
+    return v >= p.max_terrain_level ? p.max_terrain_level - 1 : v;
+  }
+};
+
+__global__ void __launch_bounds__(128)
+reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
+                     const __grid_constant__ Ti5Rng r, int phases) {
+  extern __shared__ float smem[];      // per warp: 32 x K observation frames, then 32 x P privileged frames
+  __shared__ int s_warp[32];
+  __shared__ float s_lvl[4];
+  __shared__ bool s_last;
+
+  const int N = p.num_envs, K = p.num_single_obs, P = p.priv_frame, H = p.frame_stack, CH = p.c_frame_stack;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool live = e < N;
+  Ti5Globals* g = b.globals;
+  const int64_t step = g->step_index;
+  const int64_t pushes = step * p.decimation;            // lag pushes completed after this step
+  const bool any_reset = g->n_reset > 0;
+  const bool do_reset = (phases & TI5_RO_RESET) != 0, do_obs = (phases & TI5_RO_OBSERVE) != 0;
+  const int dm = p.div_mode;
+  const ObsRng rng{p, r, (uint64_t)step, p.rng_mode == TI5_RNG_PHILOX};
+  const int Kp = K | 1, Pp = P | 1;                      // odd row strides: conflict-free staging
+  float* s_obs = smem + (size_t)warp * 32 * (Kp + Pp);
+  float* s_priv = s_obs + 32 * Kp;
+
+  const bool reset = live && do_reset && b.reset_buf[e] != 0;
+  float level_f = 0.0f;
+
+  if (live) {
+    float root[RB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) root[i] = b.root_states[(size_t)e * RB + i];
+    float q[D], qd[D];
+    {
+      const float4* ds = reinterpret_cast<const float4*>(b.dof_state + (size_t)e * 2 * D);
+#pragma unroll
+      for (int i = 0; i < D / 2; ++i) {
+        const float4 v = ds[i];
+        q[2 * i] = v.x; qd[2 * i] = v.y; q[2 * i + 1] = v.z; qd[2 * i + 1] = v.w;
+      }
+    }
+    float act[D];
+    load12(b.actions, e, act);
+    float4 cmd = reinterpret_cast<const float4*>(b.commands)[e];
+    int64_t ep_len = b.episode_length_buf[e];
+    int64_t phase_len = b.phase_length_buf[e];
+    float gait_start = b.gait_start[e];
+    int64_t stamp = b.ring_stamp[e];
+    int lag_dof = b.lag_timestep[e * 3 + 1], lag_imu = b.lag_timestep[e * 3 + 2];
+    float lin[3], ang[3], eul[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      lin[i] = b.base_lin_vel[e * 3 + i];
+      ang[i] = b.base_ang_vel[e * 3 + i];
+      eul[i] = b.base_euler_xyz[e * 3 + i];
+    }
+    float last_act[D];
+    load12(b.last_actions, e, last_act);
+
+    // =========================== reset scatter (t1:483-559) ===============================
+    if (reset) {
+      if (p.flags & TI5_F_TERRAIN_CURRICULUM) {                        // lr:1138-1158
+        const float ox = b.env_origins[e * 3 + 0], oy = b.env_origins[e * 3 + 1];
+        const float dx = root[0] - ox, dy = root[1] - oy;
+        const float dist = sqrtf(dx * dx + dy * dy);
+        const bool up = dist > (float)(p.terrain_env_length / 2.0);
+        const float cn = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y);
+        const bool down = (dist < cn * p.max_episode_length_s * 0.5f) && !up;
+        int64_t lvl = b.terrain_levels[e] + (up ? 1 : 0) - (down ? 1 : 0);
+        lvl = lvl >= p.max_terrain_level ? rng.terrain_level(e) : (lvl < 0 ? 0 : lvl);
+        b.terrain_levels[e] = lvl;
+        const float* o = b.terrain_origins + ((size_t)lvl * p.terrain_cols + b.terrain_types[e]) * 3;
+        b.env_origins[e * 3 + 0] = o[0]; b.env_origins[e * 3 + 1] = o[1]; b.env_origins[e * 3 + 2] = o[2];
+      }
+      // lr:1076-1090 joint state; lr:1092-1120 root state
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        q[i] = p.default_dof_pos[i] + affine(p.dof_reset_w, p.dof_reset_lo, rng.dofs(e, i));
+        qd[i] = 0.0f;
+      }
+      {
+        float4* ds = reinterpret_cast<float4*>(b.dof_state + (size_t)e * 2 * D);
+#pragma unroll
+        for (int i = 0; i < D / 2; ++i) ds[i] = make_float4(q[2 * i], 0.0f, q[2 * i + 1], 0.0f);
+      }
+#pragma unroll
+      for (int i = 0; i < RB; ++i) root[i] = p.base_init_state[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) root[i] += b.env_origins[e * 3 + i];
+      if (p.flags & TI5_F_CUSTOM_ORIGINS) {
+        root[0] += affine(p.root_xy_w, p.root_xy_lo, rng.root_xy(e, 0));
+        root[1] += affine(p.root_xy_w, p.root_xy_lo, rng.root_xy(e, 1));
+      }
+#pragma unroll
+      for (int i = 0; i < RB; ++i) b.root_states[(size_t)e * RB + i] = root[i];
+      // lr:732-783 actuator randomisation
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const size_t o = (size_t)e * D + i;
+        if (p.flags & TI5_F_RAND_TORQUE) b.torque_multi[o] = affine(p.torque_multi_w, p.torque_multi_lo, rng.dr(e, 0, i));
+        if (p.flags & TI5_F_RAND_MOTOR_OFFSET) b.motor_offsets[o] = affine(p.motor_offset_w, p.motor_offset_lo, rng.dr(e, 1, i));
+        if (p.flags & TI5_F_RAND_GAINS) {
+          b.p_gains_r[o] = affine(p.kp_mult_w, p.kp_mult_lo, rng.dr(e, 2, i)) * p.p_gains[i];
+          b.d_gains_r[o] = affine(p.kd_mult_w, p.kd_mult_lo, rng.dr(e, 3, i)) * p.d_gains[i];
+        }
+        if (p.flags & TI5_F_RAND_COULOMB) {
+          b.coulomb[o] = affine(p.coulomb_w, p.coulomb_lo, rng.dr(e, 4, i));
+          b.viscous[o] = affine(p.viscous_w, p.viscous_lo, rng.dr(e, 5, i));
+        }
+        if (p.flags & TI5_F_RAND_ARMATURE) b.joint_armatures[o] = affine(p.armature_w[i], p.armature_lo[i], rng.dr(e, 6, i));
+      }
+      // lr:604-633: the env's lag rings read as zero from now on; new lag indices
+      stamp = pushes;
+      b.ring_stamp[e] = stamp;
+      if (p.flags & TI5_F_ADD_LAG)
+        b.lag_timestep[e * 3 + 0] = (p.flags & TI5_F_RAND_LAG_STEPS) ? rng.lag_idx(e, 0) : p.lag_range[0][1];
+      if (p.flags & TI5_F_ADD_DOF_LAG)
+        b.lag_timestep[e * 3 + 1] = lag_dof = (p.flags & TI5_F_RAND_DOF_LAG_STEPS) ? rng.lag_idx(e, 1) : p.lag_range[1][1];
+      if (p.flags & TI5_F_ADD_IMU_LAG)
+        b.lag_timestep[e * 3 + 2] = lag_imu = (p.flags & TI5_F_RAND_IMU_LAG_STEPS) ? rng.lag_idx(e, 2) : p.lag_range[2][1];
+      // t1:513-523
+#pragma unroll
+      for (int i = 0; i < D; ++i) { act[i] = 0.0f; last_act[i] = 0.0f; }
+      store12(b.actions, e, act);
+      b.feet_air_time[e * 2 + 0] = 0.0f; b.feet_air_time[e * 2 + 1] = 0.0f;
+      ep_len = 0;
+      phase_len = 0;
+      b.episode_length_buf[e] = 0;
+      gait_start = rng.gait_start(e);
+      b.gait_start[e] = gait_start;
+      {   // t1:109-124 generate_gait_time
+        float rg[TI5_MAX_GAITS], sum = 0.0f;
+        for (int gi = 0; gi < p.num_gaits; ++gi) {
+          rg[gi] = affine(p.gait_time_w[gi], p.gait_time_lo[gi], rng.gait_time(e, gi));
+          sum += rg[gi];
+        }
+        const float fac = (1.0f / sum) * (float)p.max_episode_length;   // Tensor.__rtruediv__: reciprocal, then multiply
+        float run = (rg[0] * fac) * 0.0f;
+        b.gait_time[e * p.num_gaits + 0] = (int32_t)run;
+        for (int gi = 1; gi < p.num_gaits; ++gi) {
+          run += rg[gi - 1] * fac;
+          b.gait_time[e * p.num_gaits + gi] = (int32_t)run;
+        }
+      }
+      for (int t = 0; t < TI5_NUM_TERMS; ++t)                           // t1:533
+        if (p.term_mask & (1u << t)) b.episode_sums[(size_t)t * N + e] = 0.0f;
+      // t1:548-552 derived state of the re-spawned base
+      const float bq[4] = {root[3], root[4], root[5], root[6]};
+      const V3 l = quat_rotate_inverse(bq, V3{root[7], root[8], root[9]});
+      const V3 a = quat_rotate_inverse(bq, V3{root[10], root[11], root[12]});
+      const V3 gr = quat_rotate_inverse(bq, V3{0.0f, 0.0f, -1.0f});
+      euler_xyz(bq, eul);
+      lin[0] = l.x; lin[1] = l.y; lin[2] = l.z;
+      ang[0] = a.x; ang[1] = a.y; ang[2] = a.z;
+      reinterpret_cast<float4*>(b.base_quat)[e] = make_float4(bq[0], bq[1], bq[2], bq[3]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        b.base_lin_vel[e * 3 + i] = lin[i];
+        b.base_ang_vel[e * 3 + i] = ang[i];
+        b.base_euler_xyz[e * 3 + i] = eul[i];
+      }
+      b.projected_gravity[e * 3 + 0] = gr.x; b.projected_gravity[e * 3 + 1] = gr.y; b.projected_gravity[e * 3 + 2] = gr.z;
+    }
+    // t1:527 `_resample_commands()` runs over ALL envs whenever anything reset (appendix A24)
+    if (do_reset && any_reset) {
+      for (int gi = 0; gi < p.num_gaits; ++gi) {
+        if (ep_len != (int64_t)b.gait_time[e * p.num_gaits + gi]) continue;
+        const int kind = p.gait_kind[gi];
+        const bool mx = kind == TI5_GAIT_WALK_SAGITTAL || kind == TI5_GAIT_WALK_OMNI;
+        const bool my = kind == TI5_GAIT_WALK_LATERAL || kind == TI5_GAIT_WALK_OMNI;
+        const bool mz = kind == TI5_GAIT_ROTATE || kind == TI5_GAIT_WALK_OMNI;
+        cmd.x = mx ? affine((float)(g->cmd_range[0][1] - g->cmd_range[0][0]), (float)g->cmd_range[0][0], rng.cmd(1, gi, e, 0, N)) : 0.0f;
+        cmd.y = my ? affine((float)(g->cmd_range[1][1] - g->cmd_range[1][0]), (float)g->cmd_range[1][0], rng.cmd(1, gi, e, 1, N)) : 0.0f;
+        cmd.z = mz ? affine((float)(g->cmd_range[2][1] - g->cmd_range[2][0]), (float)g->cmd_range[2][0], rng.cmd(1, gi, e, 2, N)) : 0.0f;
+      }
+      reinterpret_cast<float4*>(b.commands)[e] = cmd;
+      if (b.time_outs_latched) b.time_outs_latched[e] = b.time_out_buf[e];      // t1:540-541 (appendix A23)
+    }
+    if (p.flags & TI5_F_TRIMESH) level_f = (float)b.terrain_levels[e];
+
+    // =========================== observations (t1:368-481) =================================
+    if (do_obs) {
+      const bool stand = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y + cmd.z * cmd.z) <= p.stand_threshold;
+      if (stand) phase_len = 0;                                               // t1:86 side effect
+      b.phase_length_buf[e] = phase_len;
+      const float phase = (py_mod(sdiv((float)phase_len * p.dt, p.cycle_time, dm), 1.0f) + gait_start) * (stand ? 0.0f : 1.0f);
+      const float ang_ph = TWO_PI_F * phase;
+      const float s = sinf(ang_ph), c = cosf(ang_ph);
+      // t1:250-274 reference pose
+      float ref[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) ref[i] = 0.0f;
+      {
+        const float sl = s > 0.0f ? 0.0f : s, sr = s < 0.0f ? 0.0f : s;
+        const float a1 = p.target_joint_pos_scale, a2 = p.target_joint_pos_scale2;
+        ref[2] = sl * a1; ref[3] = (-sl) * a2; ref[4] = sl * a1;
+        ref[8] = (-sr) * a1; ref[9] = sr * a2; ref[10] = (-sr) * a1;
+        if (fabsf(s) < 0.1f) {
+#pragma unroll
+          for (int i = 0; i < D; ++i) ref[i] = 0.0f;
+        }
+      }
+      float ref_act[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) { ref_act[i] = 2.0f * ref[i]; ref[i] = ref[i] + p.default_dof_pos[i]; }
+      store12(b.ref_action, e, ref_act);
+      store12(b.ref_dof_pos, e, ref);
+      float stance[2] = {s >= 0.0f ? 1.0f : 0.0f, s < 0.0f ? 1.0f : 0.0f};
+      if (fabsf(s) < 0.1f) stance[0] = stance[1] = 1.0f;
+      const float fz0 = b.contact_forces[((size_t)e * NB + p.feet[0]) * 3 + 2];
+      const float fz1 = b.contact_forces[((size_t)e * NB + p.feet[1]) * 3 + 2];
+
+      float* po = s_priv + lane * Pp;
+      float* oo = s_obs + lane * Kp;
+      const float ci[5] = {s, c, cmd.x * p.cmd_scale[0], cmd.y * p.cmd_scale[1], cmd.z * p.cmd_scale[2]};
+#pragma unroll
+      for (int i = 0; i < 5; ++i) { po[i] = ci[i]; oo[i] = ci[i]; }
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        po[5 + i] = (q[i] - p.default_dof_pos[i]) * p.obs_dof_pos;
+        po[17 + i] = qd[i] * p.obs_dof_vel;
+        po[29 + i] = act[i];
+        po[41 + i] = q[i] - ref[i];
+        oo[29 + i] = act[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        po[53 + i] = lin[i] * p.obs_lin_vel;
+        po[56 + i] = ang[i] * p.obs_ang_vel;
+        po[59 + i] = eul[i] * p.obs_quat;
+      }
+      if (p.flags & TI5_F_ADD_EXT_FORCE) {                                     // t1:386-388
+        po[62] = sdiv(b.ext_forces[e * 3 + 0], p.ext_force_div, dm);
+        po[63] = sdiv(b.ext_forces[e * 3 + 1], p.ext_force_div, dm);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) po[64 + i] = sdiv(b.ext_torques[e * 3 + i], p.ext_torque_div, dm);
+      } else {
+        po[62] = b.rand_push_force[e * 3 + 0];
+        po[63] = b.rand_push_force[e * 3 + 1];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) po[64 + i] = b.rand_push_torque[e * 3 + i];
+      }
+      po[67] = b.env_frictions[e];
+      po[68] = sdiv(b.body_mass[e], 30.0f, dm);
+      po[69] = stance[0]; po[70] = stance[1];
+      po[71] = fz0 > 5.0f ? 1.0f : 0.0f; po[72] = fz1 > 5.0f ? 1.0f : 0.0f;
+      if (p.flags & TI5_F_MEASURE_HEIGHTS) {                                   // t1:466-468
+        const float* mh = b.measured_heights + (size_t)e * p.num_height_points;
+        for (int i = 0; i < p.num_height_points; ++i)
+          po[73 + i] = clampf((root[2] - 0.5f) - mh[i], -1.0f, 1.0f) * p.obs_height;
+      }
+      // lagged proprioception (t1:407-451): rows pushed before the env's last reset read as zero
+      {
+        float lq[D], lqd[D];
+        const int64_t jj = (pushes - 1) - lag_dof;
+        if (!(p.flags & TI5_F_ADD_DOF_LAG)) {
+#pragma unroll
+          for (int i = 0; i < D; ++i) { lq[i] = q[i]; lqd[i] = qd[i]; }
+        } else if (jj >= stamp && jj >= 0) {
+          const float* row = b.dof_ring + ((size_t)ring_slot(jj, p.dof_lag_len) * N + e) * (2 * D);
+          load12(row, 0, lq);
+          load12(row + D, 0, lqd);
+        } else {
+#pragma unroll
+          for (int i = 0; i < D; ++i) { lq[i] = 0.0f; lqd[i] = 0.0f; }
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          oo[5 + i] = (lq[i] - p.default_dof_pos[i]) * p.obs_dof_pos;
+          oo[17 + i] = lqd[i] * p.obs_dof_vel;
+        }
+        float imu[6];
+        const int64_t ji = (pushes - 1) - lag_imu;
+        if (!(p.flags & TI5_F_ADD_IMU_LAG)) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) { imu[i] = ang[i]; imu[3 + i] = eul[i]; }
+        } else if (ji >= stamp && ji >= 0) {
+          const float* row = b.imu_ring + ((size_t)ring_slot(ji, p.imu_lag_len) * N + e) * 6;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) imu[i] = row[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) imu[i] = 0.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          oo[41 + i] = imu[i] * p.obs_ang_vel;
+          oo[44 + i] = imu[3 + i] * p.obs_quat;
+        }
+      }
+      if (p.flags & TI5_F_ADD_NOISE) {                                         // t1:471-472
+        for (int k = 0; k < K; ++k)
+          oo[k] = oo[k] + ((2.0f * rng.noise(e, k) - 1.0f) * p.noise_vec[k]) * p.noise_level;
+      }
+      // lr:496-499 previous-step copies (live state only; the dead ones are not kept)
+      store12(b.last_last_actions, e, last_act);
+      store12(b.last_actions, e, act);
+      store12(b.last_dof_vel, e, qd);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) b.last_root_vel[e * 6 + i] = root[7 + i];
+    } else if (reset) {
+      // stand-alone reset: the zeroed previous-step buffers of t1:513-518
+      store12(b.last_last_actions, e, last_act);
+      store12(b.last_actions, e, last_act);
+      float z[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) z[i] = 0.0f;
+      store12(b.last_dof_vel, e, z);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) b.last_root_vel[e * 6 + i] = 0.0f;
+      b.phase_length_buf[e] = phase_len;
+    }
+  }
+
+  // ---- history rings: zero the rows of re-spawned envs (t1:556-559, `*= 0`), then append -----
+  const size_t obs_row = (size_t)2 * H * K, priv_row = (size_t)2 * CH * P;
+  const int warp_env0 = blockIdx.x * blockDim.x + warp * 32;
+  unsigned rmask = __ballot_sync(0xffffffffu, reset);
+  while (rmask) {
+    const int src = __ffs(rmask) - 1;
+    rmask &= rmask - 1;
+    float* orow = b.obs_ring + (size_t)(warp_env0 + src) * obs_row;
+    for (size_t i = lane; i < obs_row; i += 32) orow[i] = orow[i] * 0.0f;
+    float* prow = b.priv_ring + (size_t)(warp_env0 + src) * priv_row;
+    for (size_t i = lane; i < priv_row; i += 32) prow[i] = prow[i] * 0.0f;
+  }
+  __syncwarp();
+  if (do_obs) {
+    const int n_here = min(32, N - warp_env0);
+    const int hs = (int)((step - 1) % H), cs = (int)((step - 1) % CH);     // slot of this step's frame
+    const float lim = p.clip_obs;
+    for (int i = lane; i < n_here * K; i += 32) {
+      const int en = i / K, k = i - en * K;
+      const float v = clampf(s_obs[en * Kp + k], -lim, lim);
+      float* rowp = b.obs_ring + (size_t)(warp_env0 + en) * obs_row;
+      rowp[(size_t)hs * K + k] = v;
+      rowp[(size_t)(hs + H) * K + k] = v;
+    }
+    for (int i = lane; i < n_here * P; i += 32) {
+      const int en = i / P, k = i - en * P;
+      const float v = clampf(s_priv[en * Pp + k], -lim, lim);
+      float* rowp = b.priv_ring + (size_t)(warp_env0 + en) * priv_row;
+      rowp[(size_t)cs * P + k] = v;
+      rowp[(size_t)(cs + CH) * P + k] = v;
+    }
+  }
+
+  // ---- ascending id list of the envs reset this step (lr:490) --------------------------------
+  const BlockRank br = block_rank(reset, s_warp);
+  if (reset && b.reset_ids) b.reset_ids[b.block_counts[blockIdx.x] + br.rank] = e;
+
+  // ---- extras["episode"]["terrain_level"] = mean(terrain_levels) (t1:535-536) ------------------
+  if ((p.flags & TI5_F_TRIMESH) && do_reset) {
+    float v = level_f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_lvl[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.0f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_lvl[w];
+      b.block_sums[(size_t)blockIdx.x * TI5_LOG_COLS + LOG_TERRAIN_LEVEL] = t;
+      __threadfence();
+      s_last = atomicAdd(&g->tickets[1], 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+      __threadfence();
+      g->tickets[1] = 0;
+      if (any_reset) {
+        double acc = 0.0;
+        for (int i = 0; i < (int)gridDim.x; ++i)
+          acc += (double)((volatile float*)b.block_sums)[(size_t)i * TI5_LOG_COLS + LOG_TERRAIN_LEVEL];
+        b.extras_log[(size_t)(step % TI5_LOG_ROWS) * TI5_LOG_COLS + LOG_TERRAIN_LEVEL] = (float)(acc / (double)N);
+      }
+    }
+  }
+}
+
+// lr:441-446 / t1:477-481: contiguous copies of the current windows for callers that need them
+__global__ void __launch_bounds__(256) materialize_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b) {
+  const int N = p.num_envs, K = p.num_single_obs, P = p.priv_frame, H = p.frame_stack, CH = p.c_frame_stack;
+  const int64_t step = b.globals->step_index;
+  const size_t ow = (size_t)H * K, pw = (size_t)CH * P;
+  const size_t o_off = (size_t)(((step - 1) % H) + 1) * K, p_off = (size_t)(((step - 1) % CH) + 1) * P;
+  const size_t total_o = (size_t)N * ow, total_p = (size_t)N * pw;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_o + total_p; i += stride) {
+    if (i < total_o) {
+      if (b.obs_out) {
+        const size_t en = i / ow, k = i - en * ow;
+        b.obs_out[i] = b.obs_ring[en * 2 * ow + o_off + k];
+      }
+    } else if (b.priv_out) {
+      const size_t j = i - total_o, en = j / pw, k = j - en * pw;
+      b.priv_out[j] = b.priv_ring[en * 2 * pw + p_off + k];
+    }
+  }
+}
+
+}  // namespace ti5
+
+using namespace ti5;
+
+extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, int phases, void* stream) {
+  TI5_CHECK_ARGS(p && b && p->num_envs > 0 && (phases & 3) != 0);
+  TI5_CHECK_ARGS(p->env_block == 32 || p->env_block == 64 || p->env_block == 128);
+  TI5_CHECK_ARGS(p->num_single_obs == 47 && p->priv_frame >= 73 && p->num_single_obs <= 64);
+  TI5_CHECK_ARGS(p->rng_mode == TI5_RNG_PHILOX || (r && r->cmd && r->dofs && r->dr && r->gait_time && r->noise));
+  Ti5Rng rr = r ? *r : Ti5Rng{};
+  const int blocks = (p->num_envs + p->env_block - 1) / p->env_block;
+  const size_t smem = (size_t)p->env_block * ((p->num_single_obs | 1) + (p->priv_frame | 1)) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(reset_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      ti5_set_error("ti5_reset_observe: %zu bytes of shared memory per CTA not available", smem);
+      cudaGetLastError();
+      return TI5_ECUDA;
+    }
+    configured = smem;
+  }
+  reset_observe_kernel<<<blocks, p->env_block, smem, (cudaStream_t)stream>>>(*p, *b, rr, phases);
+  return ti5_check_launch("ti5_reset_observe");
+}
+
+extern "C" int ti5_reset_scatter(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, void* stream) {
+  return ti5_reset_observe(p, b, r, TI5_RO_RESET, stream);
+}
+
+extern "C" int ti5_observations(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, void* stream) {
+  return ti5_reset_observe(p, b, r, TI5_RO_OBSERVE, stream);
+}
+
+extern "C" int ti5_materialize_obs(const Ti5Params* p, const Ti5Buffers* b, void* stream) {
+  TI5_CHECK_ARGS(p && b && p->num_envs > 0 && (b->obs_out || b->priv_out));
+  materialize_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(*p, *b);
+  return ti5_check_launch("ti5_materialize_obs");
+}

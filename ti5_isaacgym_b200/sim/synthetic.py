@@ -87,3 +87,84 @@ def synthetic_height_field(rows=2100, cols=2100, seed=7, device="cpu"):
     """int16 height samples standing in for `Terrain.heightsamples` (lr:1237)."""
     g = torch.Generator().manual_seed(seed)
     return torch.randint(-20, 60, (rows, cols), generator=g, dtype=torch.int16).to(device)
+
+
+class SimParams:
+    """The two `gymapi.SimParams` fields the hot path reads (lr:96, base_task.py:26)."""
+
+    def __init__(self, dt=0.001, use_gpu_pipeline=True, substeps=1):
+        self.dt = dt
+        self.use_gpu_pipeline = use_gpu_pipeline
+        self.substeps = substeps
+
+
+class SyntheticGym:
+    """Stands where `gymapi.acquire_gym()` stands in the reference (base_task.py:14) when Isaac
+    Gym is not installed: it owns the four state tensors with the tensor-API layout and accepts
+    the tensor-API calls of the hot path (lr:403-410, 429, 464-466, 1088, 1118; t1:230, 247).
+    `simulate` is a no-op unless a `physics` callable is installed (tests use it to refresh the
+    state between substeps)."""
+
+    def __init__(self, num_envs, device):
+        self.num_envs, self.device = num_envs, device
+        self.tensors = alloc_sim_tensors(num_envs, device)
+        self.physics = None
+        self.substep = 0
+        self.indexed_calls = []      # (kind, int32 ids) of the indexed setters, newest last
+        self.applied_forces = None
+
+    def acquire_actor_root_state_tensor(self, sim=None):
+        return self.tensors.root_states
+
+    def acquire_dof_state_tensor(self, sim=None):
+        return self.tensors.dof_state
+
+    def acquire_net_contact_force_tensor(self, sim=None):
+        return self.tensors.contact_forces
+
+    def acquire_rigid_body_state_tensor(self, sim=None):
+        return self.tensors.rigid_state
+
+    def simulate(self, sim=None):
+        if self.physics is not None:
+            self.physics(self.substep)
+        self.substep += 1
+
+    def _noop(self, *a, **k):
+        return None
+
+    fetch_results = refresh_dof_state_tensor = refresh_actor_root_state_tensor = _noop
+    refresh_net_contact_force_tensor = refresh_rigid_body_state_tensor = _noop
+    set_dof_actuation_force_tensor = set_actor_root_state_tensor = _noop
+
+    def set_dof_state_tensor_indexed(self, sim, state, ids, n):
+        self.indexed_calls.append(("dof", ids))
+
+    def set_actor_root_state_tensor_indexed(self, sim, state, ids, n):
+        self.indexed_calls.append(("root", ids))
+
+    def apply_rigid_body_force_tensors(self, sim, forces, torques, space=0):
+        self.applied_forces = (forces, torques)
+
+
+class SyntheticTerrain:
+    """Stand-in for `humanoid.utils.terrain.Terrain` (one-time CPU set-up built on
+    isaacgym.terrain_utils; out of scope): a random int16 height field of
+    the real shape (2100 x 2100 for the t1 cfg) plus the (num_rows, num_cols, 3) platform-origin
+    table the terrain curriculum indexes (lr:1158, 1493)."""
+
+    def __init__(self, cfg, num_robots):
+        import numpy as np
+        self.cfg = cfg
+        self.env_length, self.env_width = cfg.terrain_length, cfg.terrain_width
+        px = int(cfg.terrain_length / cfg.horizontal_scale)
+        py = int(cfg.terrain_width / cfg.horizontal_scale)
+        border = int(cfg.border_size / cfg.horizontal_scale)
+        self.tot_rows = int(cfg.num_rows * px) + 2 * border
+        self.tot_cols = int(cfg.num_cols * py) + 2 * border
+        self.heightsamples = synthetic_height_field(self.tot_rows, self.tot_cols, seed=7).numpy()
+        self.vertices = np.zeros((3, 3), dtype=np.float32)
+        self.triangles = np.zeros((1, 3), dtype=np.uint32)
+        i, j = np.meshgrid(np.arange(cfg.num_rows), np.arange(cfg.num_cols), indexing="ij")
+        self.env_origins = np.stack(((i + 0.5) * self.env_length, (j + 0.5) * self.env_width,
+                                     0.01 * ((i * 7 + j * 3) % 11)), axis=-1).astype(np.float64)
