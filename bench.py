@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the t1_dh_stand hot path (BASELINE.json metric: env-steps/sec, step math + reward + obs,
+8192 envs/GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference's algorithm on the host CPU
+    torchrun --nproc-per-node N bench.py --gpus N ...               # one rank per GPU, envs sharded 8192/rank
+
+One "step" = one policy step of every env of the rank: 10 x (PD torque + lag push) + post-physics
+(derived state, command schedule, termination, 24 reward terms, reset scatter, observation frames +
+history rings), plus the GAE reverse scan over the 24-step rollout every 24th step.  Physics is not
+part of the metric: the simulator tensors hold one draw of the synthetic near-nominal state
+ and `simulate` is a no-op, exactly like the fake gym the reference baseline runs on.
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM and the L2
+flushed between timed steps; `e2e` goes through the public `env.step()` with pinned HOST buffers
+(H2D of the actions, D2H of reward / reset / time-out flags, a stream sync per step).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 8192
+ROLLOUT = 24
+GAMMA, LAM = 0.994, 0.9
+# algorithmic bytes per env per launch (fp32, D=12, K=47, P=73)
+BYTES_SUBSTEP = 584 + 244          # fused torque + lag push of one substep
+BYTES_POST = 2412                  # post-physics + reset/observe, ring-view variant
+BYTES_ENV_STEP = 10 * BYTES_SUBSTEP + BYTES_POST
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [s.strip() for s in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]),
+                "samples": len(self.rows), "reasons": reasons}
+
+
+def make_cfg(num_envs):
+    from ti5_isaacgym_b200.envs import DHT1StandCfg
+    cfg = DHT1StandCfg()
+    cfg.env.num_envs = num_envs
+    cfg.terrain.mesh_type = "plane"         # BASELINE config 2: flat plane
+    cfg.seed = 5
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference arm / CPU baseline: the oracle port of the reference's torch algorithm on host cores
+# ---------------------------------------------------------------------------------------------
+
+def run_cpu_port(num_envs, steps, warmup, seed=1234):
+    from types import SimpleNamespace
+    from oracle import t1_oracle as O
+    from ti5_isaacgym_b200.envs.t1.t1_robot import robot_constants
+    from ti5_isaacgym_b200.sim.synthetic import alloc_sim_tensors, fill_synthetic_state, synthetic_actions
+    cfg = make_cfg(num_envs)
+    C = O.make_consts(cfg, cfg.sim.dt, robot_constants(cfg))
+    S = O.new_state(C, num_envs)
+    gen = torch.Generator().manual_seed(seed)
+    sim = alloc_sim_tensors(num_envs, "cpu")
+    fill_synthetic_state(sim, S.env_origins, gen)
+    S.episode_length_buf[:] = torch.randint(1, 2000, (num_envs,), generator=gen)
+    S.gait_time[:, 1], S.gait_time[:, 2] = 900, 1500
+    actions = synthetic_actions(num_envs, gen, "cpu")
+    pools = O.draw_pools(C, num_envs, gen)
+    rew = torch.randn(ROLLOUT, num_envs, 1, generator=gen)
+    val = torch.randn(ROLLOUT, num_envs, 1, generator=gen)
+    done = (torch.rand(ROLLOUT, num_envs, 1, generator=gen) < 0.02).byte()
+    last = torch.randn(num_envs, 1, generator=gen)
+
+    def one(i):
+        O.step(C, S, sim, actions, pools)
+        if (i + 1) % ROLLOUT == 0:
+            O.gae_returns(rew, val, done, last, GAMMA, LAM)
+
+    with torch.inference_mode():
+        for i in range(warmup):
+            one(i)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            one(i)
+        dt = time.perf_counter() - t0
+    return num_envs * steps / dt, dt / steps * 1e3
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = torch.get_num_threads()
+    value, ms = run_cpu_port(ENVS_PER_GPU, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "env-steps/sec (step math + reward + obs)", "value": value,
+            "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": "t1_dh_stand 8192 envs, flat plane, full step + 24-step rollout GAE",
+                                            "device": "host CPU", "physics": "no-op (fake gym)"},
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} steps x {ENVS_PER_GPU} envs of the oracle port (torch CPU, "
+                                       "the reference's op chains), all host threads"},
+            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------
+
+def cuda_arm(args):
+    import torch.distributed as dist
+    from ti5_isaacgym_b200.algo.rollout_storage import gae_returns_, make_gae_scratch
+    from ti5_isaacgym_b200.envs import T1DHStandEnv
+    from ti5_isaacgym_b200.sim.synthetic import SimParams, fill_synthetic_state, synthetic_actions
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the step math has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+        group = dist.group.WORLD
+    N = args.envs
+    cfg = make_cfg(N)
+    cfg.seed = 5 + rank
+    env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, dev, True, rng_mode="philox", div_mode="reciprocal",
+                       use_cuda_graph=True, materialize_obs=args.materialize)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    fill_synthetic_state(env.gym.tensors, env.env_origins, gen)
+    env.reset()
+    env.episode_length_buf = torch.randint(1, 2000, (N,), generator=gen, device=dev)
+    actions = synthetic_actions(N, gen, dev)
+    T = ROLLOUT
+    rew = torch.randn(T, N, 1, generator=gen, device=dev)
+    val = torch.randn(T, N, 1, generator=gen, device=dev)
+    done = (torch.rand(T, N, 1, generator=gen, device=dev) < 0.02).byte()
+    last = torch.randn(N, 1, generator=gen, device=dev)
+    ret, adv = torch.empty_like(rew), torch.empty_like(rew)
+    scratch = make_gae_scratch(N, dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one(i):
+        env.step(actions)
+        if (i + 1) % T == 0:
+            gae_returns_(rew, val, done, last, ret, adv, GAMMA, LAM, scratch, group)
+
+    for i in range(max(args.warmup, 3)):
+        one(i)
+    # ---- device-timed region: K steps, L2 flushed (outside the event brackets) between steps ----
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        starts[i].record()
+        one(i)
+        ends[i].record()
+    barrier()
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    clocks = sampler.summary() if sampler else None
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    value = world * N * args.steps / (dev_ms * 1e-3)
+
+    # ---- per-launch duration of the dominant kernel family (events on the launching stream) -------
+    kt = kernel_times(env, actions, steps=min(args.steps, 48))
+
+    # ---- end to end through env.step() with pinned host buffers ------------------------------------
+    h_act = actions.cpu().pin_memory()
+    d_act = torch.empty_like(actions)
+    h_rew = torch.empty(N, dtype=torch.float32).pin_memory()
+    h_flags = torch.empty(2, N, dtype=torch.bool).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        d_act.copy_(h_act, non_blocking=True)
+        _, _, r, rs, ex = env.step(d_act)
+        if (i + 1) % T == 0:
+            gae_returns_(rew, val, done, last, ret, adv, GAMMA, LAM, scratch, group)
+        h_rew.copy_(r, non_blocking=True)
+        h_flags[0].copy_(rs, non_blocking=True)
+        h_flags[1].copy_(ex["time_outs"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * args.steps / float(t.item())
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        dom = max(kt, key=lambda k: kt[k]["share_ms"])
+        # algorithmic bytes of one launch of the dominant family (SURVEY 8d figure x envs per launch);
+        # the post phase's 2412 B/env are spread over its two launches
+        bytes_per_launch = {"substep": BYTES_SUBSTEP * N * 10 / 11, "post_physics+reset_observe": BYTES_POST * N / 2}[dom]
+        ach = bytes_per_launch / (kt[dom]["ms_per_launch"] * 1e-3) / 1e9
+        launches_per_step = env.launches_per_step
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, ms = run_cpu_port(4096, 40, 3)
+            cpu = {"value": v, "unit": "env-steps/s", "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": "40 steps x 4096 envs (BASELINE config 1) of the oracle port, torch CPU, all host threads, "
+                             f"{ms:.1f} ms/step"}
+        line = {
+            "metric": "env-steps/sec (step math + reward + obs)", "value": value, "unit": "env-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"t1_dh_stand {N} envs/GPU, flat plane, full fused step + 24-step rollout GAE",
+                       "envs_per_gpu": N, "frame_stack": cfg.env.frame_stack, "obs": "materialised" if args.materialize else "ring view",
+                       "rng": "in-kernel Philox4x32-10", "physics": "no-op (synthetic state, SURVEY 8d)",
+                       "l2": "flushed between timed steps (256 MiB write outside the event brackets)",
+                       "launch": f"one CUDA graph per step ({env.launches_per_step} kernels)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h_act.numel() * 4 * world,
+                    "d2h_bytes_per_step": (h_rew.numel() * 4 + h_flags.numel()) * world,
+                    "note": "env.step() with pinned host actions in, reward/reset/time-out flags out, stream sync every step; L2 not flushed"},
+            "gpu_launches": launches_per_step * args.steps + 2 * (args.steps // T),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch,
+                         "ms_per_launch": kt[dom]["ms_per_launch"],
+                         "whole_step": {"bytes": BYTES_ENV_STEP * N, "achieved": BYTES_ENV_STEP * N * args.steps / (dev_ms * 1e-3) / 1e9},
+                         "kernels": kt,
+                         "how": "CUDA events on the launching stream around one CUDA graph per phase (L2 flushed before each step); per-launch = phase time / launches in the phase"},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_times(env, actions, steps):
+    """Average device time of the two phases of a step, CUDA events on the launching stream around
+    the replay of one CUDA graph per phase (a single whole-step graph cannot be bracketed inside).
+    The substep phase is begin_step + DEC launches of the fused substep kernel; its per-launch time is
+    phase time / (DEC + 1).  The post phase is post_physics + reset_observe (2 launches)."""
+    g_sub, g_post = env.capture_phase_graphs()
+    dec = env._params.decimation
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=env.device)
+    env._actions_in.copy_(actions)
+    acc = {"substep": [], "post_physics+reset_observe": []}
+    marks = []
+    for i in range(steps):
+        flush.fill_(i & 0xFF)
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        g_sub.replay()
+        e1.record()
+        g_post.replay()
+        e2.record()
+        env._finish_step()
+        marks.append((e0, e1, e2))
+    torch.cuda.synchronize()
+    for e0, e1, e2 in marks:
+        acc["substep"].append(e0.elapsed_time(e1))
+        acc["post_physics+reset_observe"].append(e1.elapsed_time(e2))
+    out = {}
+    for name, v in acc.items():
+        n = dec + 1 if name == "substep" else 2
+        phase = statistics.mean(v)
+        out[name] = {"phase_ms": phase, "launches": n, "ms_per_launch": phase / n, "share_ms": phase}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=240)
+    ap.add_argument("--warmup", type=int, default=24)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU (BASELINE metric: 8192)")
+    ap.add_argument("--materialize", action="store_true", help="also write contiguous (N,3102)/(N,219) observations")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        cuda_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -152,7 +152,8 @@ typedef struct Ti5Globals {
   int64_t step_index;          /* policy steps begun so far (ti5_begin_step increments) */
   int64_t common_step_offset;  /* common_step_counter = step_index + common_step_offset */
   int32_t n_reset;             /* envs reset in the current step (lr:490) */
-  int32_t tickets[4];          /* last-CTA-done counters of the per-env kernels */
+  int32_t n_listed;            /* entries of Ti5Buffers.reset_list (unordered), zeroed by ti5_begin_step */
+  int32_t tickets[3];          /* last-CTA-done counters of the per-env kernels */
   int32_t is_first_add_force;  /* lr:90, t1:205-215 */
   double cmd_range[3][2];      /* lin_vel_x, lin_vel_y, ang_vel_yaw ranges (curriculum mutates [0]) */
 } Ti5Globals;
@@ -232,6 +233,7 @@ typedef struct Ti5Buffers {
   float* episode_sums;     /* (TI5_NUM_TERMS, N) */
   float* reward_terms;     /* (TI5_NUM_TERMS, N) scaled per-term rewards of this step, or NULL */
   int32_t* reset_ids;      /* (N) ascending ids of the envs reset this step */
+  int32_t* reset_list;     /* (N) the same ids in arrival order (work list for the history clear) */
   int32_t* block_counts;   /* scratch: (ceil(N/32) + 1) */
   float* block_sums;       /* scratch: (ceil(N/32), TI5_LOG_COLS) */
   float* extras_log;       /* (TI5_LOG_ROWS, TI5_LOG_COLS) */

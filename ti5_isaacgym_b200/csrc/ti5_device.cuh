@@ -68,7 +68,7 @@ struct V3 {
 };
 
 // isaacgym.torch_utils.quat_rotate_inverse, q = (x, y, z, w)
-__device__ __forceinline__ V3 quat_rotate_inverse(const float q[4], V3 v) {
+static __device__ __noinline__ V3 quat_rotate_inverse(const float q[4], V3 v) {
   const float qw = q[3];
   const float s = 2.0f * (qw * qw) - 1.0f;
   const float cx = q[1] * v.z - q[2] * v.y;
@@ -102,7 +102,10 @@ __device__ __forceinline__ float euler_yaw(const float q[4]) {
   const float x = q[0], y = q[1], z = q[2], w = q[3];
   return wrap_angle(atan2f(2.0f * (w * z + x * y), ((w * w + x * x) - y * y) - z * z));
 }
-__device__ __forceinline__ void euler_xyz(const float q[4], float e[3]) {
+// expf as a real call: ~25 call sites share one copy of the libdevice body (and its I-cache lines)
+static __device__ __noinline__ float expf_call(float x) { return expf(x); }
+
+static __device__ __noinline__ void euler_xyz(const float q[4], float e[3]) {
   e[0] = euler_roll(q);
   e[1] = euler_pitch(q);
   e[2] = euler_yaw(q);
@@ -115,7 +118,7 @@ __device__ __forceinline__ void euler_xyz(const float q[4], float e[3]) {
 enum RngSite { S_TORQUE = 0, S_CMD = 16, S_PUSH = 24, S_EXT, S_DOFS, S_ROOT, S_DR, S_GAIT_TIME, S_NOISE, S_LAG,
                S_GAIT_START, S_TERRAIN };
 
-__device__ __forceinline__ uint4 philox4(uint64_t seed, uint64_t step, uint32_t site, uint32_t idx) {
+static __device__ __noinline__ uint4 philox4(uint64_t seed, uint64_t step, uint32_t site, uint32_t idx) {
   uint32_t c0 = idx, c1 = site, c2 = (uint32_t)step, c3 = (uint32_t)(step >> 32);
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
@@ -138,6 +141,12 @@ __device__ __forceinline__ float philox_u(uint64_t seed, uint64_t step, uint32_t
   return u01(lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w);
 }
 
+// four uniforms of one Philox call: element group `idx4` of a site
+__device__ __forceinline__ float4 philox_u4(uint64_t seed, uint64_t step, uint32_t site, uint32_t idx4) {
+  const uint4 r = philox4(seed, step, site, idx4);
+  return make_float4(u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+}
+
 // ---------------------------------------------------------------------------------------------
 // vector loads of per-env rows
 // ---------------------------------------------------------------------------------------------
@@ -154,6 +163,49 @@ __device__ __forceinline__ void store12(float* __restrict__ base, int e, const f
   p[1] = make_float4(v[4], v[5], v[6], v[7]);
   p[2] = make_float4(v[8], v[9], v[10], v[11]);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Tile staging: global -> shared with the TMA engine (cp.async.bulk + mbarrier).  A CTA that owns a
+// contiguous block of envs pulls every per-env array it needs as one bulk copy per array: all of the
+// tile's bytes are in flight at once and the math then runs out of shared memory, instead of ~100
+// scattered, serially exposed global loads per thread.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned) completing on `bar`
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// fallback for a partial tile (byte count not a multiple of 16): the CTA's threads copy word by word
+__device__ __forceinline__ void coop_load(void* dst, const void* src, uint32_t bytes) {
+  const uint32_t words = bytes >> 2;
+  for (uint32_t i = threadIdx.x; i < words; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+  const uint32_t tail = bytes & 3u;     // byte arrays (bool masks)
+  if (threadIdx.x < tail)
+    reinterpret_cast<uint8_t*>(dst)[(words << 2) + threadIdx.x] = reinterpret_cast<const uint8_t*>(src)[(words << 2) + threadIdx.x];
+}
+
+static __device__ __noinline__ void coop_load_call(void* dst, const void* src, uint32_t bytes) { coop_load(dst, src, bytes); }
 
 // ring slot of push index j (j >= 0)
 __device__ __forceinline__ int ring_slot(int64_t j, int len) { return (int)(j % len); }

@@ -23,14 +23,20 @@ struct ObsRng {
   const Ti5Rng& r;
   uint64_t step;
   bool philox;
-  __device__ __forceinline__ float dofs(int e, int d) const {
-    return philox ? philox_u(p.seed, step, S_DOFS, e * D + d) : r.dofs[(size_t)e * D + d];
+  // the eight per-DOF uniforms of a re-spawned env: [dof reset, torque multi, motor offset, kp, kd, coulomb,
+  // viscous, armature] for DOF d (lr:1084, lr:735-783)
+  __device__ __forceinline__ void dof_draws(int e, int d, float u[8]) const {
+    if (philox) {
+      const float4 a = philox_u4(p.seed, step, S_DR, (e * D + d) * 2), c = philox_u4(p.seed, step, S_DR, (e * D + d) * 2 + 1);
+      u[0] = a.x; u[1] = a.y; u[2] = a.z; u[3] = a.w; u[4] = c.x; u[5] = c.y; u[6] = c.z; u[7] = c.w;
+    } else {
+      u[0] = r.dofs[(size_t)e * D + d];
+#pragma unroll
+      for (int row = 0; row < 7; ++row) u[1 + row] = r.dr[((size_t)e * 7 + row) * D + d];
+    }
   }
   __device__ __forceinline__ float root_xy(int e, int c) const {
     return philox ? philox_u(p.seed, step, S_ROOT, e * 2 + c) : r.root_xy[(size_t)e * 2 + c];
-  }
-  __device__ __forceinline__ float dr(int e, int row, int d) const {
-    return philox ? philox_u(p.seed, step, S_DR + 0, (e * 7 + row) * D + d) : r.dr[((size_t)e * 7 + row) * D + d];
   }
   __device__ __forceinline__ float gait_time(int e, int gi) const {
     return philox ? philox_u(p.seed, step, S_GAIT_TIME, e * TI5_MAX_GAITS + gi) : r.gait_time[(size_t)e * p.num_gaits + gi];
@@ -39,8 +45,12 @@ struct ObsRng {
     return philox ? philox_u(p.seed, step, S_CMD + 4 * pass + gi, e * 3 + c)
                   : r.cmd[((size_t)(pass * p.num_gaits + gi) * N + e) * 3 + c];
   }
-  __device__ __forceinline__ float noise(int e, int k) const {
-    return philox ? philox_u(p.seed, step, S_NOISE, e * 64 + k) : r.noise[(size_t)e * p.num_single_obs + k];
+  // uniforms 4g .. 4g+3 of the env's noise row
+  __device__ __forceinline__ float4 noise4(int e, int g4, int K) const {
+    if (philox) return philox_u4(p.seed, step, S_NOISE, e * 16 + g4);
+    const float* row = r.noise + (size_t)e * K;
+    const int k = 4 * g4;
+    return make_float4(row[k], k + 1 < K ? row[k + 1] : 0.f, k + 2 < K ? row[k + 2] : 0.f, k + 3 < K ? row[k + 3] : 0.f);
   }
   __device__ __forceinline__ int lag_idx(int e, int which) const {
     if (!philox) return (int)r.lag_idx[(size_t)e * 3 + which];
@@ -59,6 +69,105 @@ struct ObsRng {
   }
 };
 
+// t1:483-559 reset of env `es`, shared by the 32 lanes of the warp that owns it: lanes 0-11 take one DOF
+// each (joint state, actuator randomisation, zeroed action history), lane 12 the base (terrain curriculum,
+// root state, derived base quantities), lane 13 the schedule (lag indices, counters, gait times), and
+// lanes 0-27 clear one episode sum each.  Everything goes to global memory; the owning lane reloads.
+__device__ __forceinline__ void reset_env(const Ti5Params& p, const Ti5Buffers& b, const ObsRng& rng, int es, int lane,
+                                          int64_t pushes) {
+  const int N = p.num_envs;
+  if (lane < D) {
+    const int d = lane;
+    const size_t o = (size_t)es * D + d;
+    float u[8];
+    rng.dof_draws(es, d, u);
+    // lr:1076-1090 joint state
+    reinterpret_cast<float2*>(b.dof_state)[o] = make_float2(p.default_dof_pos[d] + affine(p.dof_reset_w, p.dof_reset_lo, u[0]), 0.0f);
+    // lr:732-783 actuator randomisation
+    if (p.flags & TI5_F_RAND_TORQUE) b.torque_multi[o] = affine(p.torque_multi_w, p.torque_multi_lo, u[1]);
+    if (p.flags & TI5_F_RAND_MOTOR_OFFSET) b.motor_offsets[o] = affine(p.motor_offset_w, p.motor_offset_lo, u[2]);
+    if (p.flags & TI5_F_RAND_GAINS) {
+      b.p_gains_r[o] = affine(p.kp_mult_w, p.kp_mult_lo, u[3]) * p.p_gains[d];
+      b.d_gains_r[o] = affine(p.kd_mult_w, p.kd_mult_lo, u[4]) * p.d_gains[d];
+    }
+    if (p.flags & TI5_F_RAND_COULOMB) {
+      b.coulomb[o] = affine(p.coulomb_w, p.coulomb_lo, u[5]);
+      b.viscous[o] = affine(p.viscous_w, p.viscous_lo, u[6]);
+    }
+    if (p.flags & TI5_F_RAND_ARMATURE) b.joint_armatures[o] = affine(p.armature_w[d], p.armature_lo[d], u[7]);
+    // t1:513-518
+    b.actions[o] = 0.0f; b.last_actions[o] = 0.0f; b.last_last_actions[o] = 0.0f; b.last_dof_vel[o] = 0.0f;
+  } else if (lane == 12) {
+    float* root = b.root_states + (size_t)es * RB;
+    if (p.flags & TI5_F_TERRAIN_CURRICULUM) {                        // lr:1138-1158
+      const float dx = root[0] - b.env_origins[es * 3 + 0], dy = root[1] - b.env_origins[es * 3 + 1];
+      const float dist = sqrtf(dx * dx + dy * dy);
+      const bool up = dist > (float)(p.terrain_env_length / 2.0);
+      const float cx = b.commands[es * 4 + 0], cy = b.commands[es * 4 + 1];
+      const bool down = (dist < sqrtf(cx * cx + cy * cy) * p.max_episode_length_s * 0.5f) && !up;
+      int64_t lvl = b.terrain_levels[es] + (up ? 1 : 0) - (down ? 1 : 0);
+      lvl = lvl >= p.max_terrain_level ? rng.terrain_level(es) : (lvl < 0 ? 0 : lvl);
+      b.terrain_levels[es] = lvl;
+      const float* o = b.terrain_origins + ((size_t)lvl * p.terrain_cols + b.terrain_types[es]) * 3;
+      b.env_origins[es * 3 + 0] = o[0]; b.env_origins[es * 3 + 1] = o[1]; b.env_origins[es * 3 + 2] = o[2];
+    }
+    float r0[RB];                                                     // lr:1092-1120
+#pragma unroll
+    for (int i = 0; i < RB; ++i) r0[i] = p.base_init_state[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) r0[i] += b.env_origins[es * 3 + i];
+    if (p.flags & TI5_F_CUSTOM_ORIGINS) {
+      r0[0] += affine(p.root_xy_w, p.root_xy_lo, rng.root_xy(es, 0));
+      r0[1] += affine(p.root_xy_w, p.root_xy_lo, rng.root_xy(es, 1));
+    }
+#pragma unroll
+    for (int i = 0; i < RB; ++i) root[i] = r0[i];
+    // t1:548-552 derived state of the re-spawned base
+    const float bq[4] = {r0[3], r0[4], r0[5], r0[6]};
+    const V3 l = quat_rotate_inverse(bq, V3{r0[7], r0[8], r0[9]});
+    const V3 a = quat_rotate_inverse(bq, V3{r0[10], r0[11], r0[12]});
+    const V3 gr = quat_rotate_inverse(bq, V3{0.0f, 0.0f, -1.0f});
+    float eul[3];
+    euler_xyz(bq, eul);
+    reinterpret_cast<float4*>(b.base_quat)[es] = make_float4(bq[0], bq[1], bq[2], bq[3]);
+    b.base_lin_vel[es * 3 + 0] = l.x; b.base_lin_vel[es * 3 + 1] = l.y; b.base_lin_vel[es * 3 + 2] = l.z;
+    b.base_ang_vel[es * 3 + 0] = a.x; b.base_ang_vel[es * 3 + 1] = a.y; b.base_ang_vel[es * 3 + 2] = a.z;
+    b.projected_gravity[es * 3 + 0] = gr.x; b.projected_gravity[es * 3 + 1] = gr.y; b.projected_gravity[es * 3 + 2] = gr.z;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) b.base_euler_xyz[es * 3 + i] = eul[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) b.last_root_vel[es * 6 + i] = 0.0f;
+  } else if (lane == 13) {
+    // lr:604-633: the env's lag rings read as zero from now on; new lag indices
+    b.ring_stamp[es] = pushes;
+    if (p.flags & TI5_F_ADD_LAG)
+      b.lag_timestep[es * 3 + 0] = (p.flags & TI5_F_RAND_LAG_STEPS) ? rng.lag_idx(es, 0) : p.lag_range[0][1];
+    if (p.flags & TI5_F_ADD_DOF_LAG)
+      b.lag_timestep[es * 3 + 1] = (p.flags & TI5_F_RAND_DOF_LAG_STEPS) ? rng.lag_idx(es, 1) : p.lag_range[1][1];
+    if (p.flags & TI5_F_ADD_IMU_LAG)
+      b.lag_timestep[es * 3 + 2] = (p.flags & TI5_F_RAND_IMU_LAG_STEPS) ? rng.lag_idx(es, 2) : p.lag_range[2][1];
+    b.feet_air_time[es * 2 + 0] = 0.0f; b.feet_air_time[es * 2 + 1] = 0.0f;        // t1:519-523
+    b.episode_length_buf[es] = 0;
+    b.phase_length_buf[es] = 0;
+    b.gait_start[es] = rng.gait_start(es);
+    // t1:109-124 generate_gait_time
+    float rg[TI5_MAX_GAITS], sum = 0.0f;
+    for (int gi = 0; gi < p.num_gaits; ++gi) {
+      rg[gi] = affine(p.gait_time_w[gi], p.gait_time_lo[gi], rng.gait_time(es, gi));
+      sum += rg[gi];
+    }
+    const float fac = (1.0f / sum) * (float)p.max_episode_length;   // Tensor.__rtruediv__: reciprocal, then multiply
+    float run = (rg[0] * fac) * 0.0f;
+    b.gait_time[es * p.num_gaits + 0] = (int32_t)run;
+    for (int gi = 1; gi < p.num_gaits; ++gi) {
+      run += rg[gi - 1] * fac;
+      b.gait_time[es * p.num_gaits + gi] = (int32_t)run;
+    }
+  }
+  if (lane < TI5_NUM_TERMS && (p.term_mask & (1u << lane))) b.episode_sums[(size_t)lane * N + es] = 0.0f;   // t1:533
+}
+
+template <int KC, int PC>
 __global__ void __launch_bounds__(128)
 reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
                      const __grid_constant__ Ti5Rng r, int phases) {
@@ -67,9 +176,11 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
   __shared__ float s_lvl[4];
   __shared__ bool s_last;
 
-  const int N = p.num_envs, K = p.num_single_obs, P = p.priv_frame, H = p.frame_stack, CH = p.c_frame_stack;
+  // frame widths as compile-time constants where known: the flat ring-write loops divide by them
+  const int N = p.num_envs, K = KC ? KC : p.num_single_obs, P = PC ? PC : p.priv_frame, H = p.frame_stack, CH = p.c_frame_stack;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int env_blocks = (N + blockDim.x - 1) / blockDim.x;   // CTAs beyond these only help clearing histories
   const bool live = e < N;
   Ti5Globals* g = b.globals;
   const int64_t step = g->step_index;
@@ -84,6 +195,18 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
 
   const bool reset = live && do_reset && b.reset_buf[e] != 0;
   float level_f = 0.0f;
+
+  // =========================== reset scatter (t1:483-559), one env at a time per warp ===========
+  {
+    unsigned todo = __ballot_sync(0xffffffffu, reset);
+    const int env0 = blockIdx.x * blockDim.x + warp * 32;
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      reset_env(p, b, rng, env0 + src, lane, pushes);
+    }
+    __syncwarp();
+  }
 
   if (live) {
     float root[RB];
@@ -116,110 +239,6 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
     float last_act[D];
     load12(b.last_actions, e, last_act);
 
-    // =========================== reset scatter (t1:483-559) ===============================
-    if (reset) {
-      if (p.flags & TI5_F_TERRAIN_CURRICULUM) {                        // lr:1138-1158
-        const float ox = b.env_origins[e * 3 + 0], oy = b.env_origins[e * 3 + 1];
-        const float dx = root[0] - ox, dy = root[1] - oy;
-        const float dist = sqrtf(dx * dx + dy * dy);
-        const bool up = dist > (float)(p.terrain_env_length / 2.0);
-        const float cn = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y);
-        const bool down = (dist < cn * p.max_episode_length_s * 0.5f) && !up;
-        int64_t lvl = b.terrain_levels[e] + (up ? 1 : 0) - (down ? 1 : 0);
-        lvl = lvl >= p.max_terrain_level ? rng.terrain_level(e) : (lvl < 0 ? 0 : lvl);
-        b.terrain_levels[e] = lvl;
-        const float* o = b.terrain_origins + ((size_t)lvl * p.terrain_cols + b.terrain_types[e]) * 3;
-        b.env_origins[e * 3 + 0] = o[0]; b.env_origins[e * 3 + 1] = o[1]; b.env_origins[e * 3 + 2] = o[2];
-      }
-      // lr:1076-1090 joint state; lr:1092-1120 root state
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        q[i] = p.default_dof_pos[i] + affine(p.dof_reset_w, p.dof_reset_lo, rng.dofs(e, i));
-        qd[i] = 0.0f;
-      }
-      {
-        float4* ds = reinterpret_cast<float4*>(b.dof_state + (size_t)e * 2 * D);
-#pragma unroll
-        for (int i = 0; i < D / 2; ++i) ds[i] = make_float4(q[2 * i], 0.0f, q[2 * i + 1], 0.0f);
-      }
-#pragma unroll
-      for (int i = 0; i < RB; ++i) root[i] = p.base_init_state[i];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) root[i] += b.env_origins[e * 3 + i];
-      if (p.flags & TI5_F_CUSTOM_ORIGINS) {
-        root[0] += affine(p.root_xy_w, p.root_xy_lo, rng.root_xy(e, 0));
-        root[1] += affine(p.root_xy_w, p.root_xy_lo, rng.root_xy(e, 1));
-      }
-#pragma unroll
-      for (int i = 0; i < RB; ++i) b.root_states[(size_t)e * RB + i] = root[i];
-      // lr:732-783 actuator randomisation
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        const size_t o = (size_t)e * D + i;
-        if (p.flags & TI5_F_RAND_TORQUE) b.torque_multi[o] = affine(p.torque_multi_w, p.torque_multi_lo, rng.dr(e, 0, i));
-        if (p.flags & TI5_F_RAND_MOTOR_OFFSET) b.motor_offsets[o] = affine(p.motor_offset_w, p.motor_offset_lo, rng.dr(e, 1, i));
-        if (p.flags & TI5_F_RAND_GAINS) {
-          b.p_gains_r[o] = affine(p.kp_mult_w, p.kp_mult_lo, rng.dr(e, 2, i)) * p.p_gains[i];
-          b.d_gains_r[o] = affine(p.kd_mult_w, p.kd_mult_lo, rng.dr(e, 3, i)) * p.d_gains[i];
-        }
-        if (p.flags & TI5_F_RAND_COULOMB) {
-          b.coulomb[o] = affine(p.coulomb_w, p.coulomb_lo, rng.dr(e, 4, i));
-          b.viscous[o] = affine(p.viscous_w, p.viscous_lo, rng.dr(e, 5, i));
-        }
-        if (p.flags & TI5_F_RAND_ARMATURE) b.joint_armatures[o] = affine(p.armature_w[i], p.armature_lo[i], rng.dr(e, 6, i));
-      }
-      // lr:604-633: the env's lag rings read as zero from now on; new lag indices
-      stamp = pushes;
-      b.ring_stamp[e] = stamp;
-      if (p.flags & TI5_F_ADD_LAG)
-        b.lag_timestep[e * 3 + 0] = (p.flags & TI5_F_RAND_LAG_STEPS) ? rng.lag_idx(e, 0) : p.lag_range[0][1];
-      if (p.flags & TI5_F_ADD_DOF_LAG)
-        b.lag_timestep[e * 3 + 1] = lag_dof = (p.flags & TI5_F_RAND_DOF_LAG_STEPS) ? rng.lag_idx(e, 1) : p.lag_range[1][1];
-      if (p.flags & TI5_F_ADD_IMU_LAG)
-        b.lag_timestep[e * 3 + 2] = lag_imu = (p.flags & TI5_F_RAND_IMU_LAG_STEPS) ? rng.lag_idx(e, 2) : p.lag_range[2][1];
-      // t1:513-523
-#pragma unroll
-      for (int i = 0; i < D; ++i) { act[i] = 0.0f; last_act[i] = 0.0f; }
-      store12(b.actions, e, act);
-      b.feet_air_time[e * 2 + 0] = 0.0f; b.feet_air_time[e * 2 + 1] = 0.0f;
-      ep_len = 0;
-      phase_len = 0;
-      b.episode_length_buf[e] = 0;
-      gait_start = rng.gait_start(e);
-      b.gait_start[e] = gait_start;
-      {   // t1:109-124 generate_gait_time
-        float rg[TI5_MAX_GAITS], sum = 0.0f;
-        for (int gi = 0; gi < p.num_gaits; ++gi) {
-          rg[gi] = affine(p.gait_time_w[gi], p.gait_time_lo[gi], rng.gait_time(e, gi));
-          sum += rg[gi];
-        }
-        const float fac = (1.0f / sum) * (float)p.max_episode_length;   // Tensor.__rtruediv__: reciprocal, then multiply
-        float run = (rg[0] * fac) * 0.0f;
-        b.gait_time[e * p.num_gaits + 0] = (int32_t)run;
-        for (int gi = 1; gi < p.num_gaits; ++gi) {
-          run += rg[gi - 1] * fac;
-          b.gait_time[e * p.num_gaits + gi] = (int32_t)run;
-        }
-      }
-      for (int t = 0; t < TI5_NUM_TERMS; ++t)                           // t1:533
-        if (p.term_mask & (1u << t)) b.episode_sums[(size_t)t * N + e] = 0.0f;
-      // t1:548-552 derived state of the re-spawned base
-      const float bq[4] = {root[3], root[4], root[5], root[6]};
-      const V3 l = quat_rotate_inverse(bq, V3{root[7], root[8], root[9]});
-      const V3 a = quat_rotate_inverse(bq, V3{root[10], root[11], root[12]});
-      const V3 gr = quat_rotate_inverse(bq, V3{0.0f, 0.0f, -1.0f});
-      euler_xyz(bq, eul);
-      lin[0] = l.x; lin[1] = l.y; lin[2] = l.z;
-      ang[0] = a.x; ang[1] = a.y; ang[2] = a.z;
-      reinterpret_cast<float4*>(b.base_quat)[e] = make_float4(bq[0], bq[1], bq[2], bq[3]);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        b.base_lin_vel[e * 3 + i] = lin[i];
-        b.base_ang_vel[e * 3 + i] = ang[i];
-        b.base_euler_xyz[e * 3 + i] = eul[i];
-      }
-      b.projected_gravity[e * 3 + 0] = gr.x; b.projected_gravity[e * 3 + 1] = gr.y; b.projected_gravity[e * 3 + 2] = gr.z;
-    }
     // t1:527 `_resample_commands()` runs over ALL envs whenever anything reset (appendix A24)
     if (do_reset && any_reset) {
       for (int gi = 0; gi < p.num_gaits; ++gi) {
@@ -348,8 +367,15 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
         }
       }
       if (p.flags & TI5_F_ADD_NOISE) {                                         // t1:471-472
-        for (int k = 0; k < K; ++k)
-          oo[k] = oo[k] + ((2.0f * rng.noise(e, k) - 1.0f) * p.noise_vec[k]) * p.noise_level;
+        for (int g4 = 0; 4 * g4 < K; ++g4) {
+          const float4 u = rng.noise4(e, g4, K);
+          const float uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = 4 * g4 + j;
+            if (k < K) oo[k] = oo[k] + ((2.0f * uu[j] - 1.0f) * p.noise_vec[k]) * p.noise_level;
+          }
+        }
       }
       // lr:496-499 previous-step copies (live state only; the dead ones are not kept)
       store12(b.last_last_actions, e, last_act);
@@ -357,36 +383,16 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
       store12(b.last_dof_vel, e, qd);
 #pragma unroll
       for (int i = 0; i < 6; ++i) b.last_root_vel[e * 6 + i] = root[7 + i];
-    } else if (reset) {
-      // stand-alone reset: the zeroed previous-step buffers of t1:513-518
-      store12(b.last_last_actions, e, last_act);
-      store12(b.last_actions, e, last_act);
-      float z[D];
-#pragma unroll
-      for (int i = 0; i < D; ++i) z[i] = 0.0f;
-      store12(b.last_dof_vel, e, z);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) b.last_root_vel[e * 6 + i] = 0.0f;
-      b.phase_length_buf[e] = phase_len;
     }
   }
 
-  // ---- history rings: zero the rows of re-spawned envs (t1:556-559, `*= 0`), then append -----
+  // ---- history rings: append this step's frames; clear the rows of re-spawned envs ------------
   const size_t obs_row = (size_t)2 * H * K, priv_row = (size_t)2 * CH * P;
   const int warp_env0 = blockIdx.x * blockDim.x + warp * 32;
-  unsigned rmask = __ballot_sync(0xffffffffu, reset);
-  while (rmask) {
-    const int src = __ffs(rmask) - 1;
-    rmask &= rmask - 1;
-    float* orow = b.obs_ring + (size_t)(warp_env0 + src) * obs_row;
-    for (size_t i = lane; i < obs_row; i += 32) orow[i] = orow[i] * 0.0f;
-    float* prow = b.priv_ring + (size_t)(warp_env0 + src) * priv_row;
-    for (size_t i = lane; i < priv_row; i += 32) prow[i] = prow[i] * 0.0f;
-  }
+  const int hs = (int)((step - 1) % H), cs = (int)((step - 1) % CH);       // slot of this step's frame
   __syncwarp();
-  if (do_obs) {
+  if (do_obs && warp_env0 < N) {
     const int n_here = min(32, N - warp_env0);
-    const int hs = (int)((step - 1) % H), cs = (int)((step - 1) % CH);     // slot of this step's frame
     const float lim = p.clip_obs;
     for (int i = lane; i < n_here * K; i += 32) {
       const int en = i / K, k = i - en * K;
@@ -402,6 +408,60 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
       rowp[(size_t)cs * P + k] = v;
       rowp[(size_t)(cs + CH) * P + k] = v;
     }
+  }
+
+  // t1:556-559: `hist[i][env_ids] *= 0` for every frame of the re-spawned envs.  The flagged envs were
+  // listed (in arrival order) by ti5_post_physics / ti5_reset_bookkeeping; all warps of the grid,
+  // including the helper CTAs, share the (env, 512-float chunk) work items.  The two slots of this step's
+  // frame are skipped — their owner overwrites them above — so no ordering between warps is needed.
+  const int n_list = do_reset ? g->n_listed : 0;
+  if (n_list > 0) {
+    constexpr int CHUNK = 512, U = CHUNK / 32;
+    const int oc = (int)((obs_row + CHUNK - 1) / CHUNK), pc = (int)((priv_row + CHUNK - 1) / CHUNK);
+    const int per_env = oc + pc;
+    const int wpb = blockDim.x >> 5;
+    const int total = n_list * per_env, stride = gridDim.x * wpb;
+    for (int w = blockIdx.x * wpb + warp; w < total; w += stride) {
+      const int en = b.reset_list[w / per_env];
+      int c = w % per_env;
+      const bool is_obs = c < oc;
+      if (!is_obs) c -= oc;
+      float* row = is_obs ? b.obs_ring + (size_t)en * obs_row : b.priv_ring + (size_t)en * priv_row;
+      const int len = (int)(is_obs ? obs_row : priv_row), width = is_obs ? K : P;
+      const int s0 = (is_obs ? hs : cs) * width, s1 = (is_obs ? hs + H : cs + CH) * width;
+      float v[U];
+      bool ok[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int i = c * CHUNK + j * 32 + lane;
+        ok[j] = i < len && !(do_obs && ((i >= s0 && i < s0 + width) || (i >= s1 && i < s1 + width)));
+        if (ok[j]) v[j] = row[i];
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+        if (ok[j]) row[c * CHUNK + j * 32 + lane] = v[j] * 0.0f;
+    }
+  }
+  if (blockIdx.x >= env_blocks) {             // helper CTA
+    // extras["episode"]["rew_<term>"] = mean over the re-spawned envs of the episode sums / episode_length_s
+    // (t1:531-532): one helper warp per term folds the per-CTA partials ti5_post_physics left behind.
+    const int hw = (blockIdx.x - env_blocks) * (blockDim.x >> 5) + warp;
+    const int total = g->n_reset;
+    if (do_reset && total > 0 && hw < TI5_NUM_TERMS) {
+      double acc = 0.0;
+      for (int i = lane; i < env_blocks; i += 32) {
+        const int cnt = __ldcg(b.block_counts + i + 1) - __ldcg(b.block_counts + i);
+        const float v = __ldcg(b.block_sums + (size_t)i * TI5_LOG_COLS + hw);
+        acc += cnt > 0 ? (double)v : 0.0;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) {
+        const float mean = (float)(acc / (double)total);
+        b.extras_log[(size_t)(step % TI5_LOG_ROWS) * TI5_LOG_COLS + hw] = sdiv(mean, p.max_episode_length_s, dm);
+      }
+    }
+    return;
   }
 
   // ---- ascending id list of the envs reset this step (lr:490) --------------------------------
@@ -420,7 +480,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
       for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_lvl[w];
       b.block_sums[(size_t)blockIdx.x * TI5_LOG_COLS + LOG_TERRAIN_LEVEL] = t;
       __threadfence();
-      s_last = atomicAdd(&g->tickets[1], 1) == (int)gridDim.x - 1;
+      s_last = atomicAdd(&g->tickets[1], 1) == env_blocks - 1;
     }
     __syncthreads();
     if (s_last && threadIdx.x == 0) {
@@ -428,7 +488,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
       g->tickets[1] = 0;
       if (any_reset) {
         double acc = 0.0;
-        for (int i = 0; i < (int)gridDim.x; ++i)
+        for (int i = 0; i < env_blocks; ++i)
           acc += (double)((volatile float*)b.block_sums)[(size_t)i * TI5_LOG_COLS + LOG_TERRAIN_LEVEL];
         b.extras_log[(size_t)(step % TI5_LOG_ROWS) * TI5_LOG_COLS + LOG_TERRAIN_LEVEL] = (float)(acc / (double)N);
       }
@@ -469,16 +529,17 @@ extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const 
   Ti5Rng rr = r ? *r : Ti5Rng{};
   const int blocks = (p->num_envs + p->env_block - 1) / p->env_block;
   const size_t smem = (size_t)p->env_block * ((p->num_single_obs | 1) + (p->priv_frame | 1)) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(reset_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-      ti5_set_error("ti5_reset_observe: %zu bytes of shared memory per CTA not available", smem);
-      cudaGetLastError();
-      return TI5_ECUDA;
-    }
-    configured = smem;
+  auto kernel = p->priv_frame == 73 ? reset_observe_kernel<47, 73>
+                                    : (p->priv_frame == 260 ? reset_observe_kernel<47, 260> : reset_observe_kernel<47, 0>);
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    ti5_set_error("ti5_reset_observe: %zu bytes of shared memory per CTA not available", smem);
+    cudaGetLastError();
+    return TI5_ECUDA;
   }
-  reset_observe_kernel<<<blocks, p->env_block, smem, (cudaStream_t)stream>>>(*p, *b, rr, phases);
+  // + helper CTAs (about 4 warps per SM) that only share the history-clear work of re-spawned envs
+  const int helpers = (phases & TI5_RO_RESET) ? (148 * 4 * 32) / p->env_block : 0;
+  kernel<<<blocks + helpers, p->env_block, smem, (cudaStream_t)stream>>>(*p, *b, rr, phases);
   return ti5_check_launch("ti5_reset_observe");
 }
 

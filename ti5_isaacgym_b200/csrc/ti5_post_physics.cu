@@ -7,6 +7,8 @@
 // (_post_physics_step_callback), lr:509-517 (check_termination), lr:654-680 + t1:572-946
 // (compute_reward and the reward terms), and the reductions reset_idx needs before it can run
 // (lr:490 count, t1:530-541 episode means, lr:1160-1169 command curriculum).
+#include <cstddef>
+
 #include "ti5_device.cuh"
 #include "ti5_host.h"
 
@@ -21,47 +23,48 @@ struct FootState {
 };
 
 // t1:599-628 feet_distance / knee_distance
-__device__ __forceinline__ float pair_distance_reward(float ax, float ay, float bx, float by, float lo, float hi) {
+static __device__ __noinline__ float pair_distance_reward(float ax, float ay, float bx, float by, float lo, float hi) {
   const float dx = ax - bx, dy = ay - by;
   const float d = sqrtf(dx * dx + dy * dy);
   const float near_ = clampf(d - lo, -0.5f, 0.0f);
   const float far_ = clampf(d - hi, 0.0f, 0.5f);
-  return (expf(-fabsf(near_) * 100.0f) + expf(-fabsf(far_) * 100.0f)) / 2.0f;
+  return (expf_call(-fabsf(near_) * 100.0f) + expf_call(-fabsf(far_) * 100.0f)) / 2.0f;
 }
 
-// Reset bookkeeping shared by ti5_post_physics and ti5_reset_bookkeeping: per-CTA reset counts
-// and episode-sum partials; the last CTA to finish turns the counts into exclusive offsets
-// (consumed by ti5_reset_observe for the ascending id list), publishes n_reset, writes the
-// extras["episode"] snapshot row of this step and evaluates the command curriculum.
-__device__ __forceinline__ void reset_bookkeeping(const Ti5Params& p, const Ti5Buffers& b, bool reset,
-                                                  const float (&esum)[TI5_NUM_TERMS], int64_t step, int64_t counter,
-                                                  bool force_window, bool advance_force_flag) {
+// Reset bookkeeping shared by ti5_post_physics and ti5_reset_bookkeeping: per-CTA reset counts and
+// episode-sum partials (t1:531-533); the last CTA to finish turns the counts into exclusive offsets
+// (consumed by ti5_reset_observe for the ascending id list, lr:490), publishes n_reset, evaluates the
+// command curriculum (lr:1160-1169) and prepares the extras["episode"] snapshot row of this step.  The
+// 28 episode means themselves are reduced by helper warps of ti5_reset_observe, off the critical path.
+// `sums` is the CTA's shared tile [term][tb] (post-physics) or null (read episode_sums from memory).
+static __device__ __noinline__ void reset_bookkeeping(const Ti5Params& p, const Ti5Buffers& b, bool reset, int e, int le,
+                                                      const float* sums, int tb, int64_t step, int64_t counter,
+                                                      bool force_window, bool advance_force_flag) {
   __shared__ int s_warp[32];
-  __shared__ float s_red[4][TI5_NUM_TERMS];
+  __shared__ float s_red[12][TI5_NUM_TERMS];
   __shared__ bool s_last;
   Ti5Globals* g = b.globals;
-  const int dm = p.div_mode;
-  // ---- reset bookkeeping: per-CTA count and episode-sum partials; the last CTA finishes ------
+  const int N = p.num_envs, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  if (reset) b.reset_list[atomicAdd(&g->n_listed, 1)] = e;
   const BlockRank br = block_rank(reset, s_warp);
   const int nblk = gridDim.x;
   if (br.total > 0) {
-    // sum of the resetting envs' episode sums (t1:531-533), one column per term
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
+#pragma unroll 1
     for (int t = 0; t < TI5_NUM_TERMS; ++t) {
-      float v = reset ? esum[t] : 0.0f;
+      float v = 0.0f;
+      if (reset && (p.term_mask & (1u << t))) v = sums ? sums[t * tb + le] : b.episode_sums[(size_t)t * N + e];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane == 0) s_red[warp][t] = v;
     }
     __syncthreads();
-    if (threadIdx.x < TI5_NUM_TERMS) {
+    if (tid < TI5_NUM_TERMS) {
       float v = 0.0f;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += s_red[w][threadIdx.x];
-      b.block_sums[(size_t)blockIdx.x * TI5_LOG_COLS + threadIdx.x] = v;
+      for (int w = 0; w < (nt >> 5); ++w) v += s_red[w][tid];
+      b.block_sums[(size_t)blockIdx.x * TI5_LOG_COLS + tid] = v;
     }
   }
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     b.block_counts[blockIdx.x] = br.total;
     __threadfence();
     s_last = atomicAdd(&g->tickets[0], 1) == nblk - 1;
@@ -70,66 +73,169 @@ __device__ __forceinline__ void reset_bookkeeping(const Ti5Params& p, const Ti5B
   if (!s_last) return;
   __threadfence();
 
-  // exclusive prefix of the CTA counts -> offsets consumed by ti5_reset_observe for the ascending id list
-  __shared__ int s_total;
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int i = 0; i < nblk; ++i) {
-      const int c = ((volatile int*)b.block_counts)[i];
-      b.block_counts[i] = run;
-      run += c;
-    }
-    b.block_counts[nblk] = run;
-    s_total = run;
-    g->n_reset = run;
-    g->tickets[0] = 0;
-    if (advance_force_flag && (p.flags & TI5_F_ADD_EXT_FORCE)) g->is_first_add_force = force_window ? 0 : 1;
-  }
+  // exclusive prefix of the CTA counts: whole-CTA scan through shared memory, 1024 counts per tile
+  constexpr int TILE = 1024;
+  __shared__ int s_cnt[TILE];
+  __shared__ int s_scan[384];
+  __shared__ int s_carry;
+  __shared__ double s_track;
+  if (tid == 0) { s_carry = 0; s_track = 0.0; }
   __syncthreads();
-  const int total = s_total;
-  // extras["episode"] snapshot row of this step: new means if anything reset, else the previous row (A23)
+  for (int base = 0; base < nblk; base += TILE) {
+    const int n_here = min(TILE, nblk - base);
+    for (int i = tid; i < n_here; i += nt) s_cnt[i] = __ldcg(b.block_counts + base + i);
+    __syncthreads();
+    const int per = (n_here + nt - 1) / nt, lo = min(tid * per, n_here), hi = min(lo + per, n_here);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += s_cnt[i];
+    s_scan[tid] = sum;
+    __syncthreads();
+    int before = s_carry;
+    for (int w = 0; w < tid; ++w) before += s_scan[w];
+    __syncthreads();
+    // command curriculum input: sum of the resetting envs' tracking_lin_vel episode sums (only on the
+    // steps where common_step_counter % max_episode_length == 0, lr:537)
+    if ((p.flags & TI5_F_COMMAND_CURRICULUM) && (counter % p.max_episode_length == 0)) {
+      double part = 0.0;
+      for (int i = lo; i < hi; ++i)
+        if (s_cnt[i] > 0) part += (double)__ldcg(b.block_sums + (size_t)(base + i) * TI5_LOG_COLS + T_TRACKING_LIN_VEL);
+      if (part != 0.0) atomicAdd(&s_track, part);   // at most a handful of adds, once per 2400 steps
+    }
+    for (int i = lo; i < hi; ++i) {
+      const int c = s_cnt[i];
+      b.block_counts[base + i] = before;
+      before += c;
+    }
+    if (tid == nt - 1) s_carry = before;
+    __syncthreads();
+  }
+  const int total = s_carry;
   float* row = b.extras_log + (size_t)(step % TI5_LOG_ROWS) * TI5_LOG_COLS;
   const float* prev = b.extras_log + (size_t)((step + TI5_LOG_ROWS - 1) % TI5_LOG_ROWS) * TI5_LOG_COLS;
-  __shared__ double s_track;
-  if (threadIdx.x < TI5_NUM_TERMS) {
-    const int t = threadIdx.x;
-    float out = prev[t];
-    if (total > 0) {
-      // blocks without a reset never wrote their partial: skip them via their (now exclusive) offsets
-      double acc = 0.0;
-      for (int i = 0; i < nblk; ++i) {
-        const int cnt = b.block_counts[i + 1] - b.block_counts[i];
-        if (cnt > 0) acc += (double)((volatile float*)b.block_sums)[(size_t)i * TI5_LOG_COLS + t];
-      }
-      const float mean = (float)(acc / (double)total);
-      out = sdiv(mean, p.max_episode_length_s, dm);
-      if (t == T_TRACKING_LIN_VEL) s_track = acc / (double)total;
-    }
-    row[t] = out;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  // no reset this step: extras["episode"] keeps showing the previous values (appendix A23)
+  if (total == 0 && tid < TI5_LOG_COLS) row[tid] = prev[tid];
+  if (tid == 0) {
+    b.block_counts[nblk] = total;
+    g->n_reset = total;
+    g->tickets[0] = 0;
+    if (advance_force_flag && (p.flags & TI5_F_ADD_EXT_FORCE)) g->is_first_add_force = force_window ? 0 : 1;
     // lr:1160-1169 command curriculum, evaluated before the resets of this step (lr:537-538)
     if (total > 0 && (p.flags & TI5_F_COMMAND_CURRICULUM) && (counter % p.max_episode_length == 0)) {
-      const float lhs = sdiv((float)s_track, (float)p.max_episode_length, dm);
+      const float mean = (float)(s_track / (double)total);
+      const float lhs = sdiv(mean, (float)p.max_episode_length, p.div_mode);
       if (lhs > (float)(0.8 * p.tracking_lin_vel_scale)) {
-        double lo = g->cmd_range[0][0] - 0.25, hi = g->cmd_range[0][1] + 0.5;
+        const double lo = g->cmd_range[0][0] - 0.25, hi = g->cmd_range[0][1] + 0.5;
         const double lo_min = -p.cmd_curriculum_max / 2.0;
         g->cmd_range[0][0] = lo < lo_min ? lo_min : (lo > 0.0 ? 0.0 : lo);
         g->cmd_range[0][1] = hi < 0.0 ? 0.0 : (hi > p.cmd_curriculum_max ? p.cmd_curriculum_max : hi);
       }
     }
-    row[LOG_MAX_COMMAND_X] = (float)g->cmd_range[0][1];
-    row[LOG_N_RESET] = (float)total;
-    if (total == 0) row[LOG_TERRAIN_LEVEL] = prev[LOG_TERRAIN_LEVEL];
+    if (total > 0) {
+      row[LOG_MAX_COMMAND_X] = (float)g->cmd_range[0][1];
+      row[LOG_N_RESET] = (float)total;
+      if (!(p.flags & TI5_F_TRIMESH)) row[LOG_TERRAIN_LEVEL] = 0.0f;
+    }
   }
 }
 
-__global__ void __launch_bounds__(128)
+// Shared-memory tile of the per-env inputs of one CTA (TB = blockDim.x consecutive envs), filled by the
+// TMA engine.  Offsets are in bytes and every chunk starts 16-byte aligned.
+struct PostTile {
+  float *root, *dof, *contact, *rigid, *act, *last_act, *last_last_act, *last_dof_vel, *torques, *ref, *last_root_vel, *cmd;
+  float *gait_start, *air, *feet_h, *last_z, *sums, *vals;
+  int64_t *ep_len, *phase_len;
+  int32_t* gait_time;
+  uint8_t* last_contacts;
+  uint64_t* bar;
+};
+
+__host__ __device__ inline size_t post_tile_bytes(int tb, int ng) {
+  auto up = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  size_t o = 0;
+  o += up((size_t)tb * RB * 4) + up((size_t)tb * 2 * D * 4) + up((size_t)tb * NB * 3 * 4) + up((size_t)tb * NB * RB * 4);
+  o += 6 * up((size_t)tb * D * 4) + up((size_t)tb * 6 * 4) + up((size_t)tb * 4 * 4);
+  o += up((size_t)tb * 4) + 3 * up((size_t)tb * 2 * 4) + 2 * up((size_t)TI5_NUM_TERMS * tb * 4);
+  o += 2 * up((size_t)tb * 8) + up((size_t)tb * ng * 4) + up((size_t)tb * 2) + 16;
+  return o;
+}
+
+__device__ __forceinline__ PostTile carve_post_tile(unsigned char* base, int tb, int ng) {
+  PostTile t;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { unsigned char* p = base + o; o += (bytes + 15) & ~(size_t)15; return p; };
+  t.root = (float*)take((size_t)tb * RB * 4);
+  t.dof = (float*)take((size_t)tb * 2 * D * 4);
+  t.contact = (float*)take((size_t)tb * NB * 3 * 4);
+  t.rigid = (float*)take((size_t)tb * NB * RB * 4);
+  t.act = (float*)take((size_t)tb * D * 4);
+  t.last_act = (float*)take((size_t)tb * D * 4);
+  t.last_last_act = (float*)take((size_t)tb * D * 4);
+  t.last_dof_vel = (float*)take((size_t)tb * D * 4);
+  t.torques = (float*)take((size_t)tb * D * 4);
+  t.ref = (float*)take((size_t)tb * D * 4);
+  t.last_root_vel = (float*)take((size_t)tb * 6 * 4);
+  t.cmd = (float*)take((size_t)tb * 4 * 4);
+  t.gait_start = (float*)take((size_t)tb * 4);
+  t.air = (float*)take((size_t)tb * 2 * 4);
+  t.feet_h = (float*)take((size_t)tb * 2 * 4);
+  t.last_z = (float*)take((size_t)tb * 2 * 4);
+  t.sums = (float*)take((size_t)TI5_NUM_TERMS * tb * 4);
+  t.vals = (float*)take((size_t)TI5_NUM_TERMS * tb * 4);
+  t.ep_len = (int64_t*)take((size_t)tb * 8);
+  t.phase_len = (int64_t*)take((size_t)tb * 8);
+  t.gait_time = (int32_t*)take((size_t)tb * ng * 4);
+  t.last_contacts = (uint8_t*)take((size_t)tb * 2);
+  t.bar = (uint64_t*)take(16);
+  return t;
+}
+
+// every (shared dst, global src, bytes) chunk of the tile that starts at env e0 and holds n envs
+template <class F>
+__device__ __forceinline__ void post_tile_chunks(const Ti5Params& p, const Ti5Buffers& b, const PostTile& t, int e0, int n,
+                                                 int tb, F f) {
+  const size_t e = (size_t)e0;
+  f(t.root, b.root_states + e * RB, n * RB * 4);
+  f(t.dof, b.dof_state + e * 2 * D, n * 2 * D * 4);
+  f(t.contact, b.contact_forces + e * NB * 3, n * NB * 3 * 4);
+  f(t.rigid, b.rigid_state + e * NB * RB, n * NB * RB * 4);
+  f(t.act, b.actions + e * D, n * D * 4);
+  f(t.last_act, b.last_actions + e * D, n * D * 4);
+  f(t.last_last_act, b.last_last_actions + e * D, n * D * 4);
+  f(t.last_dof_vel, b.last_dof_vel + e * D, n * D * 4);
+  f(t.torques, b.torques + e * D, n * D * 4);
+  f(t.ref, b.ref_dof_pos + e * D, n * D * 4);
+  f(t.last_root_vel, b.last_root_vel + e * 6, n * 6 * 4);
+  f(t.cmd, b.commands + e * 4, n * 4 * 4);
+  f(t.gait_start, b.gait_start + e, n * 4);
+  f(t.air, b.feet_air_time + e * 2, n * 2 * 4);
+  f(t.feet_h, b.feet_height + e * 2, n * 2 * 4);
+  f(t.last_z, b.last_feet_z + e * 2, n * 2 * 4);
+  f(t.ep_len, b.episode_length_buf + e, n * 8);
+  f(t.phase_len, b.phase_length_buf + e, n * 8);
+  f(t.gait_time, b.gait_time + e * p.num_gaits, n * p.num_gaits * 4);
+  f(t.last_contacts, b.last_contacts + e * 2, n * 2);
+#pragma unroll 1
+  for (int k = 0; k < TI5_NUM_TERMS; ++k)
+    if (p.term_mask & (1u << k)) f(t.sums + (size_t)k * tb, b.episode_sums + (size_t)k * p.num_envs + e, n * 4);
+}
+
+// The CTA owns TB = env_block consecutive envs and runs POST_ROLES x TB threads: every env is worked on by
+// three threads ("roles"), each evaluating a third of the step — at 8192 envs the kernel is bound by the
+// length of one thread's dependent instruction chain, not by bandwidth, so the chain is cut in three.
+//   role 0 (base):   counters, derived base state, push / external-force windows, termination, base terms
+//   role 1 (joints): the per-DOF reductions and the joint / distance terms, DOF-lag push
+//   role 2 (feet):   feet Euler angles, contact bookkeeping (air time, clearance) and the feet terms
+// The unscaled terms meet in shared memory; role 0 then forms the reward sum in the reference's
+// (alphabetical) order and all threads share the reset bookkeeping.
+constexpr int POST_ROLES = 3;
+
+__global__ void __launch_bounds__(POST_ROLES * 128)
 post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
                     const __grid_constant__ Ti5Rng r, int push_last) {
   const int N = p.num_envs;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int TB = p.env_block, tid = threadIdx.x;
+  const int role = tid / TB, le = tid - role * TB;
+  const int e0 = blockIdx.x * TB, e = e0 + le, n_tile = min(TB, N - e0);
   const bool live = e < N;
   Ti5Globals* g = b.globals;
   const int64_t step = g->step_index;
@@ -137,106 +243,56 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
   const bool first_force = g->is_first_add_force != 0;
   const bool philox = p.rng_mode == TI5_RNG_PHILOX;
   const int dm = p.div_mode;
+  const uint32_t mask = p.term_mask;
 
   // window predicates are uniform over the grid (t1:193-215)
   bool push_window = false, force_window = false;
   if (p.flags & TI5_F_PUSH_ROBOTS) {
     int64_t i = counter / p.push_update_step;
     if (i >= p.n_push_dur) i = p.n_push_dur - 1;
-    push_window = fmod((double)counter, (double)p.push_interval) <= p.push_duration[i];
+    push_window = (double)(counter % p.push_interval) <= p.push_duration[i];
   }
   if (p.flags & TI5_F_ADD_EXT_FORCE) {
     int64_t i = counter / p.add_update_step;
     if (i >= p.n_add_dur) i = p.n_add_dur - 1;
-    force_window = fmod((double)counter, (double)p.ext_force_interval) <= p.add_duration[i];
+    force_window = (double)(counter % p.ext_force_interval) <= p.add_duration[i];
   }
 
-  bool reset = false;
-  float esum[TI5_NUM_TERMS];   // episode sums of this env after this step (only used if it resets)
-#pragma unroll
-  for (int t = 0; t < TI5_NUM_TERMS; ++t) esum[t] = 0.0f;
+  // ---- stage the CTA's tile of inputs: one TMA bulk copy per array, all in flight together ----------
+  extern __shared__ __align__(128) unsigned char post_smem[];
+  const PostTile T = carve_post_tile(post_smem, TB, p.num_gaits);
+  if (n_tile == TB) {
+    if (tid == 0) mbar_init(T.bar, 1);
+    __syncthreads();
+    if (tid < 32) {
+      // the 32 lanes of warp 0 issue the bulk copies in parallel: lane k the k-th chunk (fixed per-env arrays
+      // first, then one column per active reward term); lane 0 also arms the barrier with the byte total
+      int k = 0;
+      post_tile_chunks(p, b, T, e0, n_tile, TB, [&](void* dst, const void* src, int bytes) {
+        if ((k++ & 31) == tid) tma_load_1d(dst, src, (uint32_t)bytes, T.bar);
+      });
+      if (tid == 0) {
+        const uint32_t row_bytes = (RB + 2 * D + NB * 3 + NB * RB + 6 * D + 6 + 4 + 1 + 3 * 2) * 4 + 2 * 8 + p.num_gaits * 4 + 2;
+        mbar_expect_tx(T.bar, (uint32_t)n_tile * (row_bytes + 4u * (uint32_t)__popc(mask)));
+      }
+    }
+    mbar_wait(T.bar, 0);
+  } else {      // partial last tile: byte counts are not multiples of 16
+    post_tile_chunks(p, b, T, e0, n_tile, TB, [&](void* dst, const void* src, int bytes) { coop_load_call(dst, src, (uint32_t)bytes); });
+    __syncthreads();
+  }
+
+  bool reset = false, time_out = false;
+  auto put = [&](int t, float v) { T.vals[t * TB + le] = v; };
 
   if (live) {
-    // ---- simulator rows ---------------------------------------------------------------------
-    float root[RB];
-#pragma unroll
-    for (int i = 0; i < RB; ++i) root[i] = b.root_states[(size_t)e * RB + i];
-    float q[D], qd[D];
-    {
-      const float4* ds = reinterpret_cast<const float4*>(b.dof_state + (size_t)e * 2 * D);
-#pragma unroll
-      for (int i = 0; i < D / 2; ++i) {
-        const float4 v = ds[i];
-        q[2 * i] = v.x; qd[2 * i] = v.y; q[2 * i + 1] = v.z; qd[2 * i + 1] = v.w;
-      }
-    }
-    FootState foot[2];
-    float knee_xy[2][2];
-#pragma unroll
-    for (int f = 0; f < 2; ++f) {
-      const float* rs = b.rigid_state + ((size_t)e * NB + p.feet[f]) * RB;
-      foot[f].pos[0] = rs[0]; foot[f].pos[1] = rs[1]; foot[f].pos[2] = rs[2];
-      foot[f].quat[0] = rs[3]; foot[f].quat[1] = rs[4]; foot[f].quat[2] = rs[5]; foot[f].quat[3] = rs[6];
-      foot[f].wxy[0] = rs[10]; foot[f].wxy[1] = rs[11];
-      const float* cf = b.contact_forces + ((size_t)e * NB + p.feet[f]) * 3;
-      foot[f].force[0] = cf[0]; foot[f].force[1] = cf[1]; foot[f].force[2] = cf[2];
-      const float* ks = b.rigid_state + ((size_t)e * NB + p.knees[f]) * RB;
-      knee_xy[f][0] = ks[0]; knee_xy[f][1] = ks[1];
-    }
-    const float* tf = b.contact_forces + ((size_t)e * NB + p.term_body) * 3;
-    const float term_force = sqrtf(tf[0] * tf[0] + tf[1] * tf[1] + tf[2] * tf[2]);
-    const float* pf = b.contact_forces + ((size_t)e * NB + p.pen_body) * 3;
-    const float pen_force = sqrtf(pf[0] * pf[0] + pf[1] * pf[1] + pf[2] * pf[2]);
-
-    // ---- optional fused lag push of the last substep (lr:412-434) --------------------------
-    if (push_last) {
-      const int64_t j = (step - 1) * p.decimation + (p.decimation - 1);
-      if (p.flags & TI5_F_ADD_DOF_LAG) {
-        float4* row = reinterpret_cast<float4*>(b.dof_ring + ((size_t)ring_slot(j, p.dof_lag_len) * N + e) * (2 * D));
-        row[0] = make_float4(q[0], q[1], q[2], q[3]);
-        row[1] = make_float4(q[4], q[5], q[6], q[7]);
-        row[2] = make_float4(q[8], q[9], q[10], q[11]);
-        row[3] = make_float4(qd[0], qd[1], qd[2], qd[3]);
-        row[4] = make_float4(qd[4], qd[5], qd[6], qd[7]);
-        row[5] = make_float4(qd[8], qd[9], qd[10], qd[11]);
-      }
-    }
-
-    // ---- lr:469-481 counters and derived base state ----------------------------------------
-    const int64_t ep_len = b.episode_length_buf[e] + 1;
-    b.episode_length_buf[e] = ep_len;
-    const float bq[4] = {root[3], root[4], root[5], root[6]};
-    const V3 lin = quat_rotate_inverse(bq, V3{root[7], root[8], root[9]});
-    const V3 ang = quat_rotate_inverse(bq, V3{root[10], root[11], root[12]});
-    const V3 grav = quat_rotate_inverse(bq, V3{0.0f, 0.0f, -1.0f});
-    float eul[3];
-    euler_xyz(bq, eul);
-    float feul[2][3];
-    euler_xyz(foot[0].quat, feul[0]);
-    euler_xyz(foot[1].quat, feul[1]);
-    foot[0].pitch = feul[0][1];
-    foot[1].pitch = feul[1][1];
-    reinterpret_cast<float4*>(b.base_quat)[e] = make_float4(bq[0], bq[1], bq[2], bq[3]);
-    b.base_lin_vel[e * 3 + 0] = lin.x; b.base_lin_vel[e * 3 + 1] = lin.y; b.base_lin_vel[e * 3 + 2] = lin.z;
-    b.base_ang_vel[e * 3 + 0] = ang.x; b.base_ang_vel[e * 3 + 1] = ang.y; b.base_ang_vel[e * 3 + 2] = ang.z;
-    b.projected_gravity[e * 3 + 0] = grav.x; b.projected_gravity[e * 3 + 1] = grav.y; b.projected_gravity[e * 3 + 2] = grav.z;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      b.base_euler_xyz[e * 3 + i] = eul[i];
-      b.feet_euler_xyz[e * 6 + i] = feul[0][i];
-      b.feet_euler_xyz[e * 6 + 3 + i] = feul[1][i];
-    }
-    if (push_last && (p.flags & TI5_F_ADD_IMU_LAG)) {
-      const int64_t j = (step - 1) * p.decimation + (p.decimation - 1);
-      float* row = b.imu_ring + ((size_t)ring_slot(j, p.imu_lag_len) * N + e) * 6;
-      row[0] = ang.x; row[1] = ang.y; row[2] = ang.z; row[3] = eul[0]; row[4] = eul[1]; row[5] = eul[2];
-    }
-
-    // ---- t1:183-184 phase counter and gait-schedule command resampling (pass 0) -------------
-    int64_t phase_len = b.phase_length_buf[e] + 1;
-    float4 cmd = reinterpret_cast<const float4*>(b.commands)[e];
+    // ======== common prologue (every role, same values): command schedule, gait phase, contacts ==========
+    // t1:183-184 phase counter and gait-schedule command resampling (pass 0)
+    const int64_t ep_len = T.ep_len[le] + 1;                                  // lr:469
+    int64_t phase_len = T.phase_len[le] + 1;
+    float4 cmd = reinterpret_cast<const float4*>(T.cmd)[le];
     for (int gi = 0; gi < p.num_gaits; ++gi) {
-      if (ep_len != (int64_t)b.gait_time[e * p.num_gaits + gi]) continue;
+      if (ep_len != (int64_t)T.gait_time[le * p.num_gaits + gi]) continue;
       const int kind = p.gait_kind[gi];
       float u[3];
 #pragma unroll
@@ -250,324 +306,351 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       cmd.y = my ? affine((float)(g->cmd_range[1][1] - g->cmd_range[1][0]), (float)g->cmd_range[1][0], u[1]) : 0.0f;
       cmd.z = mz ? affine((float)(g->cmd_range[2][1] - g->cmd_range[2][0]), (float)g->cmd_range[2][0], u[2]) : 0.0f;
     }
-    reinterpret_cast<float4*>(b.commands)[e] = cmd;
     const float cmd_norm = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y + cmd.z * cmd.z);
     const bool stand = cmd_norm <= p.stand_threshold;
-
-    // ---- t1:193-203, 217-231 push window: overwrite the base velocity ----------------------
-    if (p.flags & TI5_F_PUSH_ROBOTS) {
-      float fx = 0.0f, fy = 0.0f, tq[3] = {0.0f, 0.0f, 0.0f};
-      if (push_window) {
-        float u[5];
-#pragma unroll
-        for (int c = 0; c < 5; ++c)
-          u[c] = philox ? philox_u(p.seed, (uint64_t)step, S_PUSH, e * 5 + c) : r.push[(size_t)e * 5 + c];
-        fx = affine(p.push_vel_w, p.push_vel_lo, u[0]);
-        fy = affine(p.push_vel_w, p.push_vel_lo, u[1]);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) tq[c] = affine(p.push_ang_w, p.push_ang_lo, u[2 + c]);
-        root[7] = fx; root[8] = fy; root[10] = tq[0]; root[11] = tq[1]; root[12] = tq[2];
-        float* rw = b.root_states + (size_t)e * RB;
-        rw[7] = fx; rw[8] = fy; rw[10] = tq[0]; rw[11] = tq[1]; rw[12] = tq[2];
-        b.rand_push_force[e * 3 + 0] = fx;
-        b.rand_push_force[e * 3 + 1] = fy;
-      } else {
-        b.rand_push_force[e * 3 + 0] = 0.0f; b.rand_push_force[e * 3 + 1] = 0.0f; b.rand_push_force[e * 3 + 2] = 0.0f;
-      }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) b.rand_push_torque[e * 3 + c] = tq[c];
-    }
-
-    // ---- t1:205-215, 233-247 external force window ------------------------------------------
-    if (p.flags & TI5_F_ADD_EXT_FORCE) {
-      float af[3] = {0.0f, 0.0f, 0.0f}, at[3] = {0.0f, 0.0f, 0.0f};
-      if (force_window) {
-        if (first_force) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float uf = philox ? philox_u(p.seed, (uint64_t)step, S_EXT, e * 6 + c) : r.ext[(size_t)e * 6 + c];
-            const float ut = philox ? philox_u(p.seed, (uint64_t)step, S_EXT, e * 6 + 3 + c) : r.ext[(size_t)e * 6 + 3 + c];
-            b.ext_forces[e * 3 + c] = affine(p.ext_f_w[c], p.ext_f_lo[c], uf);
-            b.ext_torques[e * 3 + c] = affine(p.ext_t_w, p.ext_t_lo, ut);
-          }
-        } else {
-          const float s = stand ? 1.0f : 0.0f;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            af[c] = b.ext_forces[e * 3 + c] * s;
-            at[c] = b.ext_torques[e * 3 + c] * s;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { b.ext_forces[e * 3 + c] = 0.0f; b.ext_torques[e * 3 + c] = 0.0f; }
-      }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { b.applied_force[e * 3 + c] = af[c]; b.applied_torque[e * 3 + c] = at[c]; }
-    }
-
-    // ---- lr:509-517 termination ---------------------------------------------------------------
-    const bool time_out = ep_len > p.max_episode_length;
-    reset = (term_force > 1.0f) || time_out;
-    b.time_out_buf[e] = time_out ? 1 : 0;
-    b.reset_buf[e] = reset ? 1 : 0;
-
-    // ---- gait phase and stance mask (t1:80-107).  Side effect: standing envs restart the phase.
+    // gait phase and stance mask (t1:80-107).  Side effect: standing envs restart the phase.
     if (stand) phase_len = 0;
-    b.phase_length_buf[e] = phase_len;
-    const float gait_start = b.gait_start[e];
-    const float phase = (py_mod(sdiv((float)phase_len * p.dt, p.cycle_time, dm), 1.0f) + gait_start) * (stand ? 0.0f : 1.0f);
+    const float phase = (py_mod(sdiv((float)phase_len * p.dt, p.cycle_time, dm), 1.0f) + T.gait_start[le]) * (stand ? 0.0f : 1.0f);
     const float sin_pos = sinf(TWO_PI_F * phase);
     float stance[2] = {sin_pos >= 0.0f ? 1.0f : 0.0f, sin_pos < 0.0f ? 1.0f : 0.0f};
     if (fabsf(sin_pos) < 0.1f) stance[0] = stance[1] = 1.0f;
-    const bool contact[2] = {foot[0].force[2] > 5.0f, foot[1].force[2] > 5.0f};
+    const float* cf0 = T.contact + ((size_t)le * NB + p.feet[0]) * 3;
+    const float* cf1 = T.contact + ((size_t)le * NB + p.feet[1]) * 3;
+    const bool contact[2] = {cf0[2] > 5.0f, cf1[2] > 5.0f};
+    const float* qrow = T.dof + (size_t)le * 2 * D;                           // interleaved (q, qd)
 
-    // ---- lr:654-680 reward sum, alphabetical term order ------------------------------------
+    if (role == 0) {
+      // ================================ role 0: the base ===============================================
+      float root[RB];
+#pragma unroll
+      for (int i = 0; i < RB; ++i) root[i] = T.root[le * RB + i];
+      const float* tf = T.contact + ((size_t)le * NB + p.term_body) * 3;
+      const float term_force = sqrtf(tf[0] * tf[0] + tf[1] * tf[1] + tf[2] * tf[2]);
+      const float* pf = T.contact + ((size_t)le * NB + p.pen_body) * 3;
+      const float pen_force = sqrtf(pf[0] * pf[0] + pf[1] * pf[1] + pf[2] * pf[2]);
+      b.episode_length_buf[e] = ep_len;
+      b.phase_length_buf[e] = phase_len;
+      reinterpret_cast<float4*>(b.commands)[e] = cmd;
+      // lr:475-479 derived base state
+      const float bq[4] = {root[3], root[4], root[5], root[6]};
+      const V3 lin = quat_rotate_inverse(bq, V3{root[7], root[8], root[9]});
+      const V3 ang = quat_rotate_inverse(bq, V3{root[10], root[11], root[12]});
+      const V3 grav = quat_rotate_inverse(bq, V3{0.0f, 0.0f, -1.0f});
+      float eul[3];
+      euler_xyz(bq, eul);
+      reinterpret_cast<float4*>(b.base_quat)[e] = make_float4(bq[0], bq[1], bq[2], bq[3]);
+      b.base_lin_vel[e * 3 + 0] = lin.x; b.base_lin_vel[e * 3 + 1] = lin.y; b.base_lin_vel[e * 3 + 2] = lin.z;
+      b.base_ang_vel[e * 3 + 0] = ang.x; b.base_ang_vel[e * 3 + 1] = ang.y; b.base_ang_vel[e * 3 + 2] = ang.z;
+      b.projected_gravity[e * 3 + 0] = grav.x; b.projected_gravity[e * 3 + 1] = grav.y; b.projected_gravity[e * 3 + 2] = grav.z;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) b.base_euler_xyz[e * 3 + i] = eul[i];
+      if (push_last && (p.flags & TI5_F_ADD_IMU_LAG)) {                      // fused IMU-lag push of the last substep
+        const int64_t j = (step - 1) * p.decimation + (p.decimation - 1);
+        float* row = b.imu_ring + ((size_t)ring_slot(j, p.imu_lag_len) * N + e) * 6;
+        row[0] = ang.x; row[1] = ang.y; row[2] = ang.z; row[3] = eul[0]; row[4] = eul[1]; row[5] = eul[2];
+      }
+      // t1:193-203, 217-231 push window: overwrite the base velocity
+      if (p.flags & TI5_F_PUSH_ROBOTS) {
+        float fx = 0.0f, fy = 0.0f, tq[3] = {0.0f, 0.0f, 0.0f};
+        if (push_window) {
+          float u[5];
+#pragma unroll
+          for (int c = 0; c < 5; ++c)
+            u[c] = philox ? philox_u(p.seed, (uint64_t)step, S_PUSH, e * 5 + c) : r.push[(size_t)e * 5 + c];
+          fx = affine(p.push_vel_w, p.push_vel_lo, u[0]);
+          fy = affine(p.push_vel_w, p.push_vel_lo, u[1]);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) tq[c] = affine(p.push_ang_w, p.push_ang_lo, u[2 + c]);
+          root[7] = fx; root[8] = fy; root[10] = tq[0]; root[11] = tq[1]; root[12] = tq[2];
+          float* rw = b.root_states + (size_t)e * RB;
+          rw[7] = fx; rw[8] = fy; rw[10] = tq[0]; rw[11] = tq[1]; rw[12] = tq[2];
+          b.rand_push_force[e * 3 + 0] = fx;
+          b.rand_push_force[e * 3 + 1] = fy;
+        } else {
+          b.rand_push_force[e * 3 + 0] = 0.0f; b.rand_push_force[e * 3 + 1] = 0.0f; b.rand_push_force[e * 3 + 2] = 0.0f;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) b.rand_push_torque[e * 3 + c] = tq[c];
+      }
+      // t1:205-215, 233-247 external force window
+      if (p.flags & TI5_F_ADD_EXT_FORCE) {
+        float af[3] = {0.0f, 0.0f, 0.0f}, at[3] = {0.0f, 0.0f, 0.0f};
+        if (force_window) {
+          if (first_force) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float uf = philox ? philox_u(p.seed, (uint64_t)step, S_EXT, e * 6 + c) : r.ext[(size_t)e * 6 + c];
+              const float ut = philox ? philox_u(p.seed, (uint64_t)step, S_EXT, e * 6 + 3 + c) : r.ext[(size_t)e * 6 + 3 + c];
+              b.ext_forces[e * 3 + c] = affine(p.ext_f_w[c], p.ext_f_lo[c], uf);
+              b.ext_torques[e * 3 + c] = affine(p.ext_t_w, p.ext_t_lo, ut);
+            }
+          } else {
+            const float sc = stand ? 1.0f : 0.0f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              af[c] = b.ext_forces[e * 3 + c] * sc;
+              at[c] = b.ext_torques[e * 3 + c] * sc;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { b.ext_forces[e * 3 + c] = 0.0f; b.ext_torques[e * 3 + c] = 0.0f; }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { b.applied_force[e * 3 + c] = af[c]; b.applied_torque[e * 3 + c] = at[c]; }
+      }
+      // lr:509-517 termination
+      time_out = ep_len > p.max_episode_length;
+      reset = (term_force > 1.0f) || time_out;
+      b.time_out_buf[e] = time_out ? 1 : 0;
+      b.reset_buf[e] = reset ? 1 : 0;
+      // ---- base terms
+      if (mask & (1u << T_BASE_ACC)) {                      // t1:717-724
+        float sq = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const float d = T.last_root_vel[le * 6 + i] - root[7 + i];
+          sq += d * d;
+        }
+        put(T_BASE_ACC, expf_call(-sqrtf(sq) * 3.0f));
+      }
+      if (mask & (1u << T_COLLISION)) put(T_COLLISION, 1.0f * (pen_force > 0.1f ? 1.0f : 0.0f));   // t1:870-875
+      if (mask & (1u << T_LOW_SPEED)) {                     // t1:816-847 (appendix A13)
+        const float av = fabsf(lin.x), ac = fabsf(cmd.x);
+        const bool slow = av < 0.5f * ac, fast = av > 1.2f * ac;
+        float v = 0.0f;
+        if (slow) v = -1.0f;
+        if (fast) v = 0.0f;
+        if (!(slow || fast)) v = 1.2f;
+        if (signf(lin.x) != signf(cmd.x)) v = -2.0f;
+        put(T_LOW_SPEED, v * (ac > 0.05f ? 1.0f : 0.0f));
+      }
+      if (mask & (1u << T_ORIENTATION)) {                   // t1:670-677
+        const float a = expf_call(-(fabsf(eul[0]) + fabsf(eul[1])) * 10.0f);
+        const float bb = expf_call(-sqrtf(grav.x * grav.x + grav.y * grav.y) * 20.0f);
+        put(T_ORIENTATION, (a + bb) / 2.0f);
+      }
+      const float ex = cmd.x - lin.x, ey = cmd.y - lin.y, ew = cmd.z - ang.z;
+      if (mask & (1u << T_TRACK_VEL_HARD)) {                // t1:738-758
+        const float le_ = sqrtf(ex * ex + ey * ey);
+        const float ae = fabsf(ew);
+        put(T_TRACK_VEL_HARD, (expf_call(-le_ * 10.0f) + expf_call(-ae * 10.0f)) / 2.0f - 0.2f * (le_ + ae));
+      }
+      if (mask & (1u << T_TRACKING_ANG_VEL))                // t1:776-790
+        put(T_TRACKING_ANG_VEL, expf_call(stand ? -fabsf(ew) * p.tracking_sigma * 2.0f : -(ew * ew) * p.tracking_sigma));
+      if (mask & (1u << T_TRACKING_LIN_VEL))                // t1:760-774
+        put(T_TRACKING_LIN_VEL, expf_call(stand ? -(fabsf(ex) + fabsf(ey)) * p.tracking_sigma * 2.0f
+                                                : -(ex * ex + ey * ey) * p.tracking_sigma));
+      if (mask & (1u << T_VEL_MISMATCH_EXP)) {              // t1:726-736
+        const float a = expf_call(-(lin.z * lin.z) * 10.0f);
+        const float bb = expf_call(-sqrtf(ang.x * ang.x + ang.y * ang.y) * 5.0f);
+        put(T_VEL_MISMATCH_EXP, (a + bb) / 2.0f);
+      }
+    } else if (role == 1) {
+      // ================================ role 1: the joints =============================================
+      if (push_last && (p.flags & TI5_F_ADD_DOF_LAG)) {                      // fused DOF-lag push of the last substep
+        const int64_t j = (step - 1) * p.decimation + (p.decimation - 1);
+        float* row = b.dof_ring + ((size_t)ring_slot(j, p.dof_lag_len) * N + e) * (2 * D);
+#pragma unroll 1
+        for (int i = 0; i < D; ++i) { row[i] = qrow[2 * i]; row[D + i] = qrow[2 * i + 1]; }
+      }
+      const float* act = T.act + le * D;
+      const float* la = T.last_act + le * D;
+      const float* lla = T.last_last_act + le * D;
+      const float* ldv = T.last_dof_vel + le * D;
+      const float* tau = T.torques + le * D;
+      const float* ref = T.ref + le * D;
+      // one pass over the 12 DOFs feeds every per-DOF reduction (each sum keeps its own DOF order)
+      float s_d1 = 0.0f, s_d2 = 0.0f, s_abs = 0.0f, s_dq = 0.0f, s_acc = 0.0f, s_vel = 0.0f, s_tau = 0.0f, s_jp = 0.0f;
+#pragma unroll 1
+      for (int i = 0; i < D; ++i) {
+        const float qi = qrow[2 * i], qdi = qrow[2 * i + 1];
+        const float a = act[i], l = la[i];
+        const float d1 = (l - a) * 1.0f;
+        const float d2 = ((a + lla[i]) - 2.0f * l) * 1.0f;
+        s_d1 += d1 * d1;
+        s_d2 += d2 * d2;
+        s_abs += fabsf(a * 1.0f);
+        const float dq = qi - p.default_dof_pos[i];
+        s_dq += dq * dq;
+        const float ac = sdiv(ldv[i] - qdi, p.dt, dm);
+        s_acc += ac * ac;
+        s_vel += qdi * qdi;
+        s_tau += tau[i] * tau[i];
+        const float dj = qi - (stand ? p.default_dof_pos[i] : ref[i]);       // ref_dof_pos of the PREVIOUS step (A3)
+        s_jp += dj * dj;
+      }
+      auto dq0 = [&](int i) { return qrow[2 * i] - p.default_dof_pos[i]; };
+      if (mask & (1u << T_ACTION_SMOOTHNESS)) put(T_ACTION_SMOOTHNESS, (s_d1 + s_d2) + 0.05f * s_abs);   // t1:877-892
+      if (mask & (1u << T_DEFAULT_JOINT_POS)) {             // t1:686-703
+        const float l = sqrtf((dq0(0) * dq0(0) + dq0(1) * dq0(1)) + dq0(5) * dq0(5));
+        const float rr = sqrtf((dq0(6) * dq0(6) + dq0(7) * dq0(7)) + dq0(11) * dq0(11));
+        const float yr = clampf((l + rr) - 0.1f, 0.0f, 50.0f);
+        put(T_DEFAULT_JOINT_POS, expf_call(-yr * 100.0f) - 0.01f * sqrtf(s_dq));
+      }
+      if (mask & (1u << T_DOF_ACC)) put(T_DOF_ACC, s_acc);       // t1:863-868
+      if (mask & (1u << T_DOF_VEL)) put(T_DOF_VEL, s_vel);       // t1:856-861
+      if (mask & (1u << T_JOINT_POS)) {                     // t1:576-596
+        const float n = sqrtf(s_jp);
+        const float v = expf_call(-2.0f * n) - 0.2f * clampf(n, 0.0f, 0.5f);
+        put(T_JOINT_POS, stand ? 1.0f : v);
+      }
+      if (mask & (1u << T_STAND_SYSMETRY)) {                // t1:917-925
+        float sq = 0.0f;
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+          const float d = qrow[2 * i] - qrow[2 * (5 + i)];
+          sq += d * d;
+        }
+        put(T_STAND_SYSMETRY, stand ? expf_call(-sq) : 0.0f);
+      }
+      if (mask & (1u << T_TORQUES)) put(T_TORQUES, s_tau);       // t1:849-854
+      const float* f0 = T.rigid + ((size_t)le * NB + p.feet[0]) * RB;
+      const float* f1 = T.rigid + ((size_t)le * NB + p.feet[1]) * RB;
+      const float* k0 = T.rigid + ((size_t)le * NB + p.knees[0]) * RB;
+      const float* k1 = T.rigid + ((size_t)le * NB + p.knees[1]) * RB;
+      if (mask & (1u << T_FEET_DISTANCE))                   // t1:599-612
+        put(T_FEET_DISTANCE, pair_distance_reward(f0[0], f0[1], f1[0], f1[1], p.foot_min_dist, p.foot_max_dist));
+      if (mask & (1u << T_KNEE_DISTANCE))                   // t1:615-628
+        put(T_KNEE_DISTANCE, pair_distance_reward(k0[0], k0[1], k1[0], k1[1], p.knee_min_dist, p.knee_max_dist));
+    } else {
+      // ================================ role 2: the feet ===============================================
+      FootState foot[2];
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        const float* rs = T.rigid + ((size_t)le * NB + p.feet[f]) * RB;
+        foot[f].pos[0] = rs[0]; foot[f].pos[1] = rs[1]; foot[f].pos[2] = rs[2];
+        foot[f].quat[0] = rs[3]; foot[f].quat[1] = rs[4]; foot[f].quat[2] = rs[5]; foot[f].quat[3] = rs[6];
+        foot[f].wxy[0] = rs[10]; foot[f].wxy[1] = rs[11];
+        const float* cf = f == 0 ? cf0 : cf1;
+        foot[f].force[0] = cf[0]; foot[f].force[1] = cf[1]; foot[f].force[2] = cf[2];
+        float fe[3];
+        euler_xyz(foot[f].quat, fe);                                           // lr:480-481
+        foot[f].pitch = fe[1];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) b.feet_euler_xyz[e * 6 + 3 * f + i] = fe[i];
+      }
+      if (mask & (1u << T_BASE_HEIGHT)) {                   // t1:706-715
+        const float ground = (foot[0].pos[2] * stance[0] + foot[1].pos[2] * stance[1]) / (stance[0] + stance[1]);
+        const float h = T.root[le * RB + 2] - (ground - 0.05f);
+        put(T_BASE_HEIGHT, expf_call(-fabsf(h - p.base_height_target) * 100.0f));
+      }
+      if (mask & (1u << T_FEET_AIR_TIME)) {                 // t1:642-657 (appendix A6, A8)
+        const bool tiny = cmd_norm < 0.05f;
+        float air_sum = 0.0f;
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          const float st = tiny ? 1.0f : stance[f];
+          const bool filt = contact[f] || (st != 0.0f) || (T.last_contacts[le * 2 + f] != 0);
+          b.contact_filt[e * 2 + f] = filt ? 1 : 0;
+          b.last_contacts[e * 2 + f] = contact[f] ? 1 : 0;
+          float air = T.air[le * 2 + f];
+          const float first = (air > 0.0f && filt) ? 1.0f : 0.0f;
+          air += p.dt;
+          air_sum += clampf(air, 0.0f, 0.5f) * first;
+          b.feet_air_time[e * 2 + f] = air * (filt ? 0.0f : 1.0f);
+        }
+        put(T_FEET_AIR_TIME, air_sum);
+      }
+      if (mask & (1u << T_FEET_CLEARANCE)) {                // t1:793-814 (appendix A9)
+        float sw = 0.0f;
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          const float z = foot[f].pos[2];
+          const float h = T.feet_h[le * 2 + f] + (z - T.last_z[le * 2 + f]);
+          b.last_feet_z[e * 2 + f] = z;
+          const float swing = 1.0f - stance[f];
+          const float hit = (h > p.target_feet_height && h < p.target_feet_height_max) ? 1.0f : 0.0f;
+          sw += hit * swing;
+          b.feet_height[e * 2 + f] = h * (contact[f] ? 0.0f : 1.0f);
+        }
+        put(T_FEET_CLEARANCE, sw);
+      }
+      if (mask & (1u << T_FEET_CONTACT_FORCES)) {           // t1:679-684
+        float sq = 0.0f;
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          const float n = sqrtf((foot[f].force[0] * foot[f].force[0] + foot[f].force[1] * foot[f].force[1]) +
+                                foot[f].force[2] * foot[f].force[2]);
+          sq += clampf(n - p.max_contact_force, 0.0f, 400.0f);
+        }
+        put(T_FEET_CONTACT_FORCES, sq);
+      }
+      if (mask & (1u << T_FEET_CONTACT_NUMBER)) {           // t1:659-668 (appendix A14)
+        float sq = 0.0f;
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          const float st = stand ? 1.0f : stance[f];
+          sq += ((contact[f] ? 1.0f : 0.0f) == st) ? 1.0f : -0.3f;
+        }
+        put(T_FEET_CONTACT_NUMBER, sq / 2.0f);
+      }
+      if (mask & (1u << T_FEET_ROTATION)) {                 // t1:926-935 (appendix A11)
+        const float rot = foot[0].pitch * foot[0].pitch + foot[1].pitch * foot[1].pitch;
+        const float x = rot / 1.0f;
+        put(T_FEET_ROTATION, 1.0f * expf_call(-(x * x)));
+      }
+      if (mask & (1u << T_FEET_STUMBLE)) {                  // t1:937-940
+        bool any = false;
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+          any = any || (sqrtf(foot[f].force[0] * foot[f].force[0] + foot[f].force[1] * foot[f].force[1]) >
+                        5.0f * fabsf(foot[f].force[2]));
+        put(T_FEET_STUMBLE, any ? 1.0f : 0.0f);
+      }
+      if (mask & (1u << T_FOOT_SLIP)) {                     // t1:630-640 (appendix A10)
+        float sq = 0.0f;
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+          sq += sqrtf(sqrtf(foot[f].wxy[0] * foot[f].wxy[0] + foot[f].wxy[1] * foot[f].wxy[1])) * (contact[f] ? 1.0f : 0.0f);
+        put(T_FOOT_SLIP, sq);
+      }
+      if (mask & (1u << T_STAND_STILL)) {                   // t1:899-915 (appendix A12)
+        // dof_idx [0,1,2,3,5,6,7,8] with weights [2,2,1,1,1,2,2,1], then the two foot pitches with weight 1
+        float sq = 0.0f;
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+          const int j = i < 4 ? i : i + 1;
+          const float w = (i < 2 || i == 5 || i == 6) ? 2.0f : 1.0f;
+          const float er = (qrow[2 * j] - p.default_dof_pos[j]) * w;
+          sq += er * er;
+        }
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          const float er = foot[f].pitch * 1.0f;
+          sq += er * er;
+        }
+        put(T_STAND_STILL, stand ? expf_call(-sq) : 0.0f);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- lr:654-680: reward sum in alphabetical term order, per-term episode sums, clip at zero -----------
+  if (live && role == 0) {
     float rew = 0.0f;
-    const uint32_t mask = p.term_mask;
-    auto add_term = [&](int t, float v) {
-      const float s = v * p.reward_scale[t];
-      rew += s;
-      const float acc = b.episode_sums[(size_t)t * N + e] + s;
+#pragma unroll 1
+    for (int t = 0; t < TI5_NUM_TERMS; ++t) {
+      if (!(mask & (1u << t)) || t == T_TERMINATION) continue;
+      const float sc = T.vals[t * TB + le] * p.reward_scale[t];
+      rew += sc;
+      const float acc = T.sums[t * TB + le] + sc;
+      T.sums[t * TB + le] = acc;
       b.episode_sums[(size_t)t * N + e] = acc;
-      esum[t] = acc;
-      if (b.reward_terms) b.reward_terms[(size_t)t * N + e] = s;
-    };
-
-    float act[D];
-    load12(b.actions, e, act);
-
-    if (mask & (1u << T_ACTION_SMOOTHNESS)) {            // t1:877-892
-      float la[D], lla[D];
-      load12(b.last_actions, e, la);
-      load12(b.last_last_actions, e, lla);
-      float t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        const float d1 = (la[i] - act[i]) * 1.0f;
-        const float d2 = ((act[i] + lla[i]) - 2.0f * la[i]) * 1.0f;
-        t1 += d1 * d1;
-        t2 += d2 * d2;
-        t3 += fabsf(act[i] * 1.0f);
-      }
-      add_term(T_ACTION_SMOOTHNESS, (t1 + t2) + 0.05f * t3);
-    }
-    if (mask & (1u << T_BASE_ACC)) {                      // t1:717-724
-      float s = 0.0f;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const float d = b.last_root_vel[e * 6 + i] - root[7 + i];
-        s += d * d;
-      }
-      add_term(T_BASE_ACC, expf(-sqrtf(s) * 3.0f));
-    }
-    if (mask & (1u << T_BASE_HEIGHT)) {                   // t1:706-715
-      const float ground = (foot[0].pos[2] * stance[0] + foot[1].pos[2] * stance[1]) / (stance[0] + stance[1]);
-      const float h = root[2] - (ground - 0.05f);
-      add_term(T_BASE_HEIGHT, expf(-fabsf(h - p.base_height_target) * 100.0f));
-    }
-    if (mask & (1u << T_COLLISION)) {                     // t1:870-875
-      add_term(T_COLLISION, 1.0f * (pen_force > 0.1f ? 1.0f : 0.0f));
-    }
-    float dq0[D];                                          // q - default (joint_diff)
-#pragma unroll
-    for (int i = 0; i < D; ++i) dq0[i] = q[i] - p.default_dof_pos[i];
-    if (mask & (1u << T_DEFAULT_JOINT_POS)) {             // t1:686-703
-      const float l = sqrtf((dq0[0] * dq0[0] + dq0[1] * dq0[1]) + dq0[5] * dq0[5]);
-      const float rr = sqrtf((dq0[6] * dq0[6] + dq0[7] * dq0[7]) + dq0[11] * dq0[11]);
-      const float yr = clampf((l + rr) - 0.1f, 0.0f, 50.0f);
-      float s = 0.0f;
-#pragma unroll
-      for (int i = 0; i < D; ++i) s += dq0[i] * dq0[i];
-      add_term(T_DEFAULT_JOINT_POS, expf(-yr * 100.0f) - 0.01f * sqrtf(s));
-    }
-    if (mask & ((1u << T_DOF_ACC))) {                      // t1:863-868
-      float ldv[D];
-      load12(b.last_dof_vel, e, ldv);
-      float s = 0.0f;
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        const float a = sdiv(ldv[i] - qd[i], p.dt, dm);
-        s += a * a;
-      }
-      add_term(T_DOF_ACC, s);
-    }
-    if (mask & (1u << T_DOF_VEL)) {                       // t1:856-861
-      float s = 0.0f;
-#pragma unroll
-      for (int i = 0; i < D; ++i) s += qd[i] * qd[i];
-      add_term(T_DOF_VEL, s);
-    }
-    if (mask & (1u << T_FEET_AIR_TIME)) {                 // t1:642-657 (appendix A6, A8)
-      const bool tiny = cmd_norm < 0.05f;
-      float air_sum = 0.0f;
-#pragma unroll
-      for (int f = 0; f < 2; ++f) {
-        const float st = tiny ? 1.0f : stance[f];
-        const bool filt = contact[f] || (st != 0.0f) || (b.last_contacts[e * 2 + f] != 0);
-        b.contact_filt[e * 2 + f] = filt ? 1 : 0;
-        b.last_contacts[e * 2 + f] = contact[f] ? 1 : 0;
-        float air = b.feet_air_time[e * 2 + f];
-        const float first = (air > 0.0f && filt) ? 1.0f : 0.0f;
-        air += p.dt;
-        air_sum += clampf(air, 0.0f, 0.5f) * first;
-        b.feet_air_time[e * 2 + f] = air * (filt ? 0.0f : 1.0f);
-      }
-      add_term(T_FEET_AIR_TIME, air_sum);
-    }
-    if (mask & (1u << T_FEET_CLEARANCE)) {                // t1:793-814 (appendix A9)
-      float s = 0.0f;
-#pragma unroll
-      for (int f = 0; f < 2; ++f) {
-        const float z = foot[f].pos[2];
-        float h = b.feet_height[e * 2 + f] + (z - b.last_feet_z[e * 2 + f]);
-        b.last_feet_z[e * 2 + f] = z;
-        const float swing = 1.0f - stance[f];
-        const float hit = (h > p.target_feet_height && h < p.target_feet_height_max) ? 1.0f : 0.0f;
-        s += hit * swing;
-        b.feet_height[e * 2 + f] = h * (contact[f] ? 0.0f : 1.0f);
-      }
-      add_term(T_FEET_CLEARANCE, s);
-    }
-    if (mask & (1u << T_FEET_CONTACT_FORCES)) {           // t1:679-684
-      float s = 0.0f;
-#pragma unroll
-      for (int f = 0; f < 2; ++f) {
-        const float n = sqrtf((foot[f].force[0] * foot[f].force[0] + foot[f].force[1] * foot[f].force[1]) +
-                              foot[f].force[2] * foot[f].force[2]);
-        s += clampf(n - p.max_contact_force, 0.0f, 400.0f);
-      }
-      add_term(T_FEET_CONTACT_FORCES, s);
-    }
-    if (mask & (1u << T_FEET_CONTACT_NUMBER)) {           // t1:659-668 (appendix A14)
-      float s = 0.0f;
-#pragma unroll
-      for (int f = 0; f < 2; ++f) {
-        const float st = stand ? 1.0f : stance[f];
-        s += ((contact[f] ? 1.0f : 0.0f) == st) ? 1.0f : -0.3f;
-      }
-      add_term(T_FEET_CONTACT_NUMBER, s / 2.0f);
-    }
-    if (mask & (1u << T_FEET_DISTANCE)) {                 // t1:599-612
-      add_term(T_FEET_DISTANCE, pair_distance_reward(foot[0].pos[0], foot[0].pos[1], foot[1].pos[0], foot[1].pos[1],
-                                                     p.foot_min_dist, p.foot_max_dist));
-    }
-    if (mask & (1u << T_FEET_ROTATION)) {                 // t1:926-935 (appendix A11)
-      const float rot = foot[0].pitch * foot[0].pitch + foot[1].pitch * foot[1].pitch;
-      const float x = rot / 1.0f;
-      add_term(T_FEET_ROTATION, 1.0f * expf(-(x * x)));
-    }
-    if (mask & (1u << T_FEET_STUMBLE)) {                  // t1:937-940
-      bool any = false;
-#pragma unroll
-      for (int f = 0; f < 2; ++f)
-        any = any || (sqrtf(foot[f].force[0] * foot[f].force[0] + foot[f].force[1] * foot[f].force[1]) >
-                      5.0f * fabsf(foot[f].force[2]));
-      add_term(T_FEET_STUMBLE, any ? 1.0f : 0.0f);
-    }
-    if (mask & (1u << T_FOOT_SLIP)) {                     // t1:630-640 (appendix A10)
-      float s = 0.0f;
-#pragma unroll
-      for (int f = 0; f < 2; ++f)
-        s += sqrtf(sqrtf(foot[f].wxy[0] * foot[f].wxy[0] + foot[f].wxy[1] * foot[f].wxy[1])) * (contact[f] ? 1.0f : 0.0f);
-      add_term(T_FOOT_SLIP, s);
-    }
-    if (mask & (1u << T_JOINT_POS)) {                     // t1:576-596; ref_dof_pos of the PREVIOUS step (A3)
-      float ref[D];
-      load12(b.ref_dof_pos, e, ref);
-      float s = 0.0f;
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        const float d = q[i] - (stand ? p.default_dof_pos[i] : ref[i]);
-        s += d * d;
-      }
-      const float n = sqrtf(s);
-      const float v = expf(-2.0f * n) - 0.2f * clampf(n, 0.0f, 0.5f);
-      add_term(T_JOINT_POS, stand ? 1.0f : v);
-    }
-    if (mask & (1u << T_KNEE_DISTANCE)) {                 // t1:615-628
-      add_term(T_KNEE_DISTANCE, pair_distance_reward(knee_xy[0][0], knee_xy[0][1], knee_xy[1][0], knee_xy[1][1],
-                                                     p.knee_min_dist, p.knee_max_dist));
-    }
-    if (mask & (1u << T_LOW_SPEED)) {                     // t1:816-847 (appendix A13)
-      const float av = fabsf(lin.x), ac = fabsf(cmd.x);
-      const bool slow = av < 0.5f * ac, fast = av > 1.2f * ac;
-      float v = 0.0f;
-      if (slow) v = -1.0f;
-      if (fast) v = 0.0f;
-      if (!(slow || fast)) v = 1.2f;
-      if (signf(lin.x) != signf(cmd.x)) v = -2.0f;
-      add_term(T_LOW_SPEED, v * (ac > 0.05f ? 1.0f : 0.0f));
-    }
-    if (mask & (1u << T_ORIENTATION)) {                   // t1:670-677
-      const float a = expf(-(fabsf(eul[0]) + fabsf(eul[1])) * 10.0f);
-      const float bb = expf(-sqrtf(grav.x * grav.x + grav.y * grav.y) * 20.0f);
-      add_term(T_ORIENTATION, (a + bb) / 2.0f);
-    }
-    if (mask & (1u << T_STAND_STILL)) {                   // t1:899-915 (appendix A12)
-      const int idx[8] = {0, 1, 2, 3, 5, 6, 7, 8};
-      const float w[10] = {2.0f, 2.0f, 1.0f, 1.0f, 1.0f, 2.0f, 2.0f, 1.0f, 1.0f, 1.0f};
-      float s = 0.0f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float er = dq0[idx[i]] * w[i];
-        s += er * er;
-      }
-#pragma unroll
-      for (int f = 0; f < 2; ++f) {
-        const float er = foot[f].pitch * w[8 + f];
-        s += er * er;
-      }
-      add_term(T_STAND_STILL, stand ? expf(-s) : 0.0f);
-    }
-    if (mask & (1u << T_STAND_SYSMETRY)) {                // t1:917-925
-      float s = 0.0f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float d = q[i] - q[5 + i];
-        s += d * d;
-      }
-      add_term(T_STAND_SYSMETRY, stand ? expf(-s) : 0.0f);
-    }
-    if (mask & (1u << T_TORQUES)) {                       // t1:849-854
-      float tau[D];
-      load12(b.torques, e, tau);
-      float s = 0.0f;
-#pragma unroll
-      for (int i = 0; i < D; ++i) s += tau[i] * tau[i];
-      add_term(T_TORQUES, s);
-    }
-    const float ex = cmd.x - lin.x, ey = cmd.y - lin.y, ew = cmd.z - ang.z;
-    if (mask & (1u << T_TRACK_VEL_HARD)) {                // t1:738-758
-      const float le = sqrtf(ex * ex + ey * ey);
-      const float ae = fabsf(ew);
-      add_term(T_TRACK_VEL_HARD, (expf(-le * 10.0f) + expf(-ae * 10.0f)) / 2.0f - 0.2f * (le + ae));
-    }
-    if (mask & (1u << T_TRACKING_ANG_VEL)) {              // t1:776-790
-      add_term(T_TRACKING_ANG_VEL, stand ? expf(-fabsf(ew) * p.tracking_sigma * 2.0f) : expf(-(ew * ew) * p.tracking_sigma));
-    }
-    if (mask & (1u << T_TRACKING_LIN_VEL)) {              // t1:760-774
-      add_term(T_TRACKING_LIN_VEL, stand ? expf(-(fabsf(ex) + fabsf(ey)) * p.tracking_sigma * 2.0f)
-                                         : expf(-(ex * ex + ey * ey) * p.tracking_sigma));
-    }
-    if (mask & (1u << T_VEL_MISMATCH_EXP)) {              // t1:726-736
-      const float a = expf(-(lin.z * lin.z) * 10.0f);
-      const float bb = expf(-sqrtf(ang.x * ang.x + ang.y * ang.y) * 5.0f);
-      add_term(T_VEL_MISMATCH_EXP, (a + bb) / 2.0f);
+      if (b.reward_terms) b.reward_terms[(size_t)t * N + e] = sc;
     }
     if ((p.flags & TI5_F_ONLY_POSITIVE) && rew < 0.0f) rew = 0.0f;     // clip(min=0); NaN passes
     if (mask & (1u << T_TERMINATION)) {                   // lr:677-680, t1:894-896: added after the clip
-      const float s = ((reset && !time_out) ? 1.0f : 0.0f) * p.reward_scale[T_TERMINATION];
-      rew += s;
-      const float acc = b.episode_sums[(size_t)T_TERMINATION * N + e] + s;
+      const float sc = ((reset && !time_out) ? 1.0f : 0.0f) * p.reward_scale[T_TERMINATION];
+      rew += sc;
+      const float acc = T.sums[T_TERMINATION * TB + le] + sc;
+      T.sums[T_TERMINATION * TB + le] = acc;
       b.episode_sums[(size_t)T_TERMINATION * N + e] = acc;
-      esum[T_TERMINATION] = acc;
-      if (b.reward_terms) b.reward_terms[(size_t)T_TERMINATION * N + e] = s;
+      if (b.reward_terms) b.reward_terms[(size_t)T_TERMINATION * N + e] = sc;
     }
     b.rew_buf[e] = rew;
   }
-
-  reset_bookkeeping(p, b, reset, esum, step, counter, force_window, true);
+  reset_bookkeeping(p, b, reset, e, le, T.sums, TB, step, counter, force_window, true);
 }
 
 // Bookkeeping for an explicit `reset_idx(env_ids)` call (lr:450-455 `reset()`): the caller has
@@ -579,10 +662,7 @@ reset_bookkeeping_kernel(const __grid_constant__ Ti5Params p, const __grid_const
   const int64_t step = b.globals->step_index;
   const int64_t counter = step + b.globals->common_step_offset;
   const bool reset = e < N && b.reset_buf[e] != 0;
-  float esum[TI5_NUM_TERMS];
-#pragma unroll
-  for (int t = 0; t < TI5_NUM_TERMS; ++t) esum[t] = reset ? b.episode_sums[(size_t)t * N + e] : 0.0f;
-  reset_bookkeeping(p, b, reset, esum, step, counter, false, false);
+  reset_bookkeeping(p, b, reset, e, threadIdx.x, nullptr, 0, step, counter, false, false);
 }
 
 }  // namespace ti5
@@ -593,6 +673,7 @@ extern "C" int ti5_reset_bookkeeping(const Ti5Params* p, const Ti5Buffers* b, vo
   TI5_CHECK_ARGS(p && b && p->num_envs > 0);
   TI5_CHECK_ARGS(p->env_block == 32 || p->env_block == 64 || p->env_block == 128);
   const int blocks = (p->num_envs + p->env_block - 1) / p->env_block;
+  cudaMemsetAsync(reinterpret_cast<char*>(b->globals) + offsetof(Ti5Globals, n_listed), 0, sizeof(int32_t), (cudaStream_t)stream);
   reset_bookkeeping_kernel<<<blocks, p->env_block, 0, (cudaStream_t)stream>>>(*p, *b);
   return ti5_check_launch("ti5_reset_bookkeeping");
 }
@@ -604,6 +685,16 @@ extern "C" int ti5_post_physics(const Ti5Params* p, const Ti5Buffers* b, const T
   TI5_CHECK_ARGS((p->term_mask & (1u << T_DOF_VEL_LIMITS)) == 0);   // the reference term reads a cfg field t1 lacks
   Ti5Rng rr = r ? *r : Ti5Rng{};
   const int blocks = (p->num_envs + p->env_block - 1) / p->env_block;
-  post_physics_kernel<<<blocks, p->env_block, 0, (cudaStream_t)stream>>>(*p, *b, rr, push_last);
+  const size_t smem = post_tile_bytes(p->env_block, p->num_gaits);
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(post_physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      ti5_set_error("ti5_post_physics: %zu bytes of shared memory per CTA not available", smem);
+      cudaGetLastError();
+      return TI5_ECUDA;
+    }
+    configured = smem;
+  }
+  post_physics_kernel<<<blocks, POST_ROLES * p->env_block, smem, (cudaStream_t)stream>>>(*p, *b, rr, push_last);
   return ti5_check_launch("ti5_post_physics");
 }

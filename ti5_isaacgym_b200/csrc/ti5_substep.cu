@@ -1,8 +1,8 @@
 // Substep phase (10x per policy step): PD torques with action lag, and the DOF / IMU lag pushes.
 //
 // Replaces lr:393-394 (action clip), lr:1019-1074 (_compute_torques) and lr:412-434 (lag pushes).
-// One thread per (env, DOF) element: every (N,12) array is read/written fully coalesced, the AoS
-// dof_state is read as one float2 per thread.  The reference shifts its (N,12,31)/(N,24,31)/(N,6,11)
+// One thread per (env, 4 DOFs): every (N,12) array is read/written as coalesced float4, the AoS
+// dof_state as two float4 per thread.  The reference shifts its (N,12,31)/(N,24,31)/(N,6,11)
 // lag buffers by a full clone every substep (17.9 KB/env); here they are slot-major rings
 // (len, N, width): a push is one coalesced row-block write, a lagged read a 48-byte gather.
 #include "ti5_device.cuh"
@@ -13,75 +13,125 @@ namespace ti5 {
 __global__ void __launch_bounds__(256) begin_step_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
                                                         const float* __restrict__ actions_in) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx == 0) b.globals->step_index += 1;   // nobody in this launch reads it
+  if (idx == 0) {                             // nobody in this launch reads these
+    b.globals->step_index += 1;
+    b.globals->n_listed = 0;
+  }
   if (idx >= p.num_envs * D) return;
   b.actions[idx] = clampf(actions_in[idx], -p.clip_actions, p.clip_actions);
 }
 
-// value pushed to IMU-lag column c of env e: cat(base_ang_vel, base_euler_xyz) (lr:430-434)
-__device__ __forceinline__ float imu_component(const float* __restrict__ root, int c) {
-  float q[4] = {root[3], root[4], root[5], root[6]};
-  if (c < 3) {
-    const V3 w = quat_rotate_inverse(q, V3{root[10], root[11], root[12]});
-    return c == 0 ? w.x : (c == 1 ? w.y : w.z);
-  }
-  return c == 3 ? euler_roll(q) : (c == 4 ? euler_pitch(q) : euler_yaw(q));
-}
-
-__global__ void __launch_bounds__(256)
+// One thread per (env, group of four DOFs): every per-DOF array moves as one float4 per thread, the
+// interleaved dof_state as two, and one Philox call yields the four motor-strength multipliers.
+__global__ void __launch_bounds__(64)
 substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
                const __grid_constant__ Ti5Rng r, int k_push, int k_torque, int phases) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int N = p.num_envs;
-  if (idx >= N * D) return;
-  const int e = idx / D, d = idx - e * D;
-  const int64_t step = b.globals->step_index;           // >= 1 inside a step
-  const int64_t base = (step - 1) * p.decimation;        // pushes completed before this step
-  const float2 qs = reinterpret_cast<const float2*>(b.dof_state)[idx];   // (pos, vel)
+  if (idx >= N * 3) return;
+  const int e = idx / 3, gq = idx - e * 3, d0 = 4 * gq;
+  const bool do_push = phases & TI5_SUB_PUSH, do_torque = phases & TI5_SUB_TORQUE;
+  const bool rg = p.flags & TI5_F_RAND_GAINS, fric = p.flags & TI5_F_RAND_COULOMB, rt = p.flags & TI5_F_RAND_TORQUE;
+  const bool lagged = p.flags & TI5_F_ADD_LAG, imu = do_push && (p.flags & TI5_F_ADD_IMU_LAG);
+  auto ld4 = [&](const float* base_ptr) { return reinterpret_cast<const float4*>(base_ptr)[idx]; };
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  if (phases & TI5_SUB_PUSH) {
+  // ---- every load that does not depend on another load, issued back to back ----------------------
+  const int64_t step = b.globals->step_index;           // >= 1 inside a step
+  const float4* ds = reinterpret_cast<const float4*>(b.dof_state);
+  const float4 s0 = ds[2 * idx], s1 = ds[2 * idx + 1];   // (q, qd) of DOFs d0..d0+3, interleaved
+  float root[7] = {0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f};   // quat xyzw | ang vel
+  if (imu) {
+    const float* rp = b.root_states + (size_t)e * RB;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) root[i] = rp[3 + i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) root[4 + i] = rp[10 + i];
+  }
+  float4 a4 = zero4, kp4 = zero4, kd4 = zero4, off4 = zero4, vis4 = zero4, cou4 = zero4, u4 = zero4;
+  int lag = 0;
+  int64_t stamp = 0;
+  if (do_torque) {
+    a4 = ld4(b.actions);
+    off4 = ld4(b.motor_offsets);
+    if (lagged) { lag = b.lag_timestep[e * 3 + 0]; stamp = b.ring_stamp[e]; }
+    if (rg) { kp4 = ld4(b.p_gains_r); kd4 = ld4(b.d_gains_r); }
+    if (fric) { vis4 = ld4(b.viscous); cou4 = ld4(b.coulomb); }
+    if (rt && p.rng_mode != TI5_RNG_PHILOX) u4 = reinterpret_cast<const float4*>(r.torque)[(size_t)k_torque * N * 3 + idx];
+  }
+  const int64_t base = (step - 1) * p.decimation;        // pushes completed before this step
+  const float q[4] = {s0.x, s0.z, s1.x, s1.z}, qd[4] = {s0.y, s0.w, s1.y, s1.w};
+
+  // ---- the one dependent load: the lagged action row (lr:1045) ---------------------------------------
+  float4* ring = reinterpret_cast<float4*>(b.act_ring);
+  const int64_t jt = base + k_torque, jj = jt - lag;     // push index now / the one the controller sees
+  float4 t4 = zero4;                                     // rows pushed before the env's last reset read as zero (lr:606)
+  const bool need_ring = do_torque && lagged && lag > 0;
+  if (need_ring && jj >= stamp && jj >= 0) t4 = ring[(size_t)ring_slot(jj, p.lag_len) * N * 3 + idx];
+
+  if (do_push) {                                         // lr:412-434
     const int64_t j = base + k_push;
     if (p.flags & TI5_F_ADD_DOF_LAG) {
       float* row = b.dof_ring + ((size_t)ring_slot(j, p.dof_lag_len) * N + e) * (2 * D);
-      row[d] = qs.x;
-      row[D + d] = qs.y;
+      *reinterpret_cast<float4*>(row + d0) = make_float4(q[0], q[1], q[2], q[3]);
+      *reinterpret_cast<float4*>(row + D + d0) = make_float4(qd[0], qd[1], qd[2], qd[3]);
     }
-    if ((p.flags & TI5_F_ADD_IMU_LAG) && d < 6) {
-      b.imu_ring[((size_t)ring_slot(j, p.imu_lag_len) * N + e) * 6 + d] = imu_component(b.root_states + (size_t)e * RB, d);
+    if (imu) {                                           // cat(base_ang_vel, base_euler_xyz), lr:430-434
+      const float bq[4] = {root[0], root[1], root[2], root[3]};
+      float* row = b.imu_ring + ((size_t)ring_slot(j, p.imu_lag_len) * N + e) * 6;
+      if (gq == 0) {
+        const V3 w = quat_rotate_inverse(bq, V3{root[4], root[5], root[6]});
+        row[0] = w.x; row[1] = w.y; row[2] = w.z;
+      } else if (gq == 1) {
+        row[3] = euler_roll(bq);
+        row[4] = euler_pitch(bq);
+      } else {
+        row[5] = euler_yaw(bq);
+      }
     }
   }
 
-  if (phases & TI5_SUB_TORQUE) {
-    const int64_t j = base + k_torque;
-    const float a = b.actions[idx] * p.action_scale;
-    float target = a;
-    if (p.flags & TI5_F_ADD_LAG) {
-      b.act_ring[((size_t)ring_slot(j, p.lag_len) * N) * D + idx] = a;
-      const int lag = b.lag_timestep[e * 3 + 0];
-      if (lag > 0) {
-        const int64_t jj = j - lag;     // push index the controller sees; rows pushed before the
-        target = (jj >= b.ring_stamp[e] && jj >= 0)   // env's last reset read as zero (lr:606)
-                     ? b.act_ring[((size_t)ring_slot(jj, p.lag_len) * N) * D + idx] : 0.0f;
+  if (do_torque) {                                       // lr:1019-1074
+    const float a[4] = {a4.x * p.action_scale, a4.y * p.action_scale, a4.z * p.action_scale, a4.w * p.action_scale};
+    if (lagged) ring[(size_t)ring_slot(jt, p.lag_len) * N * 3 + idx] = make_float4(a[0], a[1], a[2], a[3]);
+    const float target[4] = {need_ring ? t4.x : a[0], need_ring ? t4.y : a[1], need_ring ? t4.z : a[2], need_ring ? t4.w : a[3]};
+    float kp[4] = {kp4.x, kp4.y, kp4.z, kp4.w}, kd[4] = {kd4.x, kd4.y, kd4.z, kd4.w};
+    if (!rg) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { kp[i] = p.p_gains[d0 + i]; kd[i] = p.d_gains[d0 + i]; }
+    }
+    const float off[4] = {off4.x, off4.y, off4.z, off4.w};
+    float tau[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float err = ((target[i] + p.default_dof_pos[d0 + i]) - q[i]) + off[i];
+      tau[i] = kp[i] * err - kd[i] * qd[i];
+    }
+    if (fric) {
+      const float vis[4] = {vis4.x, vis4.y, vis4.z, vis4.w}, cou[4] = {cou4.x, cou4.y, cou4.z, cou4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        tau[i] = tau[i] - vis[i] * qd[i];
+        tau[i] = tau[i] - cou[i] * signf(qd[i]);
       }
     }
-    const bool rg = p.flags & TI5_F_RAND_GAINS;
-    const float kp = rg ? b.p_gains_r[idx] : p.p_gains[d];
-    const float kd = rg ? b.d_gains_r[idx] : p.d_gains[d];
-    const float err = ((target + p.default_dof_pos[d]) - qs.x) + b.motor_offsets[idx];
-    float tau = kp * err - kd * qs.y;
-    if (p.flags & TI5_F_RAND_COULOMB) {
-      tau = tau - b.viscous[idx] * qs.y;
-      tau = tau - b.coulomb[idx] * signf(qs.y);
+    if (rt) {
+      if (p.rng_mode == TI5_RNG_PHILOX) u4 = philox_u4(p.seed, (uint64_t)step, S_TORQUE + k_torque, idx);
+      const float u[4] = {u4.x, u4.y, u4.z, u4.w};
+      float m[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        m[i] = affine(p.torque_multi_w, p.torque_multi_lo, u[i]);
+        tau[i] = tau[i] * m[i];
+      }
+      reinterpret_cast<float4*>(b.torque_multi)[idx] = make_float4(m[0], m[1], m[2], m[3]);
     }
-    if (p.flags & TI5_F_RAND_TORQUE) {
-      const float u = p.rng_mode == TI5_RNG_PHILOX ? philox_u(p.seed, (uint64_t)step, S_TORQUE + k_torque, idx)
-                                                   : r.torque[(size_t)k_torque * N * D + idx];
-      const float m = affine(p.torque_multi_w, p.torque_multi_lo, u);
-      b.torque_multi[idx] = m;
-      tau = tau * m;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float lim = p.torque_limits[d0 + i];
+      tau[i] = clampf(tau[i], -lim, lim);
     }
-    const float lim = p.torque_limits[d];
-    b.torques[idx] = clampf(tau, -lim, lim);
+    reinterpret_cast<float4*>(b.torques)[idx] = make_float4(tau[0], tau[1], tau[2], tau[3]);
   }
 }
 
@@ -102,11 +152,11 @@ extern "C" int ti5_substep(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng
   TI5_CHECK_ARGS(!(phases & TI5_SUB_TORQUE) || p->rng_mode == TI5_RNG_PHILOX || !(p->flags & TI5_F_RAND_TORQUE) ||
                  (r && r->torque));
   Ti5Rng rr = r ? *r : Ti5Rng{};
-  const int n = p->num_envs * D;
+  const int n = p->num_envs * 3;
   // fused form: push the result of simulator substep k-1, then the torque of substep k
   const int k_push = (phases & TI5_SUB_TORQUE) ? k - 1 : k;
   TI5_CHECK_ARGS(!(phases & TI5_SUB_PUSH) || k_push >= 0);
-  substep_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*p, *b, rr, k_push, k, phases);
+  substep_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(*p, *b, rr, k_push, k, phases);
   return ti5_check_launch("ti5_substep");
 }
 

@@ -231,6 +231,7 @@ class LeggedRobot(BaseTask):
         self._episode_sums = f32(C["TI5_NUM_TERMS"], N)
         self._reward_terms = f32(C["TI5_NUM_TERMS"], N)
         self.reset_ids = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._reset_list = torch.zeros(N, dtype=torch.int32, device=dev)
         # kernel-side layout
         self._act_ring, self._dof_ring, self._imu_ring = f32(p.lag_len, N, D), f32(p.dof_lag_len, N, 2 * D), f32(p.imu_lag_len, N, 6)
         self._lag_timestep = torch.zeros(N, 3, dtype=torch.int32, device=dev)
@@ -346,7 +347,7 @@ class LeggedRobot(BaseTask):
             measured_heights=self.measured_heights if torch.is_tensor(self.measured_heights) else None,
             rew_buf=self.rew_buf, reset_buf=self.reset_buf, time_out_buf=self.time_out_buf,
             time_outs_latched=self._time_outs_latched, episode_sums=self._episode_sums,
-            reward_terms=self._reward_terms, reset_ids=self.reset_ids, block_counts=self._block_counts,
+            reward_terms=self._reward_terms, reset_ids=self.reset_ids, reset_list=self._reset_list, block_counts=self._block_counts,
             block_sums=self._block_sums, extras_log=self._extras_log, obs_ring=self._obs_ring,
             priv_ring=self._priv_ring, obs_out=self._obs_out, priv_out=self._priv_out)
         for name, t in pairs.items():
@@ -454,14 +455,12 @@ class LeggedRobot(BaseTask):
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _launch_step(self, actions_ptr, with_physics):
-        """Enqueue the kernels of one policy step on the current stream."""
+    def _launch_substeps(self, actions_ptr, with_physics):
+        """lr:393-434: action clip, then DEC x (torque -> simulate -> lag push)."""
         lib, p, b, r, st = self._lib, self._p_ref, self._b_ref, self._rng_ref(), self._stream()
-        dec = self._params.decimation
         _lib.check(lib.ti5_begin_step(p, b, actions_ptr, st))
-        for k in range(dec):
+        for k in range(self._params.decimation):
             if with_physics:
-                # lr:401-434 with a simulator in the loop: torque -> simulate -> lag push
                 _lib.check(lib.ti5_torque_substep(p, b, r, k, st))
                 self.gym.set_dof_actuation_force_tensor(self.sim, self.torques)
                 self.gym.simulate(self.sim)
@@ -472,6 +471,10 @@ class LeggedRobot(BaseTask):
                 # nothing runs between push k-1 and torque k: one fused launch per substep
                 phases = C["TI5_SUB_TORQUE"] | (C["TI5_SUB_PUSH"] if k > 0 else 0)
                 _lib.check(lib.ti5_substep(p, b, r, k, phases, st))
+
+    def _launch_post(self, with_physics):
+        """lr:458-506 post_physics_step + the observation clip of lr:441-446."""
+        lib, p, b, r, st = self._lib, self._p_ref, self._b_ref, self._rng_ref(), self._stream()
         if with_physics:
             self.gym.refresh_net_contact_force_tensor(self.sim)
             self.gym.refresh_rigid_body_state_tensor(self.sim)
@@ -481,6 +484,28 @@ class LeggedRobot(BaseTask):
         _lib.check(lib.ti5_reset_observe(p, b, r, C["TI5_RO_RESET"] | C["TI5_RO_OBSERVE"], st))
         if self._materialize:
             _lib.check(lib.ti5_materialize_obs(p, b, st))
+
+    def _launch_step(self, actions_ptr, with_physics):
+        """Enqueue the kernels of one policy step on the current stream."""
+        self._launch_substeps(actions_ptr, with_physics)
+        self._launch_post(with_physics)
+
+    def capture_phase_graphs(self):
+        """Two CUDA graphs (substep phase, post-physics phase) instead of one, so that a benchmark can
+        bracket each phase with CUDA events.  Replay both, then call `_finish_step()`."""
+        torch.cuda.synchronize(self.device)
+        graphs = []
+        for fn in (lambda: self._launch_substeps(ctypes.c_void_p(self._actions_in.data_ptr()), False),
+                   lambda: self._launch_post(False)):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=torch.cuda.Stream(self.device)):
+                fn()
+            graphs.append(g)
+        return graphs
+
+    @property
+    def launches_per_step(self):
+        return 1 + self._params.decimation + 2 + (1 if self._params.num_height_points else 0) + (1 if self._materialize else 0)
 
     def step(self, actions):
         with_physics = getattr(self.gym, "physics", None) is not None or not hasattr(self.gym, "physics")
