@@ -859,3 +859,37 @@ def gae_returns(rewards, values, dones, last_values, gamma, lam):
         returns[t] = adv + values[t]
     a = returns - values
     return returns, (a - a.mean()) / (a.std() + 1e-8)
+
+
+# ------------------------------------------------------------------------------------------
+# state exchange with the fixtures / the CUDA env (flat dict, reference attribute names)
+# ------------------------------------------------------------------------------------------
+
+_PLAIN_STATE = ("torques actions last_actions last_last_actions last_dof_vel last_root_vel commands feet_air_time "
+                "feet_height last_contacts contact_filt base_quat base_lin_vel base_ang_vel projected_gravity "
+                "base_euler_xyz feet_euler_xyz ext_forces ext_torques rand_push_force rand_push_torque ref_dof_pos "
+                "gait_time gait_start torque_multi motor_offsets randomized_p_gains randomized_d_gains "
+                "randomized_joint_coulomb randomized_joint_viscous joint_armatures lag_buffer dof_lag_buffer "
+                "imu_lag_buffer lag_timestep dof_lag_timestep imu_lag_timestep episode_length_buf phase_length_buf "
+                "rew_buf reset_buf time_out_buf env_origins env_frictions body_mass").split()
+
+
+def load_state(C, S, state):
+    """Adopt a flat state dict (the `state0.*` entries of tests/golden/*.npz)."""
+    for k in _PLAIN_STATE:
+        setattr(S, k, torch.as_tensor(state[k]).clone().to(C.device))
+    S.last_feet_z = torch.as_tensor(state["last_feet_z"]).clone().to(C.device)
+    S.obs_history = torch.as_tensor(state["obs_history"]).clone().to(C.device)
+    S.critic_history = torch.as_tensor(state["critic_history"]).clone().to(C.device)
+    es = torch.as_tensor(state["episode_sums"]).to(C.device)
+    S.episode_sums = {k: es[i].clone() for i, k in enumerate(C.reward_names)}
+    cnt = [int(v) for v in state["counters"]]
+    S.common_step_counter, S.is_first_add_force, S.is_first_push = cnt[0], bool(cnt[1]), bool(cnt[2])
+    cr = torch.as_tensor(state["command_ranges"]).tolist()
+    S.command_ranges = dict(S.command_ranges)
+    for i, k in enumerate(("lin_vel_x", "lin_vel_y", "ang_vel_yaw")):
+        S.command_ranges[k] = list(cr[i])
+    if "terrain_levels" in state:
+        S.terrain_levels = torch.as_tensor(state["terrain_levels"]).clone().to(C.device)
+        S.terrain_types = torch.as_tensor(state["terrain_types"]).clone().to(C.device)
+    return S

@@ -1,0 +1,158 @@
+"""Stand-alone kernels through the C ABI: GAE, reset-index compaction, height sampling; and the
+properties of the production configuration (Philox RNG, CUDA graph, ring-buffer observation views)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, close, exact, make_env, scenario_cfg
+
+from oracle import t1_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+# ----------------------------------------------------------------------------- GAE (rs:97-119)
+def _gae_case(T, N, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(T, N, 1, generator=g), torch.randn(T, N, 1, generator=g),
+            (torch.rand(T, N, 1, generator=g) < 0.02).byte(), torch.randn(N, 1, generator=g))
+
+
+@pytest.mark.parametrize("T,N", [(24, 64), (24, 8192), (5, 7), (1, 1), (24, 65536), (100, 129)])
+def test_gae_matches_oracle(T, N):
+    from ti5_isaacgym_b200.algo.rollout_storage import gae_returns_
+    rew, val, done, last = _gae_case(T, N, 99)
+    o_ret, o_adv = O.gae_returns(rew, val, done, last, 0.994, 0.9)
+    ret, adv = torch.empty(T, N, 1, device="cuda"), torch.empty(T, N, 1, device="cuda")
+    gae_returns_(rew.cuda(), val.cuda(), done.cuda(), last.cuda(), ret, adv, 0.994, 0.9)
+    close(ret, o_ret, "returns", atol=1e-5)
+    if T * N > 1:
+        close(adv, o_adv, "advantages", atol=1e-5)
+
+
+def test_gae_matches_reference_fixture_and_storage_class():
+    from ti5_isaacgym_b200.algo.rollout_storage import RolloutStorage
+    z = np.load(os.path.join(GOLDEN, "gae_T24_N64.npz"))
+    st = RolloutStorage(64, 24, [4], [4], [2], device="cuda")
+    st.rewards.copy_(torch.from_numpy(z["rewards"]))
+    st.values.copy_(torch.from_numpy(z["values"]))
+    st.dones.copy_(torch.from_numpy(z["dones"]))
+    st.compute_returns(torch.from_numpy(z["last_values"]).cuda(), float(z["gamma"]), float(z["lam"]))
+    close(st.returns, torch.from_numpy(z["returns"]), "returns vs reference", atol=1e-5)
+    close(st.advantages, torch.from_numpy(z["advantages"]), "advantages vs reference", atol=1e-5)
+    # size-independent property: normalised advantages have zero mean, unit (unbiased) std
+    assert abs(float(st.advantages.mean())) < 1e-5 and abs(float(st.advantages.std()) - 1) < 1e-4
+
+
+# ----------------------------------------------------------------------------- compaction (lr:490)
+@pytest.mark.parametrize("n,rate", [(0, 0.5), (1, 1.0), (31, 0.3), (1024, 0.0), (1025, 1.0), (8192, 0.01), (65536, 0.05),
+                                    (100000, 0.5)])
+def test_compaction_is_ascending_nonzero(n, rate):
+    from ti5_isaacgym_b200 import _lib
+    lib = _lib.load_library()
+    g = torch.Generator().manual_seed(n + 1)
+    mask = (torch.rand(max(n, 1), generator=g) < rate)[:n].cuda()
+    ids = torch.full((max(n, 1),), -1, dtype=torch.int32, device="cuda")
+    count = torch.zeros(1, dtype=torch.int32, device="cuda")
+    scratch = torch.zeros((n + 1023) // 1024 + 2, dtype=torch.int32, device="cuda")
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    for _ in range(2):       # twice: the scratch ticket must be left clean
+        _lib.check(lib.ti5_compact_resets(p(mask), n, p(ids), p(count), p(scratch), None))
+    want = mask.nonzero().flatten().to(torch.int32)
+    assert int(count) == len(want)
+    exact(ids[:len(want)], want, "compacted ids")
+
+
+# ----------------------------------------------------------------------------- production configuration
+def _production_env(N, **kw):
+    from ti5_isaacgym_b200.envs import T1DHStandEnv
+    from ti5_isaacgym_b200.sim.synthetic import SimParams, fill_synthetic_state
+    cfg = scenario_cfg("plane_default", N)
+    env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, "cuda:0", True, seed=11, **kw)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    fill_synthetic_state(env.gym.tensors, env.env_origins, gen, base_contact_rate=0.03)
+    return env, gen
+
+
+def test_graph_replay_equals_direct_launches_and_history_layout():
+    from ti5_isaacgym_b200.sim.synthetic import synthetic_actions
+    N = 2048
+    torch.manual_seed(0)
+    a, gen_a = _production_env(N, use_cuda_graph=True)
+    torch.manual_seed(0)
+    b, gen_b = _production_env(N, use_cuda_graph=False, materialize_obs=True)
+    a.reset(), b.reset()
+    prev = None
+    for t in range(70):
+        act = synthetic_actions(N, gen_a, "cuda")
+        oa, pa, ra, da, xa = a.step(act)
+        ob, pb, rb, db, xb = b.step(act)
+        exact(oa, ob, f"step {t}: graph vs direct obs (ring view vs materialised copy)")
+        exact(pa, pb, f"step {t}: privileged obs")
+        exact(ra, rb, f"step {t}: rewards")
+        exact(da, db, f"step {t}: resets")
+        assert oa.shape == (N, 66 * 47) and oa.stride() == (2 * 66 * 47, 1) and ob.is_contiguous()
+        if prev is not None:
+            keep = ~da                                      # history of a re-spawned env is cleared (t1:556-559)
+            exact(oa[keep][:, :-47], prev[keep][:, 47:], f"step {t}: history shifts by one frame")
+            assert (oa[da][:, :-47] == 0).all()
+        prev = oa.clone()
+        assert oa.view(-1, 66, 47).shape == (N, 66, 47) and oa[..., -235:].shape == (N, 235)    # actor_critic_dh.py:154-159
+    assert float(oa.abs().max()) <= 100.0 and torch.isfinite(oa).all()
+    g = a.sync_from_device()
+    assert g.step_index == b.sync_from_device().step_index
+
+
+def test_full_size_properties_8192():
+    """BASELINE size: properties that need no oracle."""
+    from ti5_isaacgym_b200.sim.synthetic import synthetic_actions
+    N = 8192
+    env, gen = _production_env(N)
+    env.reset()
+    env.episode_length_buf = torch.randint(1, 2400, (N,), generator=gen, device="cuda")
+    for t in range(30):
+        act = synthetic_actions(N, gen, "cuda")
+        ep_before = env.episode_length_buf.clone()
+        obs, priv, rew, done, extras = env.step(act)
+        g = env.sync_from_device()
+        ids = env.reset_ids[:g.n_reset].long()
+        exact(ids, done.nonzero().flatten(), "reset ids == nonzero(reset_buf), ascending")
+        assert (rew >= 0).all() and torch.isfinite(rew).all()
+        total = sum(env.reward_terms[n] for n in env.reward_names)
+        close(rew, total.clamp(min=0), "rew = clip(sum of scaled terms)", atol=1e-5)
+        assert (env.episode_length_buf[done] == 0).all()
+        exact(env.episode_length_buf[~done], ep_before[~done] + 1, "episode counters")
+        assert (env.torques.abs() <= env.torque_limits + 1e-4).all()
+        tm = env.torque_multi
+        assert 0.8 <= float(tm.min()) and float(tm.max()) <= 1.2 and abs(float(tm.mean()) - 1.0) < 5e-3
+        close(obs[:, -47 + 29:-47 + 41], env.actions, "newest frame carries the clipped actions")
+        assert set(extras["episode"].keys()) == {"rew_" + n for n in env.reward_names} | {"max_command_x"}
+    assert priv.shape == (N, 219)
+
+
+def test_episode_length_setter_feeds_the_kernels():
+    env, gen = _production_env(256)
+    env.reset()
+    env.episode_length_buf = torch.full((256,), 2400, device="cuda")       # dh_on_policy_runner.py:101 rebinding
+    _, _, _, done, extras = env.step(torch.zeros(256, 12, device="cuda"))
+    assert done.all() and extras["time_outs"].all()
+
+
+def test_heights_match_oracle_at_scale():
+    from ti5_isaacgym_b200.envs.t1.t1_robot import robot_constants
+    from ti5_isaacgym_b200.sim.synthetic import fill_synthetic_state
+    N = 4096
+    cfg = scenario_cfg("trimesh_heights_push", N)
+    env = make_env(cfg, div_mode="reciprocal")
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    fill_synthetic_state(env.gym.tensors, env.env_origins, gen)
+    got = env._get_heights().clone()
+    C = O.make_consts(cfg, cfg.sim.dt, robot_constants(cfg), device="cuda:0")
+    S = O.new_state(C, N)
+    S.base_quat = env.root_states[:, 3:7].clone()
+    want = O.sample_heights(C, S, env.gym.tensors, env.height_samples)
+    assert float((got != want).float().mean()) < 2e-4, "index truncation may differ only where fp32 lands on a cell edge"
+    close(got[got == want], want[got == want], "heights")

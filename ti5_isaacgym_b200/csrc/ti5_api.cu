@@ -93,11 +93,13 @@ __global__ void __launch_bounds__(CB) compact_scatter_kernel(const uint8_t* __re
 
 extern "C" int ti5_compact_resets(const uint8_t* mask, int32_t n, int32_t* ids_out, int32_t* count_out,
                                   int32_t* scratch, void* stream) {
-  TI5_CHECK_ARGS(mask && ids_out && count_out && scratch && n >= 0);
-  if (n == 0) {
+  TI5_CHECK_ARGS(count_out && n >= 0);
+  if (n == 0) {   // empty mask: nothing to read, zero ids
+
     cudaMemsetAsync(count_out, 0, sizeof(int32_t), (cudaStream_t)stream);
     return ti5_check_launch("ti5_compact_resets");
   }
+  TI5_CHECK_ARGS(mask && ids_out && scratch);
   const int blocks = (n + ti5::CB - 1) / ti5::CB;
   ti5::compact_count_kernel<<<blocks, ti5::CB, 0, (cudaStream_t)stream>>>(mask, n, scratch, count_out);
   ti5::compact_scatter_kernel<<<blocks, ti5::CB, 0, (cudaStream_t)stream>>>(mask, n, scratch, ids_out);
