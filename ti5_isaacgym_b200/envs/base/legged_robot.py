@@ -561,6 +561,11 @@ class LeggedRobot(BaseTask):
         _lib.check(self._lib.ti5_sample_heights(self._p_ref, self._b_ref, self._stream()))
         return self.measured_heights
 
+    def post_physics_step(self):
+        """lr:458-506 on the current simulator state: termination, rewards, resets, observations."""
+        with_physics = getattr(self.gym, "physics", None) is not None or not hasattr(self.gym, "physics")
+        self._launch_post(with_physics)
+
     def compute_observations(self):
         """t1:368-481 on the current state (no resets)."""
         _lib.check(self._lib.ti5_reset_observe(self._p_ref, self._b_ref, self._rng_ref(), C["TI5_RO_OBSERVE"], self._stream()))
