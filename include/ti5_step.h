@@ -153,9 +153,10 @@ typedef struct Ti5Globals {
   int64_t common_step_offset;  /* common_step_counter = step_index + common_step_offset */
   int32_t n_reset;             /* envs reset in the current step (lr:490) */
   int32_t n_listed;            /* entries of Ti5Buffers.reset_list (unordered), zeroed by ti5_begin_step */
-  int32_t tickets[3];          /* last-CTA-done counters of the per-env kernels */
-  int32_t is_first_add_force;  /* lr:90, t1:205-215 */
-  double cmd_range[3][2];      /* lin_vel_x, lin_vel_y, ang_vel_yaw ranges (curriculum mutates [0]) */
+  int32_t tickets[2];          /* last-CTA-done counters (terrain-level mean) */
+  int32_t is_first_add_force[2]; /* lr:90, t1:205-215; double-buffered by step parity (read [step&1], write [(step+1)&1]) */
+  double cmd_range[2][3][2];   /* [step parity][lin_vel_x, lin_vel_y, ang_vel_yaw][lo, hi]; the command curriculum
+                                  (lr:1160-1169) writes the next step's copy */
 } Ti5Globals;
 
 /* ---- device buffers.  (N,k) means row-major per-env rows.  See DESIGN.md for the layout ---- */
@@ -242,6 +243,7 @@ typedef struct Ti5Buffers {
   float* priv_ring;
   float* obs_out;          /* optional contiguous (N, H*K) for ti5_materialize_obs */
   float* priv_out;         /* optional contiguous (N, CH*P) */
+  uint64_t* debug_ts;      /* optional (2, CTAs, 8) globaltimer probes of the two per-env kernels (profiling aid), or NULL */
 } Ti5Buffers;
 
 /* ---- caller-supplied uniforms of one step (TI5_RNG_POOLS).  All fp32 U[0,1) unless noted --- */

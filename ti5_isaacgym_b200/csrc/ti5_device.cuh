@@ -118,7 +118,7 @@ static __device__ __noinline__ void euler_xyz(const float q[4], float e[3]) {
 enum RngSite { S_TORQUE = 0, S_CMD = 16, S_PUSH = 24, S_EXT, S_DOFS, S_ROOT, S_DR, S_GAIT_TIME, S_NOISE, S_LAG,
                S_GAIT_START, S_TERRAIN };
 
-static __device__ __noinline__ uint4 philox4(uint64_t seed, uint64_t step, uint32_t site, uint32_t idx) {
+__device__ __forceinline__ uint4 philox4_inline(uint64_t seed, uint64_t step, uint32_t site, uint32_t idx) {
   uint32_t c0 = idx, c1 = site, c2 = (uint32_t)step, c3 = (uint32_t)(step >> 32);
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
@@ -133,6 +133,10 @@ static __device__ __noinline__ uint4 philox4(uint64_t seed, uint64_t step, uint3
     k1 += 0xBB67AE85u;
   }
   return make_uint4(c0, c1, c2, c3);
+}
+// out-of-line copy for the rarely taken draw sites (commands, pushes, resets): one body, many callers
+static __device__ __noinline__ uint4 philox4(uint64_t seed, uint64_t step, uint32_t site, uint32_t idx) {
+  return philox4_inline(seed, step, site, idx);
 }
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
 __device__ __forceinline__ float philox_u(uint64_t seed, uint64_t step, uint32_t site, uint32_t idx) {
@@ -206,6 +210,15 @@ __device__ __forceinline__ void coop_load(void* dst, const void* src, uint32_t b
 }
 
 static __device__ __noinline__ void coop_load_call(void* dst, const void* src, uint32_t bytes) { coop_load(dst, src, bytes); }
+
+// profiling aid: nanosecond timestamp probe `k` of this CTA (thread 0 only), when a probe buffer is bound
+__device__ __forceinline__ void probe(uint64_t* ts, int kernel, int k) {
+  if (ts != nullptr && threadIdx.x == 0) {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    ts[((size_t)kernel * 4096 + blockIdx.x) * 8 + k] = t;
+  }
+}
 
 // ring slot of push index j (j >= 0)
 __device__ __forceinline__ int ring_slot(int64_t j, int len) { return (int)(j % len); }

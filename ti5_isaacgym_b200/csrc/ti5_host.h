@@ -15,3 +15,4 @@ int ti5_check_launch(const char* what);
       return TI5_EINVAL;                                                            \
     }                                                                               \
   } while (0)
+

@@ -38,29 +38,40 @@ struct ObsRng {
   __device__ __forceinline__ float root_xy(int e, int c) const {
     return philox ? philox_u(p.seed, step, S_ROOT, e * 2 + c) : r.root_xy[(size_t)e * 2 + c];
   }
-  __device__ __forceinline__ float gait_time(int e, int gi) const {
-    return philox ? philox_u(p.seed, step, S_GAIT_TIME, e * TI5_MAX_GAITS + gi) : r.gait_time[(size_t)e * p.num_gaits + gi];
-  }
   __device__ __forceinline__ float cmd(int pass, int gi, int e, int c, int N) const {
     return philox ? philox_u(p.seed, step, S_CMD + 4 * pass + gi, e * 3 + c)
                   : r.cmd[((size_t)(pass * p.num_gaits + gi) * N + e) * 3 + c];
   }
   // uniforms 4g .. 4g+3 of the env's noise row
   __device__ __forceinline__ float4 noise4(int e, int g4, int K) const {
-    if (philox) return philox_u4(p.seed, step, S_NOISE, e * 16 + g4);
+    if (philox) {      // inlined: the caller unrolls four independent Philox chains side by side
+      const uint4 w = philox4_inline(p.seed, step, S_NOISE, e * 16 + g4);
+      return make_float4(u01(w.x), u01(w.y), u01(w.z), u01(w.w));
+    }
     const float* row = r.noise + (size_t)e * K;
     const int k = 4 * g4;
     return make_float4(row[k], k + 1 < K ? row[k + 1] : 0.f, k + 2 < K ? row[k + 2] : 0.f, k + 3 < K ? row[k + 3] : 0.f);
   }
-  __device__ __forceinline__ int lag_idx(int e, int which) const {
-    if (!philox) return (int)r.lag_idx[(size_t)e * 3 + which];
-    const int lo = p.lag_range[which][0], hi = p.lag_range[which][1];
-    int v = lo + (int)(philox_u(p.seed, step, S_LAG, e * 3 + which) * (float)(hi - lo + 1));
-    return v > hi ? hi : v;
-  }
-  __device__ __forceinline__ float gait_start(int e) const {
-    if (!philox) return (float)r.gait_start[e] * 0.5f;
-    return philox_u(p.seed, step, S_GAIT_START, e) < 0.5f ? 0.0f : 0.5f;
+  // the schedule draws of a re-spawned env: three lag indices and the gait start (lr:608-629, t1:523) from
+  // one Philox call, the gait durations (t1:116) from another
+  __device__ __forceinline__ void schedule_draws(int e, int lag[3], float& gait_start, float gait_u[TI5_MAX_GAITS]) const {
+    if (philox) {
+      const float4 a = philox_u4(p.seed, step, S_LAG, e), c = philox_u4(p.seed, step, S_GAIT_TIME, e);
+      const float ua[3] = {a.x, a.y, a.z};
+#pragma unroll
+      for (int w = 0; w < 3; ++w) {
+        const int lo = p.lag_range[w][0], hi = p.lag_range[w][1];
+        const int v = lo + (int)(ua[w] * (float)(hi - lo + 1));
+        lag[w] = v > hi ? hi : v;
+      }
+      gait_start = a.w < 0.5f ? 0.0f : 0.5f;
+      gait_u[0] = c.x; gait_u[1] = c.y; gait_u[2] = c.z; gait_u[3] = c.w;
+    } else {
+#pragma unroll
+      for (int w = 0; w < 3; ++w) lag[w] = (int)r.lag_idx[(size_t)e * 3 + w];
+      gait_start = (float)r.gait_start[e] * 0.5f;
+      for (int gi = 0; gi < p.num_gaits; ++gi) gait_u[gi] = r.gait_time[(size_t)e * p.num_gaits + gi];
+    }
   }
   __device__ __forceinline__ int64_t terrain_level(int e) const {
     if (!philox) return r.terrain_level[e] % p.max_terrain_level;
@@ -69,12 +80,10 @@ struct ObsRng {
   }
 };
 
-// t1:483-559 reset of env `es`, shared by the 32 lanes of the warp that owns it: lanes 0-11 take one DOF
-// each (joint state, actuator randomisation, zeroed action history), lane 12 the base (terrain curriculum,
-// root state, derived base quantities), lane 13 the schedule (lag indices, counters, gait times), and
-// lanes 0-27 clear one episode sum each.  Everything goes to global memory; the owning lane reloads.
-__device__ __forceinline__ void reset_env(const Ti5Params& p, const Ti5Buffers& b, const ObsRng& rng, int es, int lane,
-                                          int64_t pushes) {
+// t1:483-559 reset of env `es`, the part that is parallel over DOFs / reward terms: lanes 0-11 take one DOF
+// each (joint state, the seven actuator draws, zeroed action history), lanes 0-27 clear one episode sum each.
+// Runs once per flagged env of the warp, all 32 lanes together.
+__device__ __forceinline__ void reset_env_dofs(const Ti5Params& p, const Ti5Buffers& b, const ObsRng& rng, int es, int lane) {
   const int N = p.num_envs;
   if (lane < D) {
     const int d = lane;
@@ -97,124 +106,208 @@ __device__ __forceinline__ void reset_env(const Ti5Params& p, const Ti5Buffers& 
     if (p.flags & TI5_F_RAND_ARMATURE) b.joint_armatures[o] = affine(p.armature_w[d], p.armature_lo[d], u[7]);
     // t1:513-518
     b.actions[o] = 0.0f; b.last_actions[o] = 0.0f; b.last_last_actions[o] = 0.0f; b.last_dof_vel[o] = 0.0f;
-  } else if (lane == 12) {
-    float* root = b.root_states + (size_t)es * RB;
-    if (p.flags & TI5_F_TERRAIN_CURRICULUM) {                        // lr:1138-1158
-      const float dx = root[0] - b.env_origins[es * 3 + 0], dy = root[1] - b.env_origins[es * 3 + 1];
-      const float dist = sqrtf(dx * dx + dy * dy);
-      const bool up = dist > (float)(p.terrain_env_length / 2.0);
-      const float cx = b.commands[es * 4 + 0], cy = b.commands[es * 4 + 1];
-      const bool down = (dist < sqrtf(cx * cx + cy * cy) * p.max_episode_length_s * 0.5f) && !up;
-      int64_t lvl = b.terrain_levels[es] + (up ? 1 : 0) - (down ? 1 : 0);
-      lvl = lvl >= p.max_terrain_level ? rng.terrain_level(es) : (lvl < 0 ? 0 : lvl);
-      b.terrain_levels[es] = lvl;
-      const float* o = b.terrain_origins + ((size_t)lvl * p.terrain_cols + b.terrain_types[es]) * 3;
-      b.env_origins[es * 3 + 0] = o[0]; b.env_origins[es * 3 + 1] = o[1]; b.env_origins[es * 3 + 2] = o[2];
-    }
-    float r0[RB];                                                     // lr:1092-1120
-#pragma unroll
-    for (int i = 0; i < RB; ++i) r0[i] = p.base_init_state[i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) r0[i] += b.env_origins[es * 3 + i];
-    if (p.flags & TI5_F_CUSTOM_ORIGINS) {
-      r0[0] += affine(p.root_xy_w, p.root_xy_lo, rng.root_xy(es, 0));
-      r0[1] += affine(p.root_xy_w, p.root_xy_lo, rng.root_xy(es, 1));
-    }
-#pragma unroll
-    for (int i = 0; i < RB; ++i) root[i] = r0[i];
-    // t1:548-552 derived state of the re-spawned base
-    const float bq[4] = {r0[3], r0[4], r0[5], r0[6]};
-    const V3 l = quat_rotate_inverse(bq, V3{r0[7], r0[8], r0[9]});
-    const V3 a = quat_rotate_inverse(bq, V3{r0[10], r0[11], r0[12]});
-    const V3 gr = quat_rotate_inverse(bq, V3{0.0f, 0.0f, -1.0f});
-    float eul[3];
-    euler_xyz(bq, eul);
-    reinterpret_cast<float4*>(b.base_quat)[es] = make_float4(bq[0], bq[1], bq[2], bq[3]);
-    b.base_lin_vel[es * 3 + 0] = l.x; b.base_lin_vel[es * 3 + 1] = l.y; b.base_lin_vel[es * 3 + 2] = l.z;
-    b.base_ang_vel[es * 3 + 0] = a.x; b.base_ang_vel[es * 3 + 1] = a.y; b.base_ang_vel[es * 3 + 2] = a.z;
-    b.projected_gravity[es * 3 + 0] = gr.x; b.projected_gravity[es * 3 + 1] = gr.y; b.projected_gravity[es * 3 + 2] = gr.z;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) b.base_euler_xyz[es * 3 + i] = eul[i];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) b.last_root_vel[es * 6 + i] = 0.0f;
-  } else if (lane == 13) {
-    // lr:604-633: the env's lag rings read as zero from now on; new lag indices
-    b.ring_stamp[es] = pushes;
-    if (p.flags & TI5_F_ADD_LAG)
-      b.lag_timestep[es * 3 + 0] = (p.flags & TI5_F_RAND_LAG_STEPS) ? rng.lag_idx(es, 0) : p.lag_range[0][1];
-    if (p.flags & TI5_F_ADD_DOF_LAG)
-      b.lag_timestep[es * 3 + 1] = (p.flags & TI5_F_RAND_DOF_LAG_STEPS) ? rng.lag_idx(es, 1) : p.lag_range[1][1];
-    if (p.flags & TI5_F_ADD_IMU_LAG)
-      b.lag_timestep[es * 3 + 2] = (p.flags & TI5_F_RAND_IMU_LAG_STEPS) ? rng.lag_idx(es, 2) : p.lag_range[2][1];
-    b.feet_air_time[es * 2 + 0] = 0.0f; b.feet_air_time[es * 2 + 1] = 0.0f;        // t1:519-523
-    b.episode_length_buf[es] = 0;
-    b.phase_length_buf[es] = 0;
-    b.gait_start[es] = rng.gait_start(es);
-    // t1:109-124 generate_gait_time
-    float rg[TI5_MAX_GAITS], sum = 0.0f;
-    for (int gi = 0; gi < p.num_gaits; ++gi) {
-      rg[gi] = affine(p.gait_time_w[gi], p.gait_time_lo[gi], rng.gait_time(es, gi));
-      sum += rg[gi];
-    }
-    const float fac = (1.0f / sum) * (float)p.max_episode_length;   // Tensor.__rtruediv__: reciprocal, then multiply
-    float run = (rg[0] * fac) * 0.0f;
-    b.gait_time[es * p.num_gaits + 0] = (int32_t)run;
-    for (int gi = 1; gi < p.num_gaits; ++gi) {
-      run += rg[gi - 1] * fac;
-      b.gait_time[es * p.num_gaits + gi] = (int32_t)run;
-    }
   }
   if (lane < TI5_NUM_TERMS && (p.term_mask & (1u << lane))) b.episode_sums[(size_t)lane * N + es] = 0.0f;   // t1:533
 }
 
+// The per-env scalar parts of the reset run on the env's own lane, so all flagged envs of a warp go in parallel.
+// Base (role 0): terrain curriculum, root state, derived base quantities.
+__device__ __forceinline__ void reset_env_base(const Ti5Params& p, const Ti5Buffers& b, const ObsRng& rng, int es) {
+  float* root = b.root_states + (size_t)es * RB;
+  if (p.flags & TI5_F_TERRAIN_CURRICULUM) {                        // lr:1138-1158
+    const float dx = root[0] - b.env_origins[es * 3 + 0], dy = root[1] - b.env_origins[es * 3 + 1];
+    const float dist = sqrtf(dx * dx + dy * dy);
+    const bool up = dist > (float)(p.terrain_env_length / 2.0);
+    const float cx = b.commands[es * 4 + 0], cy = b.commands[es * 4 + 1];
+    const bool down = (dist < sqrtf(cx * cx + cy * cy) * p.max_episode_length_s * 0.5f) && !up;
+    int64_t lvl = b.terrain_levels[es] + (up ? 1 : 0) - (down ? 1 : 0);
+    lvl = lvl >= p.max_terrain_level ? rng.terrain_level(es) : (lvl < 0 ? 0 : lvl);
+    b.terrain_levels[es] = lvl;
+    const float* o = b.terrain_origins + ((size_t)lvl * p.terrain_cols + b.terrain_types[es]) * 3;
+    b.env_origins[es * 3 + 0] = o[0]; b.env_origins[es * 3 + 1] = o[1]; b.env_origins[es * 3 + 2] = o[2];
+  }
+  float r0[RB];                                                     // lr:1092-1120
+#pragma unroll
+  for (int i = 0; i < RB; ++i) r0[i] = p.base_init_state[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) r0[i] += b.env_origins[es * 3 + i];
+  if (p.flags & TI5_F_CUSTOM_ORIGINS) {
+    r0[0] += affine(p.root_xy_w, p.root_xy_lo, rng.root_xy(es, 0));
+    r0[1] += affine(p.root_xy_w, p.root_xy_lo, rng.root_xy(es, 1));
+  }
+#pragma unroll
+  for (int i = 0; i < RB; ++i) root[i] = r0[i];
+  // t1:548-552 derived state of the re-spawned base
+  const float bq[4] = {r0[3], r0[4], r0[5], r0[6]};
+  const V3 l = quat_rotate_inverse(bq, V3{r0[7], r0[8], r0[9]});
+  const V3 a = quat_rotate_inverse(bq, V3{r0[10], r0[11], r0[12]});
+  const V3 gr = quat_rotate_inverse(bq, V3{0.0f, 0.0f, -1.0f});
+  float eul[3];
+  euler_xyz(bq, eul);
+  reinterpret_cast<float4*>(b.base_quat)[es] = make_float4(bq[0], bq[1], bq[2], bq[3]);
+  b.base_lin_vel[es * 3 + 0] = l.x; b.base_lin_vel[es * 3 + 1] = l.y; b.base_lin_vel[es * 3 + 2] = l.z;
+  b.base_ang_vel[es * 3 + 0] = a.x; b.base_ang_vel[es * 3 + 1] = a.y; b.base_ang_vel[es * 3 + 2] = a.z;
+  b.projected_gravity[es * 3 + 0] = gr.x; b.projected_gravity[es * 3 + 1] = gr.y; b.projected_gravity[es * 3 + 2] = gr.z;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) b.base_euler_xyz[es * 3 + i] = eul[i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) b.last_root_vel[es * 6 + i] = 0.0f;
+}
+
+// Schedule (role 1): lag indices, counters, gait start and gait times.
+__device__ __forceinline__ void reset_env_schedule(const Ti5Params& p, const Ti5Buffers& b, const ObsRng& rng, int es,
+                                                   int64_t pushes) {
+  int lag[3];
+  float gs, gu[TI5_MAX_GAITS];
+  rng.schedule_draws(es, lag, gs, gu);
+  // lr:604-633: the env's lag rings read as zero from now on; new lag indices
+  b.ring_stamp[es] = pushes;
+  if (p.flags & TI5_F_ADD_LAG) b.lag_timestep[es * 3 + 0] = (p.flags & TI5_F_RAND_LAG_STEPS) ? lag[0] : p.lag_range[0][1];
+  if (p.flags & TI5_F_ADD_DOF_LAG) b.lag_timestep[es * 3 + 1] = (p.flags & TI5_F_RAND_DOF_LAG_STEPS) ? lag[1] : p.lag_range[1][1];
+  if (p.flags & TI5_F_ADD_IMU_LAG) b.lag_timestep[es * 3 + 2] = (p.flags & TI5_F_RAND_IMU_LAG_STEPS) ? lag[2] : p.lag_range[2][1];
+  b.feet_air_time[es * 2 + 0] = 0.0f; b.feet_air_time[es * 2 + 1] = 0.0f;        // t1:519-523
+  b.episode_length_buf[es] = 0;
+  b.phase_length_buf[es] = 0;
+  b.gait_start[es] = gs;
+  // t1:109-124 generate_gait_time
+  float rg[TI5_MAX_GAITS], sum = 0.0f;
+  for (int gi = 0; gi < p.num_gaits; ++gi) {
+    rg[gi] = affine(p.gait_time_w[gi], p.gait_time_lo[gi], gu[gi]);
+    sum += rg[gi];
+  }
+  const float fac = (1.0f / sum) * (float)p.max_episode_length;   // Tensor.__rtruediv__: reciprocal, then multiply
+  float run = (rg[0] * fac) * 0.0f;
+  b.gait_time[es * p.num_gaits + 0] = (int32_t)run;
+  for (int gi = 1; gi < p.num_gaits; ++gi) {
+    run += rg[gi - 1] * fac;
+    b.gait_time[es * p.num_gaits + gi] = (int32_t)run;
+  }
+}
+
+// The CTA owns TB = env_block consecutive envs and runs OBS_ROLES x TB threads: role 0 builds the
+// 47-float observation frame (lagged proprioception, noise) and appends it to the observation ring, role 1
+// builds the privileged frame and appends it to the critic ring — two independent halves of one thread's
+// former instruction chain.  Role 0 warps also run the reset scatter first.
+constexpr int OBS_ROLES = 2;
+
 template <int KC, int PC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(OBS_ROLES * 128)
 reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
                      const __grid_constant__ Ti5Rng r, int phases) {
-  extern __shared__ float smem[];      // per warp: 32 x K observation frames, then 32 x P privileged frames
+  extern __shared__ float smem[];      // per 32 envs: 32 x K observation frames, then 32 x P privileged frames
   __shared__ int s_warp[32];
-  __shared__ float s_lvl[4];
+  __shared__ float s_lvl[8];
   __shared__ bool s_last;
 
   // frame widths as compile-time constants where known: the flat ring-write loops divide by them
   const int N = p.num_envs, K = KC ? KC : p.num_single_obs, P = PC ? PC : p.priv_frame, H = p.frame_stack, CH = p.c_frame_stack;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int env_blocks = (N + blockDim.x - 1) / blockDim.x;   // CTAs beyond these only help clearing histories
-  const bool live = e < N;
+  const int TB = p.env_block, tid = threadIdx.x;
+  const int role = tid / TB, le = tid - role * TB;
+  const int e = blockIdx.x * TB + le;
+  const int lane = tid & 31, warp = tid >> 5, tile_warp = le >> 5;
+  const int env_blocks = (N + TB - 1) / TB;              // CTAs beyond these only help clearing histories
+  const bool live = e < N && blockIdx.x < env_blocks;
   Ti5Globals* g = b.globals;
   const int64_t step = g->step_index;
   const int64_t pushes = step * p.decimation;            // lag pushes completed after this step
-  const bool any_reset = g->n_reset > 0;
   const bool do_reset = (phases & TI5_RO_RESET) != 0, do_obs = (phases & TI5_RO_OBSERVE) != 0;
   const int dm = p.div_mode;
+
+  // ---- reset bookkeeping left by ti5_post_physics: the per-CTA counts of flagged envs.  Every CTA derives
+  // what it needs from them — the total (lr:490 `len(env_ids)`), its own offset into the ascending id list, and,
+  // on the steps where it is due, the command-curriculum decision (lr:1160-1169) — so no CTA waits on another.
+  __shared__ int s_tot[16], s_bef[16];
+  __shared__ double s_trk[16];
+  __shared__ double s_range[3][2];
+  int n_reset = 0, id_offset = 0;
+  const int64_t counter = step + g->common_step_offset;
+  const bool curriculum_due = do_reset && (p.flags & TI5_F_COMMAND_CURRICULUM) && (counter % p.max_episode_length == 0);
+  if (do_reset) {
+    int tot = 0, bef = 0;
+    double trk = 0.0;
+    for (int i = tid; i < env_blocks; i += blockDim.x) {
+      const int c = b.block_counts[i];
+      tot += c;
+      bef += i < (int)blockIdx.x ? c : 0;
+      if (curriculum_due && c > 0) trk += (double)b.block_sums[(size_t)i * TI5_LOG_COLS + T_TRACKING_LIN_VEL];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      bef += __shfl_xor_sync(0xffffffffu, bef, o);
+      trk += __shfl_xor_sync(0xffffffffu, trk, o);
+    }
+    if (lane == 0) { s_tot[warp] = tot; s_bef[warp] = bef; s_trk[warp] = trk; }
+    __syncthreads();
+    double track_sum = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { n_reset += s_tot[w]; id_offset += s_bef[w]; track_sum += s_trk[w]; }
+    if (tid < 6) {
+      const int a = tid >> 1, c = tid & 1;
+      double v = g->cmd_range[step & 1][a][c];
+      if (a == 0 && curriculum_due && n_reset > 0) {      // evaluated before the resets of this step (lr:537-538)
+        const float mean = (float)(track_sum / (double)n_reset);
+        if (sdiv(mean, (float)p.max_episode_length, dm) > (float)(0.8 * p.tracking_lin_vel_scale)) {
+          if (c == 0) { v -= 0.25; const double lo_min = -p.cmd_curriculum_max / 2.0; v = v < lo_min ? lo_min : (v > 0.0 ? 0.0 : v); }
+          else { v += 0.5; v = v < 0.0 ? 0.0 : (v > p.cmd_curriculum_max ? p.cmd_curriculum_max : v); }
+        }
+      }
+      s_range[a][c] = v;
+      if (blockIdx.x == 0) g->cmd_range[(step + 1) & 1][a][c] = v;     // the next step's copy: nobody reads it in this grid
+    }
+    __syncthreads();
+    if (blockIdx.x == 0) {
+      // extras["episode"] snapshot row of this step: previous values if nothing reset (appendix A23)
+      float* row = b.extras_log + (size_t)(step % TI5_LOG_ROWS) * TI5_LOG_COLS;
+      const float* prev = b.extras_log + (size_t)((step + TI5_LOG_ROWS - 1) % TI5_LOG_ROWS) * TI5_LOG_COLS;
+      if (n_reset == 0 && tid < TI5_LOG_COLS) row[tid] = prev[tid];
+      if (tid == 0) {
+        g->n_reset = n_reset;
+        if (n_reset > 0) {
+          row[LOG_MAX_COMMAND_X] = (float)s_range[0][1];
+          row[LOG_N_RESET] = (float)n_reset;
+          if (!(p.flags & TI5_F_TRIMESH)) row[LOG_TERRAIN_LEVEL] = 0.0f;
+        }
+      }
+    }
+  } else if (tid < 6) {
+    s_range[tid >> 1][tid & 1] = g->cmd_range[step & 1][tid >> 1][tid & 1];
+  }
+  const bool any_reset = n_reset > 0;
   const ObsRng rng{p, r, (uint64_t)step, p.rng_mode == TI5_RNG_PHILOX};
   const int Kp = K | 1, Pp = P | 1;                      // odd row strides: conflict-free staging
-  float* s_obs = smem + (size_t)warp * 32 * (Kp + Pp);
+  float* s_obs = smem + (size_t)tile_warp * 32 * (Kp + Pp);
   float* s_priv = s_obs + 32 * Kp;
 
-  const bool reset = live && do_reset && b.reset_buf[e] != 0;
+  const bool flagged = live && do_reset && b.reset_buf[e] != 0;   // both roles see the flag
+  const bool reset = flagged && role == 0;                          // ... role 0 accounts for it
   float level_f = 0.0f;
+  probe(b.debug_ts, 1, 0);
 
-  // =========================== reset scatter (t1:483-559), one env at a time per warp ===========
-  {
+  // =========================== reset scatter (t1:483-559) ==============================================
+  // role 0: the DOF-parallel part, one flagged env at a time with all lanes, then the base on the env's own lane;
+  // role 1 (otherwise idle here): the schedule on the env's own lane.  Flagged envs of a warp go in parallel.
+  if (role == 0) {
     unsigned todo = __ballot_sync(0xffffffffu, reset);
-    const int env0 = blockIdx.x * blockDim.x + warp * 32;
+    const int env0 = blockIdx.x * TB + tile_warp * 32;
     while (todo) {
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
-      reset_env(p, b, rng, env0 + src, lane, pushes);
+      reset_env_dofs(p, b, rng, env0 + src, lane);
     }
-    __syncwarp();
+    if (reset) reset_env_base(p, b, rng, e);
+  } else if (flagged) {
+    reset_env_schedule(p, b, rng, e, pushes);
   }
+  probe(b.debug_ts, 1, 1);
+  __syncthreads();       // role 1 reads what the scatter wrote
+  probe(b.debug_ts, 1, 2);
 
   if (live) {
-    float root[RB];
-#pragma unroll
-    for (int i = 0; i < RB; ++i) root[i] = b.root_states[(size_t)e * RB + i];
+    // ======== common prologue (both roles, same values) ==================================================
+    const float* dsp = b.dof_state + (size_t)e * 2 * D;
     float q[D], qd[D];
     {
-      const float4* ds = reinterpret_cast<const float4*>(b.dof_state + (size_t)e * 2 * D);
+      const float4* ds = reinterpret_cast<const float4*>(dsp);
 #pragma unroll
       for (int i = 0; i < D / 2; ++i) {
         const float4 v = ds[i];
@@ -224,20 +317,39 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
     float act[D];
     load12(b.actions, e, act);
     float4 cmd = reinterpret_cast<const float4*>(b.commands)[e];
-    int64_t ep_len = b.episode_length_buf[e];
+    const int64_t ep_len = b.episode_length_buf[e];
     int64_t phase_len = b.phase_length_buf[e];
-    float gait_start = b.gait_start[e];
-    int64_t stamp = b.ring_stamp[e];
-    int lag_dof = b.lag_timestep[e * 3 + 1], lag_imu = b.lag_timestep[e * 3 + 2];
-    float lin[3], ang[3], eul[3];
+    const float gait_start = b.gait_start[e];
+    // role-specific loads, issued with the common ones
+    int64_t stamp = 0;
+    int lag_dof = 0, lag_imu = 0;
+    float last_act[D];
+    float root[RB], lin[3], ang[3], eul[3], fz0 = 0.0f, fz1 = 0.0f, ext[5], fric = 0.0f, mass = 0.0f;
+    if (role == 0) {
+      stamp = b.ring_stamp[e];
+      lag_dof = b.lag_timestep[e * 3 + 1];
+      lag_imu = b.lag_timestep[e * 3 + 2];
+      load12(b.last_actions, e, last_act);
+    }
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 3; ++i) {       // role 0 needs them as the un-lagged IMU fallback, role 1 for the critic
       lin[i] = b.base_lin_vel[e * 3 + i];
       ang[i] = b.base_ang_vel[e * 3 + i];
       eul[i] = b.base_euler_xyz[e * 3 + i];
     }
-    float last_act[D];
-    load12(b.last_actions, e, last_act);
+    if (role == 1) {
+#pragma unroll
+      for (int i = 0; i < RB; ++i) root[i] = b.root_states[(size_t)e * RB + i];
+      fz0 = b.contact_forces[((size_t)e * NB + p.feet[0]) * 3 + 2];
+      fz1 = b.contact_forces[((size_t)e * NB + p.feet[1]) * 3 + 2];
+      const bool xf = p.flags & TI5_F_ADD_EXT_FORCE;
+      ext[0] = (xf ? b.ext_forces : b.rand_push_force)[e * 3 + 0];
+      ext[1] = (xf ? b.ext_forces : b.rand_push_force)[e * 3 + 1];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) ext[2 + i] = (xf ? b.ext_torques : b.rand_push_torque)[e * 3 + i];
+      fric = b.env_frictions[e];
+      mass = b.body_mass[e];
+    }
 
     // t1:527 `_resample_commands()` runs over ALL envs whenever anything reset (appendix A24)
     if (do_reset && any_reset) {
@@ -247,169 +359,180 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
         const bool mx = kind == TI5_GAIT_WALK_SAGITTAL || kind == TI5_GAIT_WALK_OMNI;
         const bool my = kind == TI5_GAIT_WALK_LATERAL || kind == TI5_GAIT_WALK_OMNI;
         const bool mz = kind == TI5_GAIT_ROTATE || kind == TI5_GAIT_WALK_OMNI;
-        cmd.x = mx ? affine((float)(g->cmd_range[0][1] - g->cmd_range[0][0]), (float)g->cmd_range[0][0], rng.cmd(1, gi, e, 0, N)) : 0.0f;
-        cmd.y = my ? affine((float)(g->cmd_range[1][1] - g->cmd_range[1][0]), (float)g->cmd_range[1][0], rng.cmd(1, gi, e, 1, N)) : 0.0f;
-        cmd.z = mz ? affine((float)(g->cmd_range[2][1] - g->cmd_range[2][0]), (float)g->cmd_range[2][0], rng.cmd(1, gi, e, 2, N)) : 0.0f;
+        cmd.x = mx ? affine((float)(s_range[0][1] - s_range[0][0]), (float)s_range[0][0], rng.cmd(1, gi, e, 0, N)) : 0.0f;
+        cmd.y = my ? affine((float)(s_range[1][1] - s_range[1][0]), (float)s_range[1][0], rng.cmd(1, gi, e, 1, N)) : 0.0f;
+        cmd.z = mz ? affine((float)(s_range[2][1] - s_range[2][0]), (float)s_range[2][0], rng.cmd(1, gi, e, 2, N)) : 0.0f;
       }
-      reinterpret_cast<float4*>(b.commands)[e] = cmd;
-      if (b.time_outs_latched) b.time_outs_latched[e] = b.time_out_buf[e];      // t1:540-541 (appendix A23)
+      if (role == 0) {
+        reinterpret_cast<float4*>(b.commands)[e] = cmd;
+        if (b.time_outs_latched) b.time_outs_latched[e] = b.time_out_buf[e];    // t1:540-541 (appendix A23)
+      }
     }
-    if (p.flags & TI5_F_TRIMESH) level_f = (float)b.terrain_levels[e];
+    if (role == 0 && (p.flags & TI5_F_TRIMESH)) level_f = (float)b.terrain_levels[e];
 
     // =========================== observations (t1:368-481) =================================
     if (do_obs) {
       const bool stand = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y + cmd.z * cmd.z) <= p.stand_threshold;
       if (stand) phase_len = 0;                                               // t1:86 side effect
-      b.phase_length_buf[e] = phase_len;
       const float phase = (py_mod(sdiv((float)phase_len * p.dt, p.cycle_time, dm), 1.0f) + gait_start) * (stand ? 0.0f : 1.0f);
       const float ang_ph = TWO_PI_F * phase;
       const float s = sinf(ang_ph), c = cosf(ang_ph);
-      // t1:250-274 reference pose
-      float ref[D];
-#pragma unroll
-      for (int i = 0; i < D; ++i) ref[i] = 0.0f;
-      {
-        const float sl = s > 0.0f ? 0.0f : s, sr = s < 0.0f ? 0.0f : s;
-        const float a1 = p.target_joint_pos_scale, a2 = p.target_joint_pos_scale2;
-        ref[2] = sl * a1; ref[3] = (-sl) * a2; ref[4] = sl * a1;
-        ref[8] = (-sr) * a1; ref[9] = sr * a2; ref[10] = (-sr) * a1;
-        if (fabsf(s) < 0.1f) {
-#pragma unroll
-          for (int i = 0; i < D; ++i) ref[i] = 0.0f;
-        }
-      }
-      float ref_act[D];
-#pragma unroll
-      for (int i = 0; i < D; ++i) { ref_act[i] = 2.0f * ref[i]; ref[i] = ref[i] + p.default_dof_pos[i]; }
-      store12(b.ref_action, e, ref_act);
-      store12(b.ref_dof_pos, e, ref);
-      float stance[2] = {s >= 0.0f ? 1.0f : 0.0f, s < 0.0f ? 1.0f : 0.0f};
-      if (fabsf(s) < 0.1f) stance[0] = stance[1] = 1.0f;
-      const float fz0 = b.contact_forces[((size_t)e * NB + p.feet[0]) * 3 + 2];
-      const float fz1 = b.contact_forces[((size_t)e * NB + p.feet[1]) * 3 + 2];
-
-      float* po = s_priv + lane * Pp;
-      float* oo = s_obs + lane * Kp;
       const float ci[5] = {s, c, cmd.x * p.cmd_scale[0], cmd.y * p.cmd_scale[1], cmd.z * p.cmd_scale[2]};
+
+      if (role == 0) {
+        // ---------------- role 0: the 47-float observation frame ------------------------------------
+        b.phase_length_buf[e] = phase_len;
+        float* oo = s_obs + lane * Kp;
 #pragma unroll
-      for (int i = 0; i < 5; ++i) { po[i] = ci[i]; oo[i] = ci[i]; }
+        for (int i = 0; i < 5; ++i) oo[i] = ci[i];
 #pragma unroll
-      for (int i = 0; i < D; ++i) {
-        po[5 + i] = (q[i] - p.default_dof_pos[i]) * p.obs_dof_pos;
-        po[17 + i] = qd[i] * p.obs_dof_vel;
-        po[29 + i] = act[i];
-        po[41 + i] = q[i] - ref[i];
-        oo[29 + i] = act[i];
-      }
+        for (int i = 0; i < D; ++i) oo[29 + i] = act[i];
+        // lagged proprioception (t1:407-451): rows pushed before the env's last reset read as zero
+        {
+          float lq[D], lqd[D];
+          const int64_t jj = (pushes - 1) - lag_dof;
+          if (!(p.flags & TI5_F_ADD_DOF_LAG)) {
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        po[53 + i] = lin[i] * p.obs_lin_vel;
-        po[56 + i] = ang[i] * p.obs_ang_vel;
-        po[59 + i] = eul[i] * p.obs_quat;
-      }
-      if (p.flags & TI5_F_ADD_EXT_FORCE) {                                     // t1:386-388
-        po[62] = sdiv(b.ext_forces[e * 3 + 0], p.ext_force_div, dm);
-        po[63] = sdiv(b.ext_forces[e * 3 + 1], p.ext_force_div, dm);
+            for (int i = 0; i < D; ++i) { lq[i] = q[i]; lqd[i] = qd[i]; }
+          } else if (jj >= stamp && jj >= 0) {
+            const float* row = b.dof_ring + ((size_t)ring_slot(jj, p.dof_lag_len) * N + e) * (2 * D);
+            load12(row, 0, lq);
+            load12(row + D, 0, lqd);
+          } else {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) po[64 + i] = sdiv(b.ext_torques[e * 3 + i], p.ext_torque_div, dm);
-      } else {
-        po[62] = b.rand_push_force[e * 3 + 0];
-        po[63] = b.rand_push_force[e * 3 + 1];
+            for (int i = 0; i < D; ++i) { lq[i] = 0.0f; lqd[i] = 0.0f; }
+          }
 #pragma unroll
-        for (int i = 0; i < 3; ++i) po[64 + i] = b.rand_push_torque[e * 3 + i];
-      }
-      po[67] = b.env_frictions[e];
-      po[68] = sdiv(b.body_mass[e], 30.0f, dm);
-      po[69] = stance[0]; po[70] = stance[1];
-      po[71] = fz0 > 5.0f ? 1.0f : 0.0f; po[72] = fz1 > 5.0f ? 1.0f : 0.0f;
-      if (p.flags & TI5_F_MEASURE_HEIGHTS) {                                   // t1:466-468
-        const float* mh = b.measured_heights + (size_t)e * p.num_height_points;
-        for (int i = 0; i < p.num_height_points; ++i)
-          po[73 + i] = clampf((root[2] - 0.5f) - mh[i], -1.0f, 1.0f) * p.obs_height;
-      }
-      // lagged proprioception (t1:407-451): rows pushed before the env's last reset read as zero
-      {
-        float lq[D], lqd[D];
-        const int64_t jj = (pushes - 1) - lag_dof;
-        if (!(p.flags & TI5_F_ADD_DOF_LAG)) {
+          for (int i = 0; i < D; ++i) {
+            oo[5 + i] = (lq[i] - p.default_dof_pos[i]) * p.obs_dof_pos;
+            oo[17 + i] = lqd[i] * p.obs_dof_vel;
+          }
+          float imu[6];
+          const int64_t ji = (pushes - 1) - lag_imu;
+          if (!(p.flags & TI5_F_ADD_IMU_LAG)) {
 #pragma unroll
-          for (int i = 0; i < D; ++i) { lq[i] = q[i]; lqd[i] = qd[i]; }
-        } else if (jj >= stamp && jj >= 0) {
-          const float* row = b.dof_ring + ((size_t)ring_slot(jj, p.dof_lag_len) * N + e) * (2 * D);
-          load12(row, 0, lq);
-          load12(row + D, 0, lqd);
-        } else {
+            for (int i = 0; i < 3; ++i) { imu[i] = ang[i]; imu[3 + i] = eul[i]; }
+          } else if (ji >= stamp && ji >= 0) {
+            const float* row = b.imu_ring + ((size_t)ring_slot(ji, p.imu_lag_len) * N + e) * 6;
 #pragma unroll
-          for (int i = 0; i < D; ++i) { lq[i] = 0.0f; lqd[i] = 0.0f; }
+            for (int i = 0; i < 6; ++i) imu[i] = row[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) imu[i] = 0.0f;
+          }
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            oo[41 + i] = imu[i] * p.obs_ang_vel;
+            oo[44 + i] = imu[3 + i] * p.obs_quat;
+          }
         }
+        if (p.flags & TI5_F_ADD_NOISE) {                                       // t1:471-472
+#pragma unroll 4
+          for (int g4 = 0; 4 * g4 < K; ++g4) {
+            const float4 u = rng.noise4(e, g4, K);
+            const float uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int k = 4 * g4 + j;
+              if (k < K) oo[k] = oo[k] + ((2.0f * uu[j] - 1.0f) * p.noise_vec[k]) * p.noise_level;
+            }
+          }
+        }
+        // lr:496-498 previous-step copies (live state only; the dead ones are not kept)
+        store12(b.last_last_actions, e, last_act);
+        store12(b.last_actions, e, act);
+        store12(b.last_dof_vel, e, qd);
+      } else {
+        // ---------------- role 1: reference pose and the privileged frame ---------------------------
+        float ref[D];                                                          // t1:250-274
+#pragma unroll
+        for (int i = 0; i < D; ++i) ref[i] = 0.0f;
+        {
+          const float sl = s > 0.0f ? 0.0f : s, sr = s < 0.0f ? 0.0f : s;
+          const float a1 = p.target_joint_pos_scale, a2 = p.target_joint_pos_scale2;
+          ref[2] = sl * a1; ref[3] = (-sl) * a2; ref[4] = sl * a1;
+          ref[8] = (-sr) * a1; ref[9] = sr * a2; ref[10] = (-sr) * a1;
+          if (fabsf(s) < 0.1f) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) ref[i] = 0.0f;
+          }
+        }
+        float ref_act[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) { ref_act[i] = 2.0f * ref[i]; ref[i] = ref[i] + p.default_dof_pos[i]; }
+        store12(b.ref_action, e, ref_act);
+        store12(b.ref_dof_pos, e, ref);
+        float stance[2] = {s >= 0.0f ? 1.0f : 0.0f, s < 0.0f ? 1.0f : 0.0f};
+        if (fabsf(s) < 0.1f) stance[0] = stance[1] = 1.0f;
+        float* po = s_priv + lane * Pp;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) po[i] = ci[i];
 #pragma unroll
         for (int i = 0; i < D; ++i) {
-          oo[5 + i] = (lq[i] - p.default_dof_pos[i]) * p.obs_dof_pos;
-          oo[17 + i] = lqd[i] * p.obs_dof_vel;
-        }
-        float imu[6];
-        const int64_t ji = (pushes - 1) - lag_imu;
-        if (!(p.flags & TI5_F_ADD_IMU_LAG)) {
-#pragma unroll
-          for (int i = 0; i < 3; ++i) { imu[i] = ang[i]; imu[3 + i] = eul[i]; }
-        } else if (ji >= stamp && ji >= 0) {
-          const float* row = b.imu_ring + ((size_t)ring_slot(ji, p.imu_lag_len) * N + e) * 6;
-#pragma unroll
-          for (int i = 0; i < 6; ++i) imu[i] = row[i];
-        } else {
-#pragma unroll
-          for (int i = 0; i < 6; ++i) imu[i] = 0.0f;
+          po[5 + i] = (q[i] - p.default_dof_pos[i]) * p.obs_dof_pos;
+          po[17 + i] = qd[i] * p.obs_dof_vel;
+          po[29 + i] = act[i];
+          po[41 + i] = q[i] - ref[i];
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          oo[41 + i] = imu[i] * p.obs_ang_vel;
-          oo[44 + i] = imu[3 + i] * p.obs_quat;
+          po[53 + i] = lin[i] * p.obs_lin_vel;
+          po[56 + i] = ang[i] * p.obs_ang_vel;
+          po[59 + i] = eul[i] * p.obs_quat;
         }
-      }
-      if (p.flags & TI5_F_ADD_NOISE) {                                         // t1:471-472
-        for (int g4 = 0; 4 * g4 < K; ++g4) {
-          const float4 u = rng.noise4(e, g4, K);
-          const float uu[4] = {u.x, u.y, u.z, u.w};
+        if (p.flags & TI5_F_ADD_EXT_FORCE) {                                   // t1:386-388
+          po[62] = sdiv(ext[0], p.ext_force_div, dm);
+          po[63] = sdiv(ext[1], p.ext_force_div, dm);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int k = 4 * g4 + j;
-            if (k < K) oo[k] = oo[k] + ((2.0f * uu[j] - 1.0f) * p.noise_vec[k]) * p.noise_level;
-          }
+          for (int i = 0; i < 3; ++i) po[64 + i] = sdiv(ext[2 + i], p.ext_torque_div, dm);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 5; ++i) po[62 + i] = ext[i];
         }
-      }
-      // lr:496-499 previous-step copies (live state only; the dead ones are not kept)
-      store12(b.last_last_actions, e, last_act);
-      store12(b.last_actions, e, act);
-      store12(b.last_dof_vel, e, qd);
+        po[67] = fric;
+        po[68] = sdiv(mass, 30.0f, dm);
+        po[69] = stance[0]; po[70] = stance[1];
+        po[71] = fz0 > 5.0f ? 1.0f : 0.0f; po[72] = fz1 > 5.0f ? 1.0f : 0.0f;
+        if (p.flags & TI5_F_MEASURE_HEIGHTS) {                                 // t1:466-468
+          const float* mh = b.measured_heights + (size_t)e * p.num_height_points;
+          for (int i = 0; i < p.num_height_points; ++i)
+            po[73 + i] = clampf((root[2] - 0.5f) - mh[i], -1.0f, 1.0f) * p.obs_height;
+        }
 #pragma unroll
-      for (int i = 0; i < 6; ++i) b.last_root_vel[e * 6 + i] = root[7 + i];
+        for (int i = 0; i < 6; ++i) b.last_root_vel[e * 6 + i] = root[7 + i];  // lr:499
+      }
     }
   }
 
+  probe(b.debug_ts, 1, 3);
   // ---- history rings: append this step's frames; clear the rows of re-spawned envs ------------
   const size_t obs_row = (size_t)2 * H * K, priv_row = (size_t)2 * CH * P;
-  const int warp_env0 = blockIdx.x * blockDim.x + warp * 32;
+  const int warp_env0 = blockIdx.x * TB + tile_warp * 32;
   const int hs = (int)((step - 1) % H), cs = (int)((step - 1) % CH);       // slot of this step's frame
   __syncwarp();
-  if (do_obs && warp_env0 < N) {
+  if (do_obs && blockIdx.x < env_blocks && warp_env0 < N) {
     const int n_here = min(32, N - warp_env0);
     const float lim = p.clip_obs;
-    for (int i = lane; i < n_here * K; i += 32) {
-      const int en = i / K, k = i - en * K;
-      const float v = clampf(s_obs[en * Kp + k], -lim, lim);
-      float* rowp = b.obs_ring + (size_t)(warp_env0 + en) * obs_row;
-      rowp[(size_t)hs * K + k] = v;
-      rowp[(size_t)(hs + H) * K + k] = v;
-    }
-    for (int i = lane; i < n_here * P; i += 32) {
-      const int en = i / P, k = i - en * P;
-      const float v = clampf(s_priv[en * Pp + k], -lim, lim);
-      float* rowp = b.priv_ring + (size_t)(warp_env0 + en) * priv_row;
-      rowp[(size_t)cs * P + k] = v;
-      rowp[(size_t)(cs + CH) * P + k] = v;
+    if (role == 0) {
+      for (int i = lane; i < n_here * K; i += 32) {
+        const int en = i / K, k = i - en * K;
+        const float v = clampf(s_obs[en * Kp + k], -lim, lim);
+        float* rowp = b.obs_ring + (size_t)(warp_env0 + en) * obs_row;
+        rowp[(size_t)hs * K + k] = v;
+        rowp[(size_t)(hs + H) * K + k] = v;
+      }
+    } else {
+      for (int i = lane; i < n_here * P; i += 32) {
+        const int en = i / P, k = i - en * P;
+        const float v = clampf(s_priv[en * Pp + k], -lim, lim);
+        float* rowp = b.priv_ring + (size_t)(warp_env0 + en) * priv_row;
+        rowp[(size_t)cs * P + k] = v;
+        rowp[(size_t)(cs + CH) * P + k] = v;
+      }
     }
   }
 
+  probe(b.debug_ts, 1, 4);
   // t1:556-559: `hist[i][env_ids] *= 0` for every frame of the re-spawned envs.  The flagged envs were
   // listed (in arrival order) by ti5_post_physics / ti5_reset_bookkeeping; all warps of the grid,
   // including the helper CTAs, share the (env, 512-float chunk) work items.  The two slots of this step's
@@ -442,16 +565,17 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
         if (ok[j]) row[c * CHUNK + j * 32 + lane] = v[j] * 0.0f;
     }
   }
+  probe(b.debug_ts, 1, 5);
   if (blockIdx.x >= env_blocks) {             // helper CTA
     // extras["episode"]["rew_<term>"] = mean over the re-spawned envs of the episode sums / episode_length_s
     // (t1:531-532): one helper warp per term folds the per-CTA partials ti5_post_physics left behind.
     const int hw = (blockIdx.x - env_blocks) * (blockDim.x >> 5) + warp;
-    const int total = g->n_reset;
+    const int total = n_reset;
     if (do_reset && total > 0 && hw < TI5_NUM_TERMS) {
       double acc = 0.0;
       for (int i = lane; i < env_blocks; i += 32) {
-        const int cnt = __ldcg(b.block_counts + i + 1) - __ldcg(b.block_counts + i);
-        const float v = __ldcg(b.block_sums + (size_t)i * TI5_LOG_COLS + hw);
+        const int cnt = b.block_counts[i];
+        const float v = b.block_sums[(size_t)i * TI5_LOG_COLS + hw];
         acc += cnt > 0 ? (double)v : 0.0;
       }
 #pragma unroll
@@ -466,7 +590,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
 
   // ---- ascending id list of the envs reset this step (lr:490) --------------------------------
   const BlockRank br = block_rank(reset, s_warp);
-  if (reset && b.reset_ids) b.reset_ids[b.block_counts[blockIdx.x] + br.rank] = e;
+  if (reset && b.reset_ids) b.reset_ids[id_offset + br.rank] = e;
 
   // ---- extras["episode"]["terrain_level"] = mean(terrain_levels) (t1:535-536) ------------------
   if ((p.flags & TI5_F_TRIMESH) && do_reset) {
@@ -483,14 +607,23 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
       s_last = atomicAdd(&g->tickets[1], 1) == env_blocks - 1;
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
+    if (s_last) {                                  // whole-CTA fold of the per-CTA level sums
       __threadfence();
-      g->tickets[1] = 0;
-      if (any_reset) {
-        double acc = 0.0;
-        for (int i = 0; i < env_blocks; ++i)
-          acc += (double)((volatile float*)b.block_sums)[(size_t)i * TI5_LOG_COLS + LOG_TERRAIN_LEVEL];
-        b.extras_log[(size_t)(step % TI5_LOG_ROWS) * TI5_LOG_COLS + LOG_TERRAIN_LEVEL] = (float)(acc / (double)N);
+      float part = 0.0f;
+      for (int i = threadIdx.x; i < env_blocks; i += blockDim.x)
+        part += __ldcg(b.block_sums + (size_t)i * TI5_LOG_COLS + LOG_TERRAIN_LEVEL);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      __syncthreads();
+      if (lane == 0) s_lvl[warp] = part;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        g->tickets[1] = 0;
+        if (any_reset) {
+          double acc = 0.0;
+          for (int w = 0; w < (int)(blockDim.x >> 5); ++w) acc += (double)s_lvl[w];
+          b.extras_log[(size_t)(step % TI5_LOG_ROWS) * TI5_LOG_COLS + LOG_TERRAIN_LEVEL] = (float)(acc / (double)N);
+        }
       }
     }
   }
@@ -538,8 +671,8 @@ extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const 
     return TI5_ECUDA;
   }
   // + helper CTAs (about 4 warps per SM) that only share the history-clear work of re-spawned envs
-  const int helpers = (phases & TI5_RO_RESET) ? (148 * 4 * 32) / p->env_block : 0;
-  kernel<<<blocks + helpers, p->env_block, smem, (cudaStream_t)stream>>>(*p, *b, rr, phases);
+  const int helpers = (phases & TI5_RO_RESET) ? (148 * 4 * 32) / (OBS_ROLES * p->env_block) : 0;
+  kernel<<<blocks + helpers, OBS_ROLES * p->env_block, smem, (cudaStream_t)stream>>>(*p, *b, rr, phases);
   return ti5_check_launch("ti5_reset_observe");
 }
 

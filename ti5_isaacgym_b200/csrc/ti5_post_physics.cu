@@ -31,192 +31,77 @@ static __device__ __noinline__ float pair_distance_reward(float ax, float ay, fl
   return (expf_call(-fabsf(near_) * 100.0f) + expf_call(-fabsf(far_) * 100.0f)) / 2.0f;
 }
 
-// Reset bookkeeping shared by ti5_post_physics and ti5_reset_bookkeeping: per-CTA reset counts and
-// episode-sum partials (t1:531-533); the last CTA to finish turns the counts into exclusive offsets
-// (consumed by ti5_reset_observe for the ascending id list, lr:490), publishes n_reset, evaluates the
-// command curriculum (lr:1160-1169) and prepares the extras["episode"] snapshot row of this step.  The
-// 28 episode means themselves are reduced by helper warps of ti5_reset_observe, off the critical path.
+// Reset bookkeeping shared by ti5_post_physics and ti5_reset_bookkeeping: the CTA's count of flagged envs,
+// the arrival-order work list for the history clear, and — only if the CTA has a flagged env — the partial
+// sums of their episode sums (t1:531-533).  Nothing here waits on another CTA: ti5_reset_observe, which runs
+// after this grid has completed, turns the per-CTA counts into offsets / totals itself.
 // `sums` is the CTA's shared tile [term][tb] (post-physics) or null (read episode_sums from memory).
 static __device__ __noinline__ void reset_bookkeeping(const Ti5Params& p, const Ti5Buffers& b, bool reset, int e, int le,
-                                                      const float* sums, int tb, int64_t step, int64_t counter,
-                                                      bool force_window, bool advance_force_flag) {
+                                                      const float* sums, int tb) {
   __shared__ int s_warp[32];
   __shared__ float s_red[12][TI5_NUM_TERMS];
-  __shared__ bool s_last;
-  Ti5Globals* g = b.globals;
   const int N = p.num_envs, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  if (reset) b.reset_list[atomicAdd(&g->n_listed, 1)] = e;
+  if (reset) b.reset_list[atomicAdd(&b.globals->n_listed, 1)] = e;
   const BlockRank br = block_rank(reset, s_warp);
-  const int nblk = gridDim.x;
-  if (br.total > 0) {
-#pragma unroll 1
-    for (int t = 0; t < TI5_NUM_TERMS; ++t) {
-      float v = 0.0f;
-      if (reset && (p.term_mask & (1u << t))) v = sums ? sums[t * tb + le] : b.episode_sums[(size_t)t * N + e];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) s_red[warp][t] = v;
-    }
-    __syncthreads();
-    if (tid < TI5_NUM_TERMS) {
-      float v = 0.0f;
-      for (int w = 0; w < (nt >> 5); ++w) v += s_red[w][tid];
-      b.block_sums[(size_t)blockIdx.x * TI5_LOG_COLS + tid] = v;
-    }
+  if (tid == 0) b.block_counts[blockIdx.x] = br.total;
+  if (br.total == 0) return;
+  // lanes over terms: lane t adds up term t of the warp's flagged envs (a handful), then the warps are folded
+  const unsigned flagged = __ballot_sync(0xffffffffu, reset);
+  float acc = 0.0f;
+  const int warp_le0 = le - lane;                      // first tile-env of this warp (role-0 warps hold the flags)
+  for (unsigned m = flagged; m; m &= m - 1) {
+    const int src = __ffs(m) - 1;
+    if (lane < TI5_NUM_TERMS && (p.term_mask & (1u << lane)))
+      acc += sums ? sums[lane * tb + warp_le0 + src] : b.episode_sums[(size_t)lane * N + (e - lane + src)];
   }
-  if (tid == 0) {
-    b.block_counts[blockIdx.x] = br.total;
-    __threadfence();
-    s_last = atomicAdd(&g->tickets[0], 1) == nblk - 1;
-  }
+  if (lane < TI5_NUM_TERMS) s_red[warp][lane] = acc;
   __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-
-  // exclusive prefix of the CTA counts: whole-CTA scan through shared memory, 1024 counts per tile
-  constexpr int TILE = 1024;
-  __shared__ int s_cnt[TILE];
-  __shared__ int s_scan[384];
-  __shared__ int s_carry;
-  __shared__ double s_track;
-  if (tid == 0) { s_carry = 0; s_track = 0.0; }
-  __syncthreads();
-  for (int base = 0; base < nblk; base += TILE) {
-    const int n_here = min(TILE, nblk - base);
-    for (int i = tid; i < n_here; i += nt) s_cnt[i] = __ldcg(b.block_counts + base + i);
-    __syncthreads();
-    const int per = (n_here + nt - 1) / nt, lo = min(tid * per, n_here), hi = min(lo + per, n_here);
-    int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += s_cnt[i];
-    s_scan[tid] = sum;
-    __syncthreads();
-    int before = s_carry;
-    for (int w = 0; w < tid; ++w) before += s_scan[w];
-    __syncthreads();
-    // command curriculum input: sum of the resetting envs' tracking_lin_vel episode sums (only on the
-    // steps where common_step_counter % max_episode_length == 0, lr:537)
-    if ((p.flags & TI5_F_COMMAND_CURRICULUM) && (counter % p.max_episode_length == 0)) {
-      double part = 0.0;
-      for (int i = lo; i < hi; ++i)
-        if (s_cnt[i] > 0) part += (double)__ldcg(b.block_sums + (size_t)(base + i) * TI5_LOG_COLS + T_TRACKING_LIN_VEL);
-      if (part != 0.0) atomicAdd(&s_track, part);   // at most a handful of adds, once per 2400 steps
-    }
-    for (int i = lo; i < hi; ++i) {
-      const int c = s_cnt[i];
-      b.block_counts[base + i] = before;
-      before += c;
-    }
-    if (tid == nt - 1) s_carry = before;
-    __syncthreads();
-  }
-  const int total = s_carry;
-  float* row = b.extras_log + (size_t)(step % TI5_LOG_ROWS) * TI5_LOG_COLS;
-  const float* prev = b.extras_log + (size_t)((step + TI5_LOG_ROWS - 1) % TI5_LOG_ROWS) * TI5_LOG_COLS;
-  // no reset this step: extras["episode"] keeps showing the previous values (appendix A23)
-  if (total == 0 && tid < TI5_LOG_COLS) row[tid] = prev[tid];
-  if (tid == 0) {
-    b.block_counts[nblk] = total;
-    g->n_reset = total;
-    g->tickets[0] = 0;
-    if (advance_force_flag && (p.flags & TI5_F_ADD_EXT_FORCE)) g->is_first_add_force = force_window ? 0 : 1;
-    // lr:1160-1169 command curriculum, evaluated before the resets of this step (lr:537-538)
-    if (total > 0 && (p.flags & TI5_F_COMMAND_CURRICULUM) && (counter % p.max_episode_length == 0)) {
-      const float mean = (float)(s_track / (double)total);
-      const float lhs = sdiv(mean, (float)p.max_episode_length, p.div_mode);
-      if (lhs > (float)(0.8 * p.tracking_lin_vel_scale)) {
-        const double lo = g->cmd_range[0][0] - 0.25, hi = g->cmd_range[0][1] + 0.5;
-        const double lo_min = -p.cmd_curriculum_max / 2.0;
-        g->cmd_range[0][0] = lo < lo_min ? lo_min : (lo > 0.0 ? 0.0 : lo);
-        g->cmd_range[0][1] = hi < 0.0 ? 0.0 : (hi > p.cmd_curriculum_max ? p.cmd_curriculum_max : hi);
-      }
-    }
-    if (total > 0) {
-      row[LOG_MAX_COMMAND_X] = (float)g->cmd_range[0][1];
-      row[LOG_N_RESET] = (float)total;
-      if (!(p.flags & TI5_F_TRIMESH)) row[LOG_TERRAIN_LEVEL] = 0.0f;
-    }
+  if (tid < TI5_NUM_TERMS) {
+    float v = 0.0f;
+    for (int w = 0; w < (nt >> 5); ++w) v += s_red[w][tid];
+    b.block_sums[(size_t)blockIdx.x * TI5_LOG_COLS + tid] = v;
   }
 }
 
-// Shared-memory tile of the per-env inputs of one CTA (TB = blockDim.x consecutive envs), filled by the
-// TMA engine.  Offsets are in bytes and every chunk starts 16-byte aligned.
-struct PostTile {
-  float *root, *dof, *contact, *rigid, *act, *last_act, *last_last_act, *last_dof_vel, *torques, *ref, *last_root_vel, *cmd;
-  float *gait_start, *air, *feet_h, *last_z, *sums, *vals;
-  int64_t *ep_len, *phase_len;
-  int32_t* gait_time;
-  uint8_t* last_contacts;
-  uint64_t* bar;
+// Shared-memory tile of the per-env inputs of one CTA (TB = env_block consecutive envs), filled by the TMA
+// engine.  The 20 per-env arrays are described by a table (source pointer, bytes per env, byte offset per env
+// inside the tile) built on the host, so thread k issues bulk copy k without any per-array code; the tile also
+// holds one column per reward term of the episode sums, the unscaled term values and the mbarrier.
+constexpr int POST_CHUNKS = 20;
+enum PostChunk { C_ROOT = 0, C_DOF, C_CONTACT, C_RIGID, C_ACT, C_LAST_ACT, C_LAST_LAST_ACT, C_LAST_DOF_VEL, C_TORQUES, C_REF,
+                 C_LAST_ROOT_VEL, C_CMD, C_GAIT_START, C_AIR, C_FEET_H, C_LAST_Z, C_EP_LEN, C_PHASE_LEN, C_GAIT_TIME,
+                 C_LAST_CONTACTS };
+struct PostSrc {
+  const void* ptr[POST_CHUNKS];
+  int32_t rowb[POST_CHUNKS];          // bytes per env
+  int32_t off[POST_CHUNKS + 1];       // byte offset per env of chunk k inside the tile (prefix sum of rowb)
 };
 
-__host__ __device__ inline size_t post_tile_bytes(int tb, int ng) {
-  auto up = [](size_t x) { return (x + 15) & ~(size_t)15; };
-  size_t o = 0;
-  o += up((size_t)tb * RB * 4) + up((size_t)tb * 2 * D * 4) + up((size_t)tb * NB * 3 * 4) + up((size_t)tb * NB * RB * 4);
-  o += 6 * up((size_t)tb * D * 4) + up((size_t)tb * 6 * 4) + up((size_t)tb * 4 * 4);
-  o += up((size_t)tb * 4) + 3 * up((size_t)tb * 2 * 4) + 2 * up((size_t)TI5_NUM_TERMS * tb * 4);
-  o += 2 * up((size_t)tb * 8) + up((size_t)tb * ng * 4) + up((size_t)tb * 2) + 16;
-  return o;
+static PostSrc make_post_src(const Ti5Params& p, const Ti5Buffers& b) {
+  PostSrc s;
+  const void* ptr[POST_CHUNKS] = {b.root_states, b.dof_state, b.contact_forces, b.rigid_state, b.actions, b.last_actions,
+                                  b.last_last_actions, b.last_dof_vel, b.torques, b.ref_dof_pos, b.last_root_vel, b.commands,
+                                  b.gait_start, b.feet_air_time, b.feet_height, b.last_feet_z, b.episode_length_buf,
+                                  b.phase_length_buf, b.gait_time, b.last_contacts};
+  const int rowb[POST_CHUNKS] = {RB * 4, 2 * D * 4, NB * 3 * 4, NB * RB * 4, D * 4, D * 4, D * 4, D * 4, D * 4, D * 4, 6 * 4, 4 * 4,
+                                 4, 2 * 4, 2 * 4, 2 * 4, 8, 8, p.num_gaits * 4, 2};
+  int o = 0;
+  for (int k = 0; k < POST_CHUNKS; ++k) { s.ptr[k] = ptr[k]; s.rowb[k] = rowb[k]; s.off[k] = o; o += rowb[k]; }
+  s.off[POST_CHUNKS] = o;
+  return s;
 }
 
-__device__ __forceinline__ PostTile carve_post_tile(unsigned char* base, int tb, int ng) {
-  PostTile t;
-  size_t o = 0;
-  auto take = [&](size_t bytes) { unsigned char* p = base + o; o += (bytes + 15) & ~(size_t)15; return p; };
-  t.root = (float*)take((size_t)tb * RB * 4);
-  t.dof = (float*)take((size_t)tb * 2 * D * 4);
-  t.contact = (float*)take((size_t)tb * NB * 3 * 4);
-  t.rigid = (float*)take((size_t)tb * NB * RB * 4);
-  t.act = (float*)take((size_t)tb * D * 4);
-  t.last_act = (float*)take((size_t)tb * D * 4);
-  t.last_last_act = (float*)take((size_t)tb * D * 4);
-  t.last_dof_vel = (float*)take((size_t)tb * D * 4);
-  t.torques = (float*)take((size_t)tb * D * 4);
-  t.ref = (float*)take((size_t)tb * D * 4);
-  t.last_root_vel = (float*)take((size_t)tb * 6 * 4);
-  t.cmd = (float*)take((size_t)tb * 4 * 4);
-  t.gait_start = (float*)take((size_t)tb * 4);
-  t.air = (float*)take((size_t)tb * 2 * 4);
-  t.feet_h = (float*)take((size_t)tb * 2 * 4);
-  t.last_z = (float*)take((size_t)tb * 2 * 4);
-  t.sums = (float*)take((size_t)TI5_NUM_TERMS * tb * 4);
-  t.vals = (float*)take((size_t)TI5_NUM_TERMS * tb * 4);
-  t.ep_len = (int64_t*)take((size_t)tb * 8);
-  t.phase_len = (int64_t*)take((size_t)tb * 8);
-  t.gait_time = (int32_t*)take((size_t)tb * ng * 4);
-  t.last_contacts = (uint8_t*)take((size_t)tb * 2);
-  t.bar = (uint64_t*)take(16);
-  return t;
-}
+struct PostTile {
+  unsigned char* base;
+  float *sums, *vals;
+  uint64_t* bar;
+  int tb;
+  const PostSrc* src;
+  template <class T> __device__ __forceinline__ T* at(int chunk) const { return reinterpret_cast<T*>(base + (size_t)src->off[chunk] * tb); }
+};
 
-// every (shared dst, global src, bytes) chunk of the tile that starts at env e0 and holds n envs
-template <class F>
-__device__ __forceinline__ void post_tile_chunks(const Ti5Params& p, const Ti5Buffers& b, const PostTile& t, int e0, int n,
-                                                 int tb, F f) {
-  const size_t e = (size_t)e0;
-  f(t.root, b.root_states + e * RB, n * RB * 4);
-  f(t.dof, b.dof_state + e * 2 * D, n * 2 * D * 4);
-  f(t.contact, b.contact_forces + e * NB * 3, n * NB * 3 * 4);
-  f(t.rigid, b.rigid_state + e * NB * RB, n * NB * RB * 4);
-  f(t.act, b.actions + e * D, n * D * 4);
-  f(t.last_act, b.last_actions + e * D, n * D * 4);
-  f(t.last_last_act, b.last_last_actions + e * D, n * D * 4);
-  f(t.last_dof_vel, b.last_dof_vel + e * D, n * D * 4);
-  f(t.torques, b.torques + e * D, n * D * 4);
-  f(t.ref, b.ref_dof_pos + e * D, n * D * 4);
-  f(t.last_root_vel, b.last_root_vel + e * 6, n * 6 * 4);
-  f(t.cmd, b.commands + e * 4, n * 4 * 4);
-  f(t.gait_start, b.gait_start + e, n * 4);
-  f(t.air, b.feet_air_time + e * 2, n * 2 * 4);
-  f(t.feet_h, b.feet_height + e * 2, n * 2 * 4);
-  f(t.last_z, b.last_feet_z + e * 2, n * 2 * 4);
-  f(t.ep_len, b.episode_length_buf + e, n * 8);
-  f(t.phase_len, b.phase_length_buf + e, n * 8);
-  f(t.gait_time, b.gait_time + e * p.num_gaits, n * p.num_gaits * 4);
-  f(t.last_contacts, b.last_contacts + e * 2, n * 2);
-#pragma unroll 1
-  for (int k = 0; k < TI5_NUM_TERMS; ++k)
-    if (p.term_mask & (1u << k)) f(t.sums + (size_t)k * tb, b.episode_sums + (size_t)k * p.num_envs + e, n * 4);
+__host__ __device__ inline size_t post_tile_bytes(int tb, int per_env_bytes) {
+  return (size_t)tb * per_env_bytes + 2 * (size_t)TI5_NUM_TERMS * tb * 4 + 16;
 }
 
 // The CTA owns TB = env_block consecutive envs and runs POST_ROLES x TB threads: every env is worked on by
@@ -231,7 +116,7 @@ constexpr int POST_ROLES = 3;
 
 __global__ void __launch_bounds__(POST_ROLES * 128)
 post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
-                    const __grid_constant__ Ti5Rng r, int push_last) {
+                    const __grid_constant__ Ti5Rng r, const __grid_constant__ PostSrc src, int push_last) {
   const int N = p.num_envs;
   const int TB = p.env_block, tid = threadIdx.x;
   const int role = tid / TB, le = tid - role * TB;
@@ -240,7 +125,7 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
   Ti5Globals* g = b.globals;
   const int64_t step = g->step_index;
   const int64_t counter = step + g->common_step_offset;   // common_step_counter after lr:471
-  const bool first_force = g->is_first_add_force != 0;
+  const bool first_force = g->is_first_add_force[step & 1] != 0;
   const bool philox = p.rng_mode == TI5_RNG_PHILOX;
   const int dm = p.div_mode;
   const uint32_t mask = p.term_mask;
@@ -258,41 +143,73 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
     force_window = (double)(counter % p.ext_force_interval) <= p.add_duration[i];
   }
 
+  probe(b.debug_ts, 0, 0);
   // ---- stage the CTA's tile of inputs: one TMA bulk copy per array, all in flight together ----------
   extern __shared__ __align__(128) unsigned char post_smem[];
-  const PostTile T = carve_post_tile(post_smem, TB, p.num_gaits);
+  PostTile T;
+  T.base = post_smem;
+  T.tb = TB;
+  T.src = &src;
+  T.sums = reinterpret_cast<float*>(post_smem + (size_t)src.off[POST_CHUNKS] * TB);
+  T.vals = T.sums + TI5_NUM_TERMS * TB;
+  T.bar = reinterpret_cast<uint64_t*>(T.vals + TI5_NUM_TERMS * TB);
   if (n_tile == TB) {
     if (tid == 0) mbar_init(T.bar, 1);
     __syncthreads();
-    if (tid < 32) {
-      // the 32 lanes of warp 0 issue the bulk copies in parallel: lane k the k-th chunk (fixed per-env arrays
-      // first, then one column per active reward term); lane 0 also arms the barrier with the byte total
-      int k = 0;
-      post_tile_chunks(p, b, T, e0, n_tile, TB, [&](void* dst, const void* src, int bytes) {
-        if ((k++ & 31) == tid) tma_load_1d(dst, src, (uint32_t)bytes, T.bar);
-      });
-      if (tid == 0) {
-        const uint32_t row_bytes = (RB + 2 * D + NB * 3 + NB * RB + 6 * D + 6 + 4 + 1 + 3 * 2) * 4 + 2 * 8 + p.num_gaits * 4 + 2;
-        mbar_expect_tx(T.bar, (uint32_t)n_tile * (row_bytes + 4u * (uint32_t)__popc(mask)));
-      }
+    // thread k issues bulk copy k of the table; threads 32..59 one episode-sum column each; thread 0 arms the
+    // barrier with the byte total (arrival order between the copies and the arm does not matter)
+    if (tid < POST_CHUNKS) {
+      tma_load_1d(T.base + (size_t)src.off[tid] * TB, static_cast<const char*>(src.ptr[tid]) + (size_t)e0 * src.rowb[tid],
+                  (uint32_t)(TB * src.rowb[tid]), T.bar);
+    } else if (tid >= 32 && tid < 32 + TI5_NUM_TERMS && (mask & (1u << (tid - 32)))) {
+      const int t = tid - 32;
+      tma_load_1d(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(TB * 4), T.bar);
     }
+    if (tid == 0) mbar_expect_tx(T.bar, (uint32_t)TB * (uint32_t)(src.off[POST_CHUNKS] + 4 * __popc(mask)));
     mbar_wait(T.bar, 0);
-  } else {      // partial last tile: byte counts are not multiples of 16
-    post_tile_chunks(p, b, T, e0, n_tile, TB, [&](void* dst, const void* src, int bytes) { coop_load_call(dst, src, (uint32_t)bytes); });
+  } else {      // partial last tile: byte counts need not be multiples of 16, copy word by word
+#pragma unroll 1
+    for (int k = 0; k < POST_CHUNKS; ++k)
+      coop_load(T.base + (size_t)src.off[k] * TB, static_cast<const char*>(src.ptr[k]) + (size_t)e0 * src.rowb[k],
+                (uint32_t)(n_tile * src.rowb[k]));
+#pragma unroll 1
+    for (int t = 0; t < TI5_NUM_TERMS; ++t)
+      if (mask & (1u << t)) coop_load(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(n_tile * 4));
     __syncthreads();
   }
-
+  // typed views of the tile
+  const float* t_root = T.at<float>(C_ROOT);
+  const float* t_dof = T.at<float>(C_DOF);
+  const float* t_contact = T.at<float>(C_CONTACT);
+  const float* t_rigid = T.at<float>(C_RIGID);
+  const float* t_act = T.at<float>(C_ACT);
+  const float* t_last_act = T.at<float>(C_LAST_ACT);
+  const float* t_last_last_act = T.at<float>(C_LAST_LAST_ACT);
+  const float* t_last_dof_vel = T.at<float>(C_LAST_DOF_VEL);
+  const float* t_torques = T.at<float>(C_TORQUES);
+  const float* t_ref = T.at<float>(C_REF);
+  const float* t_last_root_vel = T.at<float>(C_LAST_ROOT_VEL);
+  const float* t_cmd = T.at<float>(C_CMD);
+  const float* t_gait_start = T.at<float>(C_GAIT_START);
+  const float* t_air = T.at<float>(C_AIR);
+  const float* t_feet_h = T.at<float>(C_FEET_H);
+  const float* t_last_z = T.at<float>(C_LAST_Z);
+  const int64_t* t_ep_len = T.at<int64_t>(C_EP_LEN);
+  const int64_t* t_phase_len = T.at<int64_t>(C_PHASE_LEN);
+  const int32_t* t_gait_time = T.at<int32_t>(C_GAIT_TIME);
+  const uint8_t* t_last_contacts = T.at<uint8_t>(C_LAST_CONTACTS);
+  probe(b.debug_ts, 0, 1);
   bool reset = false, time_out = false;
   auto put = [&](int t, float v) { T.vals[t * TB + le] = v; };
 
   if (live) {
     // ======== common prologue (every role, same values): command schedule, gait phase, contacts ==========
     // t1:183-184 phase counter and gait-schedule command resampling (pass 0)
-    const int64_t ep_len = T.ep_len[le] + 1;                                  // lr:469
-    int64_t phase_len = T.phase_len[le] + 1;
-    float4 cmd = reinterpret_cast<const float4*>(T.cmd)[le];
+    const int64_t ep_len = t_ep_len[le] + 1;                                  // lr:469
+    int64_t phase_len = t_phase_len[le] + 1;
+    float4 cmd = reinterpret_cast<const float4*>(t_cmd)[le];
     for (int gi = 0; gi < p.num_gaits; ++gi) {
-      if (ep_len != (int64_t)T.gait_time[le * p.num_gaits + gi]) continue;
+      if (ep_len != (int64_t)t_gait_time[le * p.num_gaits + gi]) continue;
       const int kind = p.gait_kind[gi];
       float u[3];
 #pragma unroll
@@ -302,31 +219,32 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       const bool mx = kind == TI5_GAIT_WALK_SAGITTAL || kind == TI5_GAIT_WALK_OMNI;
       const bool my = kind == TI5_GAIT_WALK_LATERAL || kind == TI5_GAIT_WALK_OMNI;
       const bool mz = kind == TI5_GAIT_ROTATE || kind == TI5_GAIT_WALK_OMNI;
-      cmd.x = mx ? affine((float)(g->cmd_range[0][1] - g->cmd_range[0][0]), (float)g->cmd_range[0][0], u[0]) : 0.0f;
-      cmd.y = my ? affine((float)(g->cmd_range[1][1] - g->cmd_range[1][0]), (float)g->cmd_range[1][0], u[1]) : 0.0f;
-      cmd.z = mz ? affine((float)(g->cmd_range[2][1] - g->cmd_range[2][0]), (float)g->cmd_range[2][0], u[2]) : 0.0f;
+      const double (*cr)[2] = g->cmd_range[step & 1];    // ranges before this step's curriculum update (lr:537 runs later)
+      cmd.x = mx ? affine((float)(cr[0][1] - cr[0][0]), (float)cr[0][0], u[0]) : 0.0f;
+      cmd.y = my ? affine((float)(cr[1][1] - cr[1][0]), (float)cr[1][0], u[1]) : 0.0f;
+      cmd.z = mz ? affine((float)(cr[2][1] - cr[2][0]), (float)cr[2][0], u[2]) : 0.0f;
     }
     const float cmd_norm = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y + cmd.z * cmd.z);
     const bool stand = cmd_norm <= p.stand_threshold;
     // gait phase and stance mask (t1:80-107).  Side effect: standing envs restart the phase.
     if (stand) phase_len = 0;
-    const float phase = (py_mod(sdiv((float)phase_len * p.dt, p.cycle_time, dm), 1.0f) + T.gait_start[le]) * (stand ? 0.0f : 1.0f);
+    const float phase = (py_mod(sdiv((float)phase_len * p.dt, p.cycle_time, dm), 1.0f) + t_gait_start[le]) * (stand ? 0.0f : 1.0f);
     const float sin_pos = sinf(TWO_PI_F * phase);
     float stance[2] = {sin_pos >= 0.0f ? 1.0f : 0.0f, sin_pos < 0.0f ? 1.0f : 0.0f};
     if (fabsf(sin_pos) < 0.1f) stance[0] = stance[1] = 1.0f;
-    const float* cf0 = T.contact + ((size_t)le * NB + p.feet[0]) * 3;
-    const float* cf1 = T.contact + ((size_t)le * NB + p.feet[1]) * 3;
+    const float* cf0 = t_contact + ((size_t)le * NB + p.feet[0]) * 3;
+    const float* cf1 = t_contact + ((size_t)le * NB + p.feet[1]) * 3;
     const bool contact[2] = {cf0[2] > 5.0f, cf1[2] > 5.0f};
-    const float* qrow = T.dof + (size_t)le * 2 * D;                           // interleaved (q, qd)
+    const float* qrow = t_dof + (size_t)le * 2 * D;                           // interleaved (q, qd)
 
     if (role == 0) {
       // ================================ role 0: the base ===============================================
       float root[RB];
 #pragma unroll
-      for (int i = 0; i < RB; ++i) root[i] = T.root[le * RB + i];
-      const float* tf = T.contact + ((size_t)le * NB + p.term_body) * 3;
+      for (int i = 0; i < RB; ++i) root[i] = t_root[le * RB + i];
+      const float* tf = t_contact + ((size_t)le * NB + p.term_body) * 3;
       const float term_force = sqrtf(tf[0] * tf[0] + tf[1] * tf[1] + tf[2] * tf[2]);
-      const float* pf = T.contact + ((size_t)le * NB + p.pen_body) * 3;
+      const float* pf = t_contact + ((size_t)le * NB + p.pen_body) * 3;
       const float pen_force = sqrtf(pf[0] * pf[0] + pf[1] * pf[1] + pf[2] * pf[2]);
       b.episode_length_buf[e] = ep_len;
       b.phase_length_buf[e] = phase_len;
@@ -409,7 +327,7 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
         float sq = 0.0f;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-          const float d = T.last_root_vel[le * 6 + i] - root[7 + i];
+          const float d = t_last_root_vel[le * 6 + i] - root[7 + i];
           sq += d * d;
         }
         put(T_BASE_ACC, expf_call(-sqrtf(sq) * 3.0f));
@@ -454,12 +372,12 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
 #pragma unroll 1
         for (int i = 0; i < D; ++i) { row[i] = qrow[2 * i]; row[D + i] = qrow[2 * i + 1]; }
       }
-      const float* act = T.act + le * D;
-      const float* la = T.last_act + le * D;
-      const float* lla = T.last_last_act + le * D;
-      const float* ldv = T.last_dof_vel + le * D;
-      const float* tau = T.torques + le * D;
-      const float* ref = T.ref + le * D;
+      const float* act = t_act + le * D;
+      const float* la = t_last_act + le * D;
+      const float* lla = t_last_last_act + le * D;
+      const float* ldv = t_last_dof_vel + le * D;
+      const float* tau = t_torques + le * D;
+      const float* ref = t_ref + le * D;
       // one pass over the 12 DOFs feeds every per-DOF reduction (each sum keeps its own DOF order)
       float s_d1 = 0.0f, s_d2 = 0.0f, s_abs = 0.0f, s_dq = 0.0f, s_acc = 0.0f, s_vel = 0.0f, s_tau = 0.0f, s_jp = 0.0f;
 #pragma unroll 1
@@ -505,10 +423,10 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
         put(T_STAND_SYSMETRY, stand ? expf_call(-sq) : 0.0f);
       }
       if (mask & (1u << T_TORQUES)) put(T_TORQUES, s_tau);       // t1:849-854
-      const float* f0 = T.rigid + ((size_t)le * NB + p.feet[0]) * RB;
-      const float* f1 = T.rigid + ((size_t)le * NB + p.feet[1]) * RB;
-      const float* k0 = T.rigid + ((size_t)le * NB + p.knees[0]) * RB;
-      const float* k1 = T.rigid + ((size_t)le * NB + p.knees[1]) * RB;
+      const float* f0 = t_rigid + ((size_t)le * NB + p.feet[0]) * RB;
+      const float* f1 = t_rigid + ((size_t)le * NB + p.feet[1]) * RB;
+      const float* k0 = t_rigid + ((size_t)le * NB + p.knees[0]) * RB;
+      const float* k1 = t_rigid + ((size_t)le * NB + p.knees[1]) * RB;
       if (mask & (1u << T_FEET_DISTANCE))                   // t1:599-612
         put(T_FEET_DISTANCE, pair_distance_reward(f0[0], f0[1], f1[0], f1[1], p.foot_min_dist, p.foot_max_dist));
       if (mask & (1u << T_KNEE_DISTANCE))                   // t1:615-628
@@ -518,7 +436,7 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       FootState foot[2];
 #pragma unroll
       for (int f = 0; f < 2; ++f) {
-        const float* rs = T.rigid + ((size_t)le * NB + p.feet[f]) * RB;
+        const float* rs = t_rigid + ((size_t)le * NB + p.feet[f]) * RB;
         foot[f].pos[0] = rs[0]; foot[f].pos[1] = rs[1]; foot[f].pos[2] = rs[2];
         foot[f].quat[0] = rs[3]; foot[f].quat[1] = rs[4]; foot[f].quat[2] = rs[5]; foot[f].quat[3] = rs[6];
         foot[f].wxy[0] = rs[10]; foot[f].wxy[1] = rs[11];
@@ -532,7 +450,7 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       }
       if (mask & (1u << T_BASE_HEIGHT)) {                   // t1:706-715
         const float ground = (foot[0].pos[2] * stance[0] + foot[1].pos[2] * stance[1]) / (stance[0] + stance[1]);
-        const float h = T.root[le * RB + 2] - (ground - 0.05f);
+        const float h = t_root[le * RB + 2] - (ground - 0.05f);
         put(T_BASE_HEIGHT, expf_call(-fabsf(h - p.base_height_target) * 100.0f));
       }
       if (mask & (1u << T_FEET_AIR_TIME)) {                 // t1:642-657 (appendix A6, A8)
@@ -541,10 +459,10 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
 #pragma unroll
         for (int f = 0; f < 2; ++f) {
           const float st = tiny ? 1.0f : stance[f];
-          const bool filt = contact[f] || (st != 0.0f) || (T.last_contacts[le * 2 + f] != 0);
+          const bool filt = contact[f] || (st != 0.0f) || (t_last_contacts[le * 2 + f] != 0);
           b.contact_filt[e * 2 + f] = filt ? 1 : 0;
           b.last_contacts[e * 2 + f] = contact[f] ? 1 : 0;
-          float air = T.air[le * 2 + f];
+          float air = t_air[le * 2 + f];
           const float first = (air > 0.0f && filt) ? 1.0f : 0.0f;
           air += p.dt;
           air_sum += clampf(air, 0.0f, 0.5f) * first;
@@ -557,7 +475,7 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
 #pragma unroll
         for (int f = 0; f < 2; ++f) {
           const float z = foot[f].pos[2];
-          const float h = T.feet_h[le * 2 + f] + (z - T.last_z[le * 2 + f]);
+          const float h = t_feet_h[le * 2 + f] + (z - t_last_z[le * 2 + f]);
           b.last_feet_z[e * 2 + f] = z;
           const float swing = 1.0f - stance[f];
           const float hit = (h > p.target_feet_height && h < p.target_feet_height_max) ? 1.0f : 0.0f;
@@ -624,7 +542,9 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       }
     }
   }
+  probe(b.debug_ts, 0, 2);
   __syncthreads();
+  probe(b.debug_ts, 0, 3);
 
   // ---- lr:654-680: reward sum in alphabetical term order, per-term episode sums, clip at zero -----------
   if (live && role == 0) {
@@ -650,7 +570,11 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
     }
     b.rew_buf[e] = rew;
   }
-  reset_bookkeeping(p, b, reset, e, le, T.sums, TB, step, counter, force_window, true);
+  probe(b.debug_ts, 0, 4);
+  // t1:205-215: `is_first_add_force` of the next step (double-buffered by step parity: no CTA of this grid reads it)
+  if (blockIdx.x == 0 && tid == 0 && (p.flags & TI5_F_ADD_EXT_FORCE)) g->is_first_add_force[(step + 1) & 1] = force_window ? 0 : 1;
+  reset_bookkeeping(p, b, reset, e, le, T.sums, TB);
+  probe(b.debug_ts, 0, 5);
 }
 
 // Bookkeeping for an explicit `reset_idx(env_ids)` call (lr:450-455 `reset()`): the caller has
@@ -659,10 +583,8 @@ __global__ void __launch_bounds__(128)
 reset_bookkeeping_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b) {
   const int N = p.num_envs;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t step = b.globals->step_index;
-  const int64_t counter = step + b.globals->common_step_offset;
   const bool reset = e < N && b.reset_buf[e] != 0;
-  reset_bookkeeping(p, b, reset, e, threadIdx.x, nullptr, 0, step, counter, false, false);
+  reset_bookkeeping(p, b, reset, e, threadIdx.x, nullptr, 0);
 }
 
 }  // namespace ti5
@@ -685,7 +607,8 @@ extern "C" int ti5_post_physics(const Ti5Params* p, const Ti5Buffers* b, const T
   TI5_CHECK_ARGS((p->term_mask & (1u << T_DOF_VEL_LIMITS)) == 0);   // the reference term reads a cfg field t1 lacks
   Ti5Rng rr = r ? *r : Ti5Rng{};
   const int blocks = (p->num_envs + p->env_block - 1) / p->env_block;
-  const size_t smem = post_tile_bytes(p->env_block, p->num_gaits);
+  const PostSrc src = make_post_src(*p, *b);
+  const size_t smem = post_tile_bytes(p->env_block, src.off[POST_CHUNKS]);
   static size_t configured = 0;
   if (smem > configured) {
     if (cudaFuncSetAttribute(post_physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -695,6 +618,6 @@ extern "C" int ti5_post_physics(const Ti5Params* p, const Ti5Buffers* b, const T
     }
     configured = smem;
   }
-  post_physics_kernel<<<blocks, POST_ROLES * p->env_block, smem, (cudaStream_t)stream>>>(*p, *b, rr, push_last);
+  post_physics_kernel<<<blocks, POST_ROLES * p->env_block, smem, (cudaStream_t)stream>>>(*p, *b, rr, src, push_last);
   return ti5_check_launch("ti5_post_physics");
 }

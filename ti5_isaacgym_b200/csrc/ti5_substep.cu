@@ -29,6 +29,7 @@ substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5B
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int N = p.num_envs;
   if (idx >= N * 3) return;
+  probe(b.debug_ts, 2, 0);
   const int e = idx / 3, gq = idx - e * 3, d0 = 4 * gq;
   const bool do_push = phases & TI5_SUB_PUSH, do_torque = phases & TI5_SUB_TORQUE;
   const bool rg = p.flags & TI5_F_RAND_GAINS, fric = p.flags & TI5_F_RAND_COULOMB, rt = p.flags & TI5_F_RAND_TORQUE;
@@ -40,13 +41,19 @@ substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5B
   const int64_t step = b.globals->step_index;           // >= 1 inside a step
   const float4* ds = reinterpret_cast<const float4*>(b.dof_state);
   const float4 s0 = ds[2 * idx], s1 = ds[2 * idx + 1];   // (q, qd) of DOFs d0..d0+3, interleaved
+  // IMU push (lr:430-434): its three pieces — body-frame angular velocity + pitch, roll, yaw — are dealt out by
+  // idx / N, so that a warp holds ONE kind of piece (no divergence between the atan2 / asin / rotation paths);
+  // the env it works on, idx % N, is unrelated to the env of this thread's four DOFs.
+  const int imu_piece = idx / N, imu_env = idx - imu_piece * N;
   float root[7] = {0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f};   // quat xyzw | ang vel
   if (imu) {
-    const float* rp = b.root_states + (size_t)e * RB;
+    const float* rp = b.root_states + (size_t)imu_env * RB;
 #pragma unroll
     for (int i = 0; i < 4; ++i) root[i] = rp[3 + i];
+    if (imu_piece == 0) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) root[4 + i] = rp[10 + i];
+      for (int i = 0; i < 3; ++i) root[4 + i] = rp[10 + i];
+    }
   }
   float4 a4 = zero4, kp4 = zero4, kd4 = zero4, off4 = zero4, vis4 = zero4, cou4 = zero4, u4 = zero4;
   int lag = 0;
@@ -69,6 +76,8 @@ substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5B
   const bool need_ring = do_torque && lagged && lag > 0;
   if (need_ring && jj >= stamp && jj >= 0) t4 = ring[(size_t)ring_slot(jj, p.lag_len) * N * 3 + idx];
 
+  if (s0.x == 12345.678f) probe(b.debug_ts, 2, 7);   // (keeps the first load batch ahead of probe 1)
+  probe(b.debug_ts, 2, 1);
   if (do_push) {                                         // lr:412-434
     const int64_t j = base + k_push;
     if (p.flags & TI5_F_ADD_DOF_LAG) {
@@ -76,21 +85,25 @@ substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5B
       *reinterpret_cast<float4*>(row + d0) = make_float4(q[0], q[1], q[2], q[3]);
       *reinterpret_cast<float4*>(row + D + d0) = make_float4(qd[0], qd[1], qd[2], qd[3]);
     }
-    if (imu) {                                           // cat(base_ang_vel, base_euler_xyz), lr:430-434
+    if (imu) {                                           // cat(base_ang_vel, base_euler_xyz)
       const float bq[4] = {root[0], root[1], root[2], root[3]};
-      float* row = b.imu_ring + ((size_t)ring_slot(j, p.imu_lag_len) * N + e) * 6;
-      if (gq == 0) {
+      float* row = b.imu_ring + ((size_t)ring_slot(j, p.imu_lag_len) * N + imu_env) * 6;
+      if (imu_piece == 0) {
         const V3 w = quat_rotate_inverse(bq, V3{root[4], root[5], root[6]});
         row[0] = w.x; row[1] = w.y; row[2] = w.z;
-      } else if (gq == 1) {
-        row[3] = euler_roll(bq);
         row[4] = euler_pitch(bq);
       } else {
-        row[5] = euler_yaw(bq);
+        // roll and yaw are the same atan2 form on different quaternion products (lr:30-33, 41-44)
+        const float x = bq[0], y = bq[1], z = bq[2], w = bq[3];
+        const bool yaw = imu_piece == 2;
+        const float num = 2.0f * (yaw ? (w * z + x * y) : (w * x + y * z));
+        const float den = yaw ? (((w * w + x * x) - y * y) - z * z) : (((w * w - x * x) - y * y) + z * z);
+        row[yaw ? 5 : 3] = wrap_angle(atan2f(num, den));
       }
     }
   }
 
+  probe(b.debug_ts, 2, 2);
   if (do_torque) {                                       // lr:1019-1074
     const float a[4] = {a4.x * p.action_scale, a4.y * p.action_scale, a4.z * p.action_scale, a4.w * p.action_scale};
     if (lagged) ring[(size_t)ring_slot(jt, p.lag_len) * N * 3 + idx] = make_float4(a[0], a[1], a[2], a[3]);
@@ -133,6 +146,7 @@ substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5B
     }
     reinterpret_cast<float4*>(b.torques)[idx] = make_float4(tau[0], tau[1], tau[2], tau[3]);
   }
+  probe(b.debug_ts, 2, 3);
 }
 
 }  // namespace ti5

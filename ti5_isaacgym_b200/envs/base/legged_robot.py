@@ -242,6 +242,7 @@ class LeggedRobot(BaseTask):
         self._block_sums = f32(nblk, C["TI5_LOG_COLS"])
         self._extras_log = f32(C["TI5_LOG_ROWS"], C["TI5_LOG_COLS"])
         self._globals = torch.zeros(ctypes.sizeof(_lib.Ti5Globals), dtype=torch.uint8, device=dev)
+        self._debug_ts = None        # set to a (2, 4096, 8) int64 CUDA tensor and re-bind to collect kernel probes
         self._obs_out = f32(N, H * K) if self._materialize else None
         self._priv_out = f32(N, CH * P) if self._materialize else None
         self.measured_heights = f32(N, max(p.num_height_points, 1)) if p.num_height_points else 0
@@ -311,9 +312,10 @@ class LeggedRobot(BaseTask):
         g = _lib.Ti5Globals()
         g.step_index = self._step_index
         g.common_step_offset = self.common_step_counter - self._step_index
-        g.is_first_add_force = 1
-        for i, key in enumerate(("lin_vel_x", "lin_vel_y", "ang_vel_yaw")):
-            g.cmd_range[i][0], g.cmd_range[i][1] = self.command_ranges[key]
+        for par in (0, 1):
+            g.is_first_add_force[par] = 1
+            for i, key in enumerate(("lin_vel_x", "lin_vel_y", "ang_vel_yaw")):
+                g.cmd_range[par][i][0], g.cmd_range[par][i][1] = self.command_ranges[key]
         self._globals.copy_(torch.frombuffer(bytearray(bytes(g)), dtype=torch.uint8))
 
     def _read_globals(self):
@@ -349,7 +351,7 @@ class LeggedRobot(BaseTask):
             time_outs_latched=self._time_outs_latched, episode_sums=self._episode_sums,
             reward_terms=self._reward_terms, reset_ids=self.reset_ids, reset_list=self._reset_list, block_counts=self._block_counts,
             block_sums=self._block_sums, extras_log=self._extras_log, obs_ring=self._obs_ring,
-            priv_ring=self._priv_ring, obs_out=self._obs_out, priv_out=self._priv_out)
+            priv_ring=self._priv_ring, obs_out=self._obs_out, priv_out=self._priv_out, debug_ts=self._debug_ts)
         for name, t in pairs.items():
             if t is not None:
                 assert t.is_contiguous(), name
@@ -598,7 +600,8 @@ class LeggedRobot(BaseTask):
         """Refresh the host mirrors of device-resident scalars (command ranges, reset count)."""
         g = self._read_globals()
         for i, key in enumerate(("lin_vel_x", "lin_vel_y", "ang_vel_yaw")):
-            self.command_ranges[key] = [g.cmd_range[i][0], g.cmd_range[i][1]]
+            cur = g.cmd_range[(g.step_index + 1) & 1][i]      # the copy the next step will read
+            self.command_ranges[key] = [cur[0], cur[1]]
         self.num_resets_last_step = int(g.n_reset)
         return g
 
@@ -642,7 +645,7 @@ class LeggedRobot(BaseTask):
         self._step_index = STEP_INDEX0
         self._write_globals()
         g = self._read_globals()
-        g.is_first_add_force = cnt[1]
+        g.is_first_add_force[0] = g.is_first_add_force[1] = cnt[1]
         self._globals.copy_(torch.frombuffer(bytearray(bytes(g)), dtype=torch.uint8))
         # lag buffers: age a (slot 0 = newest) was push index pushes-1-a
         pushes = self._step_index * self._params.decimation

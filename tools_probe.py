@@ -1,0 +1,31 @@
+import torch, sys
+sys.path.insert(0, '/root/repo')
+from bench import make_cfg
+from ti5_isaacgym_b200.envs import T1DHStandEnv
+from ti5_isaacgym_b200.sim.synthetic import SimParams, fill_synthetic_state, synthetic_actions
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+cfg = make_cfg(N)
+env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, 'cuda:0', True, use_cuda_graph=True)
+gen = torch.Generator(device='cuda').manual_seed(1)
+fill_synthetic_state(env.gym.tensors, env.env_origins, gen)
+env.reset()
+env.episode_length_buf = torch.randint(1, 2000, (N,), generator=gen, device='cuda')
+env._debug_ts = torch.zeros(3, 4096, 8, dtype=torch.int64, device='cuda')
+env._bind_buffers(); env._graph = None
+act = synthetic_actions(N, gen, 'cuda')
+flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+for i in range(20):
+    flush.fill_(i); env.step(act)
+torch.cuda.synchronize()
+ts = env._debug_ts.cpu().double()
+for kern, name, nprobe in ((0, 'post_physics', 7), (1, 'reset_observe', 6), (2, 'substep(last)', 4)):
+    t = ts[kern]
+    used = t[:, 0] > 0
+    t = t[used]
+    t0 = t[:, 0].min()
+    print(name, 'CTAs', int(used.sum()))
+    for k in range(nprobe):
+        col = t[:, k]; col = col[col > 0]
+        if len(col): print('  probe %d: n=%4d  min %7.2f  median %7.2f  max %7.2f us' % (k, len(col), (col.min()-t0)/1e3, (col.median()-t0)/1e3, (col.max()-t0)/1e3))
+b1_end = ts[0][:, 5].max(); b2_start = ts[1][:, 0][ts[1][:, 0] > 0].min()
+print('gap B1 end -> B2 start: %.2f us' % ((b2_start - b1_end) / 1e3))
