@@ -39,6 +39,25 @@ BYTES_POST = 2412                  # post-physics + reset/observe, ring-view var
 BYTES_ENV_STEP = 10 * BYTES_SUBSTEP + BYTES_POST
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel family, from the committed
+    `ncu --set full` capture of this same command (profiles/r01_ncu_full_summary_8192.json); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_full_summary_8192.json")
+    if not os.path.exists(path):
+        return None
+    key = {"substep": "substep_kernel", "post_physics+reset_observe": "post_physics_kernel"}[kernel]
+    rows = json.load(open(path)).get(key)
+    if not rows:
+        return None
+    unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+    def to_bytes(s):
+        v, u = s.split()
+        return float(v) * unit[u]
+    r = rows[len(rows) // 2]
+    return to_bytes(r["dram__bytes_read.sum"]) + to_bytes(r["dram__bytes_write.sum"])
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -224,20 +243,16 @@ def cuda_arm(args):
 
     # ---- end to end through env.step() with pinned host buffers ------------------------------------
     h_act = actions.cpu().pin_memory()
-    d_act = torch.empty_like(actions)
-    h_rew = torch.empty(N, dtype=torch.float32).pin_memory()
-    h_flags = torch.empty(2, N, dtype=torch.bool).pin_memory()
+    h_out = torch.empty(6 * N, dtype=torch.uint8).pin_memory()      # [rew f32 | reset bool | time_outs bool]
+    stream = torch.cuda.current_stream()
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        d_act.copy_(h_act, non_blocking=True)
-        _, _, r, rs, ex = env.step(d_act)
+        env.step(h_act)                                  # H2D of the pinned actions happens inside step()
         if (i + 1) % T == 0:
             gae_returns_(rew, val, done, last, ret, adv, GAMMA, LAM, scratch, group)
-        h_rew.copy_(r, non_blocking=True)
-        h_flags[0].copy_(rs, non_blocking=True)
-        h_flags[1].copy_(ex["time_outs"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        h_out.copy_(env.step_outputs_packed, non_blocking=True)
+        stream.synchronize()
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -250,7 +265,7 @@ def cuda_arm(args):
         dom = max(kt, key=lambda k: kt[k]["share_ms"])
         # algorithmic bytes of one launch of the dominant family (SURVEY 8d figure x envs per launch);
         # the post phase's 2412 B/env are spread over its two launches
-        bytes_per_launch = {"substep": BYTES_SUBSTEP * N * 10 / 11, "post_physics+reset_observe": BYTES_POST * N / 2}[dom]
+        bytes_per_launch = {"substep": BYTES_SUBSTEP * N, "post_physics+reset_observe": BYTES_POST * N / 2}[dom]
         ach = bytes_per_launch / (kt[dom]["ms_per_launch"] * 1e-3) / 1e9
         launches_per_step = env.launches_per_step
         cpu = None
@@ -270,11 +285,11 @@ def cuda_arm(args):
                        "launch": f"one CUDA graph per step ({env.launches_per_step} kernels)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h_act.numel() * 4 * world,
-                    "d2h_bytes_per_step": (h_rew.numel() * 4 + h_flags.numel()) * world,
+                    "d2h_bytes_per_step": h_out.numel() * world,
                     "note": "env.step() with pinned host actions in, reward/reset/time-out flags out, stream sync every step; L2 not flushed"},
             "gpu_launches": launches_per_step * args.steps + 2 * (args.steps // T),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch,
+                         "traffic": ncu_traffic(dom) if N == ENVS_PER_GPU else None, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch,
                          "ms_per_launch": kt[dom]["ms_per_launch"],
                          "whole_step": {"bytes": BYTES_ENV_STEP * N, "achieved": BYTES_ENV_STEP * N * args.steps / (dev_ms * 1e-3) / 1e9},
                          "kernels": kt,
@@ -289,8 +304,8 @@ def cuda_arm(args):
 def kernel_times(env, actions, steps):
     """Average device time of the two phases of a step, CUDA events on the launching stream around
     the replay of one CUDA graph per phase (a single whole-step graph cannot be bracketed inside).
-    The substep phase is begin_step + DEC launches of the fused substep kernel; its per-launch time is
-    phase time / (DEC + 1).  The post phase is post_physics + reset_observe (2 launches)."""
+    The substep phase is DEC launches of the fused substep kernel (the action clip rides in the first); its
+    per-launch time is phase time / DEC.  The post phase is post_physics + reset_observe (2 launches)."""
     g_sub, g_post = env.capture_phase_graphs()
     dec = env._params.decimation
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -314,7 +329,7 @@ def kernel_times(env, actions, steps):
         acc["post_physics+reset_observe"].append(e1.elapsed_time(e2))
     out = {}
     for name, v in acc.items():
-        n = dec + 1 if name == "substep" else 2
+        n = dec if name == "substep" else 2
         phase = statistics.mean(v)
         out[name] = {"phase_ms": phase, "launches": n, "ms_per_launch": phase / n, "share_ms": phase}
     return out

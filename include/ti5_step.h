@@ -14,7 +14,7 @@
  *   - return value 0 = OK, otherwise a negative TI5_E* code; ti5_last_error() describes it;
  *     nothing throws across the ABI; there is NO CPU fallback;
  *   - one policy step is the call sequence
- *         ti5_begin_step
+ *         ti5_begin_step                                                (or ti5_first_substep = clip + torque 0)
  *         DEC x { ti5_torque_substep ; <simulate> ; ti5_lag_push }      (or the fused ti5_substep)
  *         [ti5_sample_heights] ; ti5_post_physics ; ti5_reset_observe ; [ti5_materialize_obs]
  *     and all per-step counters live in device memory (Ti5Globals), so the sequence can be
@@ -149,7 +149,8 @@ typedef struct Ti5Params {
 
 /* ---- device-resident counters and curriculum state (single instance per env object) -------- */
 typedef struct Ti5Globals {
-  int64_t step_index;          /* policy steps begun so far (ti5_begin_step increments) */
+  int64_t step_index;          /* policy steps COMPLETED (advanced by the observation kernel, the last of a step) */
+  int64_t step_now;            /* index of the step in progress, published by ti5_post_physics / ti5_reset_bookkeeping */
   int64_t common_step_offset;  /* common_step_counter = step_index + common_step_offset */
   int32_t n_reset;             /* envs reset in the current step (lr:490) */
   int32_t n_listed;            /* entries of Ti5Buffers.reset_list (unordered), zeroed by ti5_begin_step */
@@ -270,8 +271,10 @@ const char* ti5_last_error(void);
 int ti5_struct_sizes(int32_t out[4]);
 const char* ti5_reward_name(int term);
 
-/* lr:393-394  `self.actions = clip(actions, +-clip_actions)`; also advances Ti5Globals.step_index */
+/* lr:393-394  `self.actions = clip(actions, +-clip_actions)` */
 int ti5_begin_step(const Ti5Params* p, const Ti5Buffers* b, const float* actions_in, void* stream);
+/* the same clip fused with the torque of substep 0 (one launch less per step) */
+int ti5_first_substep(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, const float* actions_in, void* stream);
 
 /* lr:1019-1074 `_compute_torques` for substep `k` in [0, DEC) */
 int ti5_torque_substep(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, int k, void* stream);

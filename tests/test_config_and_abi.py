@@ -133,7 +133,7 @@ def test_params_match_oracle_constants():
 
 def test_env_block_choice_fills_the_sms():
     from ti5_isaacgym_b200.envs.base.step_params import pick_env_block
-    assert pick_env_block(8192) == 32 and pick_env_block(65536) == 128 and pick_env_block(20000) == 64
+    assert pick_env_block(8192) == 32 and pick_env_block(65536) == 64 and pick_env_block(20000) == 64
 
 
 def test_unsupported_options_raise():

@@ -208,7 +208,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
   const int env_blocks = (N + TB - 1) / TB;              // CTAs beyond these only help clearing histories
   const bool live = e < N && blockIdx.x < env_blocks;
   Ti5Globals* g = b.globals;
-  const int64_t step = g->step_index;
+  const int64_t step = g->step_now;                      // published by ti5_post_physics / ti5_reset_bookkeeping
   const int64_t pushes = step * p.decimation;            // lag pushes completed after this step
   const bool do_reset = (phases & TI5_RO_RESET) != 0, do_obs = (phases & TI5_RO_OBSERVE) != 0;
   const int dm = p.div_mode;
@@ -588,6 +588,9 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
     return;
   }
 
+  // the step is complete once the observations are out: advance the counter (no CTA of this grid reads it)
+  if (do_obs && blockIdx.x == 0 && tid == 0) g->step_index = step;
+
   // ---- ascending id list of the envs reset this step (lr:490) --------------------------------
   const BlockRank br = block_rank(reset, s_warp);
   if (reset && b.reset_ids) b.reset_ids[id_offset + br.rank] = e;
@@ -632,7 +635,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
 // lr:441-446 / t1:477-481: contiguous copies of the current windows for callers that need them
 __global__ void __launch_bounds__(256) materialize_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b) {
   const int N = p.num_envs, K = p.num_single_obs, P = p.priv_frame, H = p.frame_stack, CH = p.c_frame_stack;
-  const int64_t step = b.globals->step_index;
+  const int64_t step = b.globals->step_index;            // runs after the step has been completed
   const size_t ow = (size_t)H * K, pw = (size_t)CH * P;
   const size_t o_off = (size_t)(((step - 1) % H) + 1) * K, p_off = (size_t)(((step - 1) % CH) + 1) * P;
   const size_t total_o = (size_t)N * ow, total_p = (size_t)N * pw;

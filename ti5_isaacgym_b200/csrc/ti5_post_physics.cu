@@ -123,7 +123,7 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
   const int e0 = blockIdx.x * TB, e = e0 + le, n_tile = min(TB, N - e0);
   const bool live = e < N;
   Ti5Globals* g = b.globals;
-  const int64_t step = g->step_index;
+  const int64_t step = g->step_index + 1;                 // index of the step in progress
   const int64_t counter = step + g->common_step_offset;   // common_step_counter after lr:471
   const bool first_force = g->is_first_add_force[step & 1] != 0;
   const bool philox = p.rng_mode == TI5_RNG_PHILOX;
@@ -572,7 +572,10 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
   }
   probe(b.debug_ts, 0, 4);
   // t1:205-215: `is_first_add_force` of the next step (double-buffered by step parity: no CTA of this grid reads it)
-  if (blockIdx.x == 0 && tid == 0 && (p.flags & TI5_F_ADD_EXT_FORCE)) g->is_first_add_force[(step + 1) & 1] = force_window ? 0 : 1;
+  if (blockIdx.x == 0 && tid == 0) {
+    g->step_now = step;                              // read by ti5_reset_observe (nobody in this grid reads it)
+    if (p.flags & TI5_F_ADD_EXT_FORCE) g->is_first_add_force[(step + 1) & 1] = force_window ? 0 : 1;
+  }
   reset_bookkeeping(p, b, reset, e, le, T.sums, TB);
   probe(b.debug_ts, 0, 5);
 }
@@ -584,6 +587,8 @@ reset_bookkeeping_kernel(const __grid_constant__ Ti5Params p, const __grid_const
   const int N = p.num_envs;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const bool reset = e < N && b.reset_buf[e] != 0;
+  // an explicit reset happens between steps: the scatter that follows works at the count of completed steps
+  if (e == 0) b.globals->step_now = b.globals->step_index;
   reset_bookkeeping(p, b, reset, e, threadIdx.x, nullptr, 0);
 }
 

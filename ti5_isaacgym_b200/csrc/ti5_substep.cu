@@ -13,10 +13,7 @@ namespace ti5 {
 __global__ void __launch_bounds__(256) begin_step_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
                                                         const float* __restrict__ actions_in) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx == 0) {                             // nobody in this launch reads these
-    b.globals->step_index += 1;
-    b.globals->n_listed = 0;
-  }
+  if (idx == 0) b.globals->n_listed = 0;      // work list of the history clear, refilled by ti5_post_physics
   if (idx >= p.num_envs * D) return;
   b.actions[idx] = clampf(actions_in[idx], -p.clip_actions, p.clip_actions);
 }
@@ -25,11 +22,10 @@ __global__ void __launch_bounds__(256) begin_step_kernel(const __grid_constant__
 // interleaved dof_state as two, and one Philox call yields the four motor-strength multipliers.
 __global__ void __launch_bounds__(64)
 substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
-               const __grid_constant__ Ti5Rng r, int k_push, int k_torque, int phases) {
+               const __grid_constant__ Ti5Rng r, const float* __restrict__ actions_in, int k_push, int k_torque, int phases) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int N = p.num_envs;
   if (idx >= N * 3) return;
-  probe(b.debug_ts, 2, 0);
   const int e = idx / 3, gq = idx - e * 3, d0 = 4 * gq;
   const bool do_push = phases & TI5_SUB_PUSH, do_torque = phases & TI5_SUB_TORQUE;
   const bool rg = p.flags & TI5_F_RAND_GAINS, fric = p.flags & TI5_F_RAND_COULOMB, rt = p.flags & TI5_F_RAND_TORQUE;
@@ -38,7 +34,7 @@ substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5B
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
   // ---- every load that does not depend on another load, issued back to back ----------------------
-  const int64_t step = b.globals->step_index;           // >= 1 inside a step
+  const int64_t step = b.globals->step_index + 1;       // index of the step in progress
   const float4* ds = reinterpret_cast<const float4*>(b.dof_state);
   const float4 s0 = ds[2 * idx], s1 = ds[2 * idx + 1];   // (q, qd) of DOFs d0..d0+3, interleaved
   // IMU push (lr:430-434): its three pieces — body-frame angular velocity + pitch, roll, yaw — are dealt out by
@@ -59,7 +55,15 @@ substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5B
   int lag = 0;
   int64_t stamp = 0;
   if (do_torque) {
-    a4 = ld4(b.actions);
+    if (actions_in != nullptr) {                         // fused lr:393-394 action clip (first substep only)
+      a4 = ld4(actions_in);
+      a4 = make_float4(clampf(a4.x, -p.clip_actions, p.clip_actions), clampf(a4.y, -p.clip_actions, p.clip_actions),
+                       clampf(a4.z, -p.clip_actions, p.clip_actions), clampf(a4.w, -p.clip_actions, p.clip_actions));
+      reinterpret_cast<float4*>(b.actions)[idx] = a4;
+      if (idx == 0) b.globals->n_listed = 0;
+    } else {
+      a4 = ld4(b.actions);
+    }
     off4 = ld4(b.motor_offsets);
     if (lagged) { lag = b.lag_timestep[e * 3 + 0]; stamp = b.ring_stamp[e]; }
     if (rg) { kp4 = ld4(b.p_gains_r); kd4 = ld4(b.d_gains_r); }
@@ -76,8 +80,6 @@ substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5B
   const bool need_ring = do_torque && lagged && lag > 0;
   if (need_ring && jj >= stamp && jj >= 0) t4 = ring[(size_t)ring_slot(jj, p.lag_len) * N * 3 + idx];
 
-  if (s0.x == 12345.678f) probe(b.debug_ts, 2, 7);   // (keeps the first load batch ahead of probe 1)
-  probe(b.debug_ts, 2, 1);
   if (do_push) {                                         // lr:412-434
     const int64_t j = base + k_push;
     if (p.flags & TI5_F_ADD_DOF_LAG) {
@@ -103,7 +105,6 @@ substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5B
     }
   }
 
-  probe(b.debug_ts, 2, 2);
   if (do_torque) {                                       // lr:1019-1074
     const float a[4] = {a4.x * p.action_scale, a4.y * p.action_scale, a4.z * p.action_scale, a4.w * p.action_scale};
     if (lagged) ring[(size_t)ring_slot(jt, p.lag_len) * N * 3 + idx] = make_float4(a[0], a[1], a[2], a[3]);
@@ -146,7 +147,6 @@ substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5B
     }
     reinterpret_cast<float4*>(b.torques)[idx] = make_float4(tau[0], tau[1], tau[2], tau[3]);
   }
-  probe(b.debug_ts, 2, 3);
 }
 
 }  // namespace ti5
@@ -160,7 +160,8 @@ extern "C" int ti5_begin_step(const Ti5Params* p, const Ti5Buffers* b, const flo
   return ti5_check_launch("ti5_begin_step");
 }
 
-extern "C" int ti5_substep(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, int k, int phases, void* stream) {
+static int launch_substep(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, const float* actions_in, int k, int phases,
+                          void* stream) {
   TI5_CHECK_ARGS(p && b && p->num_envs > 0 && k >= 0 && k <= p->decimation && (phases & 3) != 0);
   TI5_CHECK_ARGS(!(phases & TI5_SUB_TORQUE) || k < p->decimation);
   TI5_CHECK_ARGS(!(phases & TI5_SUB_TORQUE) || p->rng_mode == TI5_RNG_PHILOX || !(p->flags & TI5_F_RAND_TORQUE) ||
@@ -170,8 +171,17 @@ extern "C" int ti5_substep(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng
   // fused form: push the result of simulator substep k-1, then the torque of substep k
   const int k_push = (phases & TI5_SUB_TORQUE) ? k - 1 : k;
   TI5_CHECK_ARGS(!(phases & TI5_SUB_PUSH) || k_push >= 0);
-  substep_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(*p, *b, rr, k_push, k, phases);
+  substep_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(*p, *b, rr, actions_in, k_push, k, phases);
   return ti5_check_launch("ti5_substep");
+}
+
+extern "C" int ti5_substep(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, int k, int phases, void* stream) {
+  return launch_substep(p, b, r, nullptr, k, phases, stream);
+}
+
+extern "C" int ti5_first_substep(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, const float* actions_in, void* stream) {
+  TI5_CHECK_ARGS(actions_in != nullptr);
+  return launch_substep(p, b, r, actions_in, 0, TI5_SUB_TORQUE, stream);
 }
 
 extern "C" int ti5_torque_substep(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, int k, void* stream) {

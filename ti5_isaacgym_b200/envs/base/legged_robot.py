@@ -225,8 +225,13 @@ class LeggedRobot(BaseTask):
         self.rand_push_force, self.rand_push_torque = f32(N, 3), f32(N, 3)
         self.applied_force, self.applied_torque = f32(N, 3), f32(N, 3)
         self.env_frictions, self.body_mass = f32(N, 1), f32(N, 1)
-        self.rew_buf = f32(N)
-        self.reset_buf, self.time_out_buf, self._time_outs_latched = u8(N), u8(N), u8(N)
+        # the per-step scalar outputs share one allocation, so a host consumer needs a single D2H copy:
+        # [rew_buf f32 (4N bytes) | reset_buf bool (N) | extras["time_outs"] bool (N)]
+        self.step_outputs_packed = torch.zeros(6 * N, dtype=torch.uint8, device=dev)
+        self.rew_buf = self.step_outputs_packed[:4 * N].view(torch.float32)
+        self.reset_buf = self.step_outputs_packed[4 * N:5 * N].view(torch.bool)
+        self._time_outs_latched = self.step_outputs_packed[5 * N:].view(torch.bool)
+        self.time_out_buf = u8(N)
         self.reset_buf[:] = True
         self._episode_sums = f32(C["TI5_NUM_TERMS"], N)
         self._reward_terms = f32(C["TI5_NUM_TERMS"], N)
@@ -460,7 +465,8 @@ class LeggedRobot(BaseTask):
     def _launch_substeps(self, actions_ptr, with_physics):
         """lr:393-434: action clip, then DEC x (torque -> simulate -> lag push)."""
         lib, p, b, r, st = self._lib, self._p_ref, self._b_ref, self._rng_ref(), self._stream()
-        _lib.check(lib.ti5_begin_step(p, b, actions_ptr, st))
+        if with_physics:
+            _lib.check(lib.ti5_begin_step(p, b, actions_ptr, st))
         for k in range(self._params.decimation):
             if with_physics:
                 _lib.check(lib.ti5_torque_substep(p, b, r, k, st))
@@ -471,8 +477,10 @@ class LeggedRobot(BaseTask):
                 _lib.check(lib.ti5_lag_push(p, b, k, st))
             else:
                 # nothing runs between push k-1 and torque k: one fused launch per substep
-                phases = C["TI5_SUB_TORQUE"] | (C["TI5_SUB_PUSH"] if k > 0 else 0)
-                _lib.check(lib.ti5_substep(p, b, r, k, phases, st))
+                if k == 0:      # action clip fused into the first torque launch
+                    _lib.check(lib.ti5_first_substep(p, b, r, actions_ptr, st))
+                else:
+                    _lib.check(lib.ti5_substep(p, b, r, k, C["TI5_SUB_TORQUE"] | C["TI5_SUB_PUSH"], st))
 
     def _launch_post(self, with_physics):
         """lr:458-506 post_physics_step + the observation clip of lr:441-446."""
@@ -507,14 +515,14 @@ class LeggedRobot(BaseTask):
 
     @property
     def launches_per_step(self):
-        return 1 + self._params.decimation + 2 + (1 if self._params.num_height_points else 0) + (1 if self._materialize else 0)
+        return self._params.decimation + 2 + (1 if self._params.num_height_points else 0) + (1 if self._materialize else 0)
 
     def step(self, actions):
         with_physics = getattr(self.gym, "physics", None) is not None or not hasattr(self.gym, "physics")
         if self._use_graph and not with_physics:
             if self._graph is None:
                 self._capture_graph()
-            self._actions_in.copy_(actions)
+            self._actions_in.copy_(actions, non_blocking=True)     # device tensor or pinned host memory
             self._graph.replay()
         else:
             a = actions.to(device=self.device, dtype=torch.float32).contiguous()

@@ -18,7 +18,7 @@ for i in range(20):
     flush.fill_(i); env.step(act)
 torch.cuda.synchronize()
 ts = env._debug_ts.cpu().double()
-for kern, name, nprobe in ((0, 'post_physics', 7), (1, 'reset_observe', 6), (2, 'substep(last)', 4)):
+for kern, name, nprobe in ((0, 'post_physics', 7), (1, 'reset_observe', 6)):
     t = ts[kern]
     used = t[:, 0] > 0
     t = t[used]
