@@ -66,36 +66,59 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks / throttle reasons through NVML (every 5 ms) while the timed regions run;
+    falls back to polling nvidia-smi when pynvml is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.index, self.sm, self.reasons, self.sm_max, self.stop_flag = index, [], set(), None, threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20)):
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout
+        parts = [x.strip() for x in out.strip().split(",")]
+        if len(parts) >= 6:
+            self.sm.append(float(parts[0]))
+            self.sm_max = float(parts[1])
+            for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+                if parts[2 + i].lower().startswith("active"):
+                    self.reasons.add(name)
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [s.strip() for s in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.rows.append(parts)
+                self._sample_nvml() if self.nvml else self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.005 if self.nvml else 0.2)
 
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]),
-                "samples": len(self.rows), "reasons": reasons}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unsampled"]}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.sm_max, "samples": len(self.sm),
+                "reasons": sorted(self.reasons), "via": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def make_cfg(num_envs):
@@ -151,14 +174,20 @@ def reference_arm(args):
     if rank != 0:
         return
     cores = torch.get_num_threads()
-    value, ms = run_cpu_port(ENVS_PER_GPU, args.steps, args.warmup)
+    # bounded sample: the whole run should end within ~2 minutes on the host cores (~30 us per env-step with all
+    # threads), so large --steps shrink the number of envs stepped per step (never below 256, at most the workload's 8192)
+    budget_env_steps = 3.0e6
+    sample_envs = ENVS_PER_GPU
+    while sample_envs > 256 and sample_envs * (args.steps + args.warmup) > budget_env_steps:
+        sample_envs //= 2
+    value, ms = run_cpu_port(sample_envs, args.steps, args.warmup)
     line = {"impl": "reference", "metric": "env-steps/sec (step math + reward + obs)", "value": value,
             "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": "t1_dh_stand 8192 envs, flat plane, full step + 24-step rollout GAE",
                                             "device": "host CPU", "physics": "no-op (fake gym)"},
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} steps x {ENVS_PER_GPU} envs of the oracle port (torch CPU, "
+                             "sample": f"{args.steps} steps x {sample_envs} envs of the oracle port (torch CPU, "
                                        "the reference's op chains), all host threads"},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -231,7 +260,6 @@ def cuda_arm(args):
         ends[i].record()
     barrier()
     dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
-    clocks = sampler.summary() if sampler else None
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -259,6 +287,7 @@ def cuda_arm(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * N * args.steps / float(t.item())
+    clocks = sampler.summary() if sampler else None      # sampled across the device-timed, per-phase and e2e regions
 
     if rank == 0:
         peak, peak_src = peaks()
