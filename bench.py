@@ -134,25 +134,27 @@ def make_cfg(num_envs):
 # the reference arm / CPU baseline: the oracle port of the reference's torch algorithm on host cores
 # ---------------------------------------------------------------------------------------------
 
-def run_cpu_port(num_envs, steps, warmup, seed=1234):
+def run_cpu_port(num_envs, steps, warmup, seed=1234, device="cpu"):
     from types import SimpleNamespace
     from oracle import t1_oracle as O
     from ti5_isaacgym_b200.envs.t1.t1_robot import robot_constants
     from ti5_isaacgym_b200.sim.synthetic import alloc_sim_tensors, fill_synthetic_state, synthetic_actions
     cfg = make_cfg(num_envs)
-    C = O.make_consts(cfg, cfg.sim.dt, robot_constants(cfg))
+    C = O.make_consts(cfg, cfg.sim.dt, robot_constants(cfg), device=device)
     S = O.new_state(C, num_envs)
     gen = torch.Generator().manual_seed(seed)
     sim = alloc_sim_tensors(num_envs, "cpu")
-    fill_synthetic_state(sim, S.env_origins, gen)
-    S.episode_length_buf[:] = torch.randint(1, 2000, (num_envs,), generator=gen)
+    fill_synthetic_state(sim, S.env_origins.cpu(), gen)
+    sim = SimpleNamespace(**{k: v.to(device) for k, v in vars(sim).items()})
+    S.episode_length_buf[:] = torch.randint(1, 2000, (num_envs,), generator=gen).to(device)
     S.gait_time[:, 1], S.gait_time[:, 2] = 900, 1500
-    actions = synthetic_actions(num_envs, gen, "cpu")
-    pools = O.draw_pools(C, num_envs, gen)
-    rew = torch.randn(ROLLOUT, num_envs, 1, generator=gen)
-    val = torch.randn(ROLLOUT, num_envs, 1, generator=gen)
-    done = (torch.rand(ROLLOUT, num_envs, 1, generator=gen) < 0.02).byte()
-    last = torch.randn(num_envs, 1, generator=gen)
+    actions = synthetic_actions(num_envs, gen, "cpu").to(device)
+    pools = {k: v.to(device) for k, v in O.draw_pools(C, num_envs, gen).items()}
+    rew = torch.randn(ROLLOUT, num_envs, 1, generator=gen).to(device)
+    val = torch.randn(ROLLOUT, num_envs, 1, generator=gen).to(device)
+    done = (torch.rand(ROLLOUT, num_envs, 1, generator=gen) < 0.02).byte().to(device)
+    last = torch.randn(num_envs, 1, generator=gen).to(device)
+    sync = torch.cuda.synchronize if device != "cpu" else (lambda: None)
 
     def one(i):
         O.step(C, S, sim, actions, pools)
@@ -162,9 +164,11 @@ def run_cpu_port(num_envs, steps, warmup, seed=1234):
     with torch.inference_mode():
         for i in range(warmup):
             one(i)
+        sync()
         t0 = time.perf_counter()
         for i in range(steps):
             one(i)
+        sync()
         dt = time.perf_counter() - t0
     return num_envs * steps / dt, dt / steps * 1e3
 
@@ -297,12 +301,16 @@ def cuda_arm(args):
         bytes_per_launch = {"substep": BYTES_SUBSTEP * N, "post_physics+reset_observe": BYTES_POST * N / 2}[dom]
         ach = bytes_per_launch / (kt[dom]["ms_per_launch"] * 1e-3) / 1e9
         launches_per_step = env.launches_per_step
-        cpu = None
+        cpu = torch_gpu = None
         if world == 1 and not args.no_cpu_baseline:
             v, ms = run_cpu_port(4096, 40, 3)
             cpu = {"value": v, "unit": "env-steps/s", "cores": torch.get_num_threads(), "kind": "port",
                    "sample": "40 steps x 4096 envs (BASELINE config 1) of the oracle port, torch CPU, all host threads, "
                              f"{ms:.1f} ms/step"}
+            # the reference's eager-torch algorithm on THIS GPU (the north_star's 20x denominator); context only
+            v, ms = run_cpu_port(N, 24, 3, device=dev)
+            torch_gpu = {"value": v, "unit": "env-steps/s", "ms_per_step": ms,
+                         "sample": f"24 steps x {N} envs of the oracle port in eager torch on the same B200"}
         line = {
             "metric": "env-steps/sec (step math + reward + obs)", "value": value, "unit": "env-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
@@ -324,6 +332,7 @@ def cuda_arm(args):
                          "kernels": kt,
                          "how": "CUDA events on the launching stream around one CUDA graph per phase (L2 flushed before each step); per-launch = phase time / launches in the phase"},
             "cpu_baseline": cpu,
+            "reference_torch_gpu": torch_gpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

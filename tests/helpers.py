@@ -23,10 +23,10 @@ def load_golden(name):
     return state0, inputs, outputs, final
 
 
-def scenario_cfg(name, num_envs):
+def scenario_cfg(name, num_envs, frame_stack=66):
     """The product config edited like oracle/pin_against_reference.py SCENARIOS."""
-    from ti5_isaacgym_b200.envs import DHT1StandCfg
-    cfg = DHT1StandCfg()
+    from ti5_isaacgym_b200.envs import make_t1_cfg
+    cfg = make_t1_cfg(frame_stack=frame_stack)()
     cfg.env.num_envs = num_envs
     cfg.terrain.mesh_type = "trimesh" if name.startswith("trimesh") else "plane"
     if name == "trimesh_heights_push":

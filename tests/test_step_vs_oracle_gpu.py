@@ -13,10 +13,10 @@ from oracle import t1_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def _build(name, N, device, seed=3):
+def _build(name, N, device, seed=3, frame_stack=66):
     from ti5_isaacgym_b200.envs.t1.t1_robot import robot_constants
     from ti5_isaacgym_b200.sim.synthetic import SyntheticTerrain, synthetic_height_field
-    cfg = scenario_cfg(name, N)
+    cfg = scenario_cfg(name, N, frame_stack)
     terrain = heights = None
     if cfg.terrain.mesh_type == "trimesh":
         st = SyntheticTerrain(cfg.terrain, N)
@@ -56,16 +56,17 @@ def _build(name, N, device, seed=3):
     return cfg, C, S, terrain, heights, gen
 
 
-@pytest.mark.parametrize("name,N,steps,where", [
-    ("plane_events", 1024, 40, "cpu"), ("plane_events", 1024, 40, "cuda"),
-    ("trimesh_heights_push", 512, 24, "cpu"), ("trimesh_heights_push", 512, 24, "cuda"),
-    ("plane_events", 8192, 6, "cuda"),
+@pytest.mark.parametrize("name,N,steps,where,H", [
+    ("plane_events", 1024, 40, "cpu", 66), ("plane_events", 1024, 40, "cuda", 66),
+    ("trimesh_heights_push", 512, 24, "cpu", 66), ("trimesh_heights_push", 512, 24, "cuda", 66),
+    ("plane_events", 8192, 6, "cuda", 66),
+    ("plane_events", 100, 12, "cpu", 5), ("plane_events", 333, 12, "cuda", 15), ("plane_events", 64, 8, "cuda", 100),   # BASELINE config 5: H sweep, ragged N
 ])
-def test_env_follows_oracle(name, N, steps, where):
+def test_env_follows_oracle(name, N, steps, where, H):
     from ti5_isaacgym_b200.sim.synthetic import alloc_sim_tensors, fill_synthetic_state, synthetic_actions
     device = "cuda:0" if where == "cuda" else "cpu"
-    cfg, C, S, terrain, heights, gen = _build(name, N, device)
-    env = make_env(scenario_cfg(name, N), div_mode="ieee" if where == "cpu" else "reciprocal")
+    cfg, C, S, terrain, heights, gen = _build(name, N, device, frame_stack=H)
+    env = make_env(scenario_cfg(name, N, H), div_mode="ieee" if where == "cpu" else "reciprocal")
     state = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in state_from_oracle(S, C).items()}
     if terrain is not None:
         state["terrain_origins"] = terrain.origins.cpu()

@@ -158,14 +158,22 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
     __syncthreads();
     // thread k issues bulk copy k of the table; threads 32..59 one episode-sum column each; thread 0 arms the
     // barrier with the byte total (arrival order between the copies and the arm does not matter)
+    // (the (TERMS, N) episode-sum columns start 16-byte aligned only when N is a multiple of 4)
+    const bool sums_by_tma = (N & 3) == 0;
     if (tid < POST_CHUNKS) {
       tma_load_1d(T.base + (size_t)src.off[tid] * TB, static_cast<const char*>(src.ptr[tid]) + (size_t)e0 * src.rowb[tid],
                   (uint32_t)(TB * src.rowb[tid]), T.bar);
-    } else if (tid >= 32 && tid < 32 + TI5_NUM_TERMS && (mask & (1u << (tid - 32)))) {
+    } else if (sums_by_tma && tid >= 32 && tid < 32 + TI5_NUM_TERMS && (mask & (1u << (tid - 32)))) {
       const int t = tid - 32;
       tma_load_1d(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(TB * 4), T.bar);
     }
-    if (tid == 0) mbar_expect_tx(T.bar, (uint32_t)TB * (uint32_t)(src.off[POST_CHUNKS] + 4 * __popc(mask)));
+    if (tid == 0) mbar_expect_tx(T.bar, (uint32_t)TB * (uint32_t)(src.off[POST_CHUNKS] + (sums_by_tma ? 4 * __popc(mask) : 0)));
+    if (!sums_by_tma) {
+#pragma unroll 1
+      for (int t = 0; t < TI5_NUM_TERMS; ++t)
+        if (mask & (1u << t)) coop_load(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(TB * 4));
+      __syncthreads();
+    }
     mbar_wait(T.bar, 0);
   } else {      // partial last tile: byte counts need not be multiples of 16, copy word by word
 #pragma unroll 1
