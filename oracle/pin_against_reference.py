@@ -57,7 +57,7 @@ def snapshot_state(S, C):
     out = {k: getattr(S, k).clone() for k in STATE_KEYS}
     out["last_feet_z"] = torch.zeros(S.N, 2) if isinstance(S.last_feet_z, int) else S.last_feet_z.clone()
     out["obs_history"], out["critic_history"] = S.obs_history.clone(), S.critic_history.clone()
-    out["episode_sums"] = torch.stack([S.episode_sums[k] for k in C.reward_names], 0)
+    out["episode_sums"] = torch.stack([S.episode_sums[k] for k in C.reward_scales], 0)
     out["env_frictions"], out["body_mass"] = S.env_frictions.clone(), S.body_mass.clone()
     out["counters"] = torch.tensor([S.common_step_counter, int(S.is_first_add_force), int(S.is_first_push)])
     out["command_ranges"] = torch.tensor([S.command_ranges[k] for k in ("lin_vel_x", "lin_vel_y", "ang_vel_yaw")],
@@ -76,6 +76,11 @@ SCENARIOS = {
                                                  setattr(c.env, "num_privileged_obs", 3 * (73 + 187)),
                                                  setattr(c.domain_rand, "push_robots", True))),
     "big_plane": dict(N=512, steps=12, mesh="plane", contact_rate=0.03, events=True, golden=False),
+    # the reward terms the task defines but t1_cfg leaves at zero scale (t1:894-896, 917-925, 937-940)
+    "plane_extra_terms": dict(N=16, steps=12, mesh="plane", contact_rate=0.08, events=True,
+                              edit=lambda c: (setattr(c.rewards.scales, "feet_stumble", -0.5),
+                                              setattr(c.rewards.scales, "stand_sysmetry", 0.3),
+                                              setattr(c.rewards.scales, "termination", -1.0))),
 }
 
 
@@ -164,8 +169,8 @@ def run_scenario(name, spec, write_dir=None, verbose=True):
             rew=r_rew.clone(), reset=r_reset.clone(), time_out=env.time_out_buf.clone(), torques=env.torques.clone(),
             commands=env.commands.clone(), contact_filt=env.contact_filt.clone(), feet_air_time=env.feet_air_time.clone(),
             ref_dof_pos=env.ref_dof_pos.clone(), root_after=drv.sim.root_states.clone(), dof_after=drv.sim.dof_state.clone(),
-            episode_sums=torch.stack([env.episode_sums[k] for k in C.reward_names], 0),
-            reward_terms=torch.stack([S.reward_terms[k] for k in C.reward_names], 0),
+            episode_sums=torch.stack([env.episode_sums[k] for k in C.reward_scales], 0),
+            reward_terms=torch.stack([S.reward_terms[k] for k in C.reward_scales], 0),
             n_reset=torch.tensor(int(r_reset.sum()))))
     n_resets = sum(int(o["n_reset"]) for o in rec["outputs"])
     if verbose:

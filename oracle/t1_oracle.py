@@ -601,6 +601,14 @@ def reward_terms(C, S, sim):
         ae = torch.abs(S.commands[:, 2] - S.base_ang_vel[:, 2])
         return (torch.exp(-le * 10) + torch.exp(-ae * 10)) / 2. - 0.2 * (le + ae)
 
+    def feet_stumble():                                                    # t1:937-940 (inactive in t1_cfg)
+        return torch.any(torch.norm(cf[:, C.feet, :2], dim=2) > 5 * torch.abs(cf[:, C.feet, 2]), dim=1)
+
+    def stand_sysmetry():                                                  # t1:917-925 (inactive in t1_cfg)
+        err = q[:, [0, 1, 2, 3]] - q[:, [5, 6, 7, 8]]
+        r = torch.exp(-torch.sum(torch.square(err), dim=1))
+        return torch.where(stand_command(C, S), r, torch.zeros_like(r))
+
     def tracking_ang_vel():                                                # t1:776-790
         e = S.commands[:, 2] - S.base_ang_vel[:, 2]
         return torch.where(stand_command(C, S), torch.exp(-torch.abs(e) * rw.tracking_sigma * 2),
@@ -619,8 +627,8 @@ def reward_terms(C, S, sim):
 
     return {f.__name__: f for f in (
         action_smoothness, base_acc, base_height, collision, default_joint_pos, dof_acc, dof_vel, feet_air_time,
-        feet_clearance, feet_contact_forces, feet_contact_number, feet_distance, feet_rotation, foot_slip,
-        joint_pos, knee_distance, low_speed, orientation, stand_still, torques, track_vel_hard,
+        feet_clearance, feet_contact_forces, feet_contact_number, feet_distance, feet_rotation, feet_stumble, foot_slip,
+        joint_pos, knee_distance, low_speed, orientation, stand_still, stand_sysmetry, torques, track_vel_hard,
         tracking_ang_vel, tracking_lin_vel, vel_mismatch_exp)}
 
 
@@ -637,7 +645,11 @@ def compute_reward(C, S, sim):
         out[name] = r
     if C.cfg.rewards.only_positive_rewards:
         S.rew_buf[:] = torch.clip(S.rew_buf[:], min=0)
-    assert "termination" not in C.reward_scales, "t1_dh_stand has no termination scale (t1_cfg:383-414)"
+    if "termination" in C.reward_scales:                                   # lr:677-680, t1:894-896: after the clip
+        r = (S.reset_buf * ~S.time_out_buf) * C.reward_scales["termination"]
+        S.rew_buf += r
+        S.episode_sums["termination"] += r
+        out["termination"] = r
     return out
 
 
@@ -882,7 +894,7 @@ def load_state(C, S, state):
     S.obs_history = torch.as_tensor(state["obs_history"]).clone().to(C.device)
     S.critic_history = torch.as_tensor(state["critic_history"]).clone().to(C.device)
     es = torch.as_tensor(state["episode_sums"]).to(C.device)
-    S.episode_sums = {k: es[i].clone() for i, k in enumerate(C.reward_names)}
+    S.episode_sums = {k: es[i].clone() for i, k in enumerate(C.reward_scales)}
     cnt = [int(v) for v in state["counters"]]
     S.common_step_counter, S.is_first_add_force, S.is_first_push = cnt[0], bool(cnt[1]), bool(cnt[2])
     cr = torch.as_tensor(state["command_ranges"]).tolist()

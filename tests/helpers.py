@@ -29,6 +29,10 @@ def scenario_cfg(name, num_envs, frame_stack=66):
     cfg = make_t1_cfg(frame_stack=frame_stack)()
     cfg.env.num_envs = num_envs
     cfg.terrain.mesh_type = "trimesh" if name.startswith("trimesh") else "plane"
+    if name == "plane_extra_terms":
+        cfg.rewards.scales.feet_stumble = -0.5
+        cfg.rewards.scales.stand_sysmetry = 0.3
+        cfg.rewards.scales.termination = -1.0
     if name == "trimesh_heights_push":
         cfg.terrain.measure_heights = True
         cfg.env.num_privileged_obs = 3 * (73 + 187)
@@ -88,7 +92,7 @@ def state_from_oracle(S, C):
     out = {k: getattr(S, k).clone() for k in keys}
     out["last_feet_z"] = torch.zeros(S.N, 2) if isinstance(S.last_feet_z, int) else S.last_feet_z.clone()
     out["obs_history"], out["critic_history"] = S.obs_history.clone(), S.critic_history.clone()
-    out["episode_sums"] = torch.stack([S.episode_sums[k] for k in C.reward_names], 0)
+    out["episode_sums"] = torch.stack([S.episode_sums[k] for k in C.reward_scales], 0)
     out["counters"] = torch.tensor([S.common_step_counter, int(S.is_first_add_force), int(S.is_first_push)])
     out["command_ranges"] = torch.tensor([S.command_ranges[k] for k in ("lin_vel_x", "lin_vel_y", "ang_vel_yaw")],
                                          dtype=torch.float64)

@@ -22,7 +22,7 @@ def _terrain_of(state0, cfg):
     return t, synthetic_height_field(2100, 2100, seed=7)
 
 
-@pytest.mark.parametrize("name", ["plane_default", "plane_events", "trimesh_heights_push"])
+@pytest.mark.parametrize("name", ["plane_default", "plane_events", "trimesh_heights_push", "plane_extra_terms"])
 def test_oracle_replays_reference_fixture(name):
     from ti5_isaacgym_b200.envs.t1.t1_robot import robot_constants
     state0, inputs, outputs, final = load_golden(name)

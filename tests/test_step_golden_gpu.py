@@ -9,7 +9,7 @@ from helpers import close, exact, load_golden, make_env, pools_of, scenario_cfg,
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["plane_default", "plane_events", "trimesh_heights_push"])
+@pytest.mark.parametrize("name", ["plane_default", "plane_events", "trimesh_heights_push", "plane_extra_terms"])
 def test_step_matches_reference_fixture(name):
     state0, inputs, outputs, final = load_golden(name)
     N = state0["commands"].shape[0]
@@ -34,8 +34,8 @@ def test_step_matches_reference_fixture(name):
         close(env.commands, out["commands"], tag + "commands")
         close(env.feet_air_time, out["feet_air_time"], tag + "feet_air_time")
         close(env.ref_dof_pos, out["ref_dof_pos"], tag + "ref_dof_pos")
-        close(torch.stack([env.reward_terms[n] for n in env.reward_names]), out["reward_terms"], tag + "reward terms")
-        close(torch.stack([env.episode_sums[n] for n in env.reward_names]), out["episode_sums"], tag + "episode_sums")
+        close(torch.stack([env.reward_terms[n] for n in env.reward_scales]), out["reward_terms"], tag + "reward terms")
+        close(torch.stack([env.episode_sums[n] for n in env.reward_scales]), out["episode_sums"], tag + "episode_sums")
         close(obs[:, -K:], out["obs_new"], tag + "newest obs frame")
         close(priv[:, -P:], out["priv_new"], tag + "newest privileged frame")
         close(env.root_states, out["root_after"], tag + "root_states after resets")

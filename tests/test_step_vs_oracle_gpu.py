@@ -102,7 +102,7 @@ def test_env_follows_oracle(name, N, steps, where, H):
         close(obs, o_obs, tag + "obs_buf")
         close(priv, o_priv, tag + "privileged_obs_buf")
         close(env.commands, S.commands, tag + "commands")
-        for nm in env.reward_names:
+        for nm in env.reward_scales:
             close(env.reward_terms[nm], S.reward_terms[nm], tag + "term " + nm)
             close(env.episode_sums[nm], S.episode_sums[nm], tag + "episode_sums " + nm)
         for attr in ("base_lin_vel", "base_ang_vel", "projected_gravity", "base_euler_xyz", "feet_euler_xyz", "feet_air_time",
@@ -152,3 +152,52 @@ def test_command_curriculum_fires_on_device():
     assert S.command_ranges["lin_vel_x"] == [-0.75, 1.0]
     assert env.command_ranges["lin_vel_x"] == [-0.75, 1.0]
     close(env.commands, S.commands, "commands drawn from the widened range")
+
+
+def test_simulator_in_the_loop_uses_the_unfused_entry_points():
+    """With a simulator between torque and lag push (lr:401-434) the env drives ti5_begin_step /
+    ti5_torque_substep / ti5_lag_push per substep; the state changes at every substep, like PhysX would."""
+    from ti5_isaacgym_b200.sim.synthetic import alloc_sim_tensors, fill_synthetic_state, synthetic_actions
+    name, N, steps = "plane_events", 512, 14
+    cfg, C, S, _, _, gen = _build(name, N, "cpu")
+    env = make_env(scenario_cfg(name, N))
+    env.load_state(state_from_oracle(S, C))
+    sim = alloc_sim_tensors(N, "cpu")
+    for t in range(steps):
+        fill_synthetic_state(sim, S.env_origins, gen, base_contact_rate=0.04)
+        actions, pools = synthetic_actions(N, gen, "cpu"), O.draw_pools(C, N, gen)
+        # ten successor states of the joints and the base, one per simulator substep
+        dofs = [sim.dof_state + 0.01 * torch.randn(sim.dof_state.shape, generator=gen) for _ in range(10)]
+        roots = []
+        for _ in range(10):
+            r = sim.root_states.clone()
+            r[:, 3:7] += 0.01 * torch.randn(N, 4, generator=gen)
+            r[:, 3:7] /= r[:, 3:7].norm(dim=1, keepdim=True)
+            r[:, 7:13] += 0.02 * torch.randn(N, 6, generator=gen)
+            roots.append(r)
+        for k in SIM_KEYS:
+            getattr(env.gym.tensors, k).copy_(getattr(sim, k))
+        osim = SimpleNamespace(**{k: getattr(sim, k).clone() for k in SIM_KEYS})
+
+        def physics_oracle(k):
+            osim.dof_state.copy_(dofs[k])
+            osim.root_states.copy_(roots[k])
+
+        def physics_env(k):
+            env.gym.tensors.dof_state.copy_(dofs[k])
+            env.gym.tensors.root_states.copy_(roots[k])
+
+        env.gym.physics = physics_env
+        env.set_rng_pools(pools)
+        obs, priv, rew, reset, _ = env.step(actions.cuda())
+        o_obs, o_priv, o_rew, o_reset, _ = O.step(C, S, osim, actions, pools, physics=physics_oracle)
+        tag = f"simulator in the loop, step {t}: "
+        exact(reset, o_reset, tag + "reset_buf")
+        close(env.torques, S.torques, tag + "torques")
+        close(rew, o_rew, tag + "rew_buf")
+        close(obs, o_obs, tag + "obs_buf")
+        close(priv, o_priv, tag + "privileged_obs_buf")
+        close(env.dof_lag_buffer, S.dof_lag_buffer, tag + "dof_lag_buffer")
+        close(env.imu_lag_buffer, S.imu_lag_buffer, tag + "imu_lag_buffer")
+        close(env.lag_buffer, S.lag_buffer, tag + "lag_buffer")
+    env.gym.physics = None

@@ -638,7 +638,7 @@ class LeggedRobot(BaseTask):
         self.reset_buf.copy_(torch.as_tensor(state["reset_buf"]).to(dev).bool())
         for col, name in enumerate(("lag_timestep", "dof_lag_timestep", "imu_lag_timestep")):
             self._lag_timestep[:, col] = torch.as_tensor(state[name]).to(dev).to(torch.int32)
-        for i, name in enumerate(self.reward_names):
+        for i, name in enumerate(self.reward_scales):
             self.episode_sums[name].copy_(torch.as_tensor(state["episode_sums"][i]).to(dev))
         if "terrain_levels" in state:
             self.terrain_levels.copy_(torch.as_tensor(state["terrain_levels"]).to(dev))
