@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TI5_ABI_VERSION 3
+#define TI5_ABI_VERSION 4
 
 #define TI5_NUM_DOF 12      /* leg_l1..l6, leg_r1..r6 */
 #define TI5_NUM_BODIES 13   /* base_link + 12 leg links after collapse_fixed_joints */
@@ -109,7 +109,7 @@ typedef struct Ti5Params {
   int32_t n_push_dur, n_add_dur;
   int32_t terrain_rows, terrain_cols, max_terrain_level;
   uint32_t term_mask;                     /* bit i set = reward term i has a non-zero scale */
-  uint32_t _pad0;
+  int32_t log_len;                        /* L: rows of the frame logs (0 = no log); must be >= rollout length + H */
   int64_t max_episode_length;             /* ceil(episode_length_s / dt) = 2400 */
   int64_t push_interval, ext_force_interval, push_update_step, add_update_step;
   uint64_t seed;                          /* Philox key */
@@ -244,6 +244,13 @@ typedef struct Ti5Buffers {
   float* priv_ring;
   float* obs_out;          /* optional contiguous (N, H*K) for ti5_materialize_obs */
   float* priv_out;         /* optional contiguous (N, CH*P) */
+  /* frame logs for the rollout storage (Ti5Params.log_len = L > 0, else NULL): every frame the observation kernel
+   * appends is also kept, un-cleared, in row (step - 1) % L, with the number of frames of that step's window that
+   * are not zeroed by an earlier reset (t1:556-559) */
+  float* frame_log;        /* (N, L, K) */
+  float* priv_log;         /* (N, L, P) */
+  int16_t* valid_log;      /* (L, N) */
+  int32_t* hist_valid;     /* (N) frames appended since the env's histories were last cleared, capped at H */
   uint64_t* debug_ts;      /* optional (2, CTAs, 8) globaltimer probes of the two per-env kernels (profiling aid), or NULL */
 } Ti5Buffers;
 
@@ -267,8 +274,9 @@ typedef struct Ti5Rng {
 
 int ti5_version(void);
 const char* ti5_last_error(void);
-/* sizeof(Ti5Params), sizeof(Ti5Buffers), sizeof(Ti5Rng), sizeof(Ti5Globals): lets a binding check its mirror */
-int ti5_struct_sizes(int32_t out[4]);
+/* sizeof(Ti5Params), sizeof(Ti5Buffers), sizeof(Ti5Rng), sizeof(Ti5Globals), sizeof(Ti5Rollout), sizeof(Ti5Transition),
+ * sizeof(Ti5Batch): lets a binding check its mirrors */
+int ti5_struct_sizes(int32_t out[7]);
 const char* ti5_reward_name(int term);
 
 /* lr:393-394  `self.actions = clip(actions, +-clip_actions)` */
@@ -320,6 +328,71 @@ int ti5_gae_normalize(float* advantages, int32_t T, int32_t N, const double* sta
 int ti5_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
             float* returns, float* advantages, int32_t T, int32_t N, float gamma, float lam,
             double* stats, int32_t* ticket, void* stream);
+
+/* ---- rollout storage: rs:59-74 `add_transitions`, rs:129-173 `mini_batch_generator`, dh_ppo.py:93-103
+ * `process_env_step`, dh_on_policy_runner.py:149-168 episode bookkeeping ------------------------------
+ * The reference keeps every step's (N, H*K) observation window: (T,N,3102) fp32 = 2.4 GB at 8192 envs.  Here the
+ * storage keeps only the per-step scalars and reads the windows back out of the env's frame logs (one K-float
+ * frame per env and step) when a mini-batch is drawn.  All (T,N,.) arrays are row-major, flat index t*N + e as in
+ * `flatten(0, 1)` (rs:134-150). */
+typedef struct Ti5Rollout {
+  int32_t num_envs, num_steps;                 /* N, T */
+  int32_t frame_stack, c_frame_stack;          /* H, CH */
+  int32_t num_single_obs, priv_frame;          /* K, P */
+  int32_t log_len, num_actions;                /* L, A */
+  const float* frame_log;                      /* (N, L, K)  written by ti5_reset_observe */
+  const float* priv_log;                       /* (N, L, P) */
+  const int16_t* valid_log;                    /* (L, N) */
+  int32_t* frame_row;                          /* (T) log row holding the newest frame of step t's observation */
+  float* actions;                              /* (T,N,A) */
+  float* mu;                                   /* (T,N,A) */
+  float* sigma;                                /* (T,N,A) */
+  float* rewards;                              /* (T,N) */
+  uint8_t* dones;                              /* (T,N) */
+  float* values;                               /* (T,N) */
+  float* actions_log_prob;                     /* (T,N) */
+  float* returns;                              /* (T,N) */
+  float* advantages;                           /* (T,N) */
+  /* runner bookkeeping (optional, NULL to skip): running episode return / length per env and the finished
+   * episodes of the rollout in (step, ascending env id) order — what the runner appends to rewbuffer / lenbuffer */
+  float* cur_reward_sum;                       /* (N) */
+  float* cur_episode_length;                   /* (N) */
+  float* finished_rew;                         /* (T*N) */
+  float* finished_len;                         /* (T*N) */
+  int32_t* n_finished;                         /* [2], double-buffered by step parity; [0] zeroed by the caller at clear() */
+} Ti5Rollout;
+
+/* the (N,.) tensors of one transition (rs:4-19) as the policy and the env produced them */
+typedef struct Ti5Transition {
+  const float* actions;                        /* (N,A) */
+  const float* action_mean;                    /* (N,A) */
+  const float* action_sigma;                   /* (N,A) */
+  const float* values;                         /* (N) */
+  const float* actions_log_prob;               /* (N) */
+  const float* rewards;                        /* (N) env rewards of the step, not yet bootstrapped */
+  const uint8_t* dones;                        /* (N) bool */
+  const uint8_t* time_outs;                    /* (N) bool, or NULL (no 'time_outs' in infos) */
+} Ti5Transition;
+
+/* the gathered rows of one mini-batch (rs:152-173); any pointer may be NULL to skip that column */
+typedef struct Ti5Batch {
+  float* obs;                                  /* (B, H*K) */
+  float* critic_obs;                           /* (B, CH*P) */
+  float* actions;                              /* (B,A) */
+  float* values;                               /* (B) */
+  float* advantages;                           /* (B) */
+  float* returns;                              /* (B) */
+  float* actions_log_prob;                     /* (B) */
+  float* mu;                                   /* (B,A) */
+  float* sigma;                                /* (B,A) */
+} Ti5Batch;
+
+/* dh_ppo.py:93-103 + rs:59-74 (+ runner :149-168) in one launch: rewards += gamma * values * time_outs, the row
+ * `step` of every per-step array, the frame-log row of the step's observation, episode return / length accounting */
+int ti5_store_transition(const Ti5Rollout* ro, const Ti5Transition* tr, int32_t step, int32_t frame_row, float gamma,
+                         void* stream);
+/* rs:152-164: rows `idx[0..B)` (flat t*N + e) of every column; the observation windows are rebuilt from the logs */
+int ti5_gather_minibatch(const Ti5Rollout* ro, const int64_t* idx, int32_t B, const Ti5Batch* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -131,6 +131,189 @@ class RolloutStorage:
                 yield (*[t[idx] for t in extra], obs[idx], crit[idx], *[t[idx] for t in cols], (None, None), None)
 
 
+class FrameLogRolloutStorage(RolloutStorage):
+    """`RolloutStorage` without the (T, N, H*K) observation tensors (rs:30-33 — 2.4 GB at 8192 envs, written by a
+    strided copy every step, rs:62-63, and gathered 32 times per iteration, rs:152-153).
+
+    Consecutive observation windows of an env share H-1 of their H frames, so the env keeps each frame once
+    (`LeggedRobot.enable_frame_log`) and `ti5_gather_minibatch` rebuilds the windows a mini-batch asks for; frames
+    older than the env's last reset read as zero, as the reference's cleared deques do (t1:556-559).  One
+    `ti5_store_transition` launch per step replaces the copies of `add_transitions` and, through `store_step`,
+    the time-out bootstrap of `process_env_step` (dh_ppo.py:93-103) and the runner's episode bookkeeping
+    (dh_on_policy_runner.py:156-168) — without its per-step host sync.
+
+    The yielded batches are equal to the reference's for the same permutation (tests/test_rollout_gpu.py)."""
+
+    def __init__(self, env, num_transitions_per_env, actions_shape=None, num_single_obs=None, device=None, group=None):
+        if num_single_obs is not None:
+            raise NotImplementedError("next_proprio_obs storage (rs:48-49) is unused by DHPPO (dh_ppo.py:70 passes None)")
+        self.env = env
+        self.device = device = torch.device(device if device is not None else env.device)
+        if device.type != "cuda":
+            raise _lib.Ti5Error("FrameLogRolloutStorage lives on the env's CUDA device (there is no CPU fallback)")
+        T, N = int(num_transitions_per_env), env.num_envs
+        self.obs_shape = [env.num_obs]
+        self.privileged_obs_shape = [env.num_privileged_obs]
+        self.actions_shape = list(actions_shape) if actions_shape is not None else [env.num_actions]
+        A = self.actions_shape[0]
+        z = lambda *sh, dtype=torch.float32: torch.zeros(*sh, dtype=dtype, device=device)
+        self.rewards, self.actions_log_prob, self.values = z(T, N, 1), z(T, N, 1), z(T, N, 1)
+        self.returns, self.advantages = z(T, N, 1), z(T, N, 1)
+        self.actions, self.mu, self.sigma = z(T, N, A), z(T, N, A), z(T, N, A)
+        self.dones = z(T, N, 1, dtype=torch.uint8)
+        self.num_transitions_per_env, self.num_envs, self.num_single_obs = T, N, None
+        self.saved_hidden_states_a = self.saved_hidden_states_c = None
+        self.step = 0
+        self._group, self._scratch = group, None
+        # episode bookkeeping (runner :119-123, 156-168)
+        self.cur_reward_sum, self.cur_episode_length = z(N), z(N)
+        self._finished_rew, self._finished_len = z(T * N), z(T * N)
+        self._n_finished = z(2, dtype=torch.int32)
+        self._frame_row = z(T, dtype=torch.int32)
+        env.enable_frame_log(T)
+        self._lib = _lib.load_library()
+        self._bind()
+
+    def _bind(self):
+        logs = self.env.frame_logs()
+        ro = _lib.Ti5Rollout()
+        ro.num_envs, ro.num_steps = self.num_envs, self.num_transitions_per_env
+        ro.frame_stack, ro.c_frame_stack = logs.frame_stack, logs.c_frame_stack
+        ro.num_single_obs, ro.priv_frame = logs.num_single_obs, logs.priv_frame
+        ro.log_len, ro.num_actions = logs.log_len, self.actions_shape[0]
+        self._logs = logs
+        for name, t in (("frame_log", logs.frame_log), ("priv_log", logs.priv_log), ("valid_log", logs.valid_log),
+                        ("frame_row", self._frame_row), ("actions", self.actions), ("mu", self.mu), ("sigma", self.sigma),
+                        ("rewards", self.rewards), ("dones", self.dones), ("values", self.values),
+                        ("actions_log_prob", self.actions_log_prob), ("returns", self.returns),
+                        ("advantages", self.advantages), ("cur_reward_sum", self.cur_reward_sum),
+                        ("cur_episode_length", self.cur_episode_length), ("finished_rew", self._finished_rew),
+                        ("finished_len", self._finished_len), ("n_finished", self._n_finished)):
+            setattr(ro, name, ctypes.c_void_p(t.data_ptr()))
+        self._ro = ro
+        self._ro_plain = _lib.Ti5Rollout.from_buffer_copy(ro)      # the same storage without the episode bookkeeping
+        self._ro_plain.cur_reward_sum = None
+
+    def _rollout_ref(self, episodes=True):
+        if self._logs.frame_log is not self.env.frame_logs().frame_log:   # the env re-allocated its logs
+            self._bind()
+        return ctypes.byref(self._ro if episodes else self._ro_plain)
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _f32(self, t, numel):
+        t = t.detach()
+        if t.dtype != torch.float32 or not t.is_cuda:
+            t = t.to(device=self.device, dtype=torch.float32)
+        t = t.contiguous()
+        if t.numel() != numel:
+            raise ValueError(f"expected {numel} elements, got a tensor of shape {tuple(t.shape)}")
+        return t
+
+    def _mask(self, t):
+        t = t.detach()
+        if t.dtype not in (torch.bool, torch.uint8) or not t.is_cuda:
+            t = (t.to(self.device) != 0)
+        return t.contiguous().view(-1)
+
+    def _store(self, tr, rewards, dones, time_outs, gamma, episodes):
+        if self.step >= self.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")                        # rs:60-61
+        N, A = self.num_envs, self.actions_shape[0]
+        row = getattr(tr.observations, "ti5_frame_row", None)
+        if row is None:
+            # the runner's protocol: the stored observation is the one the policy acted on, i.e. the window
+            # before the env step that has just completed (dh_ppo.py:88, runner :134-147)
+            row = (self.env.frame_log_row - 1) % self._logs.log_len
+        keep = [self._f32(tr.actions, N * A), self._f32(tr.action_mean, N * A), self._f32(tr.action_sigma, N * A),
+                self._f32(tr.values, N), self._f32(tr.actions_log_prob, N), self._f32(rewards, N), self._mask(dones)]
+        t = _lib.Ti5Transition()
+        for name, x in zip(("actions", "action_mean", "action_sigma", "values", "actions_log_prob", "rewards", "dones"), keep):
+            setattr(t, name, ctypes.c_void_p(x.data_ptr()))
+        if time_outs is not None:
+            keep.append(self._mask(time_outs))
+            t.time_outs = ctypes.c_void_p(keep[-1].data_ptr())
+        _lib.check(self._lib.ti5_store_transition(self._rollout_ref(episodes), ctypes.byref(t), self.step, int(row),
+                                                  float(gamma), self._stream()))
+        self.step += 1
+
+    def add_transitions(self, tr):
+        """rs:59-74 with the reference's call protocol: `tr.rewards` already carries the time-out bootstrap."""
+        self._store(tr, tr.rewards, tr.dones, None, 0.0, episodes=False)
+
+    def store_step(self, tr, rewards, dones, time_outs, gamma):
+        """dh_ppo.py:93-103 + rs:59-74 + runner :156-168 in one launch: `rewards` are the env's."""
+        self._store(tr, rewards, dones, time_outs, gamma, episodes=True)
+
+    def clear(self):
+        self.step = 0
+        self._n_finished.zero_()
+
+    def finished_episodes(self):
+        """(returns, lengths) of the episodes that ended during this rollout, in the order the runner's
+        `rewbuffer.extend` / `lenbuffer.extend` see them (runner :162-164).  One device sync."""
+        n = int(self._n_finished[self.step & 1].item())
+        return self._finished_rew[:n].tolist(), self._finished_len[:n].tolist()
+
+    # -- mini-batches ------------------------------------------------------------------------------------------
+    def gather(self, idx, columns=("obs", "critic_obs", "actions", "values", "advantages", "returns",
+                                   "actions_log_prob", "mu", "sigma")):
+        """Rows `idx` (flat t*N + e, rs:134-150) of the named columns as fresh tensors."""
+        idx = idx.to(device=self.device, dtype=torch.int64).contiguous()
+        B, A = idx.numel(), self.actions_shape[0]
+        widths = dict(obs=self.obs_shape[0], critic_obs=self.privileged_obs_shape[0], actions=A, values=1, advantages=1,
+                      returns=1, actions_log_prob=1, mu=A, sigma=A)
+        out, batch = {}, _lib.Ti5Batch()
+        for c in columns:
+            out[c] = torch.empty(B, widths[c], dtype=torch.float32, device=self.device)
+            setattr(batch, c, ctypes.c_void_p(out[c].data_ptr()))
+        _lib.check(self._lib.ti5_gather_minibatch(self._rollout_ref(), ctypes.c_void_p(idx.data_ptr()), B,
+                                                  ctypes.byref(batch), self._stream()))
+        return out
+
+    def mini_batch_generator(self, num_mini_batches, num_epochs=8, indices=None):
+        """rs:129-173.  `indices` overrides the `torch.randperm` draw (parity tests)."""
+        batch = self.num_envs * self.num_transitions_per_env
+        mb = batch // num_mini_batches
+        if indices is None:
+            indices = torch.randperm(num_mini_batches * mb, requires_grad=False, device=self.device)
+        for _ in range(num_epochs):
+            for i in range(num_mini_batches):
+                g = self.gather(indices[i * mb:(i + 1) * mb])
+                yield (g["obs"], g["critic_obs"], g["actions"], g["values"], g["advantages"], g["returns"],
+                       g["actions_log_prob"], g["mu"], g["sigma"], (None, None), None)
+
+    def _all_rows(self, column):
+        T, N = self.num_transitions_per_env, self.num_envs
+        return self.gather(torch.arange(T * N, device=self.device), (column,))[column].view(T, N, -1)
+
+    @property
+    def observations(self):
+        """(T, N, H*K) as the reference stores it — rebuilt on demand (debugging / parity checks)."""
+        return self._all_rows("obs")
+
+    @property
+    def privileged_observations(self):
+        return self._all_rows("critic_obs")
+
+
+def install_frame_log_storage(alg, env, group=None):
+    """Swap a `FrameLogRolloutStorage` into a PPO object built by the reference's runner (`alg.storage`,
+    dh_ppo.py:67-70) and fuse its `process_env_step` (dh_ppo.py:93-103) into the single store launch."""
+    old = alg.storage
+    storage = FrameLogRolloutStorage(env, old.num_transitions_per_env, old.actions_shape, device=env.device, group=group)
+    alg.storage = storage
+    del old
+
+    def process_env_step(rewards, dones, infos):
+        storage.store_step(alg.transition, rewards, dones, infos.get("time_outs"), alg.gamma)
+        alg.transition.clear()
+        alg.actor_critic.reset(dones)
+    alg.process_env_step = process_env_step
+    return storage
+
+
 def patch_compute_returns(storage_cls, group=None):
     """Swap the GPU GAE into an existing storage class (e.g. the reference's own RolloutStorage)."""
     def compute_returns(self, last_values, gamma, lam):

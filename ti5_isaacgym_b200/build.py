@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libti5step.so")
-SOURCES = ("ti5_api.cu", "ti5_substep.cu", "ti5_post_physics.cu", "ti5_observe.cu", "ti5_heights.cu", "ti5_gae.cu")
+SOURCES = ("ti5_api.cu", "ti5_substep.cu", "ti5_post_physics.cu", "ti5_observe.cu", "ti5_heights.cu", "ti5_gae.cu", "ti5_rollout.cu")
 HEADERS = ("ti5_device.cuh", "ti5_host.h", os.path.join("..", "..", "include", "ti5_step.h"))
 
 # -fmad=false: every a*b+c rounds twice, like the separate eager torch ops of the reference.

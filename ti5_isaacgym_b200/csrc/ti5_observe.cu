@@ -513,6 +513,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
   if (do_obs && blockIdx.x < env_blocks && warp_env0 < N) {
     const int n_here = min(32, N - warp_env0);
     const float lim = p.clip_obs;
+    const int L = p.log_len, ls = L > 0 ? (int)((step - 1) % L) : 0;      // frame-log row of this step
     if (role == 0) {
       for (int i = lane; i < n_here * K; i += 32) {
         const int en = i / K, k = i - en * K;
@@ -520,6 +521,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
         float* rowp = b.obs_ring + (size_t)(warp_env0 + en) * obs_row;
         rowp[(size_t)hs * K + k] = v;
         rowp[(size_t)(hs + H) * K + k] = v;
+        if (L > 0) b.frame_log[((size_t)(warp_env0 + en) * L + ls) * K + k] = v;
       }
     } else {
       for (int i = lane; i < n_here * P; i += 32) {
@@ -528,8 +530,19 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
         float* rowp = b.priv_ring + (size_t)(warp_env0 + en) * priv_row;
         rowp[(size_t)cs * P + k] = v;
         rowp[(size_t)(cs + CH) * P + k] = v;
+        if (L > 0) b.priv_log[((size_t)(warp_env0 + en) * L + ls) * P + k] = v;
       }
     }
+  }
+  // frames of the env's window that no reset has cleared: 0 after reset_idx, +1 per appended frame
+  if (p.log_len > 0 && role == 0 && live) {
+    int hv = b.hist_valid[e];
+    if (do_reset && reset) hv = 0;
+    if (do_obs) {
+      hv = min(hv + 1, H);
+      b.valid_log[(size_t)((step - 1) % p.log_len) * N + e] = (int16_t)hv;
+    }
+    b.hist_valid[e] = hv;
   }
 
   probe(b.debug_ts, 1, 4);

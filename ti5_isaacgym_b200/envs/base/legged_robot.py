@@ -250,6 +250,7 @@ class LeggedRobot(BaseTask):
         self._debug_ts = None        # set to a (2, 4096, 8) int64 CUDA tensor and re-bind to collect kernel probes
         self._obs_out = f32(N, H * K) if self._materialize else None
         self._priv_out = f32(N, CH * P) if self._materialize else None
+        self._frame_log = self._priv_log = self._valid_log = self._hist_valid = None     # enable_frame_log()
         self.measured_heights = f32(N, max(p.num_height_points, 1)) if p.num_height_points else 0
         self._height_points = None
         if cfg.terrain.measure_heights:
@@ -356,7 +357,8 @@ class LeggedRobot(BaseTask):
             time_outs_latched=self._time_outs_latched, episode_sums=self._episode_sums,
             reward_terms=self._reward_terms, reset_ids=self.reset_ids, reset_list=self._reset_list, block_counts=self._block_counts,
             block_sums=self._block_sums, extras_log=self._extras_log, obs_ring=self._obs_ring,
-            priv_ring=self._priv_ring, obs_out=self._obs_out, priv_out=self._priv_out, debug_ts=self._debug_ts)
+            priv_ring=self._priv_ring, obs_out=self._obs_out, priv_out=self._priv_out, debug_ts=self._debug_ts,
+            frame_log=self._frame_log, priv_log=self._priv_log, valid_log=self._valid_log, hist_valid=self._hist_valid)
         for name, t in pairs.items():
             if t is not None:
                 assert t.is_contiguous(), name
@@ -435,6 +437,56 @@ class LeggedRobot(BaseTask):
     def critic_history(self):
         p = self._params
         return list(self._history_views()[1].reshape(self.num_envs, p.c_frame_stack, p.priv_frame).unbind(1))
+
+    # ------------------------------------------------------------------ frame logs (rollout storage)
+    def enable_frame_log(self, num_steps):
+        """Keep every appended observation / privileged frame of the last `num_steps` + H env steps, un-cleared, in
+        `(N, L, K)` / `(N, L, P)` logs next to the history rings (188 + 292 B per env and step).  The rollout
+        storage (`algo.rollout_storage.FrameLogRolloutStorage`) rebuilds the (N, H*K) windows of a mini-batch
+        from them instead of storing (T, N, H*K) observations (rs:30-31, 62-63)."""
+        p = self._params
+        H, CH, K, P, N = p.frame_stack, p.c_frame_stack, p.num_single_obs, p.priv_frame, self.num_envs
+        L = int(num_steps) + max(H, CH) + 2
+        if p.log_len >= L:
+            return self
+        dev = self.device
+        self._frame_log = torch.zeros(N, L, K, dtype=torch.float32, device=dev)
+        self._priv_log = torch.zeros(N, L, P, dtype=torch.float32, device=dev)
+        self._valid_log = torch.zeros(L, N, dtype=torch.int16, device=dev)
+        self._hist_valid = torch.zeros(N, dtype=torch.int32, device=dev)
+        p.log_len = L
+        self._bind_buffers()
+        self._graph = None
+        self._seed_frame_log()
+        return self
+
+    def _seed_frame_log(self):
+        """The frames already in the rings become the newest rows of the logs (cleared frames are zeros there, so
+        they count as valid)."""
+        p = self._params
+        L, s = p.log_len, self._step_index
+        obs, priv = self._history_views()
+        for log, win, n, w in ((self._frame_log, obs, p.frame_stack, p.num_single_obs),
+                               (self._priv_log, priv, p.c_frame_stack, p.priv_frame)):
+            rows = (s - n + torch.arange(n, device=self.device)) % L           # oldest .. newest = row (s - 1) % L
+            log[:, rows] = win.reshape(self.num_envs, n, w)
+        self._hist_valid.fill_(p.frame_stack)
+        self._valid_log[(s - 1) % L] = p.frame_stack
+
+    def frame_logs(self):
+        """What the rollout storage binds: the log tensors and their geometry."""
+        from types import SimpleNamespace
+        p = self._params
+        if not p.log_len:
+            raise _lib.Ti5Error("frame logs are off: call enable_frame_log(num_steps) first")
+        return SimpleNamespace(frame_stack=p.frame_stack, c_frame_stack=p.c_frame_stack, num_single_obs=p.num_single_obs,
+                               priv_frame=p.priv_frame, log_len=p.log_len, frame_log=self._frame_log,
+                               priv_log=self._priv_log, valid_log=self._valid_log)
+
+    @property
+    def frame_log_row(self):
+        """Log row of the newest frame of the current observation."""
+        return (self._step_index - 1) % self._params.log_len
 
     # ------------------------------------------------------------------ randomness
     def set_rng_pools(self, pools):
@@ -548,6 +600,11 @@ class LeggedRobot(BaseTask):
             self.obs_buf, self.privileged_obs_buf = self._obs_out, self._priv_out
         else:
             self.obs_buf, self.privileged_obs_buf = self._history_views()
+        if self._params.log_len:
+            # a fresh tensor object per step, tagged with the log row of its newest frame: the rollout storage
+            # receives it one env step later (dh_ppo.py:88 -> rs:62) and must know which window it was
+            self.obs_buf = self.obs_buf.view_as(self.obs_buf)
+            self.obs_buf.ti5_frame_row = self.frame_log_row
         self._publish_extras()
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
 
@@ -674,4 +731,6 @@ class LeggedRobot(BaseTask):
             ring[:, slots] = fr
             ring[:, slots + Hn] = fr
         self._graph = None
+        if self._params.log_len:
+            self._seed_frame_log()
         self.obs_buf, self.privileged_obs_buf = self._history_views()
