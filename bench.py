@@ -311,6 +311,7 @@ def cuda_arm(args):
             v, ms = run_cpu_port(N, 24, 3, device=dev)
             torch_gpu = {"value": v, "unit": "env-steps/s", "ms_per_step": ms,
                          "sample": f"24 steps x {N} envs of the oracle port in eager torch on the same B200"}
+        rollout = rollout_bench(env, gen, actions) if world == 1 and not args.no_rollout and not args.materialize else None
         line = {
             "metric": "env-steps/sec (step math + reward + obs)", "value": value, "unit": "env-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
@@ -333,10 +334,91 @@ def cuda_arm(args):
                          "how": "CUDA events on the launching stream around one CUDA graph per phase (L2 flushed before each step); per-launch = phase time / launches in the phase"},
             "cpu_baseline": cpu,
             "reference_torch_gpu": torch_gpu,
+            "rollout_storage": rollout,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def rollout_bench(env, gen, actions):
+    """SURVEY 8(f) rows 1-2 on the same env: per-step cost of recording a transition and per-mini-batch cost of
+    drawing one, frame-log storage (ti5_store_transition / ti5_gather_minibatch) next to the reference's storage
+    algorithm (rs:59-74 copies, rs:152-164 index gathers) as eager torch on the same GPU.  Device-timed with CUDA
+    events; L2 flushed before every timed gather."""
+    from ti5_isaacgym_b200.algo.rollout_storage import FrameLogRolloutStorage, RolloutStorage
+    N, dev, T, NMB = env.num_envs, env.device, ROLLOUT, 4
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    fl = FrameLogRolloutStorage(env, T)
+    plain = RolloutStorage(N, T, [env.num_obs], [env.num_privileged_obs], [12], None, dev)
+    obs, priv = env.get_observations(), env.get_privileged_observations()
+    mk = lambda: RolloutStorage.Transition()
+    val, logp, sig = torch.randn(N, 1, device=dev), torch.randn(N, device=dev), torch.full((N, 12), 0.3, device=dev)
+    t_env, t_fl, t_pl = [], [], []
+    for rollout in range(3):                     # first pass = warm-up (graph re-capture with the log, allocator)
+        fl.clear(); plain.clear()
+        for t in range(T):
+            tr = mk()
+            tr.actions, tr.values, tr.actions_log_prob, tr.action_mean, tr.action_sigma = actions, val, logp, actions, sig
+            tr.observations, tr.critic_observations = obs, priv
+            held_obs, held_priv = obs.clone(), priv.clone()          # what the reference's storage copies one step late
+            e = [ev() for _ in range(4)]
+            e[0].record()
+            obs, priv, rew, dones, infos = env.step(actions)
+            e[1].record()
+            fl.store_step(tr, rew, dones, infos["time_outs"], GAMMA)
+            e[2].record()
+            tp = mk()                                                  # dh_ppo.py:93-103 + rs:59-74 as the reference runs them
+            tp.actions, tp.values, tp.actions_log_prob, tp.action_mean, tp.action_sigma = actions, val, logp, actions, sig
+            tp.observations, tp.critic_observations = held_obs, held_priv
+            tp.rewards = rew.clone()
+            tp.dones = dones
+            tp.rewards += GAMMA * torch.squeeze(tp.values * infos["time_outs"].unsqueeze(1), 1)
+            plain.add_transitions(tp)
+            e[3].record()
+            if rollout:
+                t_env.append((e[0], e[1])); t_fl.append((e[1], e[2])); t_pl.append((e[2], e[3]))
+    torch.cuda.synchronize()
+    mean_ms = lambda pairs: statistics.mean(a.elapsed_time(b) for a, b in pairs)
+    mb = T * N // NMB
+    idx = torch.randperm(NMB * mb, device=dev, generator=gen)
+    cols = [t.flatten(0, 1) for t in (plain.observations, plain.privileged_observations, plain.actions, plain.values,
+                                      plain.advantages, plain.returns, plain.actions_log_prob, plain.mu, plain.sigma)]
+    g_fl, g_pl = [], []
+    for rep in range(3):
+        for i in range(NMB):
+            sl = idx[i * mb:(i + 1) * mb]
+            flush.fill_(i)
+            a, b = ev(), ev()
+            a.record(); out = fl.gather(sl); b.record()
+            flush.fill_(i + 1)
+            c, d = ev(), ev()
+            c.record(); ref = [col[sl] for col in cols]; d.record()
+            if rep:
+                g_fl.append((a, b)); g_pl.append((c, d))
+            if rep == 0 and i == 0:
+                same = all(torch.equal(out[k], r) for k, r in zip(("obs", "critic_obs", "actions", "values"), ref))
+            del out, ref
+    torch.cuda.synchronize()
+    row_bytes = 4 * (env.num_obs + env.num_privileged_obs + 3 * 12 + 4)
+    gather_ms = mean_ms(g_fl)
+    logs = env.frame_logs()
+    kept = sum(t.numel() * t.element_size() for t in (logs.frame_log, logs.priv_log, logs.valid_log))
+    return {
+        "rollout": f"T={T} steps x {N} envs, {NMB} mini-batches of {mb} rows (t1_cfg:455-468)",
+        "env_step_with_frame_log_ms": mean_ms(t_env),
+        "store": {"ours_us_per_step": 1e3 * mean_ms(t_fl), "launches_per_step": 1,
+                  "reference_algorithm_torch_gpu_us_per_step": 1e3 * mean_ms(t_pl),
+                  "reference_bytes_per_step": 2 * 4 * N * (env.num_obs + env.num_privileged_obs),
+                  "ours_bytes_per_step": N * (4 * (12 * 6 + 8) + 2)},
+        "gather": {"ours_ms_per_minibatch": gather_ms, "reference_algorithm_torch_gpu_ms_per_minibatch": mean_ms(g_pl),
+                   "bytes_written_per_minibatch": mb * row_bytes,
+                   "achieved_GBps_read_plus_write": 2 * mb * row_bytes / (gather_ms * 1e-3) / 1e9,
+                   "matches_reference_algorithm": bool(same), "l2": "flushed before every timed gather"},
+        "observation_storage_bytes": {"ours_frame_logs": kept,
+                                      "reference": 4 * T * N * (env.num_obs + env.num_privileged_obs)},
+    }
 
 
 def kernel_times(env, actions, steps):
@@ -382,6 +464,7 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU (BASELINE metric: 8192)")
     ap.add_argument("--materialize", action="store_true", help="also write contiguous (N,3102)/(N,219) observations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rollout", action="store_true", help="skip the rollout-storage measurement (SURVEY 8f rows 1-2)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

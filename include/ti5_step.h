@@ -274,9 +274,8 @@ typedef struct Ti5Rng {
 
 int ti5_version(void);
 const char* ti5_last_error(void);
-/* sizeof(Ti5Params), sizeof(Ti5Buffers), sizeof(Ti5Rng), sizeof(Ti5Globals), sizeof(Ti5Rollout), sizeof(Ti5Transition),
- * sizeof(Ti5Batch): lets a binding check its mirrors */
-int ti5_struct_sizes(int32_t out[7]);
+/* sizeof(Ti5Params), sizeof(Ti5Buffers), sizeof(Ti5Rng), sizeof(Ti5Globals): lets a binding check its mirror */
+int ti5_struct_sizes(int32_t out[4]);
 const char* ti5_reward_name(int term);
 
 /* lr:393-394  `self.actions = clip(actions, +-clip_actions)` */
@@ -387,12 +386,18 @@ typedef struct Ti5Batch {
   float* sigma;                                /* (B,A) */
 } Ti5Batch;
 
+/* sizeof(Ti5Rollout), sizeof(Ti5Transition), sizeof(Ti5Batch) */
+int ti5_rollout_struct_sizes(int32_t out[3]);
+
 /* dh_ppo.py:93-103 + rs:59-74 (+ runner :149-168) in one launch: rewards += gamma * values * time_outs, the row
  * `step` of every per-step array, the frame-log row of the step's observation, episode return / length accounting */
 int ti5_store_transition(const Ti5Rollout* ro, const Ti5Transition* tr, int32_t step, int32_t frame_row, float gamma,
                          void* stream);
-/* rs:152-164: rows `idx[0..B)` (flat t*N + e) of every column; the observation windows are rebuilt from the logs */
-int ti5_gather_minibatch(const Ti5Rollout* ro, const int64_t* idx, int32_t B, const Ti5Batch* out, void* stream);
+/* rs:152-164: rows `idx[0..B)` (flat t*N + e) of every column; the observation windows are rebuilt from the logs.
+ * `order` (optional permutation of [0,B), or NULL) only sets which batch row each warp produces first: sorting the
+ * rows by (env, step) lets neighbouring warps share the frames of overlapping windows; the output is unchanged. */
+int ti5_gather_minibatch(const Ti5Rollout* ro, const int64_t* idx, const int32_t* order, int32_t B, const Ti5Batch* out,
+                         void* stream);
 
 #ifdef __cplusplus
 }

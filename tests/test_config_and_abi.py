@@ -52,6 +52,9 @@ def test_library_exports_every_declared_symbol():
     sizes = (ctypes.c_int32 * 4)()
     assert lib.ti5_struct_sizes(sizes) == 0
     assert list(sizes) == [ctypes.sizeof(s) for s in (_lib.Ti5Params, _lib.Ti5Buffers, _lib.Ti5Rng, _lib.Ti5Globals)]
+    sizes = (ctypes.c_int32 * 3)()
+    assert lib.ti5_rollout_struct_sizes(sizes) == 0
+    assert list(sizes) == [ctypes.sizeof(s) for s in (_lib.Ti5Rollout, _lib.Ti5Transition, _lib.Ti5Batch)]
 
 
 def test_reward_name_table_matches_binding():

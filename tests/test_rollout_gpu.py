@@ -203,7 +203,68 @@ def test_held_ring_view_is_not_a_stored_observation():
     kept = obs.clone()
     env.step(synthetic_actions(N, gen, "cuda"))
     assert not torch.equal(obs, kept)              # the view moved on: only a copy, or the frame log, preserves it
+    # materialize_obs=True hands out fresh tensors like the reference (t1:477-481): they outlive later steps
     env2 = make_env(scenario_cfg("plane_default", N), rng_mode="philox", div_mode="reciprocal", materialize_obs=True)
     fill_synthetic_state(env2.gym.tensors, env2.env_origins, gen)
-    o2, *_ = env2.step(synthetic_actions(N, gen, "cuda"))
-    assert o2.is_contiguous()
+    o2, p2, *_ = env2.step(synthetic_actions(N, gen, "cuda"))
+    assert o2.is_contiguous() and p2.is_contiguous()
+    exact(o2, env2._history_views()[0], "materialised window")
+    k2, kp2 = o2.clone(), p2.clone()
+    for _ in range(3):
+        env2.step(synthetic_actions(N, gen, "cuda"))
+    exact(o2, k2, "held observation"); exact(p2, kp2, "held privileged observation")
+
+
+def test_collector_runs_the_runner_loop_without_per_step_syncs():
+    """runner :130-172 through RolloutCollector with a stand-in PPO object: what lands in the storage equals what
+    the reference's process_env_step / add_transitions / bookkeeping produce from the same policy outputs."""
+    from ti5_isaacgym_b200.algo.collector import RolloutCollector
+    from ti5_isaacgym_b200.algo.rollout_storage import RolloutStorage
+    from ti5_isaacgym_b200.envs import T1DHStandEnv
+    from ti5_isaacgym_b200.sim.synthetic import SimParams, fill_synthetic_state
+    N, T = 200, 12
+    cfg = scenario_cfg("plane_default", N, frame_stack=8)
+    env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, "cuda:0", True, rng_mode="philox", div_mode="reciprocal", seed=3)
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    seen = []
+
+    class Alg:                                            # the members of DHPPO the loop touches (dh_ppo.py:76-110)
+        gamma, storage = 0.994, None
+        transition = RolloutStorage.Transition()
+        actor_critic = SimpleNamespace(reset=lambda dones: None)
+
+        def act(self, obs, critic_obs):
+            tr = self.transition
+            tr.actions = torch.tanh(obs[:, -47:-35]) + 0.1 * torch.randn(N, 12, device="cuda", generator=gen)
+            tr.values = critic_obs[:, :1] * 0.5
+            tr.actions_log_prob = -tr.actions.square().sum(1)
+            tr.action_mean, tr.action_sigma = tr.actions * 0.9, torch.full((N, 12), 0.3, device="cuda")
+            tr.observations, tr.critic_observations = obs, critic_obs
+            seen.append((obs.clone(), critic_obs.clone(), tr.actions, tr.values, tr.actions_log_prob))
+            fill_synthetic_state(env.gym.tensors, env.env_origins, gen, base_contact_rate=0.08)   # next physics state
+            return tr.actions
+
+        def compute_returns(self, last_critic_obs):
+            self.storage.compute_returns(last_critic_obs[:, :1] * 0.5, self.gamma, 0.9)
+
+    env.reset()
+    alg = Alg()
+    col = RolloutCollector(env, alg, T)
+    want_rb, want_lb = [], []
+    cs, cl = torch.zeros(N), torch.zeros(N)
+    for rollout in range(2):
+        seen.clear()
+        st = col.collect()
+        assert st.step == T and len(seen) == T
+        exact(st.observations, torch.stack([s[0] for s in seen]), "stored observations = what the policy saw")
+        exact(st.privileged_observations, torch.stack([s[1] for s in seen]), "stored critic observations")
+        exact(st.actions, torch.stack([s[2] for s in seen]), "actions")
+        exact(st.actions_log_prob.squeeze(-1), torch.stack([s[4] for s in seen]), "log prob")
+        assert torch.isfinite(st.returns).all() and abs(float(st.advantages.mean())) < 1e-3
+        # no env reaches the 2400-step time-out here, so the stored rewards are the env's (dh_ppo.py:97-98 adds 0)
+        for t in range(T):
+            RO.episode_bookkeeping(cs, cl, st.rewards[t, :, 0].cpu(), st.dones[t, :, 0].cpu() > 0, want_rb, want_lb)
+        assert list(col.rewbuffer) == want_rb[-100:] and list(col.lenbuffer) == want_lb[-100:]
+    assert len(want_lb) > 20
+
+

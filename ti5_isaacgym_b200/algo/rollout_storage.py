@@ -258,7 +258,7 @@ class FrameLogRolloutStorage(RolloutStorage):
 
     # -- mini-batches ------------------------------------------------------------------------------------------
     def gather(self, idx, columns=("obs", "critic_obs", "actions", "values", "advantages", "returns",
-                                   "actions_log_prob", "mu", "sigma")):
+                                   "actions_log_prob", "mu", "sigma"), sort=False):
         """Rows `idx` (flat t*N + e, rs:134-150) of the named columns as fresh tensors."""
         idx = idx.to(device=self.device, dtype=torch.int64).contiguous()
         B, A = idx.numel(), self.actions_shape[0]
@@ -268,7 +268,14 @@ class FrameLogRolloutStorage(RolloutStorage):
         for c in columns:
             out[c] = torch.empty(B, widths[c], dtype=torch.float32, device=self.device)
             setattr(batch, c, ctypes.c_void_p(out[c].data_ptr()))
-        _lib.check(self._lib.ti5_gather_minibatch(self._rollout_ref(), ctypes.c_void_p(idx.data_ptr()), B,
+        order = None
+        if sort and B > 1 and ("obs" in columns or "critic_obs" in columns):
+            # produce the rows in (env, step) order: windows of one env overlap in all but a few frames.  Measured at
+            # 8192 envs x 24 steps: the argsort costs more (0.12 ms) than the saved reads, so it is off by default
+            N = self.num_envs
+            order = torch.argsort((idx % N) * self.num_transitions_per_env + idx // N).to(torch.int32)
+        _lib.check(self._lib.ti5_gather_minibatch(self._rollout_ref(), ctypes.c_void_p(idx.data_ptr()),
+                                                  ctypes.c_void_p(order.data_ptr()) if order is not None else None, B,
                                                   ctypes.byref(batch), self._stream()))
         return out
 
@@ -298,13 +305,16 @@ class FrameLogRolloutStorage(RolloutStorage):
         return self._all_rows("critic_obs")
 
 
-def install_frame_log_storage(alg, env, group=None):
+def install_frame_log_storage(alg, env, group=None, num_transitions_per_env=None):
     """Swap a `FrameLogRolloutStorage` into a PPO object built by the reference's runner (`alg.storage`,
     dh_ppo.py:67-70) and fuse its `process_env_step` (dh_ppo.py:93-103) into the single store launch."""
-    old = alg.storage
-    storage = FrameLogRolloutStorage(env, old.num_transitions_per_env, old.actions_shape, device=env.device, group=group)
+    old = getattr(alg, "storage", None)
+    T = num_transitions_per_env if old is None else old.num_transitions_per_env
+    shape = None if old is None else old.actions_shape
+    alg.storage = None
+    del old                                   # release the (T, N, H*K) tensors before allocating anything else
+    storage = FrameLogRolloutStorage(env, T, shape, device=env.device, group=group)
     alg.storage = storage
-    del old
 
     def process_env_step(rewards, dones, infos):
         storage.store_step(alg.transition, rewards, dones, infos.get("time_outs"), alg.gamma)

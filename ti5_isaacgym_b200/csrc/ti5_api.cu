@@ -27,15 +27,20 @@ int ti5_check_launch(const char* what) {
 extern "C" int ti5_version(void) { return TI5_ABI_VERSION; }
 extern "C" const char* ti5_last_error(void) { return g_err; }
 
-extern "C" int ti5_struct_sizes(int32_t out[7]) {
+extern "C" int ti5_struct_sizes(int32_t out[4]) {
   if (!out) return TI5_EINVAL;
   out[0] = (int32_t)sizeof(Ti5Params);
   out[1] = (int32_t)sizeof(Ti5Buffers);
   out[2] = (int32_t)sizeof(Ti5Rng);
   out[3] = (int32_t)sizeof(Ti5Globals);
-  out[4] = (int32_t)sizeof(Ti5Rollout);
-  out[5] = (int32_t)sizeof(Ti5Transition);
-  out[6] = (int32_t)sizeof(Ti5Batch);
+  return TI5_OK;
+}
+
+extern "C" int ti5_rollout_struct_sizes(int32_t out[3]) {
+  if (!out) return TI5_EINVAL;
+  out[0] = (int32_t)sizeof(Ti5Rollout);
+  out[1] = (int32_t)sizeof(Ti5Transition);
+  out[2] = (int32_t)sizeof(Ti5Batch);
   return TI5_OK;
 }
 

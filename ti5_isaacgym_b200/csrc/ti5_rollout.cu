@@ -62,7 +62,25 @@ store_transition_kernel(const __grid_constant__ Ti5Rollout ro, const __grid_cons
     // done flags in front of this tile (CTA 0: in the whole batch, to advance the list length)
     const int upto = blockIdx.x == 0 ? N : e0;
     int c = 0;
-    for (int i = tid; i < upto; i += SB) c += tr.dones[i] != 0;
+    if ((reinterpret_cast<uintptr_t>(tr.dones) & 15) == 0) {      // 16 flags per load, all loads independent
+      const uint4* d4 = reinterpret_cast<const uint4*>(tr.dones);
+      const int n16 = upto >> 4;
+      for (int i = tid; i < n16; i += SB) {
+        const uint4 w = d4[i];
+        // flags are 0 / 1 bytes (torch.bool) or any non-zero byte: count non-zero bytes
+        const unsigned x[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          unsigned nz = x[q] | (x[q] >> 4);
+          nz |= nz >> 2;
+          nz |= nz >> 1;
+          c += __popc(nz & 0x01010101u);
+        }
+      }
+      for (int i = (n16 << 4) + tid; i < upto; i += SB) c += tr.dones[i] != 0;
+    } else {
+      for (int i = tid; i < upto; i += SB) c += tr.dones[i] != 0;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((tid & 31) == 0) s_warp[tid >> 5] = c;
@@ -92,7 +110,10 @@ store_transition_kernel(const __grid_constant__ Ti5Rollout ro, const __grid_cons
   }
 }
 
-// window of `frames` rows of `width` floats ending at log row `r`, oldest first; rows further back than `nv` are zero
+// window of `frames` rows of `width` floats ending at log row `r`, oldest first; rows further back than `nv` are zero.
+// All U addresses are formed first and the loads issued unconditionally (a cleared frame's row is still a valid
+// address): with the loads under the validity branch ptxas serialised them behind one another (ncu: every
+// predicate ISETP stalled on the previous load's scoreboard).
 template <int WC>
 __device__ __forceinline__ void gather_window(const float* __restrict__ log_e, float* __restrict__ out, int frames,
                                               int width_rt, int L, int r, int nv, int lane) {
@@ -100,35 +121,40 @@ __device__ __forceinline__ void gather_window(const float* __restrict__ log_e, f
   const int total = frames * W;
   constexpr int U = 8;
   for (int i0 = 0; i0 < total; i0 += 32 * U) {
+    const float* src[U];
+    bool keep[U];
     float v[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * 32 + lane;
-      v[u] = 0.0f;
-      if (i < total) {
-        const int h = i / W, back = frames - 1 - h;
-        int row = r - back;
-        row += row < 0 ? L : 0;
-        if (back < nv) v[u] = __ldg(log_e + (size_t)row * W + (i - h * W));
-      }
+      const int i = min(i0 + u * 32 + lane, total - 1);
+      const int h = i / W, back = frames - 1 - h;
+      int row = r - back;
+      row += row < 0 ? L : 0;
+      keep[u] = back < nv;
+      src[u] = log_e + (size_t)row * W + (i - h * W);
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = __ldg(src[u]);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int i = i0 + u * 32 + lane;
-      if (i < total) __stcs(out + i, v[u]);          // streamed: the batch is consumed once by the policy
+      if (i < total) __stcs(out + i, keep[u] ? v[u] : 0.0f);     // streamed: the batch is consumed once by the policy
     }
   }
 }
 
 template <int KC, int PC>
 __global__ void __launch_bounds__(256)
-gather_minibatch_kernel(const __grid_constant__ Ti5Rollout ro, const int64_t* __restrict__ idx, int B,
-                        const __grid_constant__ Ti5Batch out) {
+gather_minibatch_kernel(const __grid_constant__ Ti5Rollout ro, const int64_t* __restrict__ idx,
+                        const int32_t* __restrict__ order, int B, const __grid_constant__ Ti5Batch out) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int N = ro.num_envs, H = ro.frame_stack, CH = ro.c_frame_stack, L = ro.log_len, A = ro.num_actions;
   const int K = KC ? KC : ro.num_single_obs, P = PC ? PC : ro.priv_frame;
-  for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < B; s += gridDim.x * wpb) {
+  // consecutive warps take consecutive entries of `order`: when the caller sorted the batch rows by (env, step),
+  // the warps of a CTA rebuild overlapping windows of one env and share its frames in L1 / L2
+  for (int j = blockIdx.x * wpb + (threadIdx.x >> 5); j < B; j += gridDim.x * wpb) {
+    const int s = order ? order[j] : j;
     const int64_t flat = idx[s];
     const int t = (int)(flat / N), e = (int)(flat - (int64_t)t * N);
     const int r = ro.frame_row[t];
@@ -177,8 +203,8 @@ extern "C" int ti5_store_transition(const Ti5Rollout* ro, const Ti5Transition* t
   return ti5_check_launch("ti5_store_transition");
 }
 
-extern "C" int ti5_gather_minibatch(const Ti5Rollout* ro, const int64_t* idx, int32_t B, const Ti5Batch* out,
-                                    void* stream) {
+extern "C" int ti5_gather_minibatch(const Ti5Rollout* ro, const int64_t* idx, const int32_t* order, int32_t B,
+                                    const Ti5Batch* out, void* stream) {
   if (int rc = check_rollout(ro)) return rc;
   TI5_CHECK_ARGS(out != nullptr && B >= 0);
   if (B == 0) return TI5_OK;
@@ -195,10 +221,10 @@ extern "C" int ti5_gather_minibatch(const Ti5Rollout* ro, const int64_t* idx, in
   if (blocks > cap) blocks = cap;
   cudaStream_t st = (cudaStream_t)stream;
   if (ro->num_single_obs == 47 && ro->priv_frame == 73)
-    gather_minibatch_kernel<47, 73><<<blocks, wpb * 32, 0, st>>>(*ro, idx, B, *out);
+    gather_minibatch_kernel<47, 73><<<blocks, wpb * 32, 0, st>>>(*ro, idx, order, B, *out);
   else if (ro->num_single_obs == 47)
-    gather_minibatch_kernel<47, 0><<<blocks, wpb * 32, 0, st>>>(*ro, idx, B, *out);
+    gather_minibatch_kernel<47, 0><<<blocks, wpb * 32, 0, st>>>(*ro, idx, order, B, *out);
   else
-    gather_minibatch_kernel<0, 0><<<blocks, wpb * 32, 0, st>>>(*ro, idx, B, *out);
+    gather_minibatch_kernel<0, 0><<<blocks, wpb * 32, 0, st>>>(*ro, idx, order, B, *out);
   return ti5_check_launch("ti5_gather_minibatch");
 }

@@ -88,7 +88,8 @@ class LeggedRobot(BaseTask):
                         `set_rng_pools`, the parity mode of SURVEY.md section 7)
         div_mode        "reciprocal" = torch-on-GPU rounding of tensor/scalar, "ieee" = torch-on-CPU
         use_cuda_graph  capture the whole step into one CUDA graph (philox mode, synthetic sim only)
-        materialize_obs return contiguous (N, H*47) / (N, CH*P) copies instead of ring views"""
+        materialize_obs return fresh contiguous (N, H*47) / (N, CH*P) tensors every step, as the reference does
+                        (t1:477-481), instead of views into the history rings that are valid until the next step"""
         self.cfg = cfg
         self.sim_params = sim_params
         self.height_samples = None
@@ -248,8 +249,7 @@ class LeggedRobot(BaseTask):
         self._extras_log = f32(C["TI5_LOG_ROWS"], C["TI5_LOG_COLS"])
         self._globals = torch.zeros(ctypes.sizeof(_lib.Ti5Globals), dtype=torch.uint8, device=dev)
         self._debug_ts = None        # set to a (2, 4096, 8) int64 CUDA tensor and re-bind to collect kernel probes
-        self._obs_out = f32(N, H * K) if self._materialize else None
-        self._priv_out = f32(N, CH * P) if self._materialize else None
+        self._obs_out = self._priv_out = None                     # allocated per step by _materialize_windows()
         self._frame_log = self._priv_log = self._valid_log = self._hist_valid = None     # enable_frame_log()
         self.measured_heights = f32(N, max(p.num_height_points, 1)) if p.num_height_points else 0
         self._height_points = None
@@ -544,8 +544,16 @@ class LeggedRobot(BaseTask):
             _lib.check(lib.ti5_sample_heights(p, b, st))
         _lib.check(lib.ti5_post_physics(p, b, r, 0 if with_physics else 1, st))
         _lib.check(lib.ti5_reset_observe(p, b, r, C["TI5_RO_RESET"] | C["TI5_RO_OBSERVE"], st))
-        if self._materialize:
-            _lib.check(lib.ti5_materialize_obs(p, b, st))
+
+    def _materialize_windows(self):
+        """lr:441-446 / t1:477-481: this step's windows as FRESH contiguous tensors (outside the captured graph: a
+        caller may keep them across later steps, like the tensors `torch.cat` returns in the reference)."""
+        p = self._params
+        self._obs_out = torch.empty(self.num_envs, p.frame_stack * p.num_single_obs, dtype=torch.float32, device=self.device)
+        self._priv_out = torch.empty(self.num_envs, p.c_frame_stack * p.priv_frame, dtype=torch.float32, device=self.device)
+        b = _lib.Ti5Buffers.from_buffer_copy(self._buffers)
+        b.obs_out, b.priv_out = self._obs_out.data_ptr(), self._priv_out.data_ptr()
+        _lib.check(self._lib.ti5_materialize_obs(self._p_ref, ctypes.byref(b), self._stream()))
 
     def _launch_step(self, actions_ptr, with_physics):
         """Enqueue the kernels of one policy step on the current stream."""
@@ -597,6 +605,7 @@ class LeggedRobot(BaseTask):
         if hasattr(self.gym, "substep"):
             self.gym.substep = 0
         if self._materialize:
+            self._materialize_windows()
             self.obs_buf, self.privileged_obs_buf = self._obs_out, self._priv_out
         else:
             self.obs_buf, self.privileged_obs_buf = self._history_views()

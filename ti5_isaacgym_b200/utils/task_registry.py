@@ -56,7 +56,11 @@ class TaskRegistry:
         self.env_cfg_for_wandb = env_cfg
         return env, env_cfg
 
-    def make_alg_runner(self, env, name=None, args=None, train_cfg=None, log_root="default"):
+    def make_alg_runner(self, env, name=None, args=None, train_cfg=None, log_root="default", storage="frame_log"):
+        """`storage="frame_log"` (default) swaps `FrameLogRolloutStorage` into the runner's PPO object: the
+        unmodified runner stores the observation it acted on one env step late (dh_ppo.py:88 -> rs:62), which a
+        view into the env's history ring does not survive.  `storage="reference"` keeps the reference's own
+        RolloutStorage and therefore needs an env built with `materialize_obs=True`."""
         args = args or default_args()
         if train_cfg is None:
             if name is None:
@@ -73,7 +77,15 @@ class TaskRegistry:
         except ImportError as e:
             raise ImportError("make_alg_runner needs the reference's `humanoid.algo` package on sys.path: the "
                               "PPO runner / actor-critic are out of this build's scope") from e
+        if storage not in ("frame_log", "reference"):
+            raise ValueError("storage must be 'frame_log' or 'reference'")
+        if storage == "reference" and not getattr(env, "_materialize", False):
+            raise ValueError("the reference's RolloutStorage copies the observation one env step after the policy saw "
+                             "it; build the env with materialize_obs=True, or use storage='frame_log'")
         runner = getattr(algo, all_cfg["runner_class_name"])(env, all_cfg, log_dir, device=args.rl_device)
+        if storage == "frame_log":
+            from ..algo.rollout_storage import install_frame_log_storage
+            install_frame_log_storage(runner.alg, env)
         return runner, train_cfg, log_dir
 
 
