@@ -274,17 +274,19 @@ def cuda_arm(args):
     kt = kernel_times(env, actions, steps=min(args.steps, 48))
 
     # ---- end to end through env.step() with pinned host buffers ------------------------------------
-    h_act = actions.cpu().pin_memory()
-    h_out = torch.empty(6 * N, dtype=torch.uint8).pin_memory()      # [rew f32 | reset bool | time_outs bool]
-    stream = torch.cuda.current_stream()
+    # pinned, device-mapped host buffers wired into the step's CUDA graph (LeggedRobot.enable_host_io): every
+    # step_host() has the first substep kernel read the actions from host memory, runs the step, has the observation
+    # kernel store [rew | reset | time_outs] into host memory, and waits for the stream
+    h_act, h_out = env.enable_host_io()
+    h_act.copy_(actions.cpu())
+    for i in range(3):
+        env.step_host()
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        env.step(h_act)                                  # H2D of the pinned actions happens inside step()
+        env.step_host()
         if (i + 1) % T == 0:
             gae_returns_(rew, val, done, last, ret, adv, GAMMA, LAM, scratch, group)
-        h_out.copy_(env.step_outputs_packed, non_blocking=True)
-        stream.synchronize()
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -324,7 +326,7 @@ def cuda_arm(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h_act.numel() * 4 * world,
                     "d2h_bytes_per_step": h_out.numel() * world,
-                    "note": "env.step() with pinned host actions in, reward/reset/time-out flags out, stream sync every step; L2 not flushed"},
+                    "note": "env.step_host(): actions read from pinned host memory by the first kernel of the step, reward/reset/time-out flags stored into pinned host memory by the last one (mapped pages, no copy-engine hop), stream sync every step; L2 not flushed"},
             "gpu_launches": launches_per_step * args.steps + 2 * (args.steps // T),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": ncu_traffic(dom) if N == ENVS_PER_GPU else None, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch,

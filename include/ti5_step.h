@@ -251,6 +251,10 @@ typedef struct Ti5Buffers {
   float* priv_log;         /* (N, L, P) */
   int16_t* valid_log;      /* (L, N) */
   int32_t* hist_valid;     /* (N) frames appended since the env's histories were last cleared, capped at H */
+  /* optional mirror of the per-step scalar outputs for a host-side caller: [rew f32 (4N bytes) | reset bool (N) |
+   * time_outs bool (N)], written by ti5_reset_observe.  Meant to point at mapped pinned host memory (the stores go
+   * straight over the bus, no copy-engine hop); the `actions_in` of ti5_first_substep may likewise be host-mapped. */
+  uint8_t* host_out;
   uint64_t* debug_ts;      /* optional (2, CTAs, 8) globaltimer probes of the two per-env kernels (profiling aid), or NULL */
 } Ti5Buffers;
 

@@ -156,3 +156,27 @@ def test_heights_match_oracle_at_scale():
     want = O.sample_heights(C, S, env.gym.tensors, env.height_samples)
     assert float((got != want).float().mean()) < 2e-4, "index truncation may differ only where fp32 lands on a cell edge"
     close(got[got == want], want[got == want], "heights")
+
+
+def test_host_io_graph_equals_the_device_path():
+    """enable_host_io(): actions read from pinned host memory by a copy node inside the step graph, results landed
+    in pinned host memory — same step as `step(actions)` on device tensors."""
+    from ti5_isaacgym_b200.sim.synthetic import synthetic_actions
+    N = 1000
+    torch.manual_seed(0)
+    a, gen_a = _production_env(N, use_cuda_graph=True)
+    torch.manual_seed(0)
+    b, _ = _production_env(N, use_cuda_graph=True)
+    a.reset(), b.reset()
+    h_act, h_out = b.enable_host_io()
+    assert h_act.is_pinned() and h_out.is_pinned() and h_act.shape == (N, 12)
+    for t in range(12):
+        act = synthetic_actions(N, gen_a, "cuda")
+        oa, pa, ra, da, xa = a.step(act)
+        h_act.copy_(act.cpu())
+        ob, pb, rb, db, xb = b.step_host()
+        exact(oa, ob, f"step {t}: obs"); exact(pa, pb, f"step {t}: privileged obs")
+        # the host copies are complete when step_host returns: no further synchronisation here
+        assert torch.equal(b.host_rew, ra.cpu()) and torch.equal(b.host_reset, da.cpu())
+        assert torch.equal(b.host_time_outs, xa["time_outs"].cpu())
+    assert int(b.sync_from_device().step_index) == int(a.sync_from_device().step_index)

@@ -604,6 +604,13 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
   // the step is complete once the observations are out: advance the counter (no CTA of this grid reads it)
   if (do_obs && blockIdx.x == 0 && tid == 0) g->step_index = step;
 
+  // host-side callers: this step's scalar outputs, stored straight into (mapped, pinned) host memory
+  if (b.host_out && do_obs && role == 0 && live) {
+    reinterpret_cast<float*>(b.host_out)[e] = b.rew_buf[e];
+    b.host_out[(size_t)4 * N + e] = b.reset_buf[e];
+    b.host_out[(size_t)5 * N + e] = b.time_outs_latched ? b.time_outs_latched[e] : 0;
+  }
+
   // ---- ascending id list of the envs reset this step (lr:490) --------------------------------
   const BlockRank br = block_rank(reset, s_warp);
   if (reset && b.reset_ids) b.reset_ids[id_offset + br.rank] = e;

@@ -265,7 +265,8 @@ class LeggedRobot(BaseTask):
         self._step_index = STEP_INDEX0
         self._write_globals()
         self._bind_buffers()
-        self._graph = None
+        self._graph = self._graph_host = None
+        self.host_actions = None                                  # enable_host_io()
         self._rng = None
         self._rng_keep = None
         self.obs_buf, self.privileged_obs_buf = self._history_views()
@@ -358,7 +359,8 @@ class LeggedRobot(BaseTask):
             reward_terms=self._reward_terms, reset_ids=self.reset_ids, reset_list=self._reset_list, block_counts=self._block_counts,
             block_sums=self._block_sums, extras_log=self._extras_log, obs_ring=self._obs_ring,
             priv_ring=self._priv_ring, obs_out=self._obs_out, priv_out=self._priv_out, debug_ts=self._debug_ts,
-            frame_log=self._frame_log, priv_log=self._priv_log, valid_log=self._valid_log, hist_valid=self._hist_valid)
+            frame_log=self._frame_log, priv_log=self._priv_log, valid_log=self._valid_log, hist_valid=self._hist_valid,
+            host_out=getattr(self, "host_outputs", None))
         for name, t in pairs.items():
             if t is not None:
                 assert t.is_contiguous(), name
@@ -456,7 +458,7 @@ class LeggedRobot(BaseTask):
         self._hist_valid = torch.zeros(N, dtype=torch.int32, device=dev)
         p.log_len = L
         self._bind_buffers()
-        self._graph = None
+        self._graph = self._graph_host = None
         self._seed_frame_log()
         return self
 
@@ -588,6 +590,43 @@ class LeggedRobot(BaseTask):
             a = actions.to(device=self.device, dtype=torch.float32).contiguous()
             self._launch_step(ctypes.c_void_p(a.data_ptr()), with_physics)
         return self._finish_step()
+
+    # ------------------------------------------------------------------ host-side callers (CPU policy / controller)
+    def enable_host_io(self):
+        """Pinned host buffers wired into the captured step, for callers whose actions live in host memory (a CPU
+        policy, a joystick loop like play.py:186-194).  The pinned pages are device-mapped (unified addressing), so
+        the first substep kernel reads `host_actions` (N,12) f32 in place and ti5_reset_observe stores the packed
+        per-step outputs [rew f32 | reset bool | time_outs bool] straight into `host_outputs`: no copy-engine hop, one
+        graph launch per step.  Returns (host_actions, host_outputs)."""
+        if not self._use_graph:
+            raise _lib.Ti5Error("host I/O rides in the step's CUDA graph: needs rng_mode='philox', use_cuda_graph=True")
+        N = self.num_envs
+        self.host_actions = torch.zeros(N, self.num_actions, dtype=torch.float32).pin_memory()
+        self.host_outputs = torch.zeros(6 * N, dtype=torch.uint8).pin_memory()
+        self.host_rew = self.host_outputs[:4 * N].view(torch.float32)
+        self.host_reset = self.host_outputs[4 * N:5 * N].view(torch.bool)
+        self.host_time_outs = self.host_outputs[5 * N:].view(torch.bool)
+        self._bind_buffers()
+        self._graph = self._graph_host = None
+        return self.host_actions, self.host_outputs
+
+    def step_host(self):
+        """`step()` for the actions currently in `host_actions`; returns once `host_rew` / `host_reset` /
+        `host_time_outs` hold this step's results (a stream synchronise, the only host wait of the step)."""
+        if self.host_actions is None:
+            self.enable_host_io()
+        if getattr(self.gym, "physics", None) is not None or not hasattr(self.gym, "physics"):
+            raise _lib.Ti5Error("step_host() needs the graph-captured step (no simulator callbacks between substeps)")
+        if self._graph_host is None:
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=torch.cuda.Stream(self.device)):
+                self._launch_step(ctypes.c_void_p(self.host_actions.data_ptr()), False)
+            self._graph_host = g
+        self._graph_host.replay()
+        out = self._finish_step()
+        torch.cuda.current_stream(self.device).synchronize()
+        return out
 
     def _capture_graph(self):
         torch.cuda.synchronize(self.device)
@@ -739,7 +778,7 @@ class LeggedRobot(BaseTask):
             fr = torch.clip(hist, -lim, lim).permute(1, 0, 2)       # the ring stores clipped frames
             ring[:, slots] = fr
             ring[:, slots + Hn] = fr
-        self._graph = None
+        self._graph = self._graph_host = None
         if self._params.log_len:
             self._seed_frame_log()
         self.obs_buf, self.privileged_obs_buf = self._history_views()
