@@ -515,6 +515,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
     const float lim = p.clip_obs;
     const int L = p.log_len, ls = L > 0 ? (int)((step - 1) % L) : 0;      // frame-log row of this step
     if (role == 0) {
+#pragma unroll 4
       for (int i = lane; i < n_here * K; i += 32) {
         const int en = i / K, k = i - en * K;
         const float v = clampf(s_obs[en * Kp + k], -lim, lim);
@@ -524,6 +525,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
         if (L > 0) b.frame_log[((size_t)(warp_env0 + en) * L + ls) * K + k] = v;
       }
     } else {
+#pragma unroll 4
       for (int i = lane; i < n_here * P; i += 32) {
         const int en = i / P, k = i - en * P;
         const float v = clampf(s_priv[en * Pp + k], -lim, lim);
@@ -556,8 +558,21 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
     const int oc = (int)((obs_row + CHUNK - 1) / CHUNK), pc = (int)((priv_row + CHUNK - 1) / CHUNK);
     const int per_env = oc + pc;
     const int wpb = blockDim.x >> 5;
-    const int total = n_list * per_env, stride = gridDim.x * wpb;
-    for (int w = blockIdx.x * wpb + warp; w < total; w += stride) {
+    const int total = n_list * per_env;
+    // The helper CTAs start on the list at once; the env CTAs get here only after their frames are out.  With the
+    // usual handful of re-spawned envs the helpers finish long before that, so they take the whole list and the
+    // clear leaves the env CTAs' critical path; a mass reset (reset() of every env) is shared by all warps.
+    const int helper_warps = ((int)gridDim.x - env_blocks) * wpb;
+    const bool helpers_only = helper_warps > 0 && total <= 8 * helper_warps;
+    int w0, stride;
+    if (helpers_only) {
+      w0 = blockIdx.x >= env_blocks ? (blockIdx.x - env_blocks) * wpb + warp : total;
+      stride = helper_warps;
+    } else {
+      w0 = blockIdx.x * wpb + warp;
+      stride = gridDim.x * wpb;
+    }
+    for (int w = w0; w < total; w += stride) {
       const int en = b.reset_list[w / per_env];
       int c = w % per_env;
       const bool is_obs = c < oc;
