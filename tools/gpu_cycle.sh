@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: tools_gpu_cycle.sh <tag>   (runs on the GPU box): tests, bench, ncu launch list
+# usage: tools/gpu_cycle.sh <tag>   (runs on the GPU box): tests, bench, ncu launch list
 tag=$1
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -4

@@ -1,4 +1,8 @@
 """Host-side cost of env.step() (enqueue only, no sync) and where it goes."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
 import cProfile, pstats, time, torch
 from ti5_isaacgym_b200.envs import T1DHStandEnv, make_t1_cfg
 from ti5_isaacgym_b200.sim.synthetic import SimParams, fill_synthetic_state, synthetic_actions

@@ -1,4 +1,4 @@
-"""usage: tools_ncu_summary.py <report.ncu-rep> <out.json>  — per-kernel key metrics of an `ncu --set full` report."""
+"""usage: tools/ncu_summary.py <report.ncu-rep> <out.json>  — per-kernel key metrics of an `ncu --set full` report."""
 import csv, json, subprocess, sys, collections
 rep, out = sys.argv[1], sys.argv[2]
 txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout

@@ -1,5 +1,7 @@
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import torch, sys
-sys.path.insert(0, '/root/repo')
 from bench import make_cfg
 from ti5_isaacgym_b200.envs import T1DHStandEnv
 from ti5_isaacgym_b200.sim.synthetic import SimParams, fill_synthetic_state, synthetic_actions

@@ -1,5 +1,9 @@
 """GPU-side probe of the rollout-storage kernels (run under ncu for profiles/): fills a T=24 rollout at N envs
 and draws mini-batches."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
 import sys
 import torch
 from ti5_isaacgym_b200.algo.rollout_storage import FrameLogRolloutStorage, RolloutStorage

@@ -1,6 +1,9 @@
 """Per-launch time of the substep phase graph (10 launches) with features switched off one at a time."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
 import sys, torch, ctypes
-sys.path.insert(0, '/root/repo')
 from bench import make_cfg
 from ti5_isaacgym_b200 import _lib
 from ti5_isaacgym_b200.envs import T1DHStandEnv
