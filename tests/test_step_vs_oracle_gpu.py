@@ -60,6 +60,7 @@ def _build(name, N, device, seed=3, frame_stack=66):
     ("plane_events", 1024, 40, "cpu", 66), ("plane_events", 1024, 40, "cuda", 66),
     ("trimesh_heights_push", 512, 24, "cpu", 66), ("trimesh_heights_push", 512, 24, "cuda", 66),
     ("plane_events", 8192, 6, "cuda", 66),
+    ("plane_events", 96, 400, "cuda", 66),        # long horizon: 400 consecutive steps (4000 substeps) with resets, no re-sync
     ("plane_events", 100, 12, "cpu", 5), ("plane_events", 333, 12, "cuda", 15), ("plane_events", 64, 8, "cuda", 100),   # BASELINE config 5: H sweep, ragged N
 ])
 def test_env_follows_oracle(name, N, steps, where, H):
