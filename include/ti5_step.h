@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TI5_ABI_VERSION 4
+#define TI5_ABI_VERSION 5
 
 #define TI5_NUM_DOF 12      /* leg_l1..l6, leg_r1..r6 */
 #define TI5_NUM_BODIES 13   /* base_link + 12 leg links after collapse_fixed_joints */
@@ -73,9 +73,14 @@ enum {
 enum { TI5_GAIT_STAND = 0, TI5_GAIT_WALK_SAGITTAL = 1, TI5_GAIT_WALK_LATERAL = 2, TI5_GAIT_ROTATE = 3,
        TI5_GAIT_WALK_OMNI = 4 };
 
-/* phases of ti5_substep / ti5_reset_observe (bit masks) */
-enum { TI5_SUB_PUSH = 1, TI5_SUB_TORQUE = 2 };
-enum { TI5_RO_RESET = 1, TI5_RO_OBSERVE = 2 };
+/* phases of ti5_substep / ti5_reset_observe, options of ti5_post_physics (bit masks).
+ * *_CHAINED: launch with a programmatic dependency on the preceding kernel of the stream, which must be the previous
+ * kernel of the fused step sequence (ti5_first_substep / ti5_substep / ti5_sample_heights / ti5_post_physics): the
+ * kernel becomes resident early, does the part of its work that depends on no other kernel of the step, and waits
+ * for the predecessor to complete before anything else.  Never chain across a simulator call. */
+enum { TI5_SUB_PUSH = 1, TI5_SUB_TORQUE = 2, TI5_SUB_CHAINED = 4 };
+enum { TI5_RO_RESET = 1, TI5_RO_OBSERVE = 2, TI5_RO_CHAINED = 4 };
+enum { TI5_POST_PUSH_LAST = 1, TI5_POST_CHAINED = 2 };
 
 /* how `tensor / python_scalar` is rounded: torch-CPU divides, torch-CUDA multiplies by the
  * reciprocal (ATen div_true_kernel_cuda); the reference therefore differs by device. */
@@ -300,8 +305,8 @@ int ti5_sample_heights(const Ti5Params* p, const Ti5Buffers* b, void* stream);
 /* lr:458-489 + t1:179-215 + lr:509-517 + lr:654-680 + t1:572-946: counters, derived base state,
  * command schedule, push / external-force windows, termination, the reward sum, and the
  * compaction bookkeeping (n_reset, per-CTA offsets, episode statistics, command curriculum).
- * `push_last` != 0 fuses the lag push of the last substep into the same launch. */
-int ti5_post_physics(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, int push_last, void* stream);
+ * `options` = TI5_POST_*: PUSH_LAST fuses the lag push of the last substep into the same launch. */
+int ti5_post_physics(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, int options, void* stream);
 
 /* The same bookkeeping for an explicit `reset_idx(env_ids)` (lr:450-455 `reset()`): the caller wrote the
  * mask into reset_buf; follow with ti5_reset_scatter. */

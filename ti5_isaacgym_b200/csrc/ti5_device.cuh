@@ -211,6 +211,18 @@ __device__ __forceinline__ void coop_load(void* dst, const void* src, uint32_t b
 
 static __device__ __noinline__ void coop_load_call(void* dst, const void* src, uint32_t bytes) { coop_load(dst, src, bytes); }
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch ("chained" launches of the fused step): a kernel launched with the
+// programmatic-serialization attribute may become resident while its predecessor on the stream is still
+// running.  chain_trigger() lets the successor's CTAs be scheduled; chain_wait() blocks until the predecessor
+// grid has completed and its writes are visible.  Everything a kernel does before chain_wait() must therefore
+// be independent of every other kernel of the step (loads of simulator tensors and of state that only the
+// previous STEP wrote, address arithmetic, random draws); every store comes after it.  Both are no-ops for a
+// launch without the attribute.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void chain_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // profiling aid: nanosecond timestamp probe `k` of this CTA (thread 0 only), when a probe buffer is bound
 __device__ __forceinline__ void probe(uint64_t* ts, int kernel, int k) {
   if (ts != nullptr && threadIdx.x == 0) {

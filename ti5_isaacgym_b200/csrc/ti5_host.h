@@ -5,6 +5,8 @@
 
 #include "../../include/ti5_step.h"
 
+#include <utility>
+
 void ti5_set_error(const char* fmt, ...);
 int ti5_check_launch(const char* what);
 
@@ -16,3 +18,22 @@ int ti5_check_launch(const char* what);
     }                                                                               \
   } while (0)
 
+
+// Kernel launch with an optional programmatic dependency on the preceding kernel of the stream (see
+// chain_trigger / chain_wait in ti5_device.cuh).  Works under stream capture: the edge becomes a programmatic
+// dependency of the CUDA graph.
+template <class... KArgs, class... Args>
+inline cudaError_t ti5_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, void* stream, bool chained,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = chained ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}

@@ -208,7 +208,9 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
   const int env_blocks = (N + TB - 1) / TB;              // CTAs beyond these only help clearing histories
   const bool live = e < N && blockIdx.x < env_blocks;
   Ti5Globals* g = b.globals;
-  const int64_t step = g->step_now;                      // published by ti5_post_physics / ti5_reset_bookkeeping
+  // index of the step in progress: published by ti5_post_physics / ti5_reset_bookkeeping; a chained launch may not
+  // read what its predecessor writes yet and is always part of a full step
+  const int64_t step = (phases & TI5_RO_CHAINED) ? g->step_index + 1 : g->step_now;
   const int64_t pushes = step * p.decimation;            // lag pushes completed after this step
   const bool do_reset = (phases & TI5_RO_RESET) != 0, do_obs = (phases & TI5_RO_OBSERVE) != 0;
   const int dm = p.div_mode;
@@ -219,6 +221,27 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
   __shared__ int s_tot[16], s_bef[16];
   __shared__ double s_trk[16];
   __shared__ double s_range[3][2];
+  const ObsRng rng{p, r, (uint64_t)step, p.rng_mode == TI5_RNG_PHILOX};
+  const int Kp = K | 1, Pp = P | 1;                      // odd row strides: conflict-free staging
+  float* s_obs = smem + (size_t)tile_warp * 32 * (Kp + Pp);
+  float* s_priv = s_obs + 32 * Kp;
+  // t1:471-472 observation noise: needs nothing from the other kernels of the step, so a chained launch draws it
+  // while ti5_post_physics is still running; it waits in the env's frame slot for the values to be added to it
+  const bool noisy = do_obs && (p.flags & TI5_F_ADD_NOISE);
+  if (noisy && live && role == 0) {
+    float* oo = s_obs + lane * Kp;
+#pragma unroll 4
+    for (int g4 = 0; 4 * g4 < K; ++g4) {
+      const float4 u = rng.noise4(e, g4, K);
+      const float uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = 4 * g4 + j;
+        if (k < K) oo[k] = ((2.0f * uu[j] - 1.0f) * p.noise_vec[k]) * p.noise_level;
+      }
+    }
+  }
+  chain_wait();                                          // ti5_post_physics is done
   int n_reset = 0, id_offset = 0;
   const int64_t counter = step + g->common_step_offset;
   const bool curriculum_due = do_reset && (p.flags & TI5_F_COMMAND_CURRICULUM) && (counter % p.max_episode_length == 0);
@@ -273,10 +296,6 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
     s_range[tid >> 1][tid & 1] = g->cmd_range[step & 1][tid >> 1][tid & 1];
   }
   const bool any_reset = n_reset > 0;
-  const ObsRng rng{p, r, (uint64_t)step, p.rng_mode == TI5_RNG_PHILOX};
-  const int Kp = K | 1, Pp = P | 1;                      // odd row strides: conflict-free staging
-  float* s_obs = smem + (size_t)tile_warp * 32 * (Kp + Pp);
-  float* s_priv = s_obs + 32 * Kp;
 
   const bool flagged = live && do_reset && b.reset_buf[e] != 0;   // both roles see the flag
   const bool reset = flagged && role == 0;                          // ... role 0 accounts for it
@@ -383,10 +402,11 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
         // ---------------- role 0: the 47-float observation frame ------------------------------------
         b.phase_length_buf[e] = phase_len;
         float* oo = s_obs + lane * Kp;
+        auto put = [&](int k, float v) { oo[k] = noisy ? v + oo[k] : v; };     // value + noise (drawn above)
 #pragma unroll
-        for (int i = 0; i < 5; ++i) oo[i] = ci[i];
+        for (int i = 0; i < 5; ++i) put(i, ci[i]);
 #pragma unroll
-        for (int i = 0; i < D; ++i) oo[29 + i] = act[i];
+        for (int i = 0; i < D; ++i) put(29 + i, act[i]);
         // lagged proprioception (t1:407-451): rows pushed before the env's last reset read as zero
         {
           float lq[D], lqd[D];
@@ -404,8 +424,8 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
           }
 #pragma unroll
           for (int i = 0; i < D; ++i) {
-            oo[5 + i] = (lq[i] - p.default_dof_pos[i]) * p.obs_dof_pos;
-            oo[17 + i] = lqd[i] * p.obs_dof_vel;
+            put(5 + i, (lq[i] - p.default_dof_pos[i]) * p.obs_dof_pos);
+            put(17 + i, lqd[i] * p.obs_dof_vel);
           }
           float imu[6];
           const int64_t ji = (pushes - 1) - lag_imu;
@@ -422,20 +442,8 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
           }
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
-            oo[41 + i] = imu[i] * p.obs_ang_vel;
-            oo[44 + i] = imu[3 + i] * p.obs_quat;
-          }
-        }
-        if (p.flags & TI5_F_ADD_NOISE) {                                       // t1:471-472
-#pragma unroll 4
-          for (int g4 = 0; 4 * g4 < K; ++g4) {
-            const float4 u = rng.noise4(e, g4, K);
-            const float uu[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int k = 4 * g4 + j;
-              if (k < K) oo[k] = oo[k] + ((2.0f * uu[j] - 1.0f) * p.noise_vec[k]) * p.noise_level;
-            }
+            put(41 + i, imu[i] * p.obs_ang_vel);
+            put(44 + i, imu[3 + i] * p.obs_quat);
           }
         }
         // lr:496-498 previous-step copies (live state only; the dead ones are not kept)
@@ -693,7 +701,9 @@ __global__ void __launch_bounds__(256) materialize_kernel(const __grid_constant_
 using namespace ti5;
 
 extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, int phases, void* stream) {
-  TI5_CHECK_ARGS(p && b && p->num_envs > 0 && (phases & 3) != 0);
+  TI5_CHECK_ARGS(p && b && p->num_envs > 0 && (phases & 3) != 0 && (phases & ~7) == 0);
+  // a chained launch takes the step index from the completed-step counter: only valid for the full step
+  TI5_CHECK_ARGS(!(phases & TI5_RO_CHAINED) || (phases & 3) == 3);
   TI5_CHECK_ARGS(p->env_block == 32 || p->env_block == 64 || p->env_block == 128);
   TI5_CHECK_ARGS(p->num_single_obs == 47 && p->priv_frame >= 73 && p->num_single_obs <= 64);
   TI5_CHECK_ARGS(p->rng_mode == TI5_RNG_PHILOX || (r && r->cmd && r->dofs && r->dr && r->gait_time && r->noise));
@@ -710,7 +720,8 @@ extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const 
   }
   // + helper CTAs (about 4 warps per SM) that only share the history-clear work of re-spawned envs
   const int helpers = (phases & TI5_RO_RESET) ? (148 * 4 * 32) / (OBS_ROLES * p->env_block) : 0;
-  kernel<<<blocks + helpers, OBS_ROLES * p->env_block, smem, (cudaStream_t)stream>>>(*p, *b, rr, phases);
+  (void)ti5_launch(kernel, dim3(blocks + helpers), dim3(OBS_ROLES * p->env_block), smem, stream, (phases & TI5_RO_CHAINED) != 0,
+                   *p, *b, rr, phases);
   return ti5_check_launch("ti5_reset_observe");
 }
 

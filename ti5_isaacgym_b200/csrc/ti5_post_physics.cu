@@ -116,7 +116,9 @@ constexpr int POST_ROLES = 3;
 
 __global__ void __launch_bounds__(POST_ROLES * 128)
 post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
-                    const __grid_constant__ Ti5Rng r, const __grid_constant__ PostSrc src, int push_last) {
+                    const __grid_constant__ Ti5Rng r, const __grid_constant__ PostSrc src, int options) {
+  chain_trigger();                                        // ti5_reset_observe may become resident
+  const int push_last = options & TI5_POST_PUSH_LAST;
   const int N = p.num_envs;
   const int TB = p.env_block, tid = threadIdx.x;
   const int role = tid / TB, le = tid - role * TB;
@@ -159,10 +161,16 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
     // thread k issues bulk copy k of the table; threads 32..59 one episode-sum column each; thread 0 arms the
     // barrier with the byte total (arrival order between the copies and the arm does not matter)
     // (the (TERMS, N) episode-sum columns start 16-byte aligned only when N is a multiple of 4)
+    // Chained launch: only `actions` and `torques` come from the substep kernels of this step; every other array is
+    // simulator state or was last written by the previous step, so its copy is issued before chain_wait().
     const bool sums_by_tma = (N & 3) == 0;
-    if (tid < POST_CHUNKS) {
+    const bool from_substeps = tid == C_ACT || tid == C_TORQUES;
+    auto issue = [&]() {
       tma_load_1d(T.base + (size_t)src.off[tid] * TB, static_cast<const char*>(src.ptr[tid]) + (size_t)e0 * src.rowb[tid],
                   (uint32_t)(TB * src.rowb[tid]), T.bar);
+    };
+    if (tid < POST_CHUNKS) {
+      if (!from_substeps) issue();
     } else if (sums_by_tma && tid >= 32 && tid < 32 + TI5_NUM_TERMS && (mask & (1u << (tid - 32)))) {
       const int t = tid - 32;
       tma_load_1d(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(TB * 4), T.bar);
@@ -174,8 +182,11 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
         if (mask & (1u << t)) coop_load(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(TB * 4));
       __syncthreads();
     }
+    chain_wait();                                         // the substep kernels are done
+    if (from_substeps) issue();
     mbar_wait(T.bar, 0);
   } else {      // partial last tile: byte counts need not be multiples of 16, copy word by word
+    chain_wait();
 #pragma unroll 1
     for (int k = 0; k < POST_CHUNKS; ++k)
       coop_load(T.base + (size_t)src.off[k] * TB, static_cast<const char*>(src.ptr[k]) + (size_t)e0 * src.rowb[k],
@@ -613,8 +624,8 @@ extern "C" int ti5_reset_bookkeeping(const Ti5Params* p, const Ti5Buffers* b, vo
   return ti5_check_launch("ti5_reset_bookkeeping");
 }
 
-extern "C" int ti5_post_physics(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, int push_last, void* stream) {
-  TI5_CHECK_ARGS(p && b && p->num_envs > 0);
+extern "C" int ti5_post_physics(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, int options, void* stream) {
+  TI5_CHECK_ARGS(p && b && p->num_envs > 0 && (options & ~3) == 0);
   TI5_CHECK_ARGS(p->env_block == 32 || p->env_block == 64 || p->env_block == 128);
   TI5_CHECK_ARGS(p->rng_mode == TI5_RNG_PHILOX || (r && r->cmd));
   TI5_CHECK_ARGS((p->term_mask & (1u << T_DOF_VEL_LIMITS)) == 0);   // the reference term reads a cfg field t1 lacks
@@ -631,6 +642,7 @@ extern "C" int ti5_post_physics(const Ti5Params* p, const Ti5Buffers* b, const T
     }
     configured = smem;
   }
-  post_physics_kernel<<<blocks, POST_ROLES * p->env_block, smem, (cudaStream_t)stream>>>(*p, *b, rr, src, push_last);
+  (void)ti5_launch(post_physics_kernel, dim3(blocks), dim3(POST_ROLES * p->env_block), smem, stream,
+                   (options & TI5_POST_CHAINED) != 0, *p, *b, rr, src, options);
   return ti5_check_launch("ti5_post_physics");
 }

@@ -23,11 +23,15 @@ __global__ void __launch_bounds__(256) begin_step_kernel(const __grid_constant__
 __global__ void __launch_bounds__(64)
 substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
                const __grid_constant__ Ti5Rng r, const float* __restrict__ actions_in, int k_push, int k_torque, int phases) {
+  chain_trigger();                                       // the next kernel of the step may become resident
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int N = p.num_envs;
   if (idx >= N * 3) return;
   const int e = idx / 3, gq = idx - e * 3, d0 = 4 * gq;
   const bool do_push = phases & TI5_SUB_PUSH, do_torque = phases & TI5_SUB_TORQUE;
+  // chained launch: this grid may run ahead of the previous substep; `actions` (stored by the first substep) is
+  // then read after chain_wait(), next to the lagged action row
+  const bool late_actions = (phases & TI5_SUB_CHAINED) && actions_in == nullptr;
   const bool rg = p.flags & TI5_F_RAND_GAINS, fric = p.flags & TI5_F_RAND_COULOMB, rt = p.flags & TI5_F_RAND_TORQUE;
   const bool lagged = p.flags & TI5_F_ADD_LAG, imu = do_push && (p.flags & TI5_F_ADD_IMU_LAG);
   auto ld4 = [&](const float* base_ptr) { return reinterpret_cast<const float4*>(base_ptr)[idx]; };
@@ -61,7 +65,7 @@ substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5B
                        clampf(a4.z, -p.clip_actions, p.clip_actions), clampf(a4.w, -p.clip_actions, p.clip_actions));
       reinterpret_cast<float4*>(b.actions)[idx] = a4;
       if (idx == 0) b.globals->n_listed = 0;
-    } else {
+    } else if (!late_actions) {
       a4 = ld4(b.actions);
     }
     off4 = ld4(b.motor_offsets);
@@ -73,12 +77,34 @@ substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5B
   const int64_t base = (step - 1) * p.decimation;        // pushes completed before this step
   const float q[4] = {s0.x, s0.z, s1.x, s1.z}, qd[4] = {s0.y, s0.w, s1.y, s1.w};
 
-  // ---- the one dependent load: the lagged action row (lr:1045) ---------------------------------------
+  // the Philox draw and the IMU arithmetic need nothing from the previous kernel either
+  if (do_torque && rt && p.rng_mode == TI5_RNG_PHILOX) u4 = philox_u4(p.seed, (uint64_t)step, S_TORQUE + k_torque, idx);
+  float imu_val[4] = {0.f, 0.f, 0.f, 0.f};
+  if (imu) {                                             // cat(base_ang_vel, base_euler_xyz), this thread's piece
+    const float bq[4] = {root[0], root[1], root[2], root[3]};
+    if (imu_piece == 0) {
+      const V3 w = quat_rotate_inverse(bq, V3{root[4], root[5], root[6]});
+      imu_val[0] = w.x; imu_val[1] = w.y; imu_val[2] = w.z;
+      imu_val[3] = euler_pitch(bq);
+    } else {
+      // roll and yaw are the same atan2 form on different quaternion products (lr:30-33, 41-44)
+      const float x = bq[0], y = bq[1], z = bq[2], w = bq[3];
+      const bool yaw = imu_piece == 2;
+      const float num = 2.0f * (yaw ? (w * z + x * y) : (w * x + y * z));
+      const float den = yaw ? (((w * w + x * x) - y * y) - z * z) : (((w * w - x * x) - y * y) + z * z);
+      imu_val[0] = wrap_angle(atan2f(num, den));
+    }
+  }
+
+  // ---- everything below depends on (or must not overtake) the previous kernel of the step -------------
+  chain_wait();
+  // the one dependent load: the lagged action row (lr:1045)
   float4* ring = reinterpret_cast<float4*>(b.act_ring);
   const int64_t jt = base + k_torque, jj = jt - lag;     // push index now / the one the controller sees
   float4 t4 = zero4;                                     // rows pushed before the env's last reset read as zero (lr:606)
   const bool need_ring = do_torque && lagged && lag > 0;
   if (need_ring && jj >= stamp && jj >= 0) t4 = ring[(size_t)ring_slot(jj, p.lag_len) * N * 3 + idx];
+  if (do_torque && late_actions) a4 = ld4(b.actions);
 
   if (do_push) {                                         // lr:412-434
     const int64_t j = base + k_push;
@@ -87,20 +113,13 @@ substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5B
       *reinterpret_cast<float4*>(row + d0) = make_float4(q[0], q[1], q[2], q[3]);
       *reinterpret_cast<float4*>(row + D + d0) = make_float4(qd[0], qd[1], qd[2], qd[3]);
     }
-    if (imu) {                                           // cat(base_ang_vel, base_euler_xyz)
-      const float bq[4] = {root[0], root[1], root[2], root[3]};
+    if (imu) {
       float* row = b.imu_ring + ((size_t)ring_slot(j, p.imu_lag_len) * N + imu_env) * 6;
       if (imu_piece == 0) {
-        const V3 w = quat_rotate_inverse(bq, V3{root[4], root[5], root[6]});
-        row[0] = w.x; row[1] = w.y; row[2] = w.z;
-        row[4] = euler_pitch(bq);
+        row[0] = imu_val[0]; row[1] = imu_val[1]; row[2] = imu_val[2];
+        row[4] = imu_val[3];
       } else {
-        // roll and yaw are the same atan2 form on different quaternion products (lr:30-33, 41-44)
-        const float x = bq[0], y = bq[1], z = bq[2], w = bq[3];
-        const bool yaw = imu_piece == 2;
-        const float num = 2.0f * (yaw ? (w * z + x * y) : (w * x + y * z));
-        const float den = yaw ? (((w * w + x * x) - y * y) - z * z) : (((w * w - x * x) - y * y) + z * z);
-        row[yaw ? 5 : 3] = wrap_angle(atan2f(num, den));
+        row[imu_piece == 2 ? 5 : 3] = imu_val[0];
       }
     }
   }
@@ -130,7 +149,6 @@ substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5B
       }
     }
     if (rt) {
-      if (p.rng_mode == TI5_RNG_PHILOX) u4 = philox_u4(p.seed, (uint64_t)step, S_TORQUE + k_torque, idx);
       const float u[4] = {u4.x, u4.y, u4.z, u4.w};
       float m[4];
 #pragma unroll
@@ -162,7 +180,7 @@ extern "C" int ti5_begin_step(const Ti5Params* p, const Ti5Buffers* b, const flo
 
 static int launch_substep(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, const float* actions_in, int k, int phases,
                           void* stream) {
-  TI5_CHECK_ARGS(p && b && p->num_envs > 0 && k >= 0 && k <= p->decimation && (phases & 3) != 0);
+  TI5_CHECK_ARGS(p && b && p->num_envs > 0 && k >= 0 && k <= p->decimation && (phases & 3) != 0 && (phases & ~7) == 0);
   TI5_CHECK_ARGS(!(phases & TI5_SUB_TORQUE) || k < p->decimation);
   TI5_CHECK_ARGS(!(phases & TI5_SUB_TORQUE) || p->rng_mode == TI5_RNG_PHILOX || !(p->flags & TI5_F_RAND_TORQUE) ||
                  (r && r->torque));
@@ -171,7 +189,8 @@ static int launch_substep(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng*
   // fused form: push the result of simulator substep k-1, then the torque of substep k
   const int k_push = (phases & TI5_SUB_TORQUE) ? k - 1 : k;
   TI5_CHECK_ARGS(!(phases & TI5_SUB_PUSH) || k_push >= 0);
-  substep_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(*p, *b, rr, actions_in, k_push, k, phases);
+  (void)ti5_launch(substep_kernel, dim3((n + 63) / 64), dim3(64), 0, stream, (phases & TI5_SUB_CHAINED) != 0, *p, *b, rr,
+                   actions_in, k_push, k, phases);
   return ti5_check_launch("ti5_substep");
 }
 

@@ -17,6 +17,7 @@ lag rings, mirrored observation rings); the reference-shaped views (`
 (lr:1239-1417) is out of scope: the simulator handle is anything with the gym tensor API.
 """
 import ctypes
+import os
 from types import SimpleNamespace
 
 import numpy as np
@@ -82,14 +83,17 @@ class EpisodeInfo(dict):
 
 class LeggedRobot(BaseTask):
     def __init__(self, cfg, sim_params, physics_engine, sim_device, headless, gym=None, rng_mode="philox",
-                 div_mode="reciprocal", use_cuda_graph=True, materialize_obs=False, seed=None):
+                 div_mode="reciprocal", use_cuda_graph=True, materialize_obs=False, seed=None, chain_launches=None):
         """Args as the reference (lr:57).  Extra keyword options:
         rng_mode        "philox" (in-kernel Philox4x32-10) or "pools" (uniforms supplied per step via
                         `set_rng_pools`, the parity mode of SURVEY.md section 7)
         div_mode        "reciprocal" = torch-on-GPU rounding of tensor/scalar, "ieee" = torch-on-CPU
         use_cuda_graph  capture the whole step into one CUDA graph (philox mode, synthetic sim only)
         materialize_obs return fresh contiguous (N, H*47) / (N, CH*P) tensors every step, as the reference does
-                        (t1:477-481), instead of views into the history rings that are valid until the next step"""
+                        (t1:477-481), instead of views into the history rings that are valid until the next step
+        chain_launches  launch the kernels of a fused step (no simulator in between) as programmatic dependents of one
+                        another: each becomes resident while its predecessor still runs and waits for it only where
+                        it needs its results (default on; env var TI5_CHAIN=0 turns it off)"""
         self.cfg = cfg
         self.sim_params = sim_params
         self.height_samples = None
@@ -100,6 +104,7 @@ class LeggedRobot(BaseTask):
         self._div_mode = C["TI5_DIV_RECIPROCAL"] if div_mode == "reciprocal" else C["TI5_DIV_IEEE"]
         self._use_graph = bool(use_cuda_graph) and rng_mode == "philox"
         self._materialize = bool(materialize_obs)
+        self._chain_launches = (os.environ.get("TI5_CHAIN", "1") != "0") if chain_launches is None else bool(chain_launches)
         self._seed = int(getattr(cfg, "seed", 0) if seed is None else seed)
         self._parse_cfg(self.cfg)
         super().__init__(self.cfg, sim_params, physics_engine, sim_device, headless, gym=gym)
@@ -516,6 +521,11 @@ class LeggedRobot(BaseTask):
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _chain(self, bit):
+        """The *_CHAINED launch option (programmatic dependent launch) for the kernels of a step that follow one
+        another on the stream with nothing in between."""
+        return C[bit] if self._chain_launches else 0
+
     def _launch_substeps(self, actions_ptr, with_physics):
         """lr:393-434: action clip, then DEC x (torque -> simulate -> lag push)."""
         lib, p, b, r, st = self._lib, self._p_ref, self._b_ref, self._rng_ref(), self._stream()
@@ -534,7 +544,7 @@ class LeggedRobot(BaseTask):
                 if k == 0:      # action clip fused into the first torque launch
                     _lib.check(lib.ti5_first_substep(p, b, r, actions_ptr, st))
                 else:
-                    _lib.check(lib.ti5_substep(p, b, r, k, C["TI5_SUB_TORQUE"] | C["TI5_SUB_PUSH"], st))
+                    _lib.check(lib.ti5_substep(p, b, r, k, C["TI5_SUB_TORQUE"] | C["TI5_SUB_PUSH"] | self._chain("TI5_SUB_CHAINED"), st))
 
     def _launch_post(self, with_physics):
         """lr:458-506 post_physics_step + the observation clip of lr:441-446."""
@@ -544,8 +554,9 @@ class LeggedRobot(BaseTask):
             self.gym.refresh_rigid_body_state_tensor(self.sim)
         if self._params.num_height_points:
             _lib.check(lib.ti5_sample_heights(p, b, st))
-        _lib.check(lib.ti5_post_physics(p, b, r, 0 if with_physics else 1, st))
-        _lib.check(lib.ti5_reset_observe(p, b, r, C["TI5_RO_RESET"] | C["TI5_RO_OBSERVE"], st))
+        fused = not with_physics
+        _lib.check(lib.ti5_post_physics(p, b, r, (C["TI5_POST_PUSH_LAST"] | self._chain("TI5_POST_CHAINED")) if fused else 0, st))
+        _lib.check(lib.ti5_reset_observe(p, b, r, C["TI5_RO_RESET"] | C["TI5_RO_OBSERVE"] | self._chain("TI5_RO_CHAINED"), st))
 
     def _materialize_windows(self):
         """lr:441-446 / t1:477-481: this step's windows as FRESH contiguous tensors (outside the captured graph: a
