@@ -224,8 +224,8 @@ __device__ __forceinline__ void chain_trigger() { asm volatile("griddepcontrol.l
 __device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // profiling aid: nanosecond timestamp probe `k` of this CTA (thread 0 only), when a probe buffer is bound
-__device__ __forceinline__ void probe(uint64_t* ts, int kernel, int k) {
-  if (ts != nullptr && threadIdx.x == 0) {
+__device__ __forceinline__ void probe(uint64_t* ts, int kernel, int k, int thread = 0) {
+  if (ts != nullptr && (int)threadIdx.x == thread) {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     ts[((size_t)kernel * 4096 + blockIdx.x) * 8 + k] = t;

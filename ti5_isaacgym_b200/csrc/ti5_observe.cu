@@ -110,12 +110,33 @@ __device__ __forceinline__ void reset_env_dofs(const Ti5Params& p, const Ti5Buff
   if (lane < TI5_NUM_TERMS && (p.term_mask & (1u << lane))) b.episode_sums[(size_t)lane * N + es] = 0.0f;   // t1:533
 }
 
+// Derived state of a re-spawned base (t1:548-552): base_init_state is the same for every env, so the rotations and
+// Euler angles of the spawn pose are computed once per CTA, before the grid wait.
+// Layout: quat(4) | base_lin_vel(3) | base_ang_vel(3) | projected_gravity(3) | euler(3)
+constexpr int SPAWN_FLOATS = 16;
+__device__ __forceinline__ void spawn_state(const Ti5Params& p, float* out) {
+  const float* r0 = p.base_init_state;
+  const float bq[4] = {r0[3], r0[4], r0[5], r0[6]};
+  const V3 l = quat_rotate_inverse(bq, V3{r0[7], r0[8], r0[9]});
+  const V3 a = quat_rotate_inverse(bq, V3{r0[10], r0[11], r0[12]});
+  const V3 gr = quat_rotate_inverse(bq, V3{0.0f, 0.0f, -1.0f});
+  float eul[3];
+  euler_xyz(bq, eul);
+  out[0] = bq[0]; out[1] = bq[1]; out[2] = bq[2]; out[3] = bq[3];
+  out[4] = l.x; out[5] = l.y; out[6] = l.z;
+  out[7] = a.x; out[8] = a.y; out[9] = a.z;
+  out[10] = gr.x; out[11] = gr.y; out[12] = gr.z;
+  out[13] = eul[0]; out[14] = eul[1]; out[15] = eul[2];
+}
+
 // The per-env scalar parts of the reset run on the env's own lane, so all flagged envs of a warp go in parallel.
-// Base (role 0): terrain curriculum, root state, derived base quantities.
-__device__ __forceinline__ void reset_env_base(const Ti5Params& p, const Ti5Buffers& b, const ObsRng& rng, int es) {
+// Base: terrain curriculum, root state, derived base quantities (`spawn`, above; `org` = the env's origin, loaded
+// before the grid wait).
+__device__ __forceinline__ void reset_env_base(const Ti5Params& p, const Ti5Buffers& b, const ObsRng& rng, int es,
+                                               const float* spawn, float org[3]) {
   float* root = b.root_states + (size_t)es * RB;
   if (p.flags & TI5_F_TERRAIN_CURRICULUM) {                        // lr:1138-1158
-    const float dx = root[0] - b.env_origins[es * 3 + 0], dy = root[1] - b.env_origins[es * 3 + 1];
+    const float dx = root[0] - org[0], dy = root[1] - org[1];
     const float dist = sqrtf(dx * dx + dy * dy);
     const bool up = dist > (float)(p.terrain_env_length / 2.0);
     const float cx = b.commands[es * 4 + 0], cy = b.commands[es * 4 + 1];
@@ -124,13 +145,14 @@ __device__ __forceinline__ void reset_env_base(const Ti5Params& p, const Ti5Buff
     lvl = lvl >= p.max_terrain_level ? rng.terrain_level(es) : (lvl < 0 ? 0 : lvl);
     b.terrain_levels[es] = lvl;
     const float* o = b.terrain_origins + ((size_t)lvl * p.terrain_cols + b.terrain_types[es]) * 3;
-    b.env_origins[es * 3 + 0] = o[0]; b.env_origins[es * 3 + 1] = o[1]; b.env_origins[es * 3 + 2] = o[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { org[i] = o[i]; b.env_origins[es * 3 + i] = org[i]; }
   }
   float r0[RB];                                                     // lr:1092-1120
 #pragma unroll
   for (int i = 0; i < RB; ++i) r0[i] = p.base_init_state[i];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) r0[i] += b.env_origins[es * 3 + i];
+  for (int i = 0; i < 3; ++i) r0[i] += org[i];
   if (p.flags & TI5_F_CUSTOM_ORIGINS) {
     r0[0] += affine(p.root_xy_w, p.root_xy_lo, rng.root_xy(es, 0));
     r0[1] += affine(p.root_xy_w, p.root_xy_lo, rng.root_xy(es, 1));
@@ -138,18 +160,14 @@ __device__ __forceinline__ void reset_env_base(const Ti5Params& p, const Ti5Buff
 #pragma unroll
   for (int i = 0; i < RB; ++i) root[i] = r0[i];
   // t1:548-552 derived state of the re-spawned base
-  const float bq[4] = {r0[3], r0[4], r0[5], r0[6]};
-  const V3 l = quat_rotate_inverse(bq, V3{r0[7], r0[8], r0[9]});
-  const V3 a = quat_rotate_inverse(bq, V3{r0[10], r0[11], r0[12]});
-  const V3 gr = quat_rotate_inverse(bq, V3{0.0f, 0.0f, -1.0f});
-  float eul[3];
-  euler_xyz(bq, eul);
-  reinterpret_cast<float4*>(b.base_quat)[es] = make_float4(bq[0], bq[1], bq[2], bq[3]);
-  b.base_lin_vel[es * 3 + 0] = l.x; b.base_lin_vel[es * 3 + 1] = l.y; b.base_lin_vel[es * 3 + 2] = l.z;
-  b.base_ang_vel[es * 3 + 0] = a.x; b.base_ang_vel[es * 3 + 1] = a.y; b.base_ang_vel[es * 3 + 2] = a.z;
-  b.projected_gravity[es * 3 + 0] = gr.x; b.projected_gravity[es * 3 + 1] = gr.y; b.projected_gravity[es * 3 + 2] = gr.z;
+  reinterpret_cast<float4*>(b.base_quat)[es] = make_float4(spawn[0], spawn[1], spawn[2], spawn[3]);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) b.base_euler_xyz[es * 3 + i] = eul[i];
+  for (int i = 0; i < 3; ++i) {
+    b.base_lin_vel[es * 3 + i] = spawn[4 + i];
+    b.base_ang_vel[es * 3 + i] = spawn[7 + i];
+    b.projected_gravity[es * 3 + i] = spawn[10 + i];
+    b.base_euler_xyz[es * 3 + i] = spawn[13 + i];
+  }
 #pragma unroll
   for (int i = 0; i < 6; ++i) b.last_root_vel[es * 6 + i] = 0.0f;
 }
@@ -188,10 +206,12 @@ __device__ __forceinline__ void reset_env_schedule(const Ti5Params& p, const Ti5
 // 47-float observation frame (lagged proprioception, noise) and appends it to the observation ring, role 1
 // builds the privileged frame and appends it to the critic ring — two independent halves of one thread's
 // former instruction chain.  Role 0 warps also run the reset scatter first.
-constexpr int OBS_ROLES = 2;
+// Up to OBS_WRITERS further warps per 32 envs ("roles" 2, 3) build nothing: they draw no frame, but share the ring
+// writes — a frame set is 240 scalar stores per warp, the longest single-warp stretch of the kernel.
+constexpr int OBS_ROLES = 2, OBS_WRITERS = 2;
 
 template <int KC, int PC>
-__global__ void __launch_bounds__(OBS_ROLES * 128)
+__global__ void __launch_bounds__(256)
 reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
                      const __grid_constant__ Ti5Rng r, int phases) {
   extern __shared__ float smem[];      // per 32 envs: 32 x K observation frames, then 32 x P privileged frames
@@ -206,7 +226,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
   const int e = blockIdx.x * TB + le;
   const int lane = tid & 31, warp = tid >> 5, tile_warp = le >> 5;
   const int env_blocks = (N + TB - 1) / TB;              // CTAs beyond these only help clearing histories
-  const bool live = e < N && blockIdx.x < env_blocks;
+  const bool live = e < N && blockIdx.x < env_blocks && role < OBS_ROLES;
   Ti5Globals* g = b.globals;
   // index of the step in progress: published by ti5_post_physics / ti5_reset_bookkeeping; a chained launch may not
   // read what its predecessor writes yet and is always part of a full step
@@ -227,6 +247,15 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
   float* s_priv = s_obs + 32 * Kp;
   // t1:471-472 observation noise: needs nothing from the other kernels of the step, so a chained launch draws it
   // while ti5_post_physics is still running; it waits in the env's frame slot for the values to be added to it
+  __shared__ float s_spawn[SPAWN_FLOATS];
+  float org[3] = {0.0f, 0.0f, 0.0f};                     // the env's origin: rewritten only by this env's own reset
+  if (do_reset) {
+    if (tid == (int)blockDim.x - 1) spawn_state(p, s_spawn);       // an otherwise idle role-1 thread
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) org[i] = b.env_origins[e * 3 + i];
+    }
+  }
   const bool noisy = do_obs && (p.flags & TI5_F_ADD_NOISE);
   if (noisy && live && role == 0) {
     float* oo = s_obs + lane * Kp;
@@ -303,8 +332,8 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
   probe(b.debug_ts, 1, 0);
 
   // =========================== reset scatter (t1:483-559) ==============================================
-  // role 0: the DOF-parallel part, one flagged env at a time with all lanes, then the base on the env's own lane;
-  // role 1 (otherwise idle here): the schedule on the env's own lane.  Flagged envs of a warp go in parallel.
+  // role 0: the DOF-parallel part, one flagged env at a time with all lanes; role 1 (otherwise idle here): the
+  // schedule and the base on the env's own lane.  Flagged envs of a warp go in parallel.
   if (role == 0) {
     unsigned todo = __ballot_sync(0xffffffffu, reset);
     const int env0 = blockIdx.x * TB + tile_warp * 32;
@@ -313,9 +342,10 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
       todo &= todo - 1;
       reset_env_dofs(p, b, rng, env0 + src, lane);
     }
-    if (reset) reset_env_base(p, b, rng, e);
-  } else if (flagged) {
+    probe(b.debug_ts, 1, 6);
+  } else if (role == 1 && flagged) {
     reset_env_schedule(p, b, rng, e, pushes);
+    reset_env_base(p, b, rng, e, s_spawn, org);
   }
   probe(b.debug_ts, 1, 1);
   __syncthreads();       // role 1 reads what the scatter wrote
@@ -517,31 +547,38 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
   const size_t obs_row = (size_t)2 * H * K, priv_row = (size_t)2 * CH * P;
   const int warp_env0 = blockIdx.x * TB + tile_warp * 32;
   const int hs = (int)((step - 1) % H), cs = (int)((step - 1) % CH);       // slot of this step's frame
-  __syncwarp();
+  __syncthreads();       // both frames of every env of the CTA are staged
+  probe(b.debug_ts, 1, 7);
   if (do_obs && blockIdx.x < env_blocks && warp_env0 < N) {
     const int n_here = min(32, N - warp_env0);
     const float lim = p.clip_obs;
     const int L = p.log_len, ls = L > 0 ? (int)((step - 1) % L) : 0;      // frame-log row of this step
-    if (role == 0) {
-#pragma unroll 4
-      for (int i = lane; i < n_here * K; i += 32) {
-        const int en = i / K, k = i - en * K;
-        const float v = clampf(s_obs[en * Kp + k], -lim, lim);
-        float* rowp = b.obs_ring + (size_t)(warp_env0 + en) * obs_row;
-        rowp[(size_t)hs * K + k] = v;
-        rowp[(size_t)(hs + H) * K + k] = v;
-        if (L > 0) b.frame_log[((size_t)(warp_env0 + en) * L + ls) * K + k] = v;
-      }
-    } else {
-#pragma unroll 4
-      for (int i = lane; i < n_here * P; i += 32) {
-        const int en = i / P, k = i - en * P;
-        const float v = clampf(s_priv[en * Pp + k], -lim, lim);
-        float* rowp = b.priv_ring + (size_t)(warp_env0 + en) * priv_row;
-        rowp[(size_t)cs * P + k] = v;
-        rowp[(size_t)(cs + CH) * P + k] = v;
-        if (L > 0) b.priv_log[((size_t)(warp_env0 + en) * L + ls) * P + k] = v;
-      }
+    // the tile's warps (frame builders and writers alike) stride over the staged obs elements, then the priv ones;
+    // small loop bodies on purpose (32-bit offsets from a uniform base, no unrolling): this is the stretch of the
+    // kernel with the most instructions per warp, and it is bound by instruction fetch / issue, not by memory
+    const int n_obs = n_here * K, n_priv = n_here * P, stride = (int)(blockDim.x / TB) * 32;
+    const uint32_t orow = (uint32_t)obs_row, prow = (uint32_t)priv_row, omir = (uint32_t)(H * K), pmir = (uint32_t)(CH * P);
+    float* ob = b.obs_ring + (size_t)warp_env0 * obs_row + (size_t)hs * K;
+    float* pb = b.priv_ring + (size_t)warp_env0 * priv_row + (size_t)cs * P;
+    float* ol = L > 0 ? b.frame_log + ((size_t)warp_env0 * L + ls) * K : nullptr;
+    float* pl = L > 0 ? b.priv_log + ((size_t)warp_env0 * L + ls) * P : nullptr;
+#pragma unroll 1
+    for (int i = role * 32 + lane; i < n_obs; i += stride) {
+      const int en = i / K, k = i - en * K;
+      const float v = clampf(s_obs[en * Kp + k], -lim, lim);
+      float* dst = ob + (uint32_t)en * orow + (uint32_t)k;
+      dst[0] = v;
+      dst[omir] = v;
+      if (L > 0) ol[(uint32_t)en * (uint32_t)(L * K) + (uint32_t)k] = v;
+    }
+#pragma unroll 1
+    for (int i = role * 32 + lane; i < n_priv; i += stride) {
+      const int en = i / P, k = i - en * P;
+      const float v = clampf(s_priv[en * Pp + k], -lim, lim);
+      float* dst = pb + (uint32_t)en * prow + (uint32_t)k;
+      dst[0] = v;
+      dst[pmir] = v;
+      if (L > 0) pl[(uint32_t)en * (uint32_t)(L * P) + (uint32_t)k] = v;
     }
   }
   // frames of the env's window that no reset has cleared: 0 after reset_idx, +1 per appended frame
@@ -718,10 +755,13 @@ extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const 
     cudaGetLastError();
     return TI5_ECUDA;
   }
+  ti5_set_carveout(kernel);
   // + helper CTAs (about 4 warps per SM) that only share the history-clear work of re-spawned envs
-  const int helpers = (phases & TI5_RO_RESET) ? (148 * 4 * 32) / (OBS_ROLES * p->env_block) : 0;
-  (void)ti5_launch(kernel, dim3(blocks + helpers), dim3(OBS_ROLES * p->env_block), smem, stream, (phases & TI5_RO_CHAINED) != 0,
-                   *p, *b, rr, phases);
+  // writer warps only for the small-grid case (env_block 32): from 16384 envs on the SMs are full of frame builders and
+  // idle writers would only take their registers
+  const int threads = (OBS_ROLES + (p->env_block == 32 ? OBS_WRITERS : 0)) * p->env_block;   // <= 256
+  const int helpers = (phases & TI5_RO_RESET) ? (148 * 4 * 32) / threads : 0;
+  (void)ti5_launch(kernel, dim3(blocks + helpers), dim3(threads), smem, stream, (phases & TI5_RO_CHAINED) != 0, *p, *b, rr, phases);
   return ti5_check_launch("ti5_reset_observe");
 }
 

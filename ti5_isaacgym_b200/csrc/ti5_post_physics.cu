@@ -175,16 +175,15 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       const int t = tid - 32;
       tma_load_1d(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(TB * 4), T.bar);
     }
-    if (tid == 0) mbar_expect_tx(T.bar, (uint32_t)TB * (uint32_t)(src.off[POST_CHUNKS] + (sums_by_tma ? 4 * __popc(mask) : 0)));
+    if (tid == 0)
+      mbar_expect_tx(T.bar, (uint32_t)TB * (uint32_t)(src.off[POST_CHUNKS] + (sums_by_tma ? 4 * __popc(mask) : 0)));
     if (!sums_by_tma) {
 #pragma unroll 1
       for (int t = 0; t < TI5_NUM_TERMS; ++t)
         if (mask & (1u << t)) coop_load(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(TB * 4));
-      __syncthreads();
     }
     chain_wait();                                         // the substep kernels are done
     if (from_substeps) issue();
-    mbar_wait(T.bar, 0);
   } else {      // partial last tile: byte counts need not be multiples of 16, copy word by word
     chain_wait();
 #pragma unroll 1
@@ -194,8 +193,9 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
 #pragma unroll 1
     for (int t = 0; t < TI5_NUM_TERMS; ++t)
       if (mask & (1u << t)) coop_load(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(n_tile * 4));
-    __syncthreads();
   }
+  __syncthreads();
+  if (n_tile == TB) mbar_wait(T.bar, 0);
   // typed views of the tile
   const float* t_root = T.at<float>(C_ROOT);
   const float* t_dof = T.at<float>(C_DOF);
@@ -562,21 +562,31 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
     }
   }
   probe(b.debug_ts, 0, 2);
+  probe(b.debug_ts, 0, 6, TB);          // role 1 done
+  probe(b.debug_ts, 0, 7, 2 * TB);      // role 2 done
   __syncthreads();
   probe(b.debug_ts, 0, 3);
 
   // ---- lr:654-680: reward sum in alphabetical term order, per-term episode sums, clip at zero -----------
+  // The per-term episode sums are independent of one another: roles 1 and 2 take every other term while role 0
+  // runs the ordered sum (the scaled term is recomputed there: same product, same bits).
+  if (live && role > 0) {
+#pragma unroll 1
+    for (int t = role - 1; t < TI5_NUM_TERMS; t += POST_ROLES - 1) {
+      if (!(mask & (1u << t)) || t == T_TERMINATION) continue;
+      const float sc = T.vals[t * TB + le] * p.reward_scale[t];
+      const float acc = T.sums[t * TB + le] + sc;
+      T.sums[t * TB + le] = acc;
+      b.episode_sums[(size_t)t * N + e] = acc;
+      if (b.reward_terms) b.reward_terms[(size_t)t * N + e] = sc;
+    }
+  }
   if (live && role == 0) {
     float rew = 0.0f;
 #pragma unroll 1
     for (int t = 0; t < TI5_NUM_TERMS; ++t) {
       if (!(mask & (1u << t)) || t == T_TERMINATION) continue;
-      const float sc = T.vals[t * TB + le] * p.reward_scale[t];
-      rew += sc;
-      const float acc = T.sums[t * TB + le] + sc;
-      T.sums[t * TB + le] = acc;
-      b.episode_sums[(size_t)t * N + e] = acc;
-      if (b.reward_terms) b.reward_terms[(size_t)t * N + e] = sc;
+      rew += T.vals[t * TB + le] * p.reward_scale[t];
     }
     if ((p.flags & TI5_F_ONLY_POSITIVE) && rew < 0.0f) rew = 0.0f;     // clip(min=0); NaN passes
     if (mask & (1u << T_TERMINATION)) {                   // lr:677-680, t1:894-896: added after the clip
@@ -641,6 +651,7 @@ extern "C" int ti5_post_physics(const Ti5Params* p, const Ti5Buffers* b, const T
       return TI5_ECUDA;
     }
     configured = smem;
+    ti5_set_carveout(post_physics_kernel);
   }
   (void)ti5_launch(post_physics_kernel, dim3(blocks), dim3(POST_ROLES * p->env_block), smem, stream,
                    (options & TI5_POST_CHAINED) != 0, *p, *b, rr, src, options);

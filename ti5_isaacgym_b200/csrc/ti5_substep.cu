@@ -5,6 +5,8 @@
 // dof_state as two float4 per thread.  The reference shifts its (N,12,31)/(N,24,31)/(N,6,11)
 // lag buffers by a full clone every substep (17.9 KB/env); here they are slot-major rings
 // (len, N, width): a push is one coalesced row-block write, a lagged read a 48-byte gather.
+#include <cstdlib>
+
 #include "ti5_device.cuh"
 #include "ti5_host.h"
 
@@ -20,7 +22,7 @@ __global__ void __launch_bounds__(256) begin_step_kernel(const __grid_constant__
 
 // One thread per (env, group of four DOFs): every per-DOF array moves as one float4 per thread, the
 // interleaved dof_state as two, and one Philox call yields the four motor-strength multipliers.
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(256)
 substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
                const __grid_constant__ Ti5Rng r, const float* __restrict__ actions_in, int k_push, int k_torque, int phases) {
   chain_trigger();                                       // the next kernel of the step may become resident
@@ -189,7 +191,10 @@ static int launch_substep(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng*
   // fused form: push the result of simulator substep k-1, then the torque of substep k
   const int k_push = (phases & TI5_SUB_TORQUE) ? k - 1 : k;
   TI5_CHECK_ARGS(!(phases & TI5_SUB_PUSH) || k_push >= 0);
-  (void)ti5_launch(substep_kernel, dim3((n + 63) / 64), dim3(64), 0, stream, (phases & TI5_SUB_CHAINED) != 0, *p, *b, rr,
+  static const int block = getenv("TI5_SUBSTEP_BLOCK") ? atoi(getenv("TI5_SUBSTEP_BLOCK")) : 64;
+  static const bool once = (ti5_set_carveout(substep_kernel), true);
+  (void)once;
+  (void)ti5_launch(substep_kernel, dim3((n + block - 1) / block), dim3(block), 0, stream, (phases & TI5_SUB_CHAINED) != 0, *p, *b, rr,
                    actions_in, k_push, k, phases);
   return ti5_check_launch("ti5_substep");
 }

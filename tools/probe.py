@@ -16,11 +16,13 @@ env._debug_ts = torch.zeros(3, 4096, 8, dtype=torch.int64, device='cuda')
 env._bind_buffers(); env._graph = None
 act = synthetic_actions(N, gen, 'cuda')
 flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+NOFLUSH = os.environ.get('NOFLUSH') == '1'
 for i in range(20):
-    flush.fill_(i); env.step(act)
+    if not NOFLUSH: flush.fill_(i)
+    env.step(act)
 torch.cuda.synchronize()
 ts = env._debug_ts.cpu().double()
-for kern, name, nprobe in ((0, 'post_physics', 7), (1, 'reset_observe', 6)):
+for kern, name, nprobe in ((0, 'post_physics', 8), (1, 'reset_observe', 8)):
     t = ts[kern]
     used = t[:, 0] > 0
     t = t[used]
@@ -29,5 +31,16 @@ for kern, name, nprobe in ((0, 'post_physics', 7), (1, 'reset_observe', 6)):
     for k in range(nprobe):
         col = t[:, k]; col = col[col > 0]
         if len(col): print('  probe %d: n=%4d  min %7.2f  median %7.2f  max %7.2f us' % (k, len(col), (col.min()-t0)/1e3, (col.median()-t0)/1e3, (col.max()-t0)/1e3))
+# reset_observe by CTA class: env CTAs holding a re-spawned env, the other env CTAs, helper CTAs
+counts = env._block_counts.cpu()[:(N + env._params.env_block - 1) // env._params.env_block]
+t = ts[1]
+nb = len(counts)
+t0 = t[:, 0][t[:, 0] > 0].min()
+for label, rows in (("env CTAs with a reset", (counts > 0).nonzero().flatten()), ("env CTAs without", (counts == 0).nonzero().flatten()),
+                    ("helper CTAs", torch.arange(nb, int((t[:, 0] > 0).sum())))):
+    print(label, len(rows))
+    for k in (0, 6, 1, 2, 3, 7, 4, 5):
+        col = t[rows, k]; col = col[col > 0]
+        if len(col): print('  probe %d: median %7.2f  max %7.2f us' % (k, (col.median()-t0)/1e3, (col.max()-t0)/1e3))
 b1_end = ts[0][:, 5].max(); b2_start = ts[1][:, 0][ts[1][:, 0] > 0].min()
 print('gap B1 end -> B2 start: %.2f us' % ((b2_start - b1_end) / 1e3))
