@@ -314,6 +314,10 @@ def cuda_arm(args):
             torch_gpu = {"value": v, "unit": "env-steps/s", "ms_per_step": ms,
                          "sample": f"24 steps x {N} envs of the oracle port in eager torch on the same B200"}
         rollout = rollout_bench(env, gen, actions) if world == 1 and not args.no_rollout and not args.materialize else None
+        sweep = None
+        if world == 1 and not args.no_sweep and N == ENVS_PER_GPU and not args.materialize:
+            del flush
+            sweep = [sweep_point(n, dev) for n in (1024, 16384, 65536)]
         line = {
             "metric": "env-steps/sec (step math + reward + obs)", "value": value, "unit": "env-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
@@ -322,7 +326,8 @@ def cuda_arm(args):
                        "envs_per_gpu": N, "frame_stack": cfg.env.frame_stack, "obs": "materialised" if args.materialize else "ring view",
                        "rng": "in-kernel Philox4x32-10", "physics": "no-op (synthetic state, SURVEY 8d)",
                        "l2": "flushed between timed steps (256 MiB write outside the event brackets)",
-                       "launch": f"one CUDA graph per step ({env.launches_per_step} kernels)"},
+                       "launch": f"one CUDA graph per step ({env.launches_per_step} kernels"
+                                 + (", programmatic dependent launches)" if env._chain_launches else ")")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h_act.numel() * 4 * world,
                     "d2h_bytes_per_step": h_out.numel() * world,
@@ -337,10 +342,61 @@ def cuda_arm(args):
             "cpu_baseline": cpu,
             "reference_torch_gpu": torch_gpu,
             "rollout_storage": rollout,
+            "sweep": sweep,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def sweep_point(N, dev, steps=48, warmup=12):
+    """One point of BASELINE config 5 (num_envs sweep): the same device-timed step (L2 flushed before every step, GAE
+    every 24th) and per-phase graph timing as the main line, on a fresh env of N envs."""
+    from ti5_isaacgym_b200.algo.rollout_storage import gae_returns_, make_gae_scratch
+    from ti5_isaacgym_b200.envs import T1DHStandEnv
+    from ti5_isaacgym_b200.sim.synthetic import SimParams, fill_synthetic_state, synthetic_actions
+    cfg = make_cfg(N)
+    env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, dev, True, rng_mode="philox", div_mode="reciprocal", use_cuda_graph=True)
+    gen = torch.Generator(device=dev).manual_seed(4321)
+    fill_synthetic_state(env.gym.tensors, env.env_origins, gen)
+    env.reset()
+    env.episode_length_buf = torch.randint(1, 2000, (N,), generator=gen, device=dev)
+    actions = synthetic_actions(N, gen, dev)
+    T = ROLLOUT
+    rew = torch.randn(T, N, 1, generator=gen, device=dev)
+    val = torch.randn(T, N, 1, generator=gen, device=dev)
+    done = (torch.rand(T, N, 1, generator=gen, device=dev) < 0.02).byte()
+    last = torch.randn(N, 1, generator=gen, device=dev)
+    ret, adv = torch.empty_like(rew), torch.empty_like(rew)
+    scratch = make_gae_scratch(N, dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def one(i):
+        env.step(actions)
+        if (i + 1) % T == 0:
+            gae_returns_(rew, val, done, last, ret, adv, GAMMA, LAM, scratch, None)
+    for i in range(warmup):
+        one(i)
+    marks = []
+    for i in range(steps):
+        flush.fill_(i & 0xFF)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); one(i); b.record()
+        marks.append((a, b))
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in marks) / steps
+    kt = kernel_times(env, actions, steps=24)
+    peak, _ = peaks()
+    sub_ms = kt["substep"]["ms_per_launch"]
+    out = {"envs_per_gpu": N, "value": N / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms,
+           "substep": {"ms_per_launch": sub_ms, "achieved": BYTES_SUBSTEP * N / (sub_ms * 1e-3) / 1e9,
+                       "frac": BYTES_SUBSTEP * N / (sub_ms * 1e-3) / 1e9 / peak},
+           "post_phase_ms": kt["post_physics+reset_observe"]["phase_ms"],
+           "whole_step": {"bytes": BYTES_ENV_STEP * N, "achieved": BYTES_ENV_STEP * N / (ms * 1e-3) / 1e9,
+                          "frac": BYTES_ENV_STEP * N / (ms * 1e-3) / 1e9 / peak}}
+    del env, flush
+    torch.cuda.empty_cache()
+    return out
 
 
 def rollout_bench(env, gen, actions):
@@ -467,6 +523,7 @@ def main():
     ap.add_argument("--materialize", action="store_true", help="also write contiguous (N,3102)/(N,219) observations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rollout", action="store_true", help="skip the rollout-storage measurement (SURVEY 8f rows 1-2)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the num_envs sweep points (BASELINE config 5)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

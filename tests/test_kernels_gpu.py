@@ -106,6 +106,36 @@ def test_graph_replay_equals_direct_launches_and_history_layout():
     assert g.step_index == b.sync_from_device().step_index
 
 
+@pytest.mark.parametrize("N,graph", [(8192, True), (1000, False), (16384, True)])
+def test_chained_launches_equal_plain_launches(N, graph):
+    """Programmatic dependent launches (TI5_*_CHAINED) only move work in front of the grid wait: every output and
+    every piece of state must be bit-identical to ordinary stream-ordered launches, resets included."""
+    from ti5_isaacgym_b200.sim.synthetic import synthetic_actions
+    torch.manual_seed(0)                                    # friction / mass draws at construction
+    a, gen = _production_env(N, use_cuda_graph=graph, chain_launches=True)
+    torch.manual_seed(0)
+    b, _ = _production_env(N, use_cuda_graph=graph, chain_launches=False)
+    a.reset(), b.reset()
+    ep = torch.randint(1, 2400, (N,), generator=gen, device="cuda")
+    ep[:8] = 2399                                           # time-outs in the first steps
+    a.episode_length_buf, b.episode_length_buf = ep.clone(), ep.clone()
+    n_reset = 0
+    for t in range(40):
+        act = synthetic_actions(N, gen, "cuda")
+        oa, pa, ra, da, _ = a.step(act)
+        ob, pb, rb, db, _ = b.step(act)
+        exact(da, db, f"step {t}: resets")
+        exact(ra, rb, f"step {t}: rewards")
+        exact(oa, ob, f"step {t}: obs")
+        exact(pa, pb, f"step {t}: privileged obs")
+        n_reset += int(da.sum())
+    assert n_reset > 0
+    for name in ("torques", "commands", "episode_length_buf", "dof_state", "root_states", "last_actions", "feet_air_time",
+                 "base_lin_vel", "base_euler_xyz", "lag_buffer", "dof_lag_buffer", "imu_lag_buffer"):
+        exact(getattr(a, name), getattr(b, name), f"state after 40 steps: {name}")
+    exact(a._episode_sums, b._episode_sums, "episode sums")
+
+
 def test_full_size_properties_8192():
     """BASELINE size: properties that need no oracle."""
     from ti5_isaacgym_b200.sim.synthetic import synthetic_actions
