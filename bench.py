@@ -41,11 +41,12 @@ BYTES_ENV_STEP = 10 * BYTES_SUBSTEP + BYTES_POST
 
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel family, from the committed
-    `ncu --set full` capture of this same command (profiles/r01_ncu_full_summary_8192.json); None if absent."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_full_summary_8192.json")
+    `ncu --set full` capture of this same command (profiles/r01b_ncu_full_summary_8192.json); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r01b_ncu_full_summary_8192.json")
     if not os.path.exists(path):
         return None
-    key = {"substep": "substep_kernel", "post_physics+reset_observe": "post_physics_kernel"}[kernel]
+    key = {"substep": "substep_kernel", "post_physics": "post_physics_kernel",
+           "reset_observe": "void reset_observe_kernel<47, 73>"}[kernel]
     rows = json.load(open(path)).get(key)
     if not rows:
         return None
@@ -177,6 +178,11 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 for N > 1: the CPU arm runs alone on rank 0 and takes every host core it may use
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, RuntimeError):
+        pass
     cores = torch.get_num_threads()
     # bounded sample: the whole run should end within ~2 minutes on the host cores (~30 us per env-step with all
     # threads), so large --steps shrink the number of envs stepped per step (never below 256, at most the workload's 8192)
@@ -300,7 +306,7 @@ def cuda_arm(args):
         dom = max(kt, key=lambda k: kt[k]["share_ms"])
         # algorithmic bytes of one launch of the dominant family (SURVEY 8d figure x envs per launch);
         # the post phase's 2412 B/env are spread over its two launches
-        bytes_per_launch = {"substep": BYTES_SUBSTEP * N, "post_physics+reset_observe": BYTES_POST * N / 2}[dom]
+        bytes_per_launch = KERNEL_BYTES[dom] * N
         ach = bytes_per_launch / (kt[dom]["ms_per_launch"] * 1e-3) / 1e9
         launches_per_step = env.launches_per_step
         cpu = torch_gpu = None
@@ -338,7 +344,7 @@ def cuda_arm(args):
                          "ms_per_launch": kt[dom]["ms_per_launch"],
                          "whole_step": {"bytes": BYTES_ENV_STEP * N, "achieved": BYTES_ENV_STEP * N * args.steps / (dev_ms * 1e-3) / 1e9},
                          "kernels": kt,
-                         "how": "CUDA events on the launching stream around one CUDA graph per phase (L2 flushed before each step); per-launch = phase time / launches in the phase"},
+                         "how": "CUDA events on the launching stream around one CUDA graph per kernel family (L2 flushed before each step); per-launch = family time / launches in the family; algorithmic bytes = SURVEY 8d per-env figure x envs (post phase split over its two kernels, see bench.py)"},
             "cpu_baseline": cpu,
             "reference_torch_gpu": torch_gpu,
             "rollout_storage": rollout,
@@ -391,7 +397,7 @@ def sweep_point(N, dev, steps=48, warmup=12):
     out = {"envs_per_gpu": N, "value": N / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms,
            "substep": {"ms_per_launch": sub_ms, "achieved": BYTES_SUBSTEP * N / (sub_ms * 1e-3) / 1e9,
                        "frac": BYTES_SUBSTEP * N / (sub_ms * 1e-3) / 1e9 / peak},
-           "post_phase_ms": kt["post_physics+reset_observe"]["phase_ms"],
+           "post_physics_ms": kt["post_physics"]["phase_ms"], "reset_observe_ms": kt["reset_observe"]["phase_ms"],
            "whole_step": {"bytes": BYTES_ENV_STEP * N, "achieved": BYTES_ENV_STEP * N / (ms * 1e-3) / 1e9,
                           "frac": BYTES_ENV_STEP * N / (ms * 1e-3) / 1e9 / peak}}
     del env, flush
@@ -479,37 +485,53 @@ def rollout_bench(env, gen, actions):
     }
 
 
+# SURVEY 8(d) row B (2412 B per env-step for the whole post phase) split over its two kernels: ti5_post_physics reads
+# every input of the phase once (922 B) and writes the derived state, counters, reward and episode sums (266 B);
+# ti5_reset_observe writes both frames into both mirrored ring slots (960 B), the last_* copies and the reference
+# pose (264 B) — its re-reads of what ti5_post_physics produced are not counted.
+BYTES_POST_PHYSICS = 922 + 266
+BYTES_RESET_OBSERVE = BYTES_POST - BYTES_POST_PHYSICS
+KERNEL_BYTES = {"substep": BYTES_SUBSTEP, "post_physics": BYTES_POST_PHYSICS, "reset_observe": BYTES_RESET_OBSERVE}
+
+
 def kernel_times(env, actions, steps):
-    """Average device time of the two phases of a step, CUDA events on the launching stream around
-    the replay of one CUDA graph per phase (a single whole-step graph cannot be bracketed inside).
-    The substep phase is DEC launches of the fused substep kernel (the action clip rides in the first); its
-    per-launch time is phase time / DEC.  The post phase is post_physics + reset_observe (2 launches)."""
-    g_sub, g_post = env.capture_phase_graphs()
+    """Average device time of the three kernel families of a step, CUDA events on the launching stream around
+    the replay of one CUDA graph per family (a single whole-step graph cannot be bracketed inside; the event
+    records also cut the programmatic launch chain at the two family boundaries, so the three times add up to
+    a little more than the whole-step time).  The substep family is DEC launches of the fused substep kernel
+    (the action clip rides in the first); its per-launch time is family time / DEC."""
+    g_sub, g_post, g_obs = env.capture_phase_graphs()
     dec = env._params.decimation
     ev = lambda: torch.cuda.Event(enable_timing=True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=env.device)
     env._actions_in.copy_(actions)
-    acc = {"substep": [], "post_physics+reset_observe": []}
+    names = ("substep", "post_physics", "reset_observe")
+    acc = {n: [] for n in names}
     marks = []
     for i in range(steps):
         flush.fill_(i & 0xFF)
-        e0, e1, e2 = ev(), ev(), ev()
-        e0.record()
+        e = [ev() for _ in range(4)]
+        e[0].record()
         g_sub.replay()
-        e1.record()
+        e[1].record()
         g_post.replay()
-        e2.record()
+        e[2].record()
+        g_obs.replay()
+        e[3].record()
         env._finish_step()
-        marks.append((e0, e1, e2))
+        marks.append(e)
     torch.cuda.synchronize()
-    for e0, e1, e2 in marks:
-        acc["substep"].append(e0.elapsed_time(e1))
-        acc["post_physics+reset_observe"].append(e1.elapsed_time(e2))
+    for e in marks:
+        for k, n in enumerate(names):
+            acc[n].append(e[k].elapsed_time(e[k + 1]))
     out = {}
     for name, v in acc.items():
-        n = dec if name == "substep" else 2
+        n = dec if name == "substep" else 1
         phase = statistics.mean(v)
-        out[name] = {"phase_ms": phase, "launches": n, "ms_per_launch": phase / n, "share_ms": phase}
+        out[name] = {"phase_ms": phase, "launches": n, "ms_per_launch": phase / n, "share_ms": phase,
+                     "bytes_per_launch": KERNEL_BYTES[name] * env.num_envs,
+                     "achieved_GBps": KERNEL_BYTES[name] * env.num_envs / (phase / n * 1e-3) / 1e9}
+    del flush
     return out
 
 

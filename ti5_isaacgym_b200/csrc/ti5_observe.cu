@@ -210,8 +210,11 @@ __device__ __forceinline__ void reset_env_schedule(const Ti5Params& p, const Ti5
 // writes — a frame set is 240 scalar stores per warp, the longest single-warp stretch of the kernel.
 constexpr int OBS_ROLES = 2, OBS_WRITERS = 2;
 
+#ifndef TI5_OBS_MINBLOCKS
+#define TI5_OBS_MINBLOCKS 1
+#endif
 template <int KC, int PC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, TI5_OBS_MINBLOCKS)
 reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
                      const __grid_constant__ Ti5Rng r, int phases) {
   extern __shared__ float smem[];      // per 32 envs: 32 x K observation frames, then 32 x P privileged frames

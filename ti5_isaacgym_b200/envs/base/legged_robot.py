@@ -546,17 +546,20 @@ class LeggedRobot(BaseTask):
                 else:
                     _lib.check(lib.ti5_substep(p, b, r, k, C["TI5_SUB_TORQUE"] | C["TI5_SUB_PUSH"] | self._chain("TI5_SUB_CHAINED"), st))
 
-    def _launch_post(self, with_physics):
-        """lr:458-506 post_physics_step + the observation clip of lr:441-446."""
+    def _launch_post(self, with_physics, part=3):
+        """lr:458-506 post_physics_step + the observation clip of lr:441-446.  `part`: 1 = ti5_post_physics only,
+        2 = ti5_reset_observe only (per-kernel timing), 3 = both."""
         lib, p, b, r, st = self._lib, self._p_ref, self._b_ref, self._rng_ref(), self._stream()
-        if with_physics:
-            self.gym.refresh_net_contact_force_tensor(self.sim)
-            self.gym.refresh_rigid_body_state_tensor(self.sim)
-        if self._params.num_height_points:
-            _lib.check(lib.ti5_sample_heights(p, b, st))
         fused = not with_physics
-        _lib.check(lib.ti5_post_physics(p, b, r, (C["TI5_POST_PUSH_LAST"] | self._chain("TI5_POST_CHAINED")) if fused else 0, st))
-        _lib.check(lib.ti5_reset_observe(p, b, r, C["TI5_RO_RESET"] | C["TI5_RO_OBSERVE"] | self._chain("TI5_RO_CHAINED"), st))
+        if part & 1:
+            if with_physics:
+                self.gym.refresh_net_contact_force_tensor(self.sim)
+                self.gym.refresh_rigid_body_state_tensor(self.sim)
+            if self._params.num_height_points:
+                _lib.check(lib.ti5_sample_heights(p, b, st))
+            _lib.check(lib.ti5_post_physics(p, b, r, (C["TI5_POST_PUSH_LAST"] | self._chain("TI5_POST_CHAINED")) if fused else 0, st))
+        if part & 2:
+            _lib.check(lib.ti5_reset_observe(p, b, r, C["TI5_RO_RESET"] | C["TI5_RO_OBSERVE"] | self._chain("TI5_RO_CHAINED"), st))
 
     def _materialize_windows(self):
         """lr:441-446 / t1:477-481: this step's windows as FRESH contiguous tensors (outside the captured graph: a
@@ -574,12 +577,12 @@ class LeggedRobot(BaseTask):
         self._launch_post(with_physics)
 
     def capture_phase_graphs(self):
-        """Two CUDA graphs (substep phase, post-physics phase) instead of one, so that a benchmark can
-        bracket each phase with CUDA events.  Replay both, then call `_finish_step()`."""
+        """Three CUDA graphs (substep phase, ti5_post_physics, ti5_reset_observe) instead of one, so that a benchmark
+        can bracket each kernel family with CUDA events.  Replay all three in order, then call `_finish_step()`."""
         torch.cuda.synchronize(self.device)
         graphs = []
         for fn in (lambda: self._launch_substeps(ctypes.c_void_p(self._actions_in.data_ptr()), False),
-                   lambda: self._launch_post(False)):
+                   lambda: self._launch_post(False, 1), lambda: self._launch_post(False, 2)):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=torch.cuda.Stream(self.device)):
                 fn()
