@@ -220,6 +220,9 @@ static __device__ __noinline__ void coop_load_call(void* dst, const void* src, u
 // previous STEP wrote, address arithmetic, random draws); every store comes after it.  Both are no-ops for a
 // launch without the attribute.
 // ---------------------------------------------------------------------------------------------
+// L2 prefetch: legal in front of chain_wait() for ANY address (it returns nothing), useful for rows that were written
+// in earlier steps and have been evicted since
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void chain_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

@@ -259,6 +259,24 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
       for (int i = 0; i < 3; ++i) org[i] = b.env_origins[e * 3 + i];
     }
   }
+  // lagged proprioception rows (pushed up to three steps ago) and the per-env constants only this kernel reads: cold in
+  // L2 by now; start fetching them (the lag indices and the stamp only change in this kernel's own reset scatter)
+  if (do_obs && live) {
+    if (role == 0) {
+      const int64_t st0 = b.ring_stamp[e];
+      const int64_t jd = (pushes - 1) - b.lag_timestep[e * 3 + 1], ji = (pushes - 1) - b.lag_timestep[e * 3 + 2];
+      if ((p.flags & TI5_F_ADD_DOF_LAG) && jd >= st0 && jd >= 0) {
+        const float* row = b.dof_ring + ((size_t)ring_slot(jd, p.dof_lag_len) * N + e) * (2 * D);
+        prefetch_l2(row);
+        prefetch_l2(row + 2 * D - 1);
+      }
+      if ((p.flags & TI5_F_ADD_IMU_LAG) && ji >= st0 && ji >= 0)
+        prefetch_l2(b.imu_ring + ((size_t)ring_slot(ji, p.imu_lag_len) * N + e) * 6);
+    } else {
+      prefetch_l2(b.env_frictions + e);
+      prefetch_l2(b.body_mass + e);
+    }
+  }
   const bool noisy = do_obs && (p.flags & TI5_F_ADD_NOISE);
   if (noisy && live && role == 0) {
     float* oo = s_obs + lane * Kp;

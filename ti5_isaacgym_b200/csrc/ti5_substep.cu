@@ -79,6 +79,13 @@ substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5B
   const int64_t base = (step - 1) * p.decimation;        // pushes completed before this step
   const float q[4] = {s0.x, s0.z, s1.x, s1.z}, qd[4] = {s0.y, s0.w, s1.y, s1.w};
 
+  // the lagged action row: pushed in an earlier step for most envs (lag > k) and cold in L2 by now — start fetching it
+  float4* ring = reinterpret_cast<float4*>(b.act_ring);
+  const int64_t jt = base + k_torque, jj = jt - lag;     // push index now / the one the controller sees
+  const bool need_ring = do_torque && lagged && lag > 0;
+  const bool ring_live = need_ring && jj >= stamp && jj >= 0;   // rows pushed before the env's last reset read as zero (lr:606)
+  const float4* ring_row = ring + (size_t)ring_slot(ring_live ? jj : 0, p.lag_len) * N * 3 + idx;
+  if (ring_live) prefetch_l2(ring_row);
   // the Philox draw and the IMU arithmetic need nothing from the previous kernel either
   if (do_torque && rt && p.rng_mode == TI5_RNG_PHILOX) u4 = philox_u4(p.seed, (uint64_t)step, S_TORQUE + k_torque, idx);
   float imu_val[4] = {0.f, 0.f, 0.f, 0.f};
@@ -101,11 +108,8 @@ substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5B
   // ---- everything below depends on (or must not overtake) the previous kernel of the step -------------
   chain_wait();
   // the one dependent load: the lagged action row (lr:1045)
-  float4* ring = reinterpret_cast<float4*>(b.act_ring);
-  const int64_t jt = base + k_torque, jj = jt - lag;     // push index now / the one the controller sees
-  float4 t4 = zero4;                                     // rows pushed before the env's last reset read as zero (lr:606)
-  const bool need_ring = do_torque && lagged && lag > 0;
-  if (need_ring && jj >= stamp && jj >= 0) t4 = ring[(size_t)ring_slot(jj, p.lag_len) * N * 3 + idx];
+  float4 t4 = zero4;
+  if (ring_live) t4 = *ring_row;
   if (do_torque && late_actions) a4 = ld4(b.actions);
 
   if (do_push) {                                         // lr:412-434
