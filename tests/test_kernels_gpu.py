@@ -136,6 +136,38 @@ def test_chained_launches_equal_plain_launches(N, graph):
     exact(a._episode_sums, b._episode_sums, "episode sums")
 
 
+def test_tiling_does_not_change_results(monkeypatch):
+    """env_block 32 (writer warps, reset draws parked in shared memory before the grid wait) and env_block 64 (neither)
+    are two schedules of the same arithmetic: bit-identical step outputs, resets included."""
+    from ti5_isaacgym_b200.sim.synthetic import synthetic_actions
+    N = 4096 + 17
+    envs = []
+    for tb in ("32", "64"):
+        monkeypatch.setenv("TI5_ENV_BLOCK", tb)
+        torch.manual_seed(0)
+        env, gen = _production_env(N, use_cuda_graph=False)
+        assert env._params.env_block == int(tb)
+        env.reset()
+        envs.append(env)
+    a, b = envs
+    ep = torch.randint(1, 2400, (N,), generator=gen, device="cuda")
+    ep[-5:] = 2399
+    a.episode_length_buf, b.episode_length_buf = ep.clone(), ep.clone()
+    n_reset = 0
+    for t in range(30):
+        act = synthetic_actions(N, gen, "cuda")
+        oa, pa, ra, da, _ = a.step(act)
+        ob, pb, rb, db, _ = b.step(act)
+        exact(da, db, f"step {t}: resets")
+        exact(ra, rb, f"step {t}: rewards")
+        exact(oa, ob, f"step {t}: obs")
+        exact(pa, pb, f"step {t}: privileged obs")
+        n_reset += int(da.sum())
+    assert n_reset > 20
+    for name in ("dof_state", "root_states", "commands", "gait_time", "lag_timestep", "motor_offsets", "randomized_p_gains"):
+        exact(getattr(a, name), getattr(b, name), f"state after 30 steps: {name}")
+
+
 def test_full_size_properties_8192():
     """BASELINE size: properties that need no oracle."""
     from ti5_isaacgym_b200.sim.synthetic import synthetic_actions

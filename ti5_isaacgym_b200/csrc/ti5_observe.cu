@@ -25,8 +25,11 @@ struct ObsRng {
   bool philox;
   // the eight per-DOF uniforms of a re-spawned env: [dof reset, torque multi, motor offset, kp, kd, coulomb,
   // viscous, armature] for DOF d (lr:1084, lr:735-783)
-  __device__ __forceinline__ void dof_draws(int e, int d, float u[8]) const {
-    if (philox) {
+  __device__ __forceinline__ void dof_draws(int e, int d, float u[8], const float* pre = nullptr) const {
+    if (pre) {                 // drawn before the grid wait (same Philox calls), parked in shared memory
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u[i] = pre[d * 8 + i];
+    } else if (philox) {
       const float4 a = philox_u4(p.seed, step, S_DR, (e * D + d) * 2), c = philox_u4(p.seed, step, S_DR, (e * D + d) * 2 + 1);
       u[0] = a.x; u[1] = a.y; u[2] = a.z; u[3] = a.w; u[4] = c.x; u[5] = c.y; u[6] = c.z; u[7] = c.w;
     } else {
@@ -38,9 +41,15 @@ struct ObsRng {
   __device__ __forceinline__ float root_xy(int e, int c) const {
     return philox ? philox_u(p.seed, step, S_ROOT, e * 2 + c) : r.root_xy[(size_t)e * 2 + c];
   }
-  __device__ __forceinline__ float cmd(int pass, int gi, int e, int c, int N) const {
-    return philox ? philox_u(p.seed, step, S_CMD + 4 * pass + gi, e * 3 + c)
-                  : r.cmd[((size_t)(pass * p.num_gaits + gi) * N + e) * 3 + c];
+  // the three command uniforms of gait `gi` (one Philox call)
+  __device__ __forceinline__ void cmd3(int pass, int gi, int e, int N, float u[3]) const {
+    if (philox) {
+      const float4 a = philox_u4(p.seed, step, S_CMD + 4 * pass + gi, e);
+      u[0] = a.x; u[1] = a.y; u[2] = a.z;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) u[c] = r.cmd[((size_t)(pass * p.num_gaits + gi) * N + e) * 3 + c];
+    }
   }
   // uniforms 4g .. 4g+3 of the env's noise row
   __device__ __forceinline__ float4 noise4(int e, int g4, int K) const {
@@ -54,9 +63,12 @@ struct ObsRng {
   }
   // the schedule draws of a re-spawned env: three lag indices and the gait start (lr:608-629, t1:523) from
   // one Philox call, the gait durations (t1:116) from another
-  __device__ __forceinline__ void schedule_draws(int e, int lag[3], float& gait_start, float gait_u[TI5_MAX_GAITS]) const {
+  __device__ __forceinline__ void schedule_draws(int e, int lag[3], float& gait_start, float gait_u[TI5_MAX_GAITS],
+                                                 const float* pre = nullptr) const {
     if (philox) {
-      const float4 a = philox_u4(p.seed, step, S_LAG, e), c = philox_u4(p.seed, step, S_GAIT_TIME, e);
+      float4 a, c;
+      if (pre) { a = make_float4(pre[0], pre[1], pre[2], pre[3]); c = make_float4(pre[4], pre[5], pre[6], pre[7]); }
+      else { a = philox_u4(p.seed, step, S_LAG, e); c = philox_u4(p.seed, step, S_GAIT_TIME, e); }
       const float ua[3] = {a.x, a.y, a.z};
 #pragma unroll
       for (int w = 0; w < 3; ++w) {
@@ -83,13 +95,14 @@ struct ObsRng {
 // t1:483-559 reset of env `es`, the part that is parallel over DOFs / reward terms: lanes 0-11 take one DOF
 // each (joint state, the seven actuator draws, zeroed action history), lanes 0-27 clear one episode sum each.
 // Runs once per flagged env of the warp, all 32 lanes together.
-__device__ __forceinline__ void reset_env_dofs(const Ti5Params& p, const Ti5Buffers& b, const ObsRng& rng, int es, int lane) {
+__device__ __forceinline__ void reset_env_dofs(const Ti5Params& p, const Ti5Buffers& b, const ObsRng& rng, int es, int lane,
+                                               const float* pre) {
   const int N = p.num_envs;
   if (lane < D) {
     const int d = lane;
     const size_t o = (size_t)es * D + d;
     float u[8];
-    rng.dof_draws(es, d, u);
+    rng.dof_draws(es, d, u, pre);
     // lr:1076-1090 joint state
     reinterpret_cast<float2*>(b.dof_state)[o] = make_float2(p.default_dof_pos[d] + affine(p.dof_reset_w, p.dof_reset_lo, u[0]), 0.0f);
     // lr:732-783 actuator randomisation
@@ -174,10 +187,10 @@ __device__ __forceinline__ void reset_env_base(const Ti5Params& p, const Ti5Buff
 
 // Schedule (role 1): lag indices, counters, gait start and gait times.
 __device__ __forceinline__ void reset_env_schedule(const Ti5Params& p, const Ti5Buffers& b, const ObsRng& rng, int es,
-                                                   int64_t pushes) {
+                                                   int64_t pushes, const float* pre) {
   int lag[3];
   float gs, gu[TI5_MAX_GAITS];
-  rng.schedule_draws(es, lag, gs, gu);
+  rng.schedule_draws(es, lag, gs, gu, pre);
   // lr:604-633: the env's lag rings read as zero from now on; new lag indices
   b.ring_stamp[es] = pushes;
   if (p.flags & TI5_F_ADD_LAG) b.lag_timestep[es * 3 + 0] = (p.flags & TI5_F_RAND_LAG_STEPS) ? lag[0] : p.lag_range[0][1];
@@ -209,6 +222,7 @@ __device__ __forceinline__ void reset_env_schedule(const Ti5Params& p, const Ti5
 // Up to OBS_WRITERS further warps per 32 envs ("roles" 2, 3) build nothing: they draw no frame, but share the ring
 // writes — a frame set is 240 scalar stores per warp, the longest single-warp stretch of the kernel.
 constexpr int OBS_ROLES = 2, OBS_WRITERS = 2;
+constexpr int DRAW_STRIDE = D * 8 + 8 + 1;     // floats per env of the parked reset draws (odd: conflict-free by env)
 
 #ifndef TI5_OBS_MINBLOCKS
 #define TI5_OBS_MINBLOCKS 1
@@ -258,6 +272,34 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < 3; ++i) org[i] = b.env_origins[e * 3 + i];
     }
+  }
+  // Reset draws ahead of time (Philox mode, small grids): which envs re-spawn is only known after the grid wait, but
+  // the draws of a re-spawn depend on (seed, step, env, DOF) alone — the otherwise idle writer warps draw them for
+  // EVERY env of the tile while ti5_post_physics runs (26 Philox calls per env, off the critical path) and park them
+  // in shared memory; the scatter of a flagged env then only reads them (1.3 -> 0.3 us per flagged env of a warp).
+  const bool pre_draws = do_reset && rng.philox && (int)blockDim.x > OBS_ROLES * TB;
+  float* s_draw = smem + (size_t)TB * (Kp + Pp) + (size_t)(tile_warp * 32 + lane) * DRAW_STRIDE;   // this lane's env
+  if (pre_draws && role >= OBS_ROLES && e < N && blockIdx.x < env_blocks) {
+    const int half = role - OBS_ROLES;                   // role 2: DOFs 0-5, role 3: DOFs 6-11 and the schedule
+#pragma unroll 1
+    for (int d = half * (D / 2); d < (half + 1) * (D / 2); ++d) {
+      float u[8];
+      rng.dof_draws(e, d, u);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s_draw[d * 8 + i] = u[i];
+    }
+    if (half == 1) {
+      const float4 a = philox_u4(p.seed, (uint64_t)step, S_LAG, e), c = philox_u4(p.seed, (uint64_t)step, S_GAIT_TIME, e);
+      float* sd = s_draw + D * 8;
+      sd[0] = a.x; sd[1] = a.y; sd[2] = a.z; sd[3] = a.w; sd[4] = c.x; sd[5] = c.y; sd[6] = c.z; sd[7] = c.w;
+    }
+  }
+  // gait schedule of the env (rewritten only by this env's own reset): for the second command pass (appendix A24)
+  int32_t gait_t[TI5_MAX_GAITS] = {0, 0, 0, 0};
+  if (do_reset && live) {
+#pragma unroll
+    for (int gi = 0; gi < TI5_MAX_GAITS; ++gi)
+      if (gi < p.num_gaits) gait_t[gi] = b.gait_time[e * p.num_gaits + gi];
   }
   // lagged proprioception rows (pushed up to three steps ago) and the per-env constants only this kernel reads: cold in
   // L2 by now; start fetching them (the lag indices and the stamp only change in this kernel's own reset scatter)
@@ -361,11 +403,11 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
     while (todo) {
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
-      reset_env_dofs(p, b, rng, env0 + src, lane);
+      reset_env_dofs(p, b, rng, env0 + src, lane, pre_draws ? s_draw + (src - lane) * DRAW_STRIDE : nullptr);
     }
     probe(b.debug_ts, 1, 6);
   } else if (role == 1 && flagged) {
-    reset_env_schedule(p, b, rng, e, pushes);
+    reset_env_schedule(p, b, rng, e, pushes, pre_draws ? s_draw + D * 8 : nullptr);
     reset_env_base(p, b, rng, e, s_spawn, org);
   }
   probe(b.debug_ts, 1, 1);
@@ -424,14 +466,17 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
     // t1:527 `_resample_commands()` runs over ALL envs whenever anything reset (appendix A24)
     if (do_reset && any_reset) {
       for (int gi = 0; gi < p.num_gaits; ++gi) {
-        if (ep_len != (int64_t)b.gait_time[e * p.num_gaits + gi]) continue;
+        const int32_t gt = flagged ? b.gait_time[e * p.num_gaits + gi] : gait_t[gi];     // a re-spawned env has a new schedule
+        if (ep_len != (int64_t)gt) continue;
         const int kind = p.gait_kind[gi];
         const bool mx = kind == TI5_GAIT_WALK_SAGITTAL || kind == TI5_GAIT_WALK_OMNI;
         const bool my = kind == TI5_GAIT_WALK_LATERAL || kind == TI5_GAIT_WALK_OMNI;
         const bool mz = kind == TI5_GAIT_ROTATE || kind == TI5_GAIT_WALK_OMNI;
-        cmd.x = mx ? affine((float)(s_range[0][1] - s_range[0][0]), (float)s_range[0][0], rng.cmd(1, gi, e, 0, N)) : 0.0f;
-        cmd.y = my ? affine((float)(s_range[1][1] - s_range[1][0]), (float)s_range[1][0], rng.cmd(1, gi, e, 1, N)) : 0.0f;
-        cmd.z = mz ? affine((float)(s_range[2][1] - s_range[2][0]), (float)s_range[2][0], rng.cmd(1, gi, e, 2, N)) : 0.0f;
+        float cu[3];
+        rng.cmd3(1, gi, e, N, cu);
+        cmd.x = mx ? affine((float)(s_range[0][1] - s_range[0][0]), (float)s_range[0][0], cu[0]) : 0.0f;
+        cmd.y = my ? affine((float)(s_range[1][1] - s_range[1][0]), (float)s_range[1][0], cu[1]) : 0.0f;
+        cmd.z = mz ? affine((float)(s_range[2][1] - s_range[2][0]), (float)s_range[2][0], cu[2]) : 0.0f;
       }
       if (role == 0) {
         reinterpret_cast<float4*>(b.commands)[e] = cmd;
@@ -767,7 +812,8 @@ extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const 
   TI5_CHECK_ARGS(p->rng_mode == TI5_RNG_PHILOX || (r && r->cmd && r->dofs && r->dr && r->gait_time && r->noise));
   Ti5Rng rr = r ? *r : Ti5Rng{};
   const int blocks = (p->num_envs + p->env_block - 1) / p->env_block;
-  const size_t smem = (size_t)p->env_block * ((p->num_single_obs | 1) + (p->priv_frame | 1)) * sizeof(float);
+  const bool writers = p->env_block == 32;
+  const size_t smem = (size_t)p->env_block * ((p->num_single_obs | 1) + (p->priv_frame | 1) + (writers ? DRAW_STRIDE : 0)) * sizeof(float);
   auto kernel = p->priv_frame == 73 ? reset_observe_kernel<47, 73>
                                     : (p->priv_frame == 260 ? reset_observe_kernel<47, 260> : reset_observe_kernel<47, 0>);
   if (smem > 48 * 1024 &&
@@ -780,7 +826,7 @@ extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const 
   // + helper CTAs (about 4 warps per SM) that only share the history-clear work of re-spawned envs
   // writer warps only for the small-grid case (env_block 32): from 16384 envs on the SMs are full of frame builders and
   // idle writers would only take their registers
-  const int threads = (OBS_ROLES + (p->env_block == 32 ? OBS_WRITERS : 0)) * p->env_block;   // <= 256
+  const int threads = (OBS_ROLES + (writers ? OBS_WRITERS : 0)) * p->env_block;   // <= 256
   const int helpers = (phases & TI5_RO_RESET) ? (148 * 4 * 32) / threads : 0;
   (void)ti5_launch(kernel, dim3(blocks + helpers), dim3(threads), smem, stream, (phases & TI5_RO_CHAINED) != 0, *p, *b, rr, phases);
   return ti5_check_launch("ti5_reset_observe");

@@ -231,10 +231,13 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       if (ep_len != (int64_t)t_gait_time[le * p.num_gaits + gi]) continue;
       const int kind = p.gait_kind[gi];
       float u[3];
+      if (philox) {                                       // one Philox call for the three components
+        const float4 a = philox_u4(p.seed, (uint64_t)step, S_CMD + gi, e);
+        u[0] = a.x; u[1] = a.y; u[2] = a.z;
+      } else {
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        u[c] = philox ? philox_u(p.seed, (uint64_t)step, S_CMD + gi, e * 3 + c)
-                      : r.cmd[((size_t)(0 * p.num_gaits + gi) * N + e) * 3 + c];
+        for (int c = 0; c < 3; ++c) u[c] = r.cmd[((size_t)(0 * p.num_gaits + gi) * N + e) * 3 + c];
+      }
       const bool mx = kind == TI5_GAIT_WALK_SAGITTAL || kind == TI5_GAIT_WALK_OMNI;
       const bool my = kind == TI5_GAIT_WALK_LATERAL || kind == TI5_GAIT_WALK_OMNI;
       const bool mz = kind == TI5_GAIT_ROTATE || kind == TI5_GAIT_WALK_OMNI;
