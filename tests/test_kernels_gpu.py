@@ -136,6 +136,33 @@ def test_chained_launches_equal_plain_launches(N, graph):
     exact(a._episode_sums, b._episode_sums, "episode sums")
 
 
+def test_graph_cache_follows_the_action_buffer():
+    """The captured step reads the caller's action tensor in place (one graph per buffer address, at most 8); beyond
+    that, and for host / strided inputs, it goes through the static copy.  Same results as direct launches."""
+    from ti5_isaacgym_b200.sim.synthetic import synthetic_actions
+    N = 1024
+    torch.manual_seed(0)
+    a, gen = _production_env(N, use_cuda_graph=True)
+    torch.manual_seed(0)
+    b, _ = _production_env(N, use_cuda_graph=False)
+    a.reset(), b.reset()
+    bufs = [synthetic_actions(N, gen, "cuda") for _ in range(12)]          # 12 live buffers: 8 graphs + the fallback
+    wide = torch.zeros(N, 24, device="cuda")
+    for t in range(30):
+        act = bufs[t % 12]
+        if t % 5 == 4:
+            wide[:, ::2] = act
+            given = wide[:, ::2]                                           # strided view: copied
+        elif t % 7 == 6:
+            given = act.cpu()                                              # host tensor: copied
+        else:
+            given = act
+        oa, pa, ra, da, _ = a.step(given)
+        ob, pb, rb, db, _ = b.step(act)
+        exact(oa, ob, f"step {t}: obs"); exact(ra, rb, f"step {t}: rewards"); exact(da, db, f"step {t}: resets")
+    assert len(a._graphs) == a._max_graphs == 8 and a._graph is not None
+
+
 def test_tiling_does_not_change_results(monkeypatch):
     """env_block 32 (writer warps, reset draws parked in shared memory before the grid wait) and env_block 64 (neither)
     are two schedules of the same arithmetic: bit-identical step outputs, resets included."""

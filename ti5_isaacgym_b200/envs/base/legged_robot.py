@@ -271,6 +271,7 @@ class LeggedRobot(BaseTask):
         self._write_globals()
         self._bind_buffers()
         self._graph = self._graph_host = None
+        self._graphs, self._max_graphs = {}, 8      # captured steps keyed by the address of the action buffer
         self.host_actions = None                                  # enable_host_io()
         self._rng = None
         self._rng_keep = None
@@ -463,7 +464,7 @@ class LeggedRobot(BaseTask):
         self._hist_valid = torch.zeros(N, dtype=torch.int32, device=dev)
         p.log_len = L
         self._bind_buffers()
-        self._graph = self._graph_host = None
+        self._drop_graphs()
         self._seed_frame_log()
         return self
 
@@ -596,10 +597,23 @@ class LeggedRobot(BaseTask):
     def step(self, actions):
         with_physics = getattr(self.gym, "physics", None) is not None or not hasattr(self.gym, "physics")
         if self._use_graph and not with_physics:
-            if self._graph is None:
-                self._capture_graph()
-            self._actions_in.copy_(actions, non_blocking=True)     # device tensor or pinned host memory
-            self._graph.replay()
+            # The captured step reads the actions where the caller left them: one graph per action buffer address (a
+            # training loop hands over a handful of recurring allocations), so no copy kernel and no extra kernel
+            # boundary in front of the step.  Other inputs (host tensors, odd dtypes / strides, too many distinct
+            # addresses) are copied into a static buffer first.
+            g = None
+            if (actions.is_cuda and actions.dtype == torch.float32 and actions.is_contiguous()
+                    and actions.device == self._actions_in.device and actions.shape == self._actions_in.shape):
+                ptr = actions.data_ptr()
+                g = self._graphs.get(ptr)
+                if g is None and len(self._graphs) < self._max_graphs:
+                    g = self._graphs[ptr] = self._capture_graph(ptr)
+            if g is None:
+                if self._graph is None:
+                    self._graph = self._capture_graph(self._actions_in.data_ptr())
+                self._actions_in.copy_(actions, non_blocking=True)     # device tensor or pinned host memory
+                g = self._graph
+            g.replay()
         else:
             a = actions.to(device=self.device, dtype=torch.float32).contiguous()
             self._launch_step(ctypes.c_void_p(a.data_ptr()), with_physics)
@@ -621,7 +635,7 @@ class LeggedRobot(BaseTask):
         self.host_reset = self.host_outputs[4 * N:5 * N].view(torch.bool)
         self.host_time_outs = self.host_outputs[5 * N:].view(torch.bool)
         self._bind_buffers()
-        self._graph = self._graph_host = None
+        self._drop_graphs()
         return self.host_actions, self.host_outputs
 
     def step_host(self):
@@ -642,14 +656,18 @@ class LeggedRobot(BaseTask):
         torch.cuda.current_stream(self.device).synchronize()
         return out
 
-    def _capture_graph(self):
+    def _drop_graphs(self):
+        """Forget every captured step (buffers were re-bound or the launch sequence changed)."""
+        self._graph = self._graph_host = None
+        self._graphs = {}
+
+    def _capture_graph(self, actions_ptr):
         torch.cuda.synchronize(self.device)
         side = torch.cuda.Stream(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=side):
-            self._launch_step(ctypes.c_void_p(self._actions_in.data_ptr()), False)
-        self._graph = g
-        # capture does not execute: device counters are untouched
+            self._launch_step(ctypes.c_void_p(actions_ptr), False)
+        return g                # capture does not execute: device counters are untouched
 
     def _finish_step(self):
         """Host-side epilogue: counters, output views, extras (all without a device sync)."""
@@ -792,7 +810,7 @@ class LeggedRobot(BaseTask):
             fr = torch.clip(hist, -lim, lim).permute(1, 0, 2)       # the ring stores clipped frames
             ring[:, slots] = fr
             ring[:, slots + Hn] = fr
-        self._graph = self._graph_host = None
+        self._drop_graphs()
         if self._params.log_len:
             self._seed_frame_log()
         self.obs_buf, self.privileged_obs_buf = self._history_views()

@@ -13,7 +13,7 @@ fill_synthetic_state(env.gym.tensors, env.env_origins, gen)
 env.reset()
 env.episode_length_buf = torch.randint(1, 2000, (N,), generator=gen, device='cuda')
 env._debug_ts = torch.zeros(3, 4096, 8, dtype=torch.int64, device='cuda')
-env._bind_buffers(); env._graph = None
+env._bind_buffers(); env._drop_graphs()
 act = synthetic_actions(N, gen, 'cuda')
 flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 NOFLUSH = os.environ.get('NOFLUSH') == '1'
