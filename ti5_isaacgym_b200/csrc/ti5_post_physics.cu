@@ -585,12 +585,15 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
     }
   }
   if (live && role == 0) {
+    // unrolled: the loads and products of all terms are independent, only the additions form a chain (in the
+    // reference's order); terms without a scale add nothing
+    float sc[TI5_NUM_TERMS];
+#pragma unroll
+    for (int t = 0; t < TI5_NUM_TERMS; ++t) sc[t] = T.vals[t * TB + le] * p.reward_scale[t];
     float rew = 0.0f;
-#pragma unroll 1
-    for (int t = 0; t < TI5_NUM_TERMS; ++t) {
-      if (!(mask & (1u << t)) || t == T_TERMINATION) continue;
-      rew += T.vals[t * TB + le] * p.reward_scale[t];
-    }
+#pragma unroll
+    for (int t = 0; t < TI5_NUM_TERMS; ++t)
+      if (t != T_TERMINATION && (mask & (1u << t))) rew += sc[t];
     if ((p.flags & TI5_F_ONLY_POSITIVE) && rew < 0.0f) rew = 0.0f;     // clip(min=0); NaN passes
     if (mask & (1u << T_TERMINATION)) {                   // lr:677-680, t1:894-896: added after the clip
       const float sc = ((reset && !time_out) ? 1.0f : 0.0f) * p.reward_scale[T_TERMINATION];
