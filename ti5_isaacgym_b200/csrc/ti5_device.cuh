@@ -53,6 +53,14 @@ __device__ __forceinline__ float py_mod(float a, float b) {
   return m;
 }
 
+// a % 1.0 (the gait phase, t1:88): fmodf(a, 1) == a - trunc(a) exactly in fp32 (Sterbenz for |a| >= 1, trunc = 0 below;
+// integers beyond 2^23 give 0, inf gives NaN either way) — two instructions instead of libdevice's reduction loop
+__device__ __forceinline__ float py_mod1(float a) {
+  float m = a - truncf(a);
+  if (m != 0.0f && m < 0.0f) m += 1.0f;
+  return m;
+}
+
 // torch.clip / clamp: min(max(x, lo), hi) with NaN passed through
 __device__ __forceinline__ float clampf(float x, float lo, float hi) {
   return x < lo ? lo : (x > hi ? hi : x);
@@ -83,8 +91,11 @@ static __device__ __noinline__ V3 quat_rotate_inverse(const float q[4], V3 v) {
 }
 
 // lr:27-53 get_euler_xyz_tensor: one wrapped angle (which = 0 roll, 1 pitch, 2 yaw)
+// The argument is an atan2f / asinf result, |a| <= pi < 2 pi, where fmodf(a, 2 pi) returns a itself: the python-style
+// remainder reduces to "add 2 pi to negatives" (-0.0 and NaN pass through like in fmodf), then the reference's fold
+// back — (a + 2 pi) - 2 pi in fp32, not a, bit for bit as torch computes it.
 __device__ __forceinline__ float wrap_angle(float a) {
-  a = py_mod(a, TWO_PI_F);
+  if (a < 0.0f) a += TWO_PI_F;
   if (a > PI_F) a -= TWO_PI_F;
   return a;
 }

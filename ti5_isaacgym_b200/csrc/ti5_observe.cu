@@ -414,8 +414,15 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
   __syncthreads();       // role 1 reads what the scatter wrote
   probe(b.debug_ts, 1, 2);
 
-  if (live) {
-    // ======== common prologue (both roles, same values) ==================================================
+  // The two frames are built in four parts — obs A (command input, actions, lagged IMU, last_* copies), obs B (lagged
+  // joint state), priv A (command input, reference pose, stance), priv B (everything that is a plain function of the
+  // loaded state) — by four warps per 32 envs where the writer warps exist, by the two role warps otherwise.
+  const int nparts = (int)(blockDim.x / TB);
+  const bool builder = e < N && blockIdx.x < env_blocks && role < 4;
+  const bool obsA = role == 0, privA = role == 1;
+  const bool obsB = nparts >= 4 ? role == 2 : role == 0, privB = nparts >= 4 ? role == 3 : role == 1;
+  if (builder) {
+    // ======== loads, all issued together ====================================================================
     const float* dsp = b.dof_state + (size_t)e * 2 * D;
     float q[D], qd[D];
     {
@@ -426,30 +433,34 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
         q[2 * i] = v.x; qd[2 * i] = v.y; q[2 * i + 1] = v.z; qd[2 * i + 1] = v.w;
       }
     }
-    float act[D];
-    load12(b.actions, e, act);
-    float4 cmd = reinterpret_cast<const float4*>(b.commands)[e];
-    const int64_t ep_len = b.episode_length_buf[e];
-    int64_t phase_len = b.phase_length_buf[e];
-    const float gait_start = b.gait_start[e];
-    // role-specific loads, issued with the common ones
-    int64_t stamp = 0;
+    float act[D], last_act[D];
+    float4 cmd = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t ep_len = 0, phase_len = 0, stamp = 0;
+    float gait_start = 0.0f;
     int lag_dof = 0, lag_imu = 0;
-    float last_act[D];
     float root[RB], lin[3], ang[3], eul[3], fz0 = 0.0f, fz1 = 0.0f, ext[5], fric = 0.0f, mass = 0.0f;
-    if (role == 0) {
-      stamp = b.ring_stamp[e];
-      lag_dof = b.lag_timestep[e * 3 + 1];
+    if (obsA || privB) load12(b.actions, e, act);
+    if (obsA || privA) {
+      cmd = reinterpret_cast<const float4*>(b.commands)[e];
+      ep_len = b.episode_length_buf[e];
+      phase_len = b.phase_length_buf[e];
+      gait_start = b.gait_start[e];
+    }
+    if (obsA || obsB) stamp = b.ring_stamp[e];
+    if (obsB) lag_dof = b.lag_timestep[e * 3 + 1];
+    if (obsA) {
       lag_imu = b.lag_timestep[e * 3 + 2];
       load12(b.last_actions, e, last_act);
     }
+    if (obsA || privB) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {       // role 0 needs them as the un-lagged IMU fallback, role 1 for the critic
-      lin[i] = b.base_lin_vel[e * 3 + i];
-      ang[i] = b.base_ang_vel[e * 3 + i];
-      eul[i] = b.base_euler_xyz[e * 3 + i];
+      for (int i = 0; i < 3; ++i) {       // obs A needs them as the un-lagged IMU fallback, priv B for the critic
+        lin[i] = b.base_lin_vel[e * 3 + i];
+        ang[i] = b.base_ang_vel[e * 3 + i];
+        eul[i] = b.base_euler_xyz[e * 3 + i];
+      }
     }
-    if (role == 1) {
+    if (privB) {
 #pragma unroll
       for (int i = 0; i < RB; ++i) root[i] = b.root_states[(size_t)e * RB + i];
       fz0 = b.contact_forces[((size_t)e * NB + p.feet[0]) * 3 + 2];
@@ -464,7 +475,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
     }
 
     // t1:527 `_resample_commands()` runs over ALL envs whenever anything reset (appendix A24)
-    if (do_reset && any_reset) {
+    if (do_reset && any_reset && (obsA || privA)) {
       for (int gi = 0; gi < p.num_gaits; ++gi) {
         const int32_t gt = flagged ? b.gait_time[e * p.num_gaits + gi] : gait_t[gi];     // a re-spawned env has a new schedule
         if (ep_len != (int64_t)gt) continue;
@@ -478,7 +489,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
         cmd.y = my ? affine((float)(s_range[1][1] - s_range[1][0]), (float)s_range[1][0], cu[1]) : 0.0f;
         cmd.z = mz ? affine((float)(s_range[2][1] - s_range[2][0]), (float)s_range[2][0], cu[2]) : 0.0f;
       }
-      if (role == 0) {
+      if (obsA) {
         reinterpret_cast<float4*>(b.commands)[e] = cmd;
         if (b.time_outs_latched) b.time_outs_latched[e] = b.time_out_buf[e];    // t1:540-541 (appendix A23)
       }
@@ -487,68 +498,74 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
 
     // =========================== observations (t1:368-481) =================================
     if (do_obs) {
-      const bool stand = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y + cmd.z * cmd.z) <= p.stand_threshold;
-      if (stand) phase_len = 0;                                               // t1:86 side effect
-      const float phase = (py_mod(sdiv((float)phase_len * p.dt, p.cycle_time, dm), 1.0f) + gait_start) * (stand ? 0.0f : 1.0f);
-      const float ang_ph = TWO_PI_F * phase;
-      const float s = sinf(ang_ph), c = cosf(ang_ph);
-      const float ci[5] = {s, c, cmd.x * p.cmd_scale[0], cmd.y * p.cmd_scale[1], cmd.z * p.cmd_scale[2]};
+      float s = 0.0f, ci[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      if (obsA || privA) {
+        const bool stand = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y + cmd.z * cmd.z) <= p.stand_threshold;
+        if (stand) phase_len = 0;                                               // t1:86 side effect
+        const float phase = (py_mod1(sdiv((float)phase_len * p.dt, p.cycle_time, dm)) + gait_start) * (stand ? 0.0f : 1.0f);
+        const float ang_ph = TWO_PI_F * phase;
+        s = sinf(ang_ph);
+        ci[0] = s; ci[1] = cosf(ang_ph);
+        ci[2] = cmd.x * p.cmd_scale[0]; ci[3] = cmd.y * p.cmd_scale[1]; ci[4] = cmd.z * p.cmd_scale[2];
+      }
+      float* oo = s_obs + lane * Kp;
+      float* po = s_priv + lane * Pp;
+      auto put = [&](int k, float v) { oo[k] = noisy ? v + oo[k] : v; };       // value + noise (drawn above)
 
-      if (role == 0) {
-        // ---------------- role 0: the 47-float observation frame ------------------------------------
+      if (obsA) {
+        // ---------------- obs A: command input, actions, lagged IMU (t1:407-451), last_* copies --------------
         b.phase_length_buf[e] = phase_len;
-        float* oo = s_obs + lane * Kp;
-        auto put = [&](int k, float v) { oo[k] = noisy ? v + oo[k] : v; };     // value + noise (drawn above)
 #pragma unroll
         for (int i = 0; i < 5; ++i) put(i, ci[i]);
 #pragma unroll
         for (int i = 0; i < D; ++i) put(29 + i, act[i]);
-        // lagged proprioception (t1:407-451): rows pushed before the env's last reset read as zero
-        {
-          float lq[D], lqd[D];
-          const int64_t jj = (pushes - 1) - lag_dof;
-          if (!(p.flags & TI5_F_ADD_DOF_LAG)) {
+        float imu[6];
+        const int64_t ji = (pushes - 1) - lag_imu;
+        if (!(p.flags & TI5_F_ADD_IMU_LAG)) {
 #pragma unroll
-            for (int i = 0; i < D; ++i) { lq[i] = q[i]; lqd[i] = qd[i]; }
-          } else if (jj >= stamp && jj >= 0) {
-            const float* row = b.dof_ring + ((size_t)ring_slot(jj, p.dof_lag_len) * N + e) * (2 * D);
-            load12(row, 0, lq);
-            load12(row + D, 0, lqd);
-          } else {
+          for (int i = 0; i < 3; ++i) { imu[i] = ang[i]; imu[3 + i] = eul[i]; }
+        } else if (ji >= stamp && ji >= 0) {
+          const float* row = b.imu_ring + ((size_t)ring_slot(ji, p.imu_lag_len) * N + e) * 6;
 #pragma unroll
-            for (int i = 0; i < D; ++i) { lq[i] = 0.0f; lqd[i] = 0.0f; }
-          }
+          for (int i = 0; i < 6; ++i) imu[i] = row[i];
+        } else {
 #pragma unroll
-          for (int i = 0; i < D; ++i) {
-            put(5 + i, (lq[i] - p.default_dof_pos[i]) * p.obs_dof_pos);
-            put(17 + i, lqd[i] * p.obs_dof_vel);
-          }
-          float imu[6];
-          const int64_t ji = (pushes - 1) - lag_imu;
-          if (!(p.flags & TI5_F_ADD_IMU_LAG)) {
+          for (int i = 0; i < 6; ++i) imu[i] = 0.0f;
+        }
 #pragma unroll
-            for (int i = 0; i < 3; ++i) { imu[i] = ang[i]; imu[3 + i] = eul[i]; }
-          } else if (ji >= stamp && ji >= 0) {
-            const float* row = b.imu_ring + ((size_t)ring_slot(ji, p.imu_lag_len) * N + e) * 6;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) imu[i] = row[i];
-          } else {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) imu[i] = 0.0f;
-          }
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            put(41 + i, imu[i] * p.obs_ang_vel);
-            put(44 + i, imu[3 + i] * p.obs_quat);
-          }
+        for (int i = 0; i < 3; ++i) {
+          put(41 + i, imu[i] * p.obs_ang_vel);
+          put(44 + i, imu[3 + i] * p.obs_quat);
         }
         // lr:496-498 previous-step copies (live state only; the dead ones are not kept)
         store12(b.last_last_actions, e, last_act);
         store12(b.last_actions, e, act);
         store12(b.last_dof_vel, e, qd);
-      } else {
-        // ---------------- role 1: reference pose and the privileged frame ---------------------------
-        float ref[D];                                                          // t1:250-274
+      }
+      if (obsB) {
+        // ---------------- obs B: lagged joint state; rows pushed before the env's last reset read as zero ------
+        float lq[D], lqd[D];
+        const int64_t jj = (pushes - 1) - lag_dof;
+        if (!(p.flags & TI5_F_ADD_DOF_LAG)) {
+#pragma unroll
+          for (int i = 0; i < D; ++i) { lq[i] = q[i]; lqd[i] = qd[i]; }
+        } else if (jj >= stamp && jj >= 0) {
+          const float* row = b.dof_ring + ((size_t)ring_slot(jj, p.dof_lag_len) * N + e) * (2 * D);
+          load12(row, 0, lq);
+          load12(row + D, 0, lqd);
+        } else {
+#pragma unroll
+          for (int i = 0; i < D; ++i) { lq[i] = 0.0f; lqd[i] = 0.0f; }
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          put(5 + i, (lq[i] - p.default_dof_pos[i]) * p.obs_dof_pos);
+          put(17 + i, lqd[i] * p.obs_dof_vel);
+        }
+      }
+      if (privA) {
+        // ---------------- priv A: command input, reference pose (t1:250-274), stance -------------------------
+        float ref[D];
 #pragma unroll
         for (int i = 0; i < D; ++i) ref[i] = 0.0f;
         {
@@ -568,15 +585,19 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
         store12(b.ref_dof_pos, e, ref);
         float stance[2] = {s >= 0.0f ? 1.0f : 0.0f, s < 0.0f ? 1.0f : 0.0f};
         if (fabsf(s) < 0.1f) stance[0] = stance[1] = 1.0f;
-        float* po = s_priv + lane * Pp;
 #pragma unroll
         for (int i = 0; i < 5; ++i) po[i] = ci[i];
+#pragma unroll
+        for (int i = 0; i < D; ++i) po[41 + i] = q[i] - ref[i];
+        po[69] = stance[0]; po[70] = stance[1];
+      }
+      if (privB) {
+        // ---------------- priv B: plain functions of the loaded state ---------------------------------------
 #pragma unroll
         for (int i = 0; i < D; ++i) {
           po[5 + i] = (q[i] - p.default_dof_pos[i]) * p.obs_dof_pos;
           po[17 + i] = qd[i] * p.obs_dof_vel;
           po[29 + i] = act[i];
-          po[41 + i] = q[i] - ref[i];
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -595,7 +616,6 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
         }
         po[67] = fric;
         po[68] = sdiv(mass, 30.0f, dm);
-        po[69] = stance[0]; po[70] = stance[1];
         po[71] = fz0 > 5.0f ? 1.0f : 0.0f; po[72] = fz1 > 5.0f ? 1.0f : 0.0f;
         if (p.flags & TI5_F_MEASURE_HEIGHTS) {                                 // t1:466-468
           const float* mh = b.measured_heights + (size_t)e * p.num_height_points;

@@ -250,7 +250,7 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
     const bool stand = cmd_norm <= p.stand_threshold;
     // gait phase and stance mask (t1:80-107).  Side effect: standing envs restart the phase.
     if (stand) phase_len = 0;
-    const float phase = (py_mod(sdiv((float)phase_len * p.dt, p.cycle_time, dm), 1.0f) + t_gait_start[le]) * (stand ? 0.0f : 1.0f);
+    const float phase = (py_mod1(sdiv((float)phase_len * p.dt, p.cycle_time, dm)) + t_gait_start[le]) * (stand ? 0.0f : 1.0f);
     const float sin_pos = sinf(TWO_PI_F * phase);
     float stance[2] = {sin_pos >= 0.0f ? 1.0f : 0.0f, sin_pos < 0.0f ? 1.0f : 0.0f};
     if (fabsf(sin_pos) < 0.1f) stance[0] = stance[1] = 1.0f;
