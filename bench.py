@@ -41,8 +41,8 @@ BYTES_ENV_STEP = 10 * BYTES_SUBSTEP + BYTES_POST
 
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel family, from the committed
-    `ncu --set full` capture of this same command (profiles/r01b_ncu_full_summary_8192.json); None if absent."""
-    path = os.path.join(ROOT, "profiles", "r01b_ncu_full_summary_8192.json")
+    `ncu --set full` capture of this same command (profiles/r01c_ncu_full_summary_8192.json); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r01c_ncu_full_summary_8192.json")
     if not os.path.exists(path):
         return None
     key = {"substep": "substep_kernel", "post_physics": "post_physics_kernel",

@@ -172,6 +172,7 @@ class FrameLogRolloutStorage(RolloutStorage):
         self._frame_row = z(T, dtype=torch.int32)
         env.enable_frame_log(T)
         self._lib = _lib.load_library()
+        self._tr_struct = _lib.Ti5Transition()
         self._bind()
 
     def _bind(self):
@@ -195,7 +196,7 @@ class FrameLogRolloutStorage(RolloutStorage):
         self._ro_plain.cur_reward_sum = None
 
     def _rollout_ref(self, episodes=True):
-        if self._logs.frame_log is not self.env.frame_logs().frame_log:   # the env re-allocated its logs
+        if self._logs.frame_log is not getattr(self.env, "_frame_log", None):   # the env re-allocated its logs
             self._bind()
         return ctypes.byref(self._ro if episodes else self._ro_plain)
 
@@ -203,6 +204,8 @@ class FrameLogRolloutStorage(RolloutStorage):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _f32(self, t, numel):
+        if t.dtype is torch.float32 and t.is_cuda and t.is_contiguous() and t.numel() == numel and not t.requires_grad:
+            return t                                      # the usual case: nothing to convert, no new tensor object
         t = t.detach()
         if t.dtype != torch.float32 or not t.is_cuda:
             t = t.to(device=self.device, dtype=torch.float32)
@@ -212,6 +215,8 @@ class FrameLogRolloutStorage(RolloutStorage):
         return t
 
     def _mask(self, t):
+        if t.dtype in (torch.bool, torch.uint8) and t.is_cuda and t.is_contiguous():
+            return t
         t = t.detach()
         if t.dtype not in (torch.bool, torch.uint8) or not t.is_cuda:
             t = (t.to(self.device) != 0)
@@ -228,12 +233,12 @@ class FrameLogRolloutStorage(RolloutStorage):
             row = (self.env.frame_log_row - 1) % self._logs.log_len
         keep = [self._f32(tr.actions, N * A), self._f32(tr.action_mean, N * A), self._f32(tr.action_sigma, N * A),
                 self._f32(tr.values, N), self._f32(tr.actions_log_prob, N), self._f32(rewards, N), self._mask(dones)]
-        t = _lib.Ti5Transition()
-        for name, x in zip(("actions", "action_mean", "action_sigma", "values", "actions_log_prob", "rewards", "dones"), keep):
-            setattr(t, name, ctypes.c_void_p(x.data_ptr()))
+        t = self._tr_struct                               # one struct, refilled: the call only borrows the pointers
+        (t.actions, t.action_mean, t.action_sigma, t.values, t.actions_log_prob, t.rewards, t.dones) = [x.data_ptr() for x in keep]
+        t.time_outs = None
         if time_outs is not None:
             keep.append(self._mask(time_outs))
-            t.time_outs = ctypes.c_void_p(keep[-1].data_ptr())
+            t.time_outs = keep[-1].data_ptr()
         _lib.check(self._lib.ti5_store_transition(self._rollout_ref(episodes), ctypes.byref(t), self.step, int(row),
                                                   float(gamma), self._stream()))
         self.step += 1
