@@ -571,13 +571,12 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
   probe(b.debug_ts, 0, 3);
 
   // ---- lr:654-680: reward sum in alphabetical term order, per-term episode sums, clip at zero -----------
-  // The per-term episode sums are independent of one another and of the ordered sum (the scaled term is recomputed
-  // there: same product, same bits): every role takes every third term, unrolled so that the loads overlap.
-  if (live) {
-#pragma unroll
-    for (int i = 0; i < (TI5_NUM_TERMS + POST_ROLES - 1) / POST_ROLES; ++i) {
-      const int t = role + i * POST_ROLES;
-      if (t >= TI5_NUM_TERMS || !(mask & (1u << t)) || t == T_TERMINATION) continue;
+  // The per-term episode sums are independent of one another: roles 1 and 2 take every other term while role 0
+  // runs the ordered sum (the scaled term is recomputed there: same product, same bits).
+  if (live && role > 0) {
+#pragma unroll 1
+    for (int t = role - 1; t < TI5_NUM_TERMS; t += POST_ROLES - 1) {
+      if (!(mask & (1u << t)) || t == T_TERMINATION) continue;
       const float sc = T.vals[t * TB + le] * p.reward_scale[t];
       const float acc = T.sums[t * TB + le] + sc;
       T.sums[t * TB + le] = acc;
