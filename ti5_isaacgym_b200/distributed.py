@@ -56,7 +56,12 @@ class FlatGradAllReduce:
     """Averages the gradients of `module` across ranks with ONE all-reduce of a flat bucket.  Call
     `reduce()` between `loss.backward()` and `clip_grad_norm_` (dh_ppo.py:180-181); the ~0.86 M
     parameters of ActorCriticDH are 3.4 MB, so a single latency-bound collective per step is the
-    right shape (no bucketing / overlap machinery)."""
+    right shape (no bucketing / overlap machinery).
+
+    Every parameter owns a view of the bucket.  After `reduce()` the parameters' `.grad` ARE those views; if the
+    optimiser keeps them (`zero_grad(set_to_none=False)`) the next backward accumulates straight into the bucket
+    and `reduce()` is the collective alone.  With the default `zero_grad()` (grads dropped, dh_ppo.py:179) the fresh
+    gradients are gathered into the bucket by one multi-tensor copy.  NCCL averages inside the collective."""
 
     def __init__(self, module, group=None):
         self.params = [p for p in module.parameters() if p.requires_grad]
@@ -64,25 +69,28 @@ class FlatGradAllReduce:
         n = sum(p.numel() for p in self.params)
         ref = self.params[0]
         self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
+        self.views, o = [], 0
+        for p in self.params:
+            self.views.append(self.flat[o:o + p.numel()].view_as(p))
+            o += p.numel()
 
     def reduce(self):
         if not (dist.is_initialized() and dist.get_world_size(self.group) > 1):
             return
-        o = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None:
-                self.flat[o:o + n].zero_()
-            else:
-                self.flat[o:o + n].copy_(p.grad.reshape(-1))
-            o += n
-        dist.all_reduce(self.flat, group=self.group)
-        self.flat /= dist.get_world_size(self.group)
-        o = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None:
-                p.grad = self.flat[o:o + n].view_as(p).clone()
-            else:
-                p.grad.copy_(self.flat[o:o + n].view_as(p))
-            o += n
+        src, dst = [], []
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is None:
+                v.zero_()
+            elif g.data_ptr() != v.data_ptr() or g.stride() != v.stride():
+                src.append(g)
+                dst.append(v)
+        if dst:
+            torch._foreach_copy_(dst, src)
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(self.flat, group=self.group)
+            self.flat /= dist.get_world_size(self.group)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
