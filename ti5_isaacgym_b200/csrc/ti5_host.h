@@ -38,14 +38,22 @@ inline cudaError_t ti5_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
-// Optional common shared-memory carve-out (TI5_CARVEOUT = percent) for the kernels of a chained step.  An SM only
-// hosts CTAs of kernels that agree on its shared memory / L1 split; with a common carve-out the CTAs of the next
-// kernels become resident several launches ahead (measured: post_physics CTAs resident 12 us before their inputs
-// exist) — but the step is bound by the dependency chain, not by CTA launch, and it measured 0.3 us slower.  Off by
-// default; kept as a knob for other grid sizes.
+// Common shared-memory carve-out for the kernels of a chained step on SMALL grids (env_block 32, i.e. < 16384 envs).
+// An SM only hosts CTAs of kernels that agree on its shared memory / L1 split; with a common carve-out the CTAs of
+// the following kernels become resident several launches ahead (measured: ti5_post_physics CTAs resident 12 us before
+// their inputs exist), which is what lets ti5_post_physics do most of its work in front of the grid wait (50.8 vs
+// 53.9 us/step at 8192 envs).  On large grids the SMs are full anyway and the smaller L1 costs the substep kernel
+// 20 % (236 vs 212 us/step at 65536 envs), so the kernels keep the default there.  TI5_CARVEOUT=<percent|-1> overrides.
 #include <cstdlib>
+#include <unordered_map>
 template <class K>
-inline void ti5_set_carveout(K kernel) {
-  static const int pct = getenv("TI5_CARVEOUT") ? atoi(getenv("TI5_CARVEOUT")) : -1;
-  if (pct >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+inline void ti5_set_carveout(K kernel, bool small_grid) {
+  static const int forced = getenv("TI5_CARVEOUT") ? atoi(getenv("TI5_CARVEOUT")) : -2;
+  static std::unordered_map<const void*, int> current;     // what each kernel is set to (host threads: one per GPU process)
+  const int want = forced != -2 ? forced : (small_grid ? 100 : -1);
+  auto it = current.find(reinterpret_cast<const void*>(kernel));
+  if (it == current.end() || it->second != want) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, want);
+    current[reinterpret_cast<const void*>(kernel)] = want;
+  }
 }

@@ -842,7 +842,7 @@ extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const 
     cudaGetLastError();
     return TI5_ECUDA;
   }
-  ti5_set_carveout(kernel);
+  ti5_set_carveout(kernel, p->env_block == 32);
   // + helper CTAs (about 4 warps per SM) that only share the history-clear work of re-spawned envs
   // writer warps only for the small-grid case (env_block 32): from 16384 envs on the SMs are full of frame builders and
   // idle writers would only take their registers

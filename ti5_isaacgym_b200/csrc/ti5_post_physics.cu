@@ -155,35 +155,49 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
   T.sums = reinterpret_cast<float*>(post_smem + (size_t)src.off[POST_CHUNKS] * TB);
   T.vals = T.sums + TI5_NUM_TERMS * TB;
   T.bar = reinterpret_cast<uint64_t*>(T.vals + TI5_NUM_TERMS * TB);
+  // Early mode (chained launch, full tile): of everything this kernel reads, only `actions` and `torques` come from the
+  // substep kernels of this step — every other array is simulator state (untouched while no simulator runs between
+  // the kernels) or was last written by the previous step.  Roles 0 and 2 and most of role 1 therefore run BEFORE the
+  // grid wait, on the first mbarrier; role 1 then waits for the substeps, pulls the two late arrays on the second
+  // mbarrier and finishes the two terms that need them.  Nothing stored in front of the wait is read or written by a
+  // substep kernel (root_states is: with push_robots the kernel keeps the plain order).
+  // Small grids only (env_block 32): there the CTAs are resident long before the substeps finish (common carve-out,
+  // ti5_host.h) and the work in front of the wait is free; on large grids the plain order measured no worse.
+  const bool early = (options & TI5_POST_CHAINED) && n_tile == TB && TB == 32 && !(p.flags & TI5_F_PUSH_ROBOTS);
+  const uint32_t late_bytes = (uint32_t)TB * (uint32_t)(src.rowb[C_ACT] + src.rowb[C_TORQUES]);
+  auto issue_late = [&]() {      // one thread: arm the second barrier and start the two copies
+    mbar_expect_tx(T.bar + 1, late_bytes);
+    tma_load_1d(T.base + (size_t)src.off[C_ACT] * TB, static_cast<const char*>(src.ptr[C_ACT]) + (size_t)e0 * src.rowb[C_ACT],
+                (uint32_t)(TB * src.rowb[C_ACT]), T.bar + 1);
+    tma_load_1d(T.base + (size_t)src.off[C_TORQUES] * TB, static_cast<const char*>(src.ptr[C_TORQUES]) + (size_t)e0 * src.rowb[C_TORQUES],
+                (uint32_t)(TB * src.rowb[C_TORQUES]), T.bar + 1);
+  };
   if (n_tile == TB) {
-    if (tid == 0) mbar_init(T.bar, 1);
+    if (tid == 0) { mbar_init(T.bar, 1); mbar_init(T.bar + 1, 1); }
     __syncthreads();
     // thread k issues bulk copy k of the table; threads 32..59 one episode-sum column each; thread 0 arms the
     // barrier with the byte total (arrival order between the copies and the arm does not matter)
     // (the (TERMS, N) episode-sum columns start 16-byte aligned only when N is a multiple of 4)
-    // Chained launch: only `actions` and `torques` come from the substep kernels of this step; every other array is
-    // simulator state or was last written by the previous step, so its copy is issued before chain_wait().
     const bool sums_by_tma = (N & 3) == 0;
-    const bool from_substeps = tid == C_ACT || tid == C_TORQUES;
-    auto issue = [&]() {
-      tma_load_1d(T.base + (size_t)src.off[tid] * TB, static_cast<const char*>(src.ptr[tid]) + (size_t)e0 * src.rowb[tid],
-                  (uint32_t)(TB * src.rowb[tid]), T.bar);
-    };
     if (tid < POST_CHUNKS) {
-      if (!from_substeps) issue();
+      if (tid != C_ACT && tid != C_TORQUES)
+        tma_load_1d(T.base + (size_t)src.off[tid] * TB, static_cast<const char*>(src.ptr[tid]) + (size_t)e0 * src.rowb[tid],
+                    (uint32_t)(TB * src.rowb[tid]), T.bar);
     } else if (sums_by_tma && tid >= 32 && tid < 32 + TI5_NUM_TERMS && (mask & (1u << (tid - 32)))) {
       const int t = tid - 32;
       tma_load_1d(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(TB * 4), T.bar);
     }
     if (tid == 0)
-      mbar_expect_tx(T.bar, (uint32_t)TB * (uint32_t)(src.off[POST_CHUNKS] + (sums_by_tma ? 4 * __popc(mask) : 0)));
+      mbar_expect_tx(T.bar, (uint32_t)TB * (uint32_t)(src.off[POST_CHUNKS] + (sums_by_tma ? 4 * __popc(mask) : 0)) - late_bytes);
     if (!sums_by_tma) {
 #pragma unroll 1
       for (int t = 0; t < TI5_NUM_TERMS; ++t)
         if (mask & (1u << t)) coop_load(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(TB * 4));
     }
-    chain_wait();                                         // the substep kernels are done
-    if (from_substeps) issue();
+    if (!early) {
+      chain_wait();                                       // the substep kernels are done
+      if (tid == TB) issue_late();
+    }
   } else {      // partial last tile: byte counts need not be multiples of 16, copy word by word
     chain_wait();
 #pragma unroll 1
@@ -195,7 +209,10 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       if (mask & (1u << t)) coop_load(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(n_tile * 4));
   }
   __syncthreads();
-  if (n_tile == TB) mbar_wait(T.bar, 0);
+  if (n_tile == TB) {
+    mbar_wait(T.bar, 0);
+    if (!early) mbar_wait(T.bar + 1, 0);
+  }
   // typed views of the tile
   const float* t_root = T.at<float>(C_ROOT);
   const float* t_dof = T.at<float>(C_DOF);
@@ -400,28 +417,21 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       const float* ldv = t_last_dof_vel + le * D;
       const float* tau = t_torques + le * D;
       const float* ref = t_ref + le * D;
-      // one pass over the 12 DOFs feeds every per-DOF reduction (each sum keeps its own DOF order)
-      float s_d1 = 0.0f, s_d2 = 0.0f, s_abs = 0.0f, s_dq = 0.0f, s_acc = 0.0f, s_vel = 0.0f, s_tau = 0.0f, s_jp = 0.0f;
+      // one pass over the 12 DOFs feeds every per-DOF reduction that needs joint state only (each sum keeps its own
+      // DOF order); the sums over `actions` and `torques` follow below, behind the grid wait in early mode
+      float s_dq = 0.0f, s_acc = 0.0f, s_vel = 0.0f, s_jp = 0.0f;
 #pragma unroll 1
       for (int i = 0; i < D; ++i) {
         const float qi = qrow[2 * i], qdi = qrow[2 * i + 1];
-        const float a = act[i], l = la[i];
-        const float d1 = (l - a) * 1.0f;
-        const float d2 = ((a + lla[i]) - 2.0f * l) * 1.0f;
-        s_d1 += d1 * d1;
-        s_d2 += d2 * d2;
-        s_abs += fabsf(a * 1.0f);
         const float dq = qi - p.default_dof_pos[i];
         s_dq += dq * dq;
         const float ac = sdiv(ldv[i] - qdi, p.dt, dm);
         s_acc += ac * ac;
         s_vel += qdi * qdi;
-        s_tau += tau[i] * tau[i];
         const float dj = qi - (stand ? p.default_dof_pos[i] : ref[i]);       // ref_dof_pos of the PREVIOUS step (A3)
         s_jp += dj * dj;
       }
       auto dq0 = [&](int i) { return qrow[2 * i] - p.default_dof_pos[i]; };
-      if (mask & (1u << T_ACTION_SMOOTHNESS)) put(T_ACTION_SMOOTHNESS, (s_d1 + s_d2) + 0.05f * s_abs);   // t1:877-892
       if (mask & (1u << T_DEFAULT_JOINT_POS)) {             // t1:686-703
         const float l = sqrtf((dq0(0) * dq0(0) + dq0(1) * dq0(1)) + dq0(5) * dq0(5));
         const float rr = sqrtf((dq0(6) * dq0(6) + dq0(7) * dq0(7)) + dq0(11) * dq0(11));
@@ -444,7 +454,6 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
         }
         put(T_STAND_SYSMETRY, stand ? expf_call(-sq) : 0.0f);
       }
-      if (mask & (1u << T_TORQUES)) put(T_TORQUES, s_tau);       // t1:849-854
       const float* f0 = t_rigid + ((size_t)le * NB + p.feet[0]) * RB;
       const float* f1 = t_rigid + ((size_t)le * NB + p.feet[1]) * RB;
       const float* k0 = t_rigid + ((size_t)le * NB + p.knees[0]) * RB;
@@ -453,6 +462,25 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
         put(T_FEET_DISTANCE, pair_distance_reward(f0[0], f0[1], f1[0], f1[1], p.foot_min_dist, p.foot_max_dist));
       if (mask & (1u << T_KNEE_DISTANCE))                   // t1:615-628
         put(T_KNEE_DISTANCE, pair_distance_reward(k0[0], k0[1], k1[0], k1[1], p.knee_min_dist, p.knee_max_dist));
+      // ---- the two terms over this step's actions and torques -------------------------------------------
+      if (early) {
+        chain_wait();                                       // the substep kernels are done
+        if (tid == TB) issue_late();
+        mbar_wait(T.bar + 1, 0);
+      }
+      float s_d1 = 0.0f, s_d2 = 0.0f, s_abs = 0.0f, s_tau = 0.0f;
+#pragma unroll 1
+      for (int i = 0; i < D; ++i) {
+        const float a = act[i], l = la[i];
+        const float d1 = (l - a) * 1.0f;
+        const float d2 = ((a + lla[i]) - 2.0f * l) * 1.0f;
+        s_d1 += d1 * d1;
+        s_d2 += d2 * d2;
+        s_abs += fabsf(a * 1.0f);
+        s_tau += tau[i] * tau[i];
+      }
+      if (mask & (1u << T_ACTION_SMOOTHNESS)) put(T_ACTION_SMOOTHNESS, (s_d1 + s_d2) + 0.05f * s_abs);   // t1:877-892
+      if (mask & (1u << T_TORQUES)) put(T_TORQUES, s_tau);       // t1:849-854
     } else {
       // ================================ role 2: the feet ===============================================
       FootState foot[2];
@@ -657,8 +685,8 @@ extern "C" int ti5_post_physics(const Ti5Params* p, const Ti5Buffers* b, const T
       return TI5_ECUDA;
     }
     configured = smem;
-    ti5_set_carveout(post_physics_kernel);
   }
+  ti5_set_carveout(post_physics_kernel, p->env_block == 32);
   (void)ti5_launch(post_physics_kernel, dim3(blocks), dim3(POST_ROLES * p->env_block), smem, stream,
                    (options & TI5_POST_CHAINED) != 0, *p, *b, rr, src, options);
   return ti5_check_launch("ti5_post_physics");
