@@ -277,7 +277,13 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
   // the draws of a re-spawn depend on (seed, step, env, DOF) alone — the otherwise idle writer warps draw them for
   // EVERY env of the tile while ti5_post_physics runs (26 Philox calls per env, off the critical path) and park them
   // in shared memory; the scatter of a flagged env then only reads them (1.3 -> 0.3 us per flagged env of a warp).
+  // (Measured: -0.5 us/step while the SMs were idle in front of the wait; +0.5 us since ti5_post_physics works there in
+  // early mode.  Compiled in with -DTI5_PRE_DRAWS only.)
+#ifdef TI5_PRE_DRAWS
   const bool pre_draws = do_reset && rng.philox && (int)blockDim.x > OBS_ROLES * TB;
+#else
+  const bool pre_draws = false;
+#endif
   float* s_draw = smem + (size_t)TB * (Kp + Pp) + (size_t)(tile_warp * 32 + lane) * DRAW_STRIDE;   // this lane's env
   if (pre_draws && role >= OBS_ROLES && e < N && blockIdx.x < env_blocks) {
     const int half = role - OBS_ROLES;                   // role 2: DOFs 0-5, role 3: DOFs 6-11 and the schedule
@@ -833,7 +839,12 @@ extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const 
   Ti5Rng rr = r ? *r : Ti5Rng{};
   const int blocks = (p->num_envs + p->env_block - 1) / p->env_block;
   const bool writers = p->env_block == 32;
-  const size_t smem = (size_t)p->env_block * ((p->num_single_obs | 1) + (p->priv_frame | 1) + (writers ? DRAW_STRIDE : 0)) * sizeof(float);
+#ifdef TI5_PRE_DRAWS
+  const int draw_floats = writers ? DRAW_STRIDE : 0;
+#else
+  const int draw_floats = 0;
+#endif
+  const size_t smem = (size_t)p->env_block * ((p->num_single_obs | 1) + (p->priv_frame | 1) + draw_floats) * sizeof(float);
   auto kernel = p->priv_frame == 73 ? reset_observe_kernel<47, 73>
                                     : (p->priv_frame == 260 ? reset_observe_kernel<47, 260> : reset_observe_kernel<47, 0>);
   if (smem > 48 * 1024 &&
