@@ -465,8 +465,14 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       // ---- the two terms over this step's actions and torques -------------------------------------------
       if (early) {
         chain_wait();                                       // the substep kernels are done
-        if (tid == TB) issue_late();
-        mbar_wait(T.bar + 1, 0);
+        // the two late rows of this env, straight from the L2 into the env's own tile rows (shorter than a bulk-copy
+        // round trip for 96 bytes per thread)
+        const float4* ga = reinterpret_cast<const float4*>(b.actions + (size_t)e * D);
+        const float4* gt = reinterpret_cast<const float4*>(b.torques + (size_t)e * D);
+        const float4 a0 = ga[0], a1 = ga[1], a2 = ga[2], t0 = gt[0], t1 = gt[1], t2 = gt[2];
+        float4* sa = reinterpret_cast<float4*>(const_cast<float*>(act));
+        float4* st = reinterpret_cast<float4*>(const_cast<float*>(tau));
+        sa[0] = a0; sa[1] = a1; sa[2] = a2; st[0] = t0; st[1] = t1; st[2] = t2;
       }
       float s_d1 = 0.0f, s_d2 = 0.0f, s_abs = 0.0f, s_tau = 0.0f;
 #pragma unroll 1
