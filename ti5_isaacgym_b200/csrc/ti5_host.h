@@ -38,7 +38,7 @@ inline cudaError_t ti5_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
-// Common shared-memory carve-out for the kernels of a chained step on SMALL grids (env_block 32, i.e. < 16384 envs).
+// Common shared-memory carve-out for the kernels of a chained step on SMALL grids (env_block 32: at most two CTAs per SM, <= 9472 envs).
 // An SM only hosts CTAs of kernels that agree on its shared memory / L1 split; with a common carve-out the CTAs of
 // the following kernels become resident several launches ahead (measured: ti5_post_physics CTAs resident 12 us before
 // their inputs exist), which is what lets ti5_post_physics do most of its work in front of the grid wait (50.8 vs

@@ -855,7 +855,7 @@ extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const 
   }
   ti5_set_carveout(kernel, p->env_block == 32);
   // + helper CTAs (about 4 warps per SM) that only share the history-clear work of re-spawned envs
-  // writer warps only for the small-grid case (env_block 32): from 16384 envs on the SMs are full of frame builders and
+  // writer warps only for the small-grid case (env_block 32): on larger grids the SMs are full of frame builders and
   // idle writers would only take their registers
   const int threads = (OBS_ROLES + (writers ? OBS_WRITERS : 0)) * p->env_block;   // <= 256
   const int helpers = (phases & TI5_RO_RESET) ? (148 * 4 * 32) / threads : 0;

@@ -25,9 +25,11 @@ UNSUPPORTED_FLAGS = ("randomize_lag_timesteps_perstep", "randomize_dof_lag_times
 
 
 def pick_env_block(num_envs, sms=148):
-    """Envs per CTA of the per-env kernels.  32 keeps all 148 SMs busy at the BASELINE size (8192 envs = 256
-    CTAs); from 16384 envs on, 64 measured a few percent faster (fewer, fatter TMA tiles) and 128 no better."""
-    return 64 if num_envs >= 16384 else 32
+    """Envs per CTA of the per-env kernels.  32 while the grid is at most two CTAs per SM (<= 9472 envs: the BASELINE
+    size, 8192 envs = 256 CTAs, is in this regime — four warps per 32 envs in ti5_reset_observe, common carve-out and
+    early mode in ti5_post_physics); 64 beyond.  Measured us/step, 32 vs 64: 4096 envs 47.9 / 50.0, 8192 envs 50.2 / 54.0,
+    10240 envs 58.6 / 56.4, 12288 envs 64.7 / 60.2, 16384 envs 79.3 / 66.4; 128 was no better than 64 anywhere."""
+    return 32 if num_envs <= 2 * sms * 32 else 64
 
 
 def reward_scales(cfg, dt):
