@@ -38,7 +38,7 @@ inline cudaError_t ti5_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
-// Common shared-memory carve-out for the kernels of a chained step on SMALL grids (env_block 32: at most two CTAs per SM, <= 9472 envs).
+// Common shared-memory carve-out for the kernels of a chained step on SMALL grids (<= 12288 envs).
 // An SM only hosts CTAs of kernels that agree on its shared memory / L1 split; with a common carve-out the CTAs of
 // the following kernels become resident several launches ahead (measured: ti5_post_physics CTAs resident 12 us before
 // their inputs exist), which is what lets ti5_post_physics do most of its work in front of the grid wait (50.8 vs
@@ -46,6 +46,8 @@ inline cudaError_t ti5_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // 20 % (236 vs 212 us/step at 65536 envs), so the kernels keep the default there.  TI5_CARVEOUT=<percent|-1> overrides.
 #include <cstdlib>
 #include <unordered_map>
+#define TI5_SMALL_GRID_ENVS 12288    /* measured: early mode + carve-out 58.8 vs 60.2 us at 12288 envs, 67.2 vs 66.5 at 16384 */
+inline bool ti5_small_grid(const Ti5Params* p) { return p->num_envs <= TI5_SMALL_GRID_ENVS; }
 template <class K>
 inline void ti5_set_carveout(K kernel, bool small_grid) {
   static const int forced = getenv("TI5_CARVEOUT") ? atoi(getenv("TI5_CARVEOUT")) : -2;

@@ -853,7 +853,7 @@ extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const 
     cudaGetLastError();
     return TI5_ECUDA;
   }
-  ti5_set_carveout(kernel, p->env_block == 32);
+  ti5_set_carveout(kernel, ti5_small_grid(p));
   // + helper CTAs (about 4 warps per SM) that only share the history-clear work of re-spawned envs
   // writer warps only for the small-grid case (env_block 32): on larger grids the SMs are full of frame builders and
   // idle writers would only take their registers

@@ -161,9 +161,9 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
   // grid wait, on the first mbarrier; role 1 then waits for the substeps, pulls the two late arrays on the second
   // mbarrier and finishes the two terms that need them.  Nothing stored in front of the wait is read or written by a
   // substep kernel (root_states is: with push_robots the kernel keeps the plain order).
-  // Small grids only (env_block 32): there the CTAs are resident long before the substeps finish (common carve-out,
-  // ti5_host.h) and the work in front of the wait is free; on large grids the plain order measured no worse.
-  const bool early = (options & TI5_POST_CHAINED) && n_tile == TB && TB == 32 && !(p.flags & TI5_F_PUSH_ROBOTS);
+  // Small grids only (<= 12288 envs): there the CTAs are resident long before the substeps finish (common
+  // carve-out, ti5_host.h) and the work in front of the wait is free; on large grids the plain order measured no worse.
+  const bool early = (options & TI5_POST_CHAINED) && n_tile == TB && N <= TI5_SMALL_GRID_ENVS && !(p.flags & TI5_F_PUSH_ROBOTS);
   const uint32_t late_bytes = (uint32_t)TB * (uint32_t)(src.rowb[C_ACT] + src.rowb[C_TORQUES]);
   auto issue_late = [&]() {      // one thread: arm the second barrier and start the two copies
     mbar_expect_tx(T.bar + 1, late_bytes);
@@ -692,7 +692,7 @@ extern "C" int ti5_post_physics(const Ti5Params* p, const Ti5Buffers* b, const T
     }
     configured = smem;
   }
-  ti5_set_carveout(post_physics_kernel, p->env_block == 32);
+  ti5_set_carveout(post_physics_kernel, ti5_small_grid(p));
   (void)ti5_launch(post_physics_kernel, dim3(blocks), dim3(POST_ROLES * p->env_block), smem, stream,
                    (options & TI5_POST_CHAINED) != 0, *p, *b, rr, src, options);
   return ti5_check_launch("ti5_post_physics");

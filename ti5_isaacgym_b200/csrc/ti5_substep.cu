@@ -196,7 +196,7 @@ static int launch_substep(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng*
   const int k_push = (phases & TI5_SUB_TORQUE) ? k - 1 : k;
   TI5_CHECK_ARGS(!(phases & TI5_SUB_PUSH) || k_push >= 0);
   static const int block = getenv("TI5_SUBSTEP_BLOCK") ? atoi(getenv("TI5_SUBSTEP_BLOCK")) : 64;
-  ti5_set_carveout(substep_kernel, p->env_block == 32);
+  ti5_set_carveout(substep_kernel, ti5_small_grid(p));
   (void)ti5_launch(substep_kernel, dim3((n + block - 1) / block), dim3(block), 0, stream, (phases & TI5_SUB_CHAINED) != 0, *p, *b, rr,
                    actions_in, k_push, k, phases);
   return ti5_check_launch("ti5_substep");
