@@ -151,3 +151,9 @@ def test_unsupported_options_raise():
     cfg.rewards.scales.dof_vel_limits = -1.0
     with pytest.raises(NotImplementedError):
         build_params(cfg, 0.001, robot_constants(cfg))
+
+
+def test_env_block_follows_the_grid_size():
+    """step_params.pick_env_block: 32 while the grid is at most two CTAs per SM (the BASELINE size), 64 beyond."""
+    from ti5_isaacgym_b200.envs.base.step_params import pick_env_block
+    assert [pick_env_block(n) for n in (1, 1024, 8192, 9472, 9473, 12288, 16384, 65536)] == [32, 32, 32, 32, 64, 64, 64, 64]
