@@ -157,3 +157,20 @@ def test_env_block_follows_the_grid_size():
     """step_params.pick_env_block: 32 while the grid is at most two CTAs per SM (the BASELINE size), 64 beyond."""
     from ti5_isaacgym_b200.envs.base.step_params import pick_env_block
     assert [pick_env_block(n) for n in (1, 1024, 8192, 9472, 9473, 12288, 16384, 65536)] == [32, 32, 32, 32, 64, 64, 64, 64]
+
+
+def test_vec_env_contract_reports_what_is_missing():
+    import torch
+    from types import SimpleNamespace
+    from ti5_isaacgym_b200.algo.vec_env import VecEnv, check_vec_env
+    ok = SimpleNamespace(num_envs=4, num_obs=6, num_short_obs=2, num_privileged_obs=None, num_actions=3, max_episode_length=2400.0,
+                         obs_buf=torch.zeros(4, 6), privileged_obs_buf=None, rew_buf=torch.zeros(4), reset_buf=torch.ones(4, dtype=torch.bool),
+                         episode_length_buf=torch.zeros(4, dtype=torch.int64), extras={}, device="cpu",
+                         step=lambda a: None, reset=lambda: None, get_observations=lambda: None,
+                         get_privileged_observations=lambda: None)
+    assert check_vec_env(ok) == [] and isinstance(ok, VecEnv)
+    ok.rew_buf = torch.zeros(5, dtype=torch.float64)
+    del ok.get_observations
+    faults = check_vec_env(ok)
+    assert any("get_observations" in f for f in faults) and any("rew_buf should be torch.float32" in f for f in faults)
+    assert any("rew_buf should have shape (4,)" in f for f in faults) and not isinstance(ok, VecEnv)

@@ -197,10 +197,12 @@ def test_tiling_does_not_change_results(monkeypatch):
 
 def test_full_size_properties_8192():
     """BASELINE size: properties that need no oracle."""
+    from ti5_isaacgym_b200.algo.vec_env import check_vec_env
     from ti5_isaacgym_b200.sim.synthetic import synthetic_actions
     N = 8192
     env, gen = _production_env(N)
     env.reset()
+    assert check_vec_env(env) == [], check_vec_env(env)
     env.episode_length_buf = torch.randint(1, 2400, (N,), generator=gen, device="cuda")
     for t in range(30):
         act = synthetic_actions(N, gen, "cuda")
