@@ -45,9 +45,9 @@ def ncu_traffic(kernel):
     path = os.path.join(ROOT, "profiles", "r01c_ncu_full_summary_8192.json")
     if not os.path.exists(path):
         return None
-    key = {"substep": "substep_kernel", "post_physics": "post_physics_kernel",
-           "reset_observe": "void reset_observe_kernel<47, 73>"}[kernel]
-    rows = json.load(open(path)).get(key)
+    want = {"substep": "substep_kernel", "post_physics": "post_physics_kernel", "reset_observe": "reset_observe_kernel"}[kernel]
+    table = json.load(open(path))
+    rows = next((v for k, v in table.items() if want in k), None)
     if not rows:
         return None
     unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}

@@ -224,11 +224,11 @@ __device__ __forceinline__ void reset_env_schedule(const Ti5Params& p, const Ti5
 constexpr int OBS_ROLES = 2, OBS_WRITERS = 2;
 constexpr int DRAW_STRIDE = D * 8 + 8 + 1;     // floats per env of the parked reset draws (odd: conflict-free by env)
 
-#ifndef TI5_OBS_MINBLOCKS
-#define TI5_OBS_MINBLOCKS 1
-#endif
-template <int KC, int PC>
-__global__ void __launch_bounds__(256, TI5_OBS_MINBLOCKS)
+// MINB = 2 caps the kernel at 128 registers (122 used, no spills) for large grids, where four CTAs of 128 threads per SM
+// instead of three are worth 10 us per step at 65536 envs; small grids keep the uncapped build (140 registers), which
+// measured 1 us faster there.
+template <int KC, int PC, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
                      const __grid_constant__ Ti5Rng r, int phases) {
   extern __shared__ float smem[];      // per 32 envs: 32 x K observation frames, then 32 x P privileged frames
@@ -845,8 +845,10 @@ extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const 
   const int draw_floats = 0;
 #endif
   const size_t smem = (size_t)p->env_block * ((p->num_single_obs | 1) + (p->priv_frame | 1) + draw_floats) * sizeof(float);
-  auto kernel = p->priv_frame == 73 ? reset_observe_kernel<47, 73>
-                                    : (p->priv_frame == 260 ? reset_observe_kernel<47, 260> : reset_observe_kernel<47, 0>);
+  const bool big = p->num_envs >= 32768;
+  auto kernel = p->priv_frame == 73 ? (big ? reset_observe_kernel<47, 73, 2> : reset_observe_kernel<47, 73, 1>)
+                : p->priv_frame == 260 ? (big ? reset_observe_kernel<47, 260, 2> : reset_observe_kernel<47, 260, 1>)
+                                       : (big ? reset_observe_kernel<47, 0, 2> : reset_observe_kernel<47, 0, 1>);
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     ti5_set_error("ti5_reset_observe: %zu bytes of shared memory per CTA not available", smem);
