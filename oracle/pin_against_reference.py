@@ -75,6 +75,17 @@ SCENARIOS = {
                                  edit=lambda c: (setattr(c.terrain, "measure_heights", True),
                                                  setattr(c.env, "num_privileged_obs", 3 * (73 + 187)),
                                                  setattr(c.domain_rand, "push_robots", True))),
+    # multi-step disturbance windows (t1:193-247) and a command-curriculum change (lr:1160-1169): at
+    # common_step_counter >= 240000 / 288000 the push window lasts 20 steps (push_duration[4] / dt) and the external-force
+    # window 16 (one draw step + add_duration[3] / dt apply steps); 288000 is a multiple of both intervals and of
+    # max_episode_length, so both windows open and the curriculum is evaluated on the step env 0 times out
+    "plane_windows": dict(N=24, steps=30, mesh="plane", contact_rate=0.05, events=True, counter=287997, track_sums=True,
+                          edit=lambda c: setattr(c.domain_rand, "push_robots", True)),
+    "trimesh_windows": dict(N=16, steps=26, mesh="trimesh", contact_rate=0.05, events=True, counter=287997,
+                            track_sums=True,
+                            edit=lambda c: (setattr(c.terrain, "measure_heights", True),
+                                            setattr(c.env, "num_privileged_obs", 3 * (73 + 187)),
+                                            setattr(c.domain_rand, "push_robots", True))),
     "big_plane": dict(N=512, steps=12, mesh="plane", contact_rate=0.03, events=True, golden=False),
     # the reward terms the task defines but t1_cfg leaves at zero scale (t1:894-896, 917-925, 937-940)
     "plane_extra_terms": dict(N=16, steps=12, mesh="plane", contact_rate=0.08, events=True,
@@ -108,14 +119,17 @@ def run_scenario(name, spec, write_dir=None, verbose=True):
         env.episode_length_buf[1] = int(env.gait_time[1, 1]) - 2       # gait switch to "stand"
         env.episode_length_buf[2] = int(env.gait_time[2, 2]) - 3       # and back to walking
         env.phase_length_buf[:] = env.episode_length_buf
-        env.common_step_counter = 2397                    # command-curriculum check at step 3, ext-force window
+        env.common_step_counter = spec.get("counter", 2397)   # command-curriculum check at step 3, ext-force window
+    if spec.get("track_sums"):        # tracking reward above 80 % of its maximum: the curriculum widens lin_vel_x
+        env.episode_sums["tracking_lin_vel"][:] = 0.9 * env.reward_scales["tracking_lin_vel"] * float(env.max_episode_length)
+    env.gym.log_calls = True
     S = adopt_reference_state(O.new_state(C, N), env)
     state0 = snapshot_state(S, C)
     if terrain is not None:
         state0["terrain_origins"] = terrain.origins.clone()
         state0["terrain_env_length"] = torch.tensor(float(terrain.env_length))
     rec = dict(inputs=[], outputs=[])
-    cov = dict(time_outs=0, stand_env_steps=0, ext_force_steps=0, push_steps=0, curriculum_changes=0, gait_switches=0)
+    cov = dict(time_outs=0, stand_env_steps=0, ext_force_steps=0, ext_apply_steps=0, push_steps=0, curriculum_changes=0, gait_switches=0)
     for t in range(steps):
         fill_synthetic_state(drv.sim, env.env_origins, gen, base_contact_rate=spec.get("contact_rate", 0.01))
         sim0 = {k: getattr(drv.sim, k).clone() for k in ("root_states", "dof_state", "contact_forces", "rigid_state")}
@@ -124,8 +138,20 @@ def run_scenario(name, spec, write_dir=None, verbose=True):
         # oracle on a private copy of the simulator tensors
         osim = SimpleNamespace(**{k: v.clone() for k, v in sim0.items()})
         o_obs, o_priv, o_rew, o_reset, o_extras = O.step(C, S, osim, actions, pools, terrain=terrain, height_samples=heights)
+        env.gym.calls.clear()
+        ranges_before = {k: list(v) for k, v in env.command_ranges.items()}
         r_obs, r_priv, r_rew, r_reset, r_extras = drv.step(actions, pools)
+        calls = list(env.gym.calls)
         bad = []
+        # what the reference handed to apply_rigid_body_force_tensors (t1:247): body 0 rows == the oracle's applied_*
+        forces = [c[1] for c in calls if c[0] == "apply_rigid_body_force_tensors"]
+        r_af, r_at = torch.zeros(N, 3), torch.zeros(N, 3)
+        if forces:
+            assert len(forces) == 1 and float(forces[0][0][:, 1:].abs().sum()) == 0 and float(forces[0][1][:, 1:].abs().sum()) == 0
+            r_af, r_at = forces[0][0][:, 0].clone(), forces[0][1][:, 0].clone()
+        if not (same(S.applied_force, r_af) and same(S.applied_torque, r_at)):
+            bad.append("applied_force/torque")
+        pushed = [c[1] for c in calls if c[0] == "set_actor_root_state_tensor"]
         for key, a, b in (("obs", o_obs, r_obs), ("priv", o_priv, r_priv), ("rew", o_rew, r_rew), ("reset", o_reset, r_reset)):
             if not same(a, b):
                 bad.append(key)
@@ -158,8 +184,9 @@ def run_scenario(name, spec, write_dir=None, verbose=True):
         cov["time_outs"] += int(env.time_out_buf.sum())
         cov["stand_env_steps"] += int(O.stand_command(C, S).sum())
         cov["ext_force_steps"] += int(bool(env.ext_forces.abs().sum() > 0))
-        cov["push_steps"] += int(bool(env.rand_push_force.abs().sum() > 0))
-        cov["curriculum_changes"] += int(env.command_ranges["lin_vel_x"][1] != 0.5 and cov["curriculum_changes"] == 0)
+        cov["ext_apply_steps"] += int(bool(r_af.abs().sum() > 0))
+        cov["push_steps"] += int(len(pushed) > 0)
+        cov["curriculum_changes"] += int({k: list(v) for k, v in env.command_ranges.items()} != ranges_before)
         cov["gait_switches"] += int(((env.episode_length_buf.unsqueeze(1) == env.gait_time[:, 1:]).any(1)).sum())
         if bad:
             raise SystemExit(f"[{name}] step {t}: oracle != reference on {bad}")
@@ -171,7 +198,13 @@ def run_scenario(name, spec, write_dir=None, verbose=True):
             ref_dof_pos=env.ref_dof_pos.clone(), root_after=drv.sim.root_states.clone(), dof_after=drv.sim.dof_state.clone(),
             episode_sums=torch.stack([env.episode_sums[k] for k in C.reward_scales], 0),
             reward_terms=torch.stack([S.reward_terms[k] for k in C.reward_scales], 0),
-            n_reset=torch.tensor(int(r_reset.sum()))))
+            n_reset=torch.tensor(int(r_reset.sum())),
+            applied_force=r_af, applied_torque=r_at, ext_forces=env.ext_forces.clone(), ext_torques=env.ext_torques.clone(),
+            rand_push_force=env.rand_push_force.clone(), rand_push_torque=env.rand_push_torque.clone(),
+            command_ranges=torch.tensor([env.command_ranges[k] for k in ("lin_vel_x", "lin_vel_y", "ang_vel_yaw")],
+                                        dtype=torch.float64),
+            # the gym tensor-API calls of this step, in order (lower boundary), as one string
+            gym_calls=torch.tensor(list(",".join(c[0] for c in calls).encode()), dtype=torch.uint8)))
     n_resets = sum(int(o["n_reset"]) for o in rec["outputs"])
     if verbose:
         print(f"[{name}] N={N} steps={steps}: oracle == reference bit-for-bit "

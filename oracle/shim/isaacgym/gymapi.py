@@ -156,7 +156,8 @@ class FakeGym:
         return 0
 
     def set_actor_dof_properties(self, env, actor, props):
-        pass
+        if self.tensors:          # after prepare_sim: a hot-path call (lr:939), not asset set-up
+            self._log("set_actor_dof_properties", (int(env), props.copy()))
 
     def get_actor_dof_properties(self, env, actor):
         return self.asset.dof_props.copy()
@@ -207,22 +208,53 @@ class FakeGym:
     def _noop(self, *a, **k):
         return None
 
-    refresh_dof_state_tensor = _noop
-    refresh_actor_root_state_tensor = _noop
-    refresh_net_contact_force_tensor = _noop
-    refresh_rigid_body_state_tensor = _noop
-    set_dof_actuation_force_tensor = _noop
-    simulate = _noop
     fetch_results = _noop
-    set_actor_root_state_tensor = _noop
-    apply_rigid_body_force_tensors = _noop
     viewer_camera_look_at = _noop
 
+    # every tensor-API call of the hot path is logged as (name, payload) — the lower boundary a drop-in env must
+    # reproduce.  Payloads are cloned where a call hands data to the simulator.  `log_calls = False`
+    # (the default) keeps only the indexed setters, which older tests read.
+    log_calls = False
+
+    def _log(self, name, payload=None):
+        if self.log_calls:
+            self.calls.append((name, payload))
+
+    def refresh_dof_state_tensor(self, sim):
+        self._log("refresh_dof_state_tensor")
+
+    def refresh_actor_root_state_tensor(self, sim):
+        self._log("refresh_actor_root_state_tensor")
+
+    def refresh_net_contact_force_tensor(self, sim):
+        self._log("refresh_net_contact_force_tensor")
+
+    def refresh_rigid_body_state_tensor(self, sim):
+        self._log("refresh_rigid_body_state_tensor")
+
+    def set_dof_actuation_force_tensor(self, sim, torques):
+        self._log("set_dof_actuation_force_tensor", torques.clone())
+
+    def simulate(self, sim):
+        self._log("simulate")
+
+    def set_actor_root_state_tensor(self, sim, state):
+        self._log("set_actor_root_state_tensor", state.clone())
+
+    def apply_rigid_body_force_tensors(self, sim, forces, torques, space=ENV_SPACE):
+        self._log("apply_rigid_body_force_tensors", (forces.clone(), torques.clone(), space))
+
     def set_dof_state_tensor_indexed(self, sim, state, ids, n):
-        self.calls.append(("dof", ids.clone()))
+        if self.log_calls:
+            self.calls.append(("set_dof_state_tensor_indexed", (state.clone(), ids.clone(), int(n))))
+        else:
+            self.calls.append(("dof", ids.clone()))
 
     def set_actor_root_state_tensor_indexed(self, sim, state, ids, n):
-        self.calls.append(("root", ids.clone()))
+        if self.log_calls:
+            self.calls.append(("set_actor_root_state_tensor_indexed", (state.clone(), ids.clone(), int(n))))
+        else:
+            self.calls.append(("root", ids.clone()))
 
 
 def acquire_gym():

@@ -235,6 +235,7 @@ def new_state(C, N):
     S.projected_gravity[:, 2] = -1
     S.base_euler_xyz, S.feet_euler_xyz = z(N, 3), z(N, 2, 3)
     S.rand_push_force, S.rand_push_torque, S.ext_forces, S.ext_torques = z(N, 3), z(N, 3), z(N, 3), z(N, 3)
+    S.applied_force, S.applied_torque = z(N, 3), z(N, 3)   # body-0 rows handed to apply_rigid_body_force_tensors (t1:247)
     S.ref_dof_pos, S.ref_action = z(N, D), z(N, D)
     S.measured_heights = 0
     S.gait_time = torch.zeros(N, len(cfg.commands.gait), dtype=torch.int, device=dev)
@@ -447,15 +448,22 @@ def ext_force(C, S, u_ext):
 # ------------------------------------------------------------------------------------------
 
 
-def sample_heights(C, S, sim, height_samples):
+def height_coords(C, S, sim):
+    """lr:1569-1575 up to (not including) the `.long()` truncation: the (N, npts, 3) fp32 grid coordinates of the scan
+    points.  Separate so that a test can tell a sample that legitimately sits on a cell edge from a wrong cell."""
     t = C.cfg.terrain
-    if t.mesh_type == "plane":
-        return torch.zeros(S.N, C.height_points.shape[0], device=C.device)
     npts = C.height_points.shape[0]
     pts = quat_apply_yaw(S.base_quat.repeat(1, npts), C.height_points.unsqueeze(0).expand(S.N, -1, -1).contiguous())
     pts = pts + sim.root_states[:, :3].unsqueeze(1)
     pts += t.border_size
-    pts = (pts / t.horizontal_scale).long()
+    return pts / t.horizontal_scale
+
+
+def sample_heights(C, S, sim, height_samples):
+    t = C.cfg.terrain
+    if t.mesh_type == "plane":
+        return torch.zeros(S.N, C.height_points.shape[0], device=C.device)
+    pts = height_coords(C, S, sim).long()
     px = torch.clip(pts[:, :, 0].reshape(-1), 0, height_samples.shape[0] - 2)
     py = torch.clip(pts[:, :, 1].reshape(-1), 0, height_samples.shape[1] - 2)
     h = torch.min(torch.min(height_samples[px, py], height_samples[px + 1, py]), height_samples[px, py + 1])

@@ -33,11 +33,22 @@ def scenario_cfg(name, num_envs, frame_stack=66):
         cfg.rewards.scales.feet_stumble = -0.5
         cfg.rewards.scales.stand_sysmetry = 0.3
         cfg.rewards.scales.termination = -1.0
-    if name == "trimesh_heights_push":
+    if name in ("trimesh_heights_push", "trimesh_windows"):
         cfg.terrain.measure_heights = True
         cfg.env.num_privileged_obs = 3 * (73 + 187)
         cfg.domain_rand.push_robots = True
+    if name == "plane_windows":
+        cfg.domain_rand.push_robots = True
     return cfg
+
+
+GOLDEN_SCENARIOS = ["plane_default", "plane_events", "trimesh_heights_push", "plane_extra_terms", "plane_windows",
+                    "trimesh_windows"]
+
+
+def gym_calls_of(out):
+    """The reference's gym tensor-API call names of one recorded step, in order."""
+    return bytes(out["gym_calls"].numpy().tolist()).decode().split(",")
 
 
 def make_env(cfg, rng_mode="pools", div_mode="ieee", **kw):
@@ -58,19 +69,29 @@ def set_sim(env, inp):
     env.rigid_state.copy_(inp["rigid_state"].view_as(env.rigid_state).to(env.device))
 
 
+def _same_device(a, b):
+    """Compare on the GPU when either side lives there (the 65536-env windows are ~1 GB each)."""
+    a, b = a.detach(), b.detach()
+    dev = a.device if a.is_cuda else b.device
+    return a.to(dev), b.to(dev)
+
+
 def close(a, b, what, rtol=RTOL, atol=ATOL):
-    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    a, b = _same_device(a, b)
+    a, b = a.float(), b.float()
     assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
     err = (a - b).abs()
     tol = atol + rtol * b.abs()
-    bad = err > tol
-    assert not bad.any(), (f"{what}: {int(bad.sum())} of {bad.numel()} beyond rtol={rtol} atol={atol}; "
-                           f"worst |err|={float(err.max()):.3e} at {np.unravel_index(int(err.argmax()), a.shape)} "
-                           f"(got {float(a.flatten()[err.argmax()]):.8g}, want {float(b.flatten()[err.argmax()]):.8g})")
+    bad = (err > tol) | (torch.isnan(a) != torch.isnan(b))
+    if bool(bad.any()):
+        i = int(err.argmax())
+        raise AssertionError(f"{what}: {int(bad.sum())} of {bad.numel()} beyond rtol={rtol} atol={atol}; "
+                             f"worst |err|={float(err.max()):.3e} at {np.unravel_index(i, a.shape)} "
+                             f"(got {float(a.flatten()[i]):.8g}, want {float(b.flatten()[i]):.8g})")
 
 
 def exact(a, b, what):
-    a, b = a.detach().cpu(), b.detach().cpu()
+    a, b = _same_device(a, b)
     assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
     assert torch.equal(a.to(b.dtype), b), f"{what}: {int((a.to(b.dtype) != b).sum())} of {b.numel()} entries differ"
 

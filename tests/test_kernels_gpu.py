@@ -245,8 +245,17 @@ def test_heights_match_oracle_at_scale():
     S = O.new_state(C, N)
     S.base_quat = env.root_states[:, 3:7].clone()
     want = O.sample_heights(C, S, env.gym.tensors, env.height_samples)
-    assert float((got != want).float().mean()) < 2e-4, "index truncation may differ only where fp32 lands on a cell edge"
-    close(got[got == want], want[got == want], "heights")
+    # The cell index is a truncation of an fp32 coordinate.  torch's CUDA `norm` reduction inside quat_apply_yaw may
+    # contract x*x + acc into an FMA where this library (-fmad=false) rounds twice, so the coordinate can differ in its
+    # last bit; that changes the cell ONLY when the coordinate sits within one ulp of a cell edge.  Everywhere else the
+    # sample must be the same cell, i.e. the same height, bit for bit.
+    coords = O.height_coords(C, S, env.gym.tensors)[..., :2]                       # (N, npts, 2) before .long()
+    ulp = torch.nextafter(coords.abs(), torch.full_like(coords, float("inf"))) - coords.abs()
+    on_edge = ((coords - coords.round()).abs() <= ulp).any(-1)
+    differ = got != want
+    assert not (differ & ~on_edge).any(), f"{int((differ & ~on_edge).sum())} samples landed in a different cell away from any cell edge"
+    assert float(differ.float().mean()) < 2e-4
+    exact(got[~differ], want[~differ], "heights")
 
 
 def test_host_io_graph_equals_the_device_path():

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN, SIM_KEYS, load_golden, pools_of, scenario_cfg
+from helpers import GOLDEN, GOLDEN_SCENARIOS, SIM_KEYS, load_golden, pools_of, scenario_cfg
 
 from oracle import t1_oracle as O
 
@@ -22,7 +22,7 @@ def _terrain_of(state0, cfg):
     return t, synthetic_height_field(2100, 2100, seed=7)
 
 
-@pytest.mark.parametrize("name", ["plane_default", "plane_events", "trimesh_heights_push", "plane_extra_terms"])
+@pytest.mark.parametrize("name", GOLDEN_SCENARIOS)
 def test_oracle_replays_reference_fixture(name):
     from ti5_isaacgym_b200.envs.t1.t1_robot import robot_constants
     state0, inputs, outputs, final = load_golden(name)
@@ -43,6 +43,11 @@ def test_oracle_replays_reference_fixture(name):
         torch.testing.assert_close(obs[:, -47:], out["obs_new"], **tight)
         torch.testing.assert_close(priv[:, -out["priv_new"].shape[1]:], out["priv_new"], **tight)
         torch.testing.assert_close(sim.root_states, out["root_after"], **tight)
+        # disturbance windows (t1:193-247) and the command curriculum (lr:1160-1169)
+        for k in ("applied_force", "applied_torque", "ext_forces", "ext_torques", "rand_push_force", "rand_push_torque"):
+            torch.testing.assert_close(getattr(S, k), out[k], **tight)
+        got = torch.tensor([S.command_ranges[k] for k in ("lin_vel_x", "lin_vel_y", "ang_vel_yaw")], dtype=torch.float64)
+        assert torch.equal(got, out["command_ranges"]), f"{name} step {t}: command ranges"
     torch.testing.assert_close(obs, final["obs"], **tight)
     torch.testing.assert_close(priv, final["priv"], **tight)
 

@@ -4,12 +4,12 @@ Bit-exact on reset flags / time-outs / reset id lists / contact masks; <= 1e-5 r
 import pytest
 import torch
 
-from helpers import close, exact, load_golden, make_env, pools_of, scenario_cfg, set_sim
+from helpers import GOLDEN_SCENARIOS, close, exact, load_golden, make_env, pools_of, scenario_cfg, set_sim
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["plane_default", "plane_events", "trimesh_heights_push", "plane_extra_terms"])
+@pytest.mark.parametrize("name", GOLDEN_SCENARIOS)
 def test_step_matches_reference_fixture(name):
     state0, inputs, outputs, final = load_golden(name)
     N = state0["commands"].shape[0]
@@ -40,6 +40,12 @@ def test_step_matches_reference_fixture(name):
         close(priv[:, -P:], out["priv_new"], tag + "newest privileged frame")
         close(env.root_states, out["root_after"], tag + "root_states after resets")
         close(env.dof_state, out["dof_after"], tag + "dof_state after resets")
+        # disturbance windows (t1:193-247): draws, what is handed to apply_rigid_body_force_tensors, pushes
+        for k in ("applied_force", "applied_torque", "ext_forces", "ext_torques", "rand_push_force", "rand_push_torque"):
+            close(getattr(env, k), out[k], tag + k)
+        # command curriculum (lr:1160-1169): the ranges the NEXT step draws from
+        got = torch.tensor([env.command_ranges[k] for k in ("lin_vel_x", "lin_vel_y", "ang_vel_yaw")], dtype=torch.float64)
+        exact(got, out["command_ranges"], tag + "command ranges")
         assert obs.shape == (N, env.cfg.env.frame_stack * K) and priv.shape == (N, env.cfg.env.c_frame_stack * P)
     close(obs, final["obs"], name + ": full observation history (layout oldest -> newest)")
     close(priv, final["priv"], name + ": full privileged frame stack")

@@ -13,7 +13,7 @@ from oracle import t1_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def _build(name, N, device, seed=3, frame_stack=66):
+def _build(name, N, device, seed=3, frame_stack=66, counter=2397):
     from ti5_isaacgym_b200.envs.t1.t1_robot import robot_constants
     from ti5_isaacgym_b200.sim.synthetic import SyntheticTerrain, synthetic_height_field
     cfg = scenario_cfg(name, N, frame_stack)
@@ -48,7 +48,9 @@ def _build(name, N, device, seed=3, frame_stack=66):
     S.commands[S.episode_length_buf > S.gait_time[:, 2], :3] = -0.5 + r(int((S.episode_length_buf > S.gait_time[:, 2]).sum()), 3)
     S.env_frictions[:] = 0.2 + 1.1 * r(N, 1)
     S.body_mass[:] = 10 + 5 * r(N, 1)
-    S.common_step_counter = 2397                                  # curriculum check + ext-force window at step 3
+    S.common_step_counter = counter                               # curriculum check + ext-force window at step 3
+    if counter > 2397:      # "windows" scenarios: tracking sums above 80 % of the maximum, the command curriculum fires
+        S.episode_sums["tracking_lin_vel"][:] = 0.9 * C.reward_scales["tracking_lin_vel"] * 2400
     if terrain is not None:
         S.terrain_levels[:] = torch.randint(0, 6, (N,), generator=gen).to(device)
         S.terrain_types[:] = torch.div(torch.arange(N), N / cfg.terrain.num_cols, rounding_mode="floor").long().to(device)
@@ -72,18 +74,27 @@ MASS = (1.0, 0.0, 0.04, 0.0, 1.0, 1.0)
     ("plane_events", 1, 12, "cuda", 66, MASS), ("plane_events", 31, 12, "cuda", 66, MASS),
     ("plane_events", 33, 12, "cuda", 66, MASS), ("plane_events", 2048, 12, "cuda", 66, MASS),
     ("trimesh_heights_push", 200, 12, "cuda", 66, MASS),
+    # multi-step push / external-force windows (20 / 16 steps at common_step_counter >= 288000) with the apply branch,
+    # window exit, and a command-curriculum change; in both rounding modes
+    ("plane_windows", 1024, 30, "cuda", 66, None), ("plane_windows", 256, 30, "cpu", 66, None),
+    ("trimesh_windows", 512, 26, "cuda", 66, None),
+    # BASELINE config 3 at its own size, and the plane step at the sizes where env_block, early mode, the carve-out and
+    # the 128-register build switch
+    ("trimesh_heights_push", 8192, 5, "cuda", 66, None),
+    ("plane_events", 16384, 4, "cuda", 66, None), ("plane_events", 65536, 3, "cuda", 66, None),
 ])
 def test_env_follows_oracle(name, N, steps, where, H, rates):
     from ti5_isaacgym_b200.sim.synthetic import alloc_sim_tensors, fill_synthetic_state, synthetic_actions
     device = "cuda:0" if where == "cuda" else "cpu"
-    cfg, C, S, terrain, heights, gen = _build(name, N, device, frame_stack=H)
+    cfg, C, S, terrain, heights, gen = _build(name, N, device, frame_stack=H, counter=287997 if "windows" in name else 2397)
     env = make_env(scenario_cfg(name, N, H), div_mode="ieee" if where == "cpu" else "reciprocal")
     state = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in state_from_oracle(S, C).items()}
     if terrain is not None:
         state["terrain_origins"] = terrain.origins.cpu()
     env.load_state(state)
     sim_cpu = alloc_sim_tensors(N, "cpu")
-    n_resets = n_stand = 0
+    n_resets = n_stand = n_apply = n_push = 0
+    range0 = list(S.command_ranges["lin_vel_x"])
     for t in range(steps):
         fill_synthetic_state(sim_cpu, S.env_origins.cpu(), gen, base_contact_rate=0.04 if rates is None else rates[t % len(rates)])
         actions = synthetic_actions(N, gen, "cpu")
@@ -118,7 +129,7 @@ def test_env_follows_oracle(name, N, steps, where, H, rates):
             close(env.episode_sums[nm], S.episode_sums[nm], tag + "episode_sums " + nm)
         for attr in ("base_lin_vel", "base_ang_vel", "projected_gravity", "base_euler_xyz", "feet_euler_xyz", "feet_air_time",
                      "feet_height", "ref_dof_pos", "last_actions", "last_last_actions", "last_dof_vel", "last_root_vel",
-                     "ext_forces", "motor_offsets", "randomized_p_gains", "randomized_joint_viscous", "joint_armatures",
+                     "ext_forces", "ext_torques", "applied_force", "applied_torque", "rand_push_force", "rand_push_torque", "motor_offsets", "randomized_p_gains", "randomized_joint_viscous", "joint_armatures",
                      "gait_start", "env_origins"):
             close(getattr(env, attr), getattr(S, attr), tag + attr)
         exact(env.lag_timestep, S.lag_timestep, tag + "lag_timestep")
@@ -133,12 +144,18 @@ def test_env_follows_oracle(name, N, steps, where, H, rates):
         if len(ids):
             for k, v in o_extras["episode"].items():
                 got = extras["episode"][k]
-                close(torch.as_tensor(got).reshape(()), torch.as_tensor(v).float().reshape(()), tag + "extras " + k, rtol=1e-4)
+                close(torch.as_tensor(got).reshape(()), torch.as_tensor(v).float().reshape(()), tag + "extras " + k)
             exact(extras["time_outs"], o_extras["time_outs"], tag + "extras time_outs")
-        assert env.command_ranges == {k: [float(x) for x in v] for k, v in S.command_ranges.items()} or True
+        for k in ("lin_vel_x", "lin_vel_y", "ang_vel_yaw"):      # lr:1160-1169, read back by sync_from_device above
+            assert [float(x) for x in env.command_ranges[k]] == [float(x) for x in S.command_ranges[k]], tag + "command range " + k
+        n_apply += int(bool(S.applied_force.abs().sum() > 0))
+        n_push += int(bool(S.rand_push_torque.abs().sum() > 0))
         n_resets += len(ids)
         n_stand += int(O.stand_command(C, S).sum())
     assert n_resets > 0 and (n_stand > 0 or rates is not None), "the scenario must exercise resets and the stand phase"
+    if "windows" in name:
+        assert n_apply >= 5 and n_push >= 5, "the multi-step apply / push branches must run"
+        assert list(S.command_ranges["lin_vel_x"]) != range0, "the command curriculum must change the range"
 
 
 def test_command_curriculum_fires_on_device():
