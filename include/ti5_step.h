@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TI5_ABI_VERSION 5
+#define TI5_ABI_VERSION 6
 
 #define TI5_NUM_DOF 12      /* leg_l1..l6, leg_r1..r6 */
 #define TI5_NUM_BODIES 13   /* base_link + 12 leg links after collapse_fixed_joints */
@@ -115,6 +115,10 @@ typedef struct Ti5Params {
   int32_t terrain_rows, terrain_cols, max_terrain_level;
   uint32_t term_mask;                     /* bit i set = reward term i has a non-zero scale */
   int32_t log_len;                        /* L: rows of the frame logs (0 = no log); must be >= rollout length + H */
+  int32_t applied_stride;                 /* floats between the rows of consecutive envs in Ti5Buffers.applied_force /
+                                             applied_torque: 3 for plain (N,3) arrays, 3 * TI5_NUM_BODIES when they
+                                             point at the body-0 rows of the (N,13,3) tensors that
+                                             apply_rigid_body_force_tensors takes (t1:234-247) */
   int64_t max_episode_length;             /* ceil(episode_length_s / dt) = 2400 */
   int64_t push_interval, ext_force_interval, push_update_step, add_update_step;
   uint64_t seed;                          /* Philox key */
@@ -220,8 +224,8 @@ typedef struct Ti5Buffers {
   float* ext_torques;      /* (N,3) */
   float* rand_push_force;  /* (N,3) */
   float* rand_push_torque; /* (N,3) */
-  float* applied_force;    /* (N,3) force handed to apply_rigid_body_force_tensors for body 0 */
-  float* applied_torque;   /* (N,3) */
+  float* applied_force;    /* force handed to apply_rigid_body_force_tensors for body 0: row e at e * applied_stride */
+  float* applied_torque;   /* likewise */
   float* env_frictions;    /* (N) */
   float* body_mass;        /* (N) */
   /* terrain */
@@ -241,6 +245,9 @@ typedef struct Ti5Buffers {
   float* reward_terms;     /* (TI5_NUM_TERMS, N) scaled per-term rewards of this step, or NULL */
   int32_t* reset_ids;      /* (N) ascending ids of the envs reset this step */
   int32_t* reset_list;     /* (N) the same ids in arrival order (work list for the history clear) */
+  float* dof_props;        /* optional (N, TI5_NUM_DOF, 3), or NULL: row r = [friction multiplier, damping multiplier,
+                              armature] per DOF of env reset_ids[r], written next to the id list by the reset scatter —
+                              lr:915-939 `_refresh_actor_dof_props` as one dense tensor (see ti5_gather_dof_props) */
   int32_t* block_counts;   /* scratch: (ceil(N/32) + 1) */
   float* block_sums;       /* scratch: (ceil(N/32), TI5_LOG_COLS) */
   float* extras_log;       /* (TI5_LOG_ROWS, TI5_LOG_COLS) */
@@ -321,6 +328,15 @@ int ti5_compact_resets(const uint8_t* mask, int32_t n, int32_t* ids_out, int32_t
 int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, int phases, void* stream);
 int ti5_reset_scatter(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, void* stream);
 int ti5_observations(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, void* stream);
+
+/* lr:915-939 `_refresh_actor_dof_props(env_ids)`: the reference walks env_ids in a Python loop and reads every
+ * randomised joint property of every env with a device->host sync per element.  This gathers them for the envs
+ * ids[0 .. min(*count, capacity)) into ONE dense (capacity, TI5_NUM_DOF, 3) tensor [friction multiplier, damping
+ * multiplier, armature] (lr:921-936; t1 randomises the armature only, the multipliers are 1), so that the simulator
+ * side needs a single copy (or none, if it takes device tensors).  `ids` / `count` are typically Ti5Buffers.reset_ids
+ * and &Ti5Globals.n_reset: no host round trip to learn how many envs were reset. */
+int ti5_gather_dof_props(const Ti5Params* p, const Ti5Buffers* b, const int32_t* ids, const int32_t* count,
+                         int32_t capacity, float* props_out, void* stream);
 
 /* lr:441-446: copy the current history windows into contiguous (N,H*K) / (N,CH*P) tensors */
 int ti5_materialize_obs(const Ti5Params* p, const Ti5Buffers* b, void* stream);

@@ -152,6 +152,16 @@ def run_scenario(name, spec, write_dir=None, verbose=True):
         if not (same(S.applied_force, r_af) and same(S.applied_torque, r_at)):
             bad.append("applied_force/torque")
         pushed = [c[1] for c in calls if c[0] == "set_actor_root_state_tensor"]
+        # lr:915-939: the per-env property structs handed back to the simulator for the re-spawned envs
+        props = [c[1] for c in calls if c[0] == "set_actor_dof_properties"]
+        props_env = torch.tensor([e for e, _ in props], dtype=torch.int64)
+        props_arm = torch.tensor(np.stack([d["armature"] for _, d in props]) if props else np.zeros((0, 12), np.float32))
+        if not (same(props_env, S.reset_ids) and same(props_arm, S.joint_armatures[S.reset_ids])):
+            bad.append("dof props")
+        for nm in ("set_dof_state_tensor_indexed", "set_actor_root_state_tensor_indexed"):
+            for c in calls:
+                if c[0] == nm and not (same(c[1][1].long(), S.reset_ids) and c[1][2] == len(S.reset_ids)):
+                    bad.append(nm + " ids")
         for key, a, b in (("obs", o_obs, r_obs), ("priv", o_priv, r_priv), ("rew", o_rew, r_rew), ("reset", o_reset, r_reset)):
             if not same(a, b):
                 bad.append(key)
@@ -203,6 +213,7 @@ def run_scenario(name, spec, write_dir=None, verbose=True):
             rand_push_force=env.rand_push_force.clone(), rand_push_torque=env.rand_push_torque.clone(),
             command_ranges=torch.tensor([env.command_ranges[k] for k in ("lin_vel_x", "lin_vel_y", "ang_vel_yaw")],
                                         dtype=torch.float64),
+            props_env=props_env, props_armature=props_arm,
             # the gym tensor-API calls of this step, in order (lower boundary), as one string
             gym_calls=torch.tensor(list(",".join(c[0] for c in calls).encode()), dtype=torch.uint8)))
     n_resets = sum(int(o["n_reset"]) for o in rec["outputs"])

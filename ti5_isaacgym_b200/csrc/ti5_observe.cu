@@ -766,6 +766,16 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
   // ---- ascending id list of the envs reset this step (lr:490) --------------------------------
   const BlockRank br = block_rank(reset, s_warp);
   if (reset && b.reset_ids) b.reset_ids[id_offset + br.rank] = e;
+  if (reset && b.dof_props) {       // lr:915-939: the re-drawn joint properties, dense, in the order of the id list
+    float* o = b.dof_props + (size_t)(id_offset + br.rank) * D * 3;
+    const float* arm = b.joint_armatures + (size_t)e * D;      // written by this CTA's scatter, before a __syncthreads
+#pragma unroll 1
+    for (int d = 0; d < D; ++d) {
+      o[d * 3 + 0] = 1.0f;
+      o[d * 3 + 1] = 1.0f;
+      o[d * 3 + 2] = (p.flags & TI5_F_RAND_ARMATURE) ? arm[d] : 0.0f;
+    }
+  }
 
   // ---- extras["episode"]["terrain_level"] = mean(terrain_levels) (t1:535-536) ------------------
   if ((p.flags & TI5_F_TRIMESH) && do_reset) {

@@ -354,7 +354,10 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
           for (int c = 0; c < 3; ++c) { b.ext_forces[e * 3 + c] = 0.0f; b.ext_torques[e * 3 + c] = 0.0f; }
         }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { b.applied_force[e * 3 + c] = af[c]; b.applied_torque[e * 3 + c] = at[c]; }
+        for (int c = 0; c < 3; ++c) {
+          b.applied_force[(size_t)e * p.applied_stride + c] = af[c];
+          b.applied_torque[(size_t)e * p.applied_stride + c] = at[c];
+        }
       }
       // lr:509-517 termination
       time_out = ep_len > p.max_episode_length;
@@ -679,6 +682,7 @@ extern "C" int ti5_post_physics(const Ti5Params* p, const Ti5Buffers* b, const T
   TI5_CHECK_ARGS(p->env_block == 32 || p->env_block == 64 || p->env_block == 128);
   TI5_CHECK_ARGS(p->rng_mode == TI5_RNG_PHILOX || (r && r->cmd));
   TI5_CHECK_ARGS((p->term_mask & (1u << T_DOF_VEL_LIMITS)) == 0);   // the reference term reads a cfg field t1 lacks
+  TI5_CHECK_ARGS(!(p->flags & TI5_F_ADD_EXT_FORCE) || p->applied_stride >= 3);
   Ti5Rng rr = r ? *r : Ti5Rng{};
   const int blocks = (p->num_envs + p->env_block - 1) / p->env_block;
   const PostSrc src = make_post_src(*p, *b);

@@ -229,7 +229,12 @@ class LeggedRobot(BaseTask):
         self.ref_dof_pos, self.ref_action = f32(N, D), f32(N, D)
         self.ext_forces, self.ext_torques = f32(N, 3), f32(N, 3)
         self.rand_push_force, self.rand_push_torque = f32(N, 3), f32(N, 3)
-        self.applied_force, self.applied_torque = f32(N, 3), f32(N, 3)
+        # what apply_rigid_body_force_tensors takes (t1:234-247): (N, NB, 3) force / torque tensors, zero except the
+        # base rows, which ti5_post_physics writes in place (Ti5Params.applied_stride)
+        self._apply_forces, self._apply_torques = f32(N, NB, 3), f32(N, NB, 3)
+        self.applied_force, self.applied_torque = self._apply_forces[:, 0, :], self._apply_torques[:, 0, :]
+        p.applied_stride = 3 * NB
+        self._dof_props = f32(N, D, 3)          # lr:915-939 as one dense tensor, rows in reset_ids order
         self.env_frictions, self.body_mass = f32(N, 1), f32(N, 1)
         # the per-step scalar outputs share one allocation, so a host consumer needs a single D2H copy:
         # [rew_buf f32 (4N bytes) | reset_buf bool (N) | extras["time_outs"] bool (N)]
@@ -253,6 +258,9 @@ class LeggedRobot(BaseTask):
         self._block_sums = f32(nblk, C["TI5_LOG_COLS"])
         self._extras_log = f32(C["TI5_LOG_ROWS"], C["TI5_LOG_COLS"])
         self._globals = torch.zeros(ctypes.sizeof(_lib.Ti5Globals), dtype=torch.uint8, device=dev)
+        # len(env_ids) of the step in progress (lr:490) where it lives: a 0-dim int32 view into the device globals
+        off = _lib.Ti5Globals.n_reset.offset
+        self.n_reset_device = self._globals[off:off + 4].view(torch.int32)[0]
         self._debug_ts = None        # set to a (2, 4096, 8) int64 CUDA tensor and re-bind to collect kernel probes
         self._obs_out = self._priv_out = None                     # allocated per step by _materialize_windows()
         self._frame_log = self._priv_log = self._valid_log = self._hist_valid = None     # enable_frame_log()
@@ -367,8 +375,9 @@ class LeggedRobot(BaseTask):
             priv_ring=self._priv_ring, obs_out=self._obs_out, priv_out=self._priv_out, debug_ts=self._debug_ts,
             frame_log=self._frame_log, priv_log=self._priv_log, valid_log=self._valid_log, hist_valid=self._hist_valid,
             host_out=getattr(self, "host_outputs", None))
+        pairs["dof_props"] = self._dof_props
         for name, t in pairs.items():
-            if t is not None:
+            if t is not None and name not in ("applied_force", "applied_torque"):      # strided rows of (N, NB, 3)
                 assert t.is_contiguous(), name
             setattr(b, name, ptr(t))
         self._buffers = b
@@ -547,20 +556,26 @@ class LeggedRobot(BaseTask):
                 else:
                     _lib.check(lib.ti5_substep(p, b, r, k, C["TI5_SUB_TORQUE"] | C["TI5_SUB_PUSH"] | self._chain("TI5_SUB_CHAINED"), st))
 
-    def _launch_post(self, with_physics, part=3):
+    def _launch_post(self, with_physics, part=3, notify=False):
         """lr:458-506 post_physics_step + the observation clip of lr:441-446.  `part`: 1 = ti5_post_physics only,
-        2 = ti5_reset_observe only (per-kernel timing), 3 = both."""
+        2 = ti5_reset_observe only (per-kernel timing), 3 = both.  `notify`: issue the simulator-facing calls of the
+        phase where the reference issues them (not while capturing a graph: `step` issues them after the replay)."""
         lib, p, b, r, st = self._lib, self._p_ref, self._b_ref, self._rng_ref(), self._stream()
         fused = not with_physics
         if part & 1:
             if with_physics:
+                self.gym.refresh_actor_root_state_tensor(self.sim)          # lr:464-466
                 self.gym.refresh_net_contact_force_tensor(self.sim)
                 self.gym.refresh_rigid_body_state_tensor(self.sim)
             if self._params.num_height_points:
                 _lib.check(lib.ti5_sample_heights(p, b, st))
             _lib.check(lib.ti5_post_physics(p, b, r, (C["TI5_POST_PUSH_LAST"] | self._chain("TI5_POST_CHAINED")) if fused else 0, st))
+            if notify:
+                self._notify_simulator_of_disturbances()
         if part & 2:
             _lib.check(lib.ti5_reset_observe(p, b, r, C["TI5_RO_RESET"] | C["TI5_RO_OBSERVE"] | self._chain("TI5_RO_CHAINED"), st))
+            if notify:
+                self._notify_simulator_of_resets()
 
     def _materialize_windows(self):
         """lr:441-446 / t1:477-481: this step's windows as FRESH contiguous tensors (outside the captured graph: a
@@ -572,10 +587,10 @@ class LeggedRobot(BaseTask):
         b.obs_out, b.priv_out = self._obs_out.data_ptr(), self._priv_out.data_ptr()
         _lib.check(self._lib.ti5_materialize_obs(self._p_ref, ctypes.byref(b), self._stream()))
 
-    def _launch_step(self, actions_ptr, with_physics):
+    def _launch_step(self, actions_ptr, with_physics, notify=False):
         """Enqueue the kernels of one policy step on the current stream."""
         self._launch_substeps(actions_ptr, with_physics)
-        self._launch_post(with_physics)
+        self._launch_post(with_physics, notify=notify)
 
     def capture_phase_graphs(self):
         """Three CUDA graphs (substep phase, ti5_post_physics, ti5_reset_observe) instead of one, so that a benchmark
@@ -614,9 +629,12 @@ class LeggedRobot(BaseTask):
                 self._actions_in.copy_(actions, non_blocking=True)     # device tensor or pinned host memory
                 g = self._graph
             g.replay()
+            # the simulator-facing calls of the step, in the reference's order; the kernels are already enqueued
+            self._notify_simulator_of_disturbances()
+            self._notify_simulator_of_resets()
         else:
             a = actions.to(device=self.device, dtype=torch.float32).contiguous()
-            self._launch_step(ctypes.c_void_p(a.data_ptr()), with_physics)
+            self._launch_step(ctypes.c_void_p(a.data_ptr()), with_physics, notify=True)
         return self._finish_step()
 
     # ------------------------------------------------------------------ host-side callers (CPU policy / controller)
@@ -652,6 +670,8 @@ class LeggedRobot(BaseTask):
                 self._launch_step(ctypes.c_void_p(self.host_actions.data_ptr()), False)
             self._graph_host = g
         self._graph_host.replay()
+        self._notify_simulator_of_disturbances()
+        self._notify_simulator_of_resets()
         out = self._finish_step()
         torch.cuda.current_stream(self.device).synchronize()
         return out
@@ -729,16 +749,94 @@ class LeggedRobot(BaseTask):
         self._notify_simulator_of_resets()
         self._publish_extras()
 
+    # ------------------------------------------------------------------ lower boundary: what the simulator is told
+    def _disturbance_windows(self, counter):
+        """t1:193-215: the push / external-force window predicates of the step whose `common_step_counter` (after
+        lr:471) is `counter` — a host-side integer schedule, the same arithmetic ti5_post_physics does on the device."""
+        p = self._params
+        push = force = False
+        if p.flags & C["TI5_F_PUSH_ROBOTS"]:
+            i = min(int(counter / p.push_update_step), p.n_push_dur - 1)
+            push = counter % p.push_interval <= p.push_duration[i]
+        if p.flags & C["TI5_F_ADD_EXT_FORCE"]:
+            i = min(int(counter / p.add_update_step), p.n_add_dur - 1)
+            force = counter % p.ext_force_interval <= p.add_duration[i]
+        return push, force
+
+    def _notify_simulator_of_disturbances(self):
+        """t1:230 / t1:247, where `_post_physics_step_callback` issues them: the pushed base velocities (written into
+        `root_states` by ti5_post_physics) go back to the simulator as the whole root tensor; the external force /
+        torque on the base as (N, NB, 3) tensors in env space.  Stream-ordered behind the kernel, no host wait."""
+        push, force = self._disturbance_windows(self.common_step_counter + 1)
+        if push:
+            self.gym.set_actor_root_state_tensor(self.sim, self.root_states)
+        if force:
+            self.gym.apply_rigid_body_force_tensors(self.sim, self._apply_forces, self._apply_torques, 0)   # gymapi.ENV_SPACE
+
     def _notify_simulator_of_resets(self):
-        """lr:1087-1090, 1117-1120: hand the re-spawned states to the simulator.  Only a real simulator
-        needs the compacted id list on the host (one D2H sync, as in the reference's `len(env_ids)`)."""
-        if not getattr(self.gym, "needs_indexed_resets", False):
+        """lr:1087-1090, 1117-1120, 915-939 for the envs ti5_reset_observe re-spawned: joint state, root state and the
+        re-drawn joint properties go to the simulator, addressed by the ascending id list the kernel left in
+        `reset_ids`.  A binding that declares `device_counts` gets the list as (buffer, device count) and the step
+        stays free of host waits; Isaac Gym's own API needs `len(env_ids)` on the host — one 4-byte read-back, where
+        the reference pays `nonzero()` (lr:490)."""
+        gym = self.gym
+        if getattr(gym, "device_counts", False):
+            n = self.n_reset_device
+            gym.set_dof_state_tensor_indexed(self.sim, self.dof_state, self.reset_ids, n)
+            gym.set_actor_root_state_tensor_indexed(self.sim, self.root_states, self.reset_ids, n)
+            self._refresh_actor_dof_props(None, n)
             return
-        n = int(self._read_globals().n_reset)
+        if not getattr(gym, "needs_indexed_resets", True):
+            return
+        n = int(self.n_reset_device)                        # the step's only host wait with a real simulator
         if n:
             ids = self.reset_ids[:n]
-            self.gym.set_dof_state_tensor_indexed(self.sim, self.dof_state, ids, n)
-            self.gym.set_actor_root_state_tensor_indexed(self.sim, self.root_states, ids, n)
+            gym.set_dof_state_tensor_indexed(self.sim, self.dof_state, ids, n)
+            gym.set_actor_root_state_tensor_indexed(self.sim, self.root_states, ids, n)
+            self._refresh_actor_dof_props(None, n)
+            gym.refresh_actor_root_state_tensor(self.sim)       # t1:544-546
+            gym.refresh_net_contact_force_tensor(self.sim)
+            gym.refresh_rigid_body_state_tensor(self.sim)
+
+    def _refresh_actor_dof_props(self, env_ids=None, n=None):
+        """lr:915-939.  The reference walks `env_ids` in Python and reads `joint_armatures[env_id, i]` element by
+        element (a device->host sync each with a GPU pipeline).  Here the properties of the listed envs are one dense
+        (n, 12, 3) tensor [friction multiplier, damping multiplier, armature]: written by the reset scatter for the
+        envs of `reset_ids` (env_ids=None), or gathered for any id list by ti5_gather_dof_props.  A simulator binding
+        with `set_actor_dof_properties_batched` takes the tensor as it is; Isaac Gym's per-env property structs are
+        filled from ONE host copy of it."""
+        gym, dr = self.gym, self.cfg.domain_rand
+        if not (dr.randomize_joint_armature or getattr(dr, "randomize_joint_friction", False)
+                or getattr(dr, "randomize_joint_damping", False)):
+            return
+        ids, props = self.reset_ids, self._dof_props
+        if env_ids is not None:
+            ids = torch.as_tensor(env_ids, device=self.device).to(torch.int32).contiguous()
+            n = len(ids)
+            if n == 0:
+                return
+            count = torch.tensor([n], dtype=torch.int32, device=self.device)
+            props = torch.empty(n, self.num_dof, 3, dtype=torch.float32, device=self.device)
+            _lib.check(self._lib.ti5_gather_dof_props(self._p_ref, self._b_ref, ctypes.c_void_p(ids.data_ptr()),
+                                                      ctypes.c_void_p(count.data_ptr()), n,
+                                                      ctypes.c_void_p(props.data_ptr()), self._stream()))
+        batched = getattr(gym, "set_actor_dof_properties_batched", None)
+        if batched is not None:
+            batched(self.sim, ids, props, n)
+            return
+        if not hasattr(gym, "set_actor_dof_properties"):
+            return
+        n = int(n)
+        ids_h, props_h = ids[:n].cpu().tolist(), props[:n].cpu().numpy()
+        for r, env_id in enumerate(ids_h):
+            dp = gym.get_actor_dof_properties(self.envs[env_id], 0)
+            if getattr(dr, "randomize_joint_friction", False):
+                dp["friction"] *= props_h[r, :, 0]
+            if getattr(dr, "randomize_joint_damping", False):
+                dp["damping"] *= props_h[r, :, 1]
+            if dr.randomize_joint_armature:
+                dp["armature"][:] = props_h[r, :, 2]
+            gym.set_actor_dof_properties(self.envs[env_id], 0, dp)
 
     # ------------------------------------------------------------------ curriculum state mirrored from the device
     def sync_from_device(self):

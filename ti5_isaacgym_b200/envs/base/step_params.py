@@ -21,7 +21,8 @@ GAIT_KIND = {"stand": C["TI5_GAIT_STAND"], "walk_sagittal": C["TI5_GAIT_WALK_SAG
              "walk_lateral": C["TI5_GAIT_WALK_LATERAL"], "rotate": C["TI5_GAIT_ROTATE"],
              "walk_omnidirectional": C["TI5_GAIT_WALK_OMNI"]}
 UNSUPPORTED_FLAGS = ("randomize_lag_timesteps_perstep", "randomize_dof_lag_timesteps_perstep",
-                     "randomize_imu_lag_timesteps_perstep", "add_dof_pos_vel_lag")
+                     "randomize_imu_lag_timesteps_perstep", "add_dof_pos_vel_lag",
+                     "randomize_joint_friction", "randomize_joint_damping")     # lr:755-773: off in t1_cfg (commented out)
 
 
 def pick_env_block(num_envs, sms=148):
@@ -76,6 +77,7 @@ def build_params(cfg, sim_dt, robot, terrain=None, height_shape=(0, 0), div_mode
     p.rng_mode = C["TI5_RNG_PHILOX"] if rng_mode is None else rng_mode
     p.env_block = env_block or int(os.environ.get("TI5_ENV_BLOCK", 0)) or pick_env_block(N)
     p.seed = seed
+    p.applied_stride = 3                    # plain (N,3) applied_force / applied_torque unless the env re-points them
     gaits = list(cm.gait)
     assert len(gaits) <= C["TI5_MAX_GAITS"]
     p.num_gaits = len(gaits)

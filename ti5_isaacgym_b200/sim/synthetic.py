@@ -103,15 +103,30 @@ class SyntheticGym:
     Gym is not installed: it owns the four state tensors with the tensor-API layout and accepts
     the tensor-API calls of the hot path (lr:403-410, 429, 464-466, 1088, 1118; t1:230, 247).
     `simulate` is a no-op unless a `physics` callable is installed (tests use it to refresh the
-    state between substeps)."""
+    state between substeps).
+
+    Two capabilities a simulator binding can declare, both beyond Isaac Gym's own API (lower boundary):
+      device_counts = True   the indexed setters take the id list as a fixed-capacity device buffer plus a DEVICE count
+                             (`n` is a 0-dim int32 tensor), so a step needs no host round trip to learn `len(env_ids)`;
+      set_actor_dof_properties_batched(sim, ids, props, n)   one (capacity, 12, 3) tensor [friction multiplier, damping
+                             multiplier, armature] for the re-spawned envs instead of lr:915-939's per-env get/set loop.
+    Without them the env falls back to what Isaac Gym offers: one 4-byte read-back of the count, then the calls of the
+    reference with host integers."""
+
+    device_counts = True
+    needs_indexed_resets = False      # True: notify like Isaac Gym needs it (host count; the reference's exact call list)
+    log_len = 64
 
     def __init__(self, num_envs, device):
+        from collections import deque
         self.num_envs, self.device = num_envs, device
         self.tensors = alloc_sim_tensors(num_envs, device)
         self.physics = None
         self.substep = 0
-        self.indexed_calls = []      # (kind, int32 ids) of the indexed setters, newest last
+        self.indexed_calls = deque(maxlen=self.log_len)      # (kind, int32 ids, n) of the indexed setters, newest last
         self.applied_forces = None
+        self.pushed_root_states = None
+        self.dof_props = None
 
     def acquire_actor_root_state_tensor(self, sim=None):
         return self.tensors.root_states
@@ -135,16 +150,84 @@ class SyntheticGym:
 
     fetch_results = refresh_dof_state_tensor = refresh_actor_root_state_tensor = _noop
     refresh_net_contact_force_tensor = refresh_rigid_body_state_tensor = _noop
-    set_dof_actuation_force_tensor = set_actor_root_state_tensor = _noop
+    set_dof_actuation_force_tensor = _noop
+
+    def set_actor_root_state_tensor(self, sim, state):
+        self.pushed_root_states = state
 
     def set_dof_state_tensor_indexed(self, sim, state, ids, n):
-        self.indexed_calls.append(("dof", ids))
+        self.indexed_calls.append(("dof", ids, n))
 
     def set_actor_root_state_tensor_indexed(self, sim, state, ids, n):
-        self.indexed_calls.append(("root", ids))
+        self.indexed_calls.append(("root", ids, n))
 
     def apply_rigid_body_force_tensors(self, sim, forces, torques, space=0):
         self.applied_forces = (forces, torques)
+
+    def set_actor_dof_properties_batched(self, sim, ids, props, n):
+        self.dof_props = (ids, props, n)
+
+
+class RecordingGym(SyntheticGym):
+    """A SyntheticGym that behaves like Isaac Gym's API surface (host counts, per-env DOF property structs, a physics
+    callback between the substeps) and logs every tensor-API call as (name, payload): the lower boundary of one
+    step, comparable call by call with what the reference issues against `oracle/shim` (tests)."""
+
+    device_counts = False
+    needs_indexed_resets = True
+    set_actor_dof_properties_batched = None
+
+    def __init__(self, num_envs, device):
+        import numpy as np
+        super().__init__(num_envs, device)
+        self.calls = []
+        self.physics = lambda k: None
+        dt = np.dtype([(k, np.float32) for k in ("lower", "upper", "velocity", "effort", "stiffness", "damping",
+                                                 "friction", "armature")])
+        self._dof_props = [np.zeros(D, dtype=dt) for _ in range(num_envs)]
+
+    def _log(self, name, payload=None):
+        self.calls.append((name, payload))
+
+    def simulate(self, sim=None):
+        self._log("simulate")
+        super().simulate(sim)
+
+    def refresh_dof_state_tensor(self, sim=None):
+        self._log("refresh_dof_state_tensor")
+
+    def refresh_actor_root_state_tensor(self, sim=None):
+        self._log("refresh_actor_root_state_tensor")
+
+    def refresh_net_contact_force_tensor(self, sim=None):
+        self._log("refresh_net_contact_force_tensor")
+
+    def refresh_rigid_body_state_tensor(self, sim=None):
+        self._log("refresh_rigid_body_state_tensor")
+
+    def set_dof_actuation_force_tensor(self, sim, torques):
+        self._log("set_dof_actuation_force_tensor", torques.clone())
+
+    def set_actor_root_state_tensor(self, sim, state):
+        self._log("set_actor_root_state_tensor", state.clone())
+
+    def apply_rigid_body_force_tensors(self, sim, forces, torques, space=0):
+        self._log("apply_rigid_body_force_tensors", (forces.clone(), torques.clone(), space))
+
+    def set_dof_state_tensor_indexed(self, sim, state, ids, n):
+        assert isinstance(n, int), "Isaac Gym takes the id count as a host integer"
+        self._log("set_dof_state_tensor_indexed", (state.clone(), ids.clone(), n))
+
+    def set_actor_root_state_tensor_indexed(self, sim, state, ids, n):
+        assert isinstance(n, int)
+        self._log("set_actor_root_state_tensor_indexed", (state.clone(), ids.clone(), n))
+
+    def get_actor_dof_properties(self, env, actor):
+        return self._dof_props[env].copy()
+
+    def set_actor_dof_properties(self, env, actor, props):
+        self._dof_props[env] = props.copy()
+        self._log("set_actor_dof_properties", (int(env), props.copy()))
 
 
 class SyntheticTerrain:
