@@ -81,6 +81,8 @@ enum { TI5_GAIT_STAND = 0, TI5_GAIT_WALK_SAGITTAL = 1, TI5_GAIT_WALK_LATERAL = 2
 enum { TI5_SUB_PUSH = 1, TI5_SUB_TORQUE = 2, TI5_SUB_CHAINED = 4 };
 enum { TI5_RO_RESET = 1, TI5_RO_OBSERVE = 2, TI5_RO_CHAINED = 4 };
 enum { TI5_POST_PUSH_LAST = 1, TI5_POST_CHAINED = 2 };
+/* ti5_fused_step: FUSED_CHAINED = the launch follows ti5_sample_heights of the same step on the stream */
+enum { TI5_FUSED_CHAINED = 2 };
 
 /* how `tensor / python_scalar` is rounded: torch-CPU divides, torch-CUDA multiplies by the
  * reciprocal (ATen div_true_kernel_cuda); the reference therefore differs by device. */
@@ -162,8 +164,10 @@ typedef struct Ti5Globals {
   int64_t step_now;            /* index of the step in progress, published by ti5_post_physics / ti5_reset_bookkeeping */
   int64_t common_step_offset;  /* common_step_counter = step_index + common_step_offset */
   int32_t n_reset;             /* envs reset in the current step (lr:490) */
-  int32_t n_listed;            /* entries of Ti5Buffers.reset_list (unordered), zeroed by ti5_begin_step */
-  int32_t tickets[2];          /* last-CTA-done counters (terrain-level mean) */
+  int32_t n_listed[2];         /* entries of Ti5Buffers.reset_list (arrival order), double-buffered by the parity of the
+                                  step in progress: a step fills [step & 1] and zeroes [(step + 1) & 1] for its successor */
+  int32_t tickets[2];          /* [0]: CTAs of ti5_reset_observe that have read step_index (the last one advances it);
+                                  [1]: last-CTA-done counter of the terrain-level mean */
   int32_t is_first_add_force[2]; /* lr:90, t1:205-215; double-buffered by step parity (read [step&1], write [(step+1)&1]) */
   double cmd_range[2][3][2];   /* [step parity][lin_vel_x, lin_vel_y, ang_vel_yaw][lo, hi]; the command curriculum
                                   (lr:1160-1169) writes the next step's copy */
@@ -314,6 +318,17 @@ int ti5_sample_heights(const Ti5Params* p, const Ti5Buffers* b, void* stream);
  * compaction bookkeeping (n_reset, per-CTA offsets, episode statistics, command curriculum).
  * `options` = TI5_POST_*: PUSH_LAST fuses the lag push of the last substep into the same launch. */
 int ti5_post_physics(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, int options, void* stream);
+
+/* One launch for everything of a policy step that precedes the resets, for the case that NO simulator runs between
+ * the substeps (synthetic state, or a simulator stepped elsewhere): lr:393-434 — action clip, DEC x [_compute_torques,
+ * DOF- and IMU-lag push] — and then ti5_post_physics, i.e. the call sequence
+ *     ti5_first_substep ; (DEC-1) x ti5_substep(PUSH|TORQUE) ; ti5_post_physics(PUSH_LAST)
+ * with bit-identical results (same Philox counters, same op order): every dependency among those launches is per env,
+ * so one CTA carries its envs through all of them — the joint state, gains and offsets are read once, the lagged
+ * action rows a substep pushed itself come from registers, every substep's torques are still stored in turn.
+ * Follow with ti5_reset_observe(TI5_RO_RESET | TI5_RO_OBSERVE | TI5_RO_CHAINED): 2 launches per step instead of 12. */
+int ti5_fused_step(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, const float* actions_in, int options,
+                   void* stream);
 
 /* The same bookkeeping for an explicit `reset_idx(env_ids)` (lr:450-455 `reset()`): the caller wrote the
  * mask into reset_buf; follow with ti5_reset_scatter. */

@@ -67,10 +67,10 @@ def test_compaction_is_ascending_nonzero(n, rate):
 
 
 # ----------------------------------------------------------------------------- production configuration
-def _production_env(N, **kw):
+def _production_env(N, name="plane_default", **kw):
     from ti5_isaacgym_b200.envs import T1DHStandEnv
     from ti5_isaacgym_b200.sim.synthetic import SimParams, fill_synthetic_state
-    cfg = scenario_cfg("plane_default", N)
+    cfg = scenario_cfg(name, N)
     env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, "cuda:0", True, seed=11, **kw)
     gen = torch.Generator(device="cuda").manual_seed(5)
     fill_synthetic_state(env.gym.tensors, env.env_origins, gen, base_contact_rate=0.03)
@@ -106,21 +106,22 @@ def test_graph_replay_equals_direct_launches_and_history_layout():
     assert g.step_index == b.sync_from_device().step_index
 
 
-@pytest.mark.parametrize("N,graph", [(8192, True), (1000, False), (16384, True)])
-def test_chained_launches_equal_plain_launches(N, graph):
+@pytest.mark.parametrize("N,graph,fused", [(8192, True, True), (1000, False, True), (16384, True, True), (8192, True, False),
+                                           (1000, False, False), (65536, True, True), (65536, True, False)])
+def test_chained_launches_equal_plain_launches(N, graph, fused):
     """Programmatic dependent launches (TI5_*_CHAINED) only move work in front of the grid wait: every output and
     every piece of state must be bit-identical to ordinary stream-ordered launches, resets included."""
     from ti5_isaacgym_b200.sim.synthetic import synthetic_actions
     torch.manual_seed(0)                                    # friction / mass draws at construction
-    a, gen = _production_env(N, use_cuda_graph=graph, chain_launches=True)
+    a, gen = _production_env(N, use_cuda_graph=graph, chain_launches=True, fused_step=fused)
     torch.manual_seed(0)
-    b, _ = _production_env(N, use_cuda_graph=graph, chain_launches=False)
+    b, _ = _production_env(N, use_cuda_graph=graph, chain_launches=False, fused_step=fused)
     a.reset(), b.reset()
     ep = torch.randint(1, 2400, (N,), generator=gen, device="cuda")
     ep[:8] = 2399                                           # time-outs in the first steps
     a.episode_length_buf, b.episode_length_buf = ep.clone(), ep.clone()
     n_reset = 0
-    for t in range(40):
+    for t in range(12 if N >= 65536 else 40):
         act = synthetic_actions(N, gen, "cuda")
         oa, pa, ra, da, _ = a.step(act)
         ob, pb, rb, db, _ = b.step(act)
@@ -134,6 +135,47 @@ def test_chained_launches_equal_plain_launches(N, graph):
                  "base_lin_vel", "base_euler_xyz", "lag_buffer", "dof_lag_buffer", "imu_lag_buffer"):
         exact(getattr(a, name), getattr(b, name), f"state after 40 steps: {name}")
     exact(a._episode_sums, b._episode_sums, "episode sums")
+
+
+@pytest.mark.parametrize("N,graph,name,chain", [
+    (8192, True, "plane_default", True), (1000, False, "plane_default", True), (4113, False, "plane_default", False),
+    (65536, True, "plane_default", True),                    # several waves of CTAs
+    (8192, True, "trimesh_heights_push", True), (517, False, "trimesh_windows", True)])
+def test_fused_step_equals_the_twelve_launch_sequence(N, graph, name, chain):
+    """ti5_fused_step (clip + DEC substeps + post-physics in one launch) against ti5_first_substep, 9 x ti5_substep,
+    ti5_post_physics: same Philox counters, same op order -> every output and every piece of state bit-identical."""
+    from ti5_isaacgym_b200.sim.synthetic import synthetic_actions
+    torch.manual_seed(0)
+    a, gen = _production_env(N, name, use_cuda_graph=graph, fused_step=True, chain_launches=chain)
+    torch.manual_seed(0)
+    b, _ = _production_env(N, name, use_cuda_graph=graph, fused_step=False, chain_launches=chain)
+    assert a.launches_per_step + 10 == b.launches_per_step
+    a.reset(), b.reset()
+    ep = torch.randint(1, 2400, (N,), generator=gen, device="cuda")
+    ep[:8] = 2399                                           # time-outs in the first steps
+    a.episode_length_buf, b.episode_length_buf = ep.clone(), ep.clone()
+    if "windows" in name:
+        a.set_common_step_counter(287997), b.set_common_step_counter(287997)
+    n_reset = 0
+    for t in range(24 if N >= 65536 else 40):
+        act = synthetic_actions(N, gen, "cuda")
+        oa, pa, ra, da, _ = a.step(act)
+        ob, pb, rb, db, _ = b.step(act)
+        exact(da, db, f"step {t}: resets")
+        exact(ra, rb, f"step {t}: rewards")
+        exact(oa, ob, f"step {t}: obs")
+        exact(pa, pb, f"step {t}: privileged obs")
+        exact(a.torques, b.torques, f"step {t}: torques")
+        exact(a.torque_multi, b.torque_multi, f"step {t}: torque multipliers")
+        n_reset += int(da.sum())
+    assert n_reset > 0
+    for nm in ("actions", "commands", "episode_length_buf", "dof_state", "root_states", "last_actions", "feet_air_time",
+               "base_lin_vel", "base_euler_xyz", "lag_buffer", "dof_lag_buffer", "imu_lag_buffer", "applied_force",
+               "rand_push_torque", "ext_forces", "reset_ids"):
+        exact(getattr(a, nm), getattr(b, nm), f"state after the run: {nm}")
+    exact(a._episode_sums, b._episode_sums, "episode sums")
+    exact(a._reward_terms, b._reward_terms, "reward terms")
+    assert int(a.sync_from_device().step_index) == int(b.sync_from_device().step_index)
 
 
 def test_graph_cache_follows_the_action_buffer():

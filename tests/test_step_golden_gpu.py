@@ -9,11 +9,12 @@ from helpers import GOLDEN_SCENARIOS, close, exact, load_golden, make_env, pools
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("fused", [True, False], ids=["fused_step", "twelve_launches"])
 @pytest.mark.parametrize("name", GOLDEN_SCENARIOS)
-def test_step_matches_reference_fixture(name):
+def test_step_matches_reference_fixture(name, fused):
     state0, inputs, outputs, final = load_golden(name)
     N = state0["commands"].shape[0]
-    env = make_env(scenario_cfg(name, N))
+    env = make_env(scenario_cfg(name, N), fused_step=fused)
     env.load_state(state0)
     K = env.cfg.env.num_single_obs
     P = env._params.priv_frame

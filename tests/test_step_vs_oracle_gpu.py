@@ -83,11 +83,11 @@ MASS = (1.0, 0.0, 0.04, 0.0, 1.0, 1.0)
     ("trimesh_heights_push", 8192, 5, "cuda", 66, None),
     ("plane_events", 16384, 4, "cuda", 66, None), ("plane_events", 65536, 3, "cuda", 66, None),
 ])
-def test_env_follows_oracle(name, N, steps, where, H, rates):
+def test_env_follows_oracle(name, N, steps, where, H, rates, fused=True):
     from ti5_isaacgym_b200.sim.synthetic import alloc_sim_tensors, fill_synthetic_state, synthetic_actions
     device = "cuda:0" if where == "cuda" else "cpu"
     cfg, C, S, terrain, heights, gen = _build(name, N, device, frame_stack=H, counter=287997 if "windows" in name else 2397)
-    env = make_env(scenario_cfg(name, N, H), div_mode="ieee" if where == "cpu" else "reciprocal")
+    env = make_env(scenario_cfg(name, N, H), div_mode="ieee" if where == "cpu" else "reciprocal", fused_step=fused)
     state = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in state_from_oracle(S, C).items()}
     if terrain is not None:
         state["terrain_origins"] = terrain.origins.cpu()
@@ -156,6 +156,13 @@ def test_env_follows_oracle(name, N, steps, where, H, rates):
     if "windows" in name:
         assert n_apply >= 5 and n_push >= 5, "the multi-step apply / push branches must run"
         assert list(S.command_ranges["lin_vel_x"]) != range0, "the command curriculum must change the range"
+
+
+@pytest.mark.parametrize("name,N,steps", [("plane_events", 1024, 20), ("trimesh_windows", 200, 26), ("plane_events", 65536, 3)])
+def test_twelve_launch_sequence_follows_oracle(name, N, steps):
+    """The unfused kernels of a step without a simulator (ti5_first_substep, ti5_substep, ti5_post_physics) against the
+    oracle: the default path of the tests above is ti5_fused_step."""
+    test_env_follows_oracle(name, N, steps, "cuda", 66, None, fused=False)
 
 
 def test_command_curriculum_fires_on_device():

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) gather_dof_props_kernel(const float* __re
 extern "C" int ti5_gather_dof_props(const Ti5Params* p, const Ti5Buffers* b, const int32_t* ids, const int32_t* count,
                                     int32_t capacity, float* props_out, void* stream) {
   TI5_CHECK_ARGS(p && b && ids && count && props_out && capacity > 0 && b->joint_armatures);
-  const int blocks = min((capacity * ti5::D + 255) / 256, 148 * 4);
+  const int blocks = min((capacity * ti5::D + 255) / 256, ti5_sm_count() * 4);
   ti5::gather_dof_props_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(b->joint_armatures, ids, count, capacity, p->flags, props_out);
   return ti5_check_launch("ti5_gather_dof_props");
 }

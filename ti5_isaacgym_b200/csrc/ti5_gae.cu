@@ -97,7 +97,7 @@ extern "C" int ti5_gae_scan(const float* rewards, const float* values, const uin
 extern "C" int ti5_gae_normalize(float* advantages, int32_t T, int32_t N, const double* stats, void* stream) {
   TI5_CHECK_ARGS(advantages && stats && T > 0 && N > 0);
   const size_t total = (size_t)T * N;
-  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  const int blocks = (int)((total + 255) / 256 < (size_t)ti5_sm_count() * 8 ? (total + 255) / 256 : (size_t)ti5_sm_count() * 8);
   ti5::gae_normalize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(advantages, total, stats);
   return ti5_check_launch("ti5_gae_normalize");
 }

@@ -9,6 +9,7 @@ namespace ti5 {
 
 __global__ void __launch_bounds__(256)
 heights_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b) {
+  chain_trigger();                       // the step kernel that follows needs nothing from this grid before its end
   const int npts = p.num_height_points;
   const size_t total = (size_t)p.num_envs * npts;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -45,17 +45,66 @@ inline cudaError_t ti5_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // 53.9 us/step at 8192 envs).  On large grids the SMs are full anyway and the smaller L1 costs the substep kernel
 // 20 % (236 vs 212 us/step at 65536 envs), so the kernels keep the default there.  TI5_CARVEOUT=<percent|-1> overrides.
 #include <cstdlib>
-#include <unordered_map>
+#include <map>
+#include <mutex>
 #define TI5_SMALL_GRID_ENVS 12288    /* measured: early mode + carve-out 58.8 vs 60.2 us at 12288 envs, 67.2 vs 66.5 at 16384 */
 inline bool ti5_small_grid(const Ti5Params* p) { return p->num_envs <= TI5_SMALL_GRID_ENVS; }
+
+// Function attributes are per DEVICE: the caches below are keyed by (current device, kernel) and guarded by a mutex, so
+// a process that drives several GPUs (or several host threads) configures every kernel on every device it launches on.
+struct Ti5AttrCache {
+  std::mutex mu;
+  std::map<std::pair<int, const void*>, int> carveout;
+  std::map<std::pair<int, const void*>, size_t> smem;
+  std::map<int, int> sms;
+};
+inline Ti5AttrCache& ti5_attr_cache() {
+  static Ti5AttrCache c;
+  return c;
+}
+inline int ti5_current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
 template <class K>
 inline void ti5_set_carveout(K kernel, bool small_grid) {
   static const int forced = getenv("TI5_CARVEOUT") ? atoi(getenv("TI5_CARVEOUT")) : -2;
-  static std::unordered_map<const void*, int> current;     // what each kernel is set to (host threads: one per GPU process)
   const int want = forced != -2 ? forced : (small_grid ? 100 : -1);
-  auto it = current.find(reinterpret_cast<const void*>(kernel));
-  if (it == current.end() || it->second != want) {
+  Ti5AttrCache& c = ti5_attr_cache();
+  const auto key = std::make_pair(ti5_current_device(), reinterpret_cast<const void*>(kernel));
+  std::lock_guard<std::mutex> lock(c.mu);
+  auto it = c.carveout.find(key);
+  if (it == c.carveout.end() || it->second != want) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, want);
-    current[reinterpret_cast<const void*>(kernel)] = want;
+    c.carveout[key] = want;
   }
+}
+// opt a kernel in to `bytes` of dynamic shared memory on the current device (no-op once done for at least that much)
+template <class K>
+inline bool ti5_ensure_smem(K kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return true;
+  Ti5AttrCache& c = ti5_attr_cache();
+  const auto key = std::make_pair(ti5_current_device(), reinterpret_cast<const void*>(kernel));
+  std::lock_guard<std::mutex> lock(c.mu);
+  auto it = c.smem.find(key);
+  if (it != c.smem.end() && it->second >= bytes) return true;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  c.smem[key] = bytes;
+  return true;
+}
+// SM count of the current device (148 on a B200)
+inline int ti5_sm_count() {
+  Ti5AttrCache& c = ti5_attr_cache();
+  const int dev = ti5_current_device();
+  std::lock_guard<std::mutex> lock(c.mu);
+  auto it = c.sms.find(dev);
+  if (it != c.sms.end()) return it->second;
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  c.sms[dev] = n;
+  return n;
 }

@@ -246,8 +246,15 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
   const bool live = e < N && blockIdx.x < env_blocks && role < OBS_ROLES;
   Ti5Globals* g = b.globals;
   // index of the step in progress: published by ti5_post_physics / ti5_reset_bookkeeping; a chained launch may not
-  // read what its predecessor writes yet and is always part of a full step
-  const int64_t step = (phases & TI5_RO_CHAINED) ? g->step_index + 1 : g->step_now;
+  // read what its predecessor writes yet and is always part of a full step.
+  // THIS kernel advances step_index, and a grid larger than one wave has CTAs that start after others have finished:
+  // one thread per CTA reads the counter; behind the grid wait (the predecessor, which reads the counter too, is
+  // complete there) it takes a ticket, and the CTA that draws the last one — every CTA of the grid has read by then —
+  // publishes the new count.
+  __shared__ int64_t s_step;
+  if (tid == 0) s_step = (phases & TI5_RO_CHAINED) ? g->step_index + 1 : g->step_now;
+  __syncthreads();
+  const int64_t step = s_step;
   const int64_t pushes = step * p.decimation;            // lag pushes completed after this step
   const bool do_reset = (phases & TI5_RO_RESET) != 0, do_obs = (phases & TI5_RO_OBSERVE) != 0;
   const int dm = p.div_mode;
@@ -340,6 +347,10 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
     }
   }
   chain_wait();                                          // ti5_post_physics is done
+  if (tid == 0 && atomicAdd(&g->tickets[0], step == INT64_MIN ? 2 : 1) == (int)gridDim.x - 1) {
+    g->tickets[0] = 0;
+    if (do_obs) g->step_index = step;                    // the step counts as completed: nobody in this grid reads it any more
+  }
   int n_reset = 0, id_offset = 0;
   const int64_t counter = step + g->common_step_offset;
   const bool curriculum_due = do_reset && (p.flags & TI5_F_COMMAND_CURRICULUM) && (counter % p.max_episode_length == 0);
@@ -689,7 +700,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
   // listed (in arrival order) by ti5_post_physics / ti5_reset_bookkeeping; all warps of the grid,
   // including the helper CTAs, share the (env, 512-float chunk) work items.  The two slots of this step's
   // frame are skipped — their owner overwrites them above — so no ordering between warps is needed.
-  const int n_list = do_reset ? g->n_listed : 0;
+  const int n_list = do_reset ? g->n_listed[step & 1] : 0;
   if (n_list > 0) {
     constexpr int CHUNK = 512, U = CHUNK / 32;
     const int oc = (int)((obs_row + CHUNK - 1) / CHUNK), pc = (int)((priv_row + CHUNK - 1) / CHUNK);
@@ -752,9 +763,6 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
     }
     return;
   }
-
-  // the step is complete once the observations are out: advance the counter (no CTA of this grid reads it)
-  if (do_obs && blockIdx.x == 0 && tid == 0) g->step_index = step;
 
   // host-side callers: this step's scalar outputs, stored straight into (mapped, pinned) host memory
   if (b.host_out && do_obs && role == 0 && live) {
@@ -859,10 +867,8 @@ extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const 
   auto kernel = p->priv_frame == 73 ? (big ? reset_observe_kernel<47, 73, 2> : reset_observe_kernel<47, 73, 1>)
                 : p->priv_frame == 260 ? (big ? reset_observe_kernel<47, 260, 2> : reset_observe_kernel<47, 260, 1>)
                                        : (big ? reset_observe_kernel<47, 0, 2> : reset_observe_kernel<47, 0, 1>);
-  if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+  if (!ti5_ensure_smem(kernel, smem)) {
     ti5_set_error("ti5_reset_observe: %zu bytes of shared memory per CTA not available", smem);
-    cudaGetLastError();
     return TI5_ECUDA;
   }
   ti5_set_carveout(kernel, ti5_small_grid(p));
@@ -870,7 +876,7 @@ extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const 
   // writer warps only for the small-grid case (env_block 32): on larger grids the SMs are full of frame builders and
   // idle writers would only take their registers
   const int threads = (OBS_ROLES + (writers ? OBS_WRITERS : 0)) * p->env_block;   // <= 256
-  const int helpers = (phases & TI5_RO_RESET) ? (148 * 4 * 32) / threads : 0;
+  const int helpers = (phases & TI5_RO_RESET) ? (ti5_sm_count() * 4 * 32) / threads : 0;
   (void)ti5_launch(kernel, dim3(blocks + helpers), dim3(threads), smem, stream, (phases & TI5_RO_CHAINED) != 0, *p, *b, rr, phases);
   return ti5_check_launch("ti5_reset_observe");
 }
@@ -885,6 +891,6 @@ extern "C" int ti5_observations(const Ti5Params* p, const Ti5Buffers* b, const T
 
 extern "C" int ti5_materialize_obs(const Ti5Params* p, const Ti5Buffers* b, void* stream) {
   TI5_CHECK_ARGS(p && b && p->num_envs > 0 && (b->obs_out || b->priv_out));
-  materialize_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(*p, *b);
+  materialize_kernel<<<ti5_sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(*p, *b);
   return ti5_check_launch("ti5_materialize_obs");
 }

@@ -37,11 +37,11 @@ static __device__ __noinline__ float pair_distance_reward(float ax, float ay, fl
 // after this grid has completed, turns the per-CTA counts into offsets / totals itself.
 // `sums` is the CTA's shared tile [term][tb] (post-physics) or null (read episode_sums from memory).
 static __device__ __noinline__ void reset_bookkeeping(const Ti5Params& p, const Ti5Buffers& b, bool reset, int e, int le,
-                                                      const float* sums, int tb) {
+                                                      const float* sums, int tb, int64_t step) {
   __shared__ int s_warp[32];
   __shared__ float s_red[12][TI5_NUM_TERMS];
   const int N = p.num_envs, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  if (reset) b.reset_list[atomicAdd(&b.globals->n_listed, 1)] = e;
+  if (reset) b.reset_list[atomicAdd(&b.globals->n_listed[step & 1], 1)] = e;
   const BlockRank br = block_rank(reset, s_warp);
   if (tid == 0) b.block_counts[blockIdx.x] = br.total;
   if (br.total == 0) return;
@@ -114,16 +114,151 @@ __host__ __device__ inline size_t post_tile_bytes(int tb, int per_env_bytes) {
 // (alphabetical) order and all threads share the reset bookkeeping.
 constexpr int POST_ROLES = 3;
 
+// named barrier between the substep workers (arrive) and role 1 (sync) of the fused kernel
+constexpr int BAR_TORQUES = 1;
+__device__ __forceinline__ void bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+// a store the compiler may not drop although the same address is stored again later in the kernel: every substep's
+// torques land in memory in turn, as they do when the substeps are separate launches (lr:401-403)
+__device__ __forceinline__ void store4_kept(float* ptr, float4 v) {
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// lr:393-434 for one (env, group of four DOFs) when no simulator runs between the substeps: the action clip, then DEC x
+// [_compute_torques, DOF-lag push] with the joint state, gains and offsets read once.  Same arithmetic, same Philox
+// counters and the same stores as DEC launches of substep_kernel (ti5_substep.cu); the IMU-lag pushes, whose values equal
+// the derived base state, are left to role 0.  DEC > 0: unrolled, all lagged rows in flight together; DEC == 0: any
+// decimation, one row at a time.  Leaves the clipped actions and the last substep's torques in the CTA's tile.
+template <int DEC>
+__device__ __forceinline__ void substep_worker(const Ti5Params& p, const Ti5Buffers& b, const Ti5Rng& r,
+                                               const float* __restrict__ actions_in, int64_t step, int idx, int e, int gq,
+                                               float* tile_act, float* tile_tau) {
+  const int N = p.num_envs, d0 = 4 * gq;
+  const int dec = DEC > 0 ? DEC : p.decimation;
+  const bool rg = p.flags & TI5_F_RAND_GAINS, fric = p.flags & TI5_F_RAND_COULOMB, rt = p.flags & TI5_F_RAND_TORQUE;
+  const bool lagged = p.flags & TI5_F_ADD_LAG, philox = p.rng_mode == TI5_RNG_PHILOX;
+  auto ld4 = [&](const float* base_ptr) { return reinterpret_cast<const float4*>(base_ptr)[idx]; };
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // ---- loads, all independent ----------------------------------------------------------------------
+  const float4* ds = reinterpret_cast<const float4*>(b.dof_state);
+  const float4 s0 = ds[2 * idx], s1 = ds[2 * idx + 1];
+  float4 a4 = ld4(actions_in);
+  const float4 off4 = ld4(b.motor_offsets);
+  float4 kp4 = zero4, kd4 = zero4, vis4 = zero4, cou4 = zero4;
+  int lag = 0;
+  int64_t stamp = 0;
+  if (lagged) { lag = b.lag_timestep[e * 3 + 0]; stamp = b.ring_stamp[e]; }
+  if (rg) { kp4 = ld4(b.p_gains_r); kd4 = ld4(b.d_gains_r); }
+  if (fric) { vis4 = ld4(b.viscous); cou4 = ld4(b.coulomb); }
+  const int64_t base = (step - 1) * p.decimation;          // pushes completed before this step
+  float4* ring = reinterpret_cast<float4*>(b.act_ring);
+  const size_t ring_row = (size_t)N * 3;
+  // ring slots of this step's pushes: one 64-bit remainder per ring, then 32-bit wrap-arounds
+  const int as0 = (int)(base % p.lag_len), ds0 = (int)(base % p.dof_lag_len);
+  auto wrap = [](int s, int len) { return s % len; };
+  // the lagged action rows of the substeps that look back past the start of this step (lr:1045); rows pushed before the
+  // env's last reset read as zero (lr:606).  Read before any row of this step is pushed: a slot this step overwrites
+  // is only ever read by an EARLIER substep than the one that overwrites it (slot(base + k') == slot(base + k - lag)
+  // needs k' = k + len - lag > k).
+  float4 old_row[DEC > 0 ? DEC : 1];
+  if (DEC > 0) {
+#pragma unroll
+    for (int k = 0; k < DEC; ++k) {
+      const int64_t jj = base + k - lag;
+      old_row[k] = zero4;
+      if (lagged && lag > k && jj >= stamp && jj >= 0) old_row[k] = ring[(size_t)ring_slot(jj, p.lag_len) * ring_row + idx];
+    }
+  }
+  a4 = make_float4(clampf(a4.x, -p.clip_actions, p.clip_actions), clampf(a4.y, -p.clip_actions, p.clip_actions),
+                   clampf(a4.z, -p.clip_actions, p.clip_actions), clampf(a4.w, -p.clip_actions, p.clip_actions));   // lr:393-394
+  reinterpret_cast<float4*>(b.actions)[idx] = a4;
+  const float q[4] = {s0.x, s0.z, s1.x, s1.z}, qd[4] = {s0.y, s0.w, s1.y, s1.w};
+  const float a[4] = {a4.x * p.action_scale, a4.y * p.action_scale, a4.z * p.action_scale, a4.w * p.action_scale};
+  const float4 as4 = make_float4(a[0], a[1], a[2], a[3]);
+  float kp[4] = {kp4.x, kp4.y, kp4.z, kp4.w}, kd[4] = {kd4.x, kd4.y, kd4.z, kd4.w};
+  if (!rg) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { kp[i] = p.p_gains[d0 + i]; kd[i] = p.d_gains[d0 + i]; }
+  }
+  const float off[4] = {off4.x, off4.y, off4.z, off4.w};
+  const float vis[4] = {vis4.x, vis4.y, vis4.z, vis4.w}, cou[4] = {cou4.x, cou4.y, cou4.z, cou4.w};
+  const float4 q4 = make_float4(q[0], q[1], q[2], q[3]), qd4 = make_float4(qd[0], qd[1], qd[2], qd[3]);
+  float tau[4] = {0.f, 0.f, 0.f, 0.f};
+  auto substep = [&](int k, float4 t4) {
+    // lr:1019-1074 torque of substep k
+    float4 u4 = zero4;
+    if (rt) u4 = philox ? philox_u4(p.seed, (uint64_t)step, S_TORQUE + k, idx)
+                        : reinterpret_cast<const float4*>(r.torque)[(size_t)k * ring_row + idx];
+    if (lagged) ring[(size_t)wrap(as0 + k, p.lag_len) * ring_row + idx] = as4;
+    const bool from_ring = lagged && lag > 0;
+    const float target[4] = {from_ring ? t4.x : a[0], from_ring ? t4.y : a[1], from_ring ? t4.z : a[2], from_ring ? t4.w : a[3]};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float err = ((target[i] + p.default_dof_pos[d0 + i]) - q[i]) + off[i];
+      tau[i] = kp[i] * err - kd[i] * qd[i];
+    }
+    if (fric) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        tau[i] = tau[i] - vis[i] * qd[i];
+        tau[i] = tau[i] - cou[i] * signf(qd[i]);
+      }
+    }
+    if (rt) {
+      const float u[4] = {u4.x, u4.y, u4.z, u4.w};
+      float m[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        m[i] = affine(p.torque_multi_w, p.torque_multi_lo, u[i]);
+        tau[i] = tau[i] * m[i];
+      }
+      store4_kept(b.torque_multi + (size_t)idx * 4, make_float4(m[0], m[1], m[2], m[3]));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float lim = p.torque_limits[d0 + i];
+      tau[i] = clampf(tau[i], -lim, lim);
+    }
+    store4_kept(b.torques + (size_t)idx * 4, make_float4(tau[0], tau[1], tau[2], tau[3]));
+    // lr:412-418 DOF-lag push after (what would be) simulator substep k
+    if (p.flags & TI5_F_ADD_DOF_LAG) {
+      float* row = b.dof_ring + ((size_t)wrap(ds0 + k, p.dof_lag_len) * N + e) * (2 * D);
+      *reinterpret_cast<float4*>(row + d0) = q4;
+      *reinterpret_cast<float4*>(row + D + d0) = qd4;
+    }
+  };
+  if (DEC > 0) {
+#pragma unroll
+    for (int k = 0; k < DEC; ++k) substep(k, lag <= k ? as4 : old_row[k]);       // rows this step pushed: from registers
+  } else {
+#pragma unroll 1
+    for (int k = 0; k < dec; ++k) {
+      const int64_t jj = base + k - lag;
+      float4 t4 = lag <= k ? as4 : zero4;
+      if (lagged && lag > k && jj >= stamp && jj >= 0) t4 = ring[(size_t)ring_slot(jj, p.lag_len) * ring_row + idx];
+      substep(k, t4);
+    }
+  }
+  // what role 1 needs of this phase
+  *reinterpret_cast<float4*>(tile_act + d0) = a4;
+  *reinterpret_cast<float4*>(tile_tau + d0) = make_float4(tau[0], tau[1], tau[2], tau[3]);
+}
+
+// FUSED: the kernel also carries the CTA's envs through the DEC substeps that precede the post-physics phase
+// (ti5_fused_step): 3 x TB further threads, one per (env, four DOFs), run them while the roles work; they meet role 1
+// on a named barrier in front of the two terms over this step's actions and torques.
+template <bool FUSED>
 __global__ void __launch_bounds__(POST_ROLES * 128)
 post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
-                    const __grid_constant__ Ti5Rng r, const __grid_constant__ PostSrc src, int options) {
+                    const __grid_constant__ Ti5Rng r, const __grid_constant__ PostSrc src,
+                    const float* __restrict__ actions_in, int options) {
   chain_trigger();                                        // ti5_reset_observe may become resident
   const int push_last = options & TI5_POST_PUSH_LAST;
   const int N = p.num_envs;
   const int TB = p.env_block, tid = threadIdx.x;
   const int role = tid / TB, le = tid - role * TB;
   const int e0 = blockIdx.x * TB, e = e0 + le, n_tile = min(TB, N - e0);
-  const bool live = e < N;
+  const bool live = e < N && role < POST_ROLES;
   Ti5Globals* g = b.globals;
   const int64_t step = g->step_index + 1;                 // index of the step in progress
   const int64_t counter = step + g->common_step_offset;   // common_step_counter after lr:471
@@ -163,7 +298,9 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
   // substep kernel (root_states is: with push_robots the kernel keeps the plain order).
   // Small grids only (<= 12288 envs): there the CTAs are resident long before the substeps finish (common
   // carve-out, ti5_host.h) and the work in front of the wait is free; on large grids the plain order measured no worse.
-  const bool early = (options & TI5_POST_CHAINED) && n_tile == TB && N <= TI5_SMALL_GRID_ENVS && !(p.flags & TI5_F_PUSH_ROBOTS);
+  const bool early = !FUSED && (options & TI5_POST_CHAINED) && n_tile == TB && N <= TI5_SMALL_GRID_ENVS && !(p.flags & TI5_F_PUSH_ROBOTS);
+  // FUSED: the two arrays come from this CTA's own substep workers (below), never from memory
+  const bool late_by_tma = !FUSED && !early;
   const uint32_t late_bytes = (uint32_t)TB * (uint32_t)(src.rowb[C_ACT] + src.rowb[C_TORQUES]);
   auto issue_late = [&]() {      // one thread: arm the second barrier and start the two copies
     mbar_expect_tx(T.bar + 1, late_bytes);
@@ -194,24 +331,41 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       for (int t = 0; t < TI5_NUM_TERMS; ++t)
         if (mask & (1u << t)) coop_load(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(TB * 4));
     }
-    if (!early) {
+    if (late_by_tma) {
       chain_wait();                                       // the substep kernels are done
       if (tid == TB) issue_late();
     }
   } else {      // partial last tile: byte counts need not be multiples of 16, copy word by word
-    chain_wait();
+    if (!FUSED) chain_wait();
 #pragma unroll 1
     for (int k = 0; k < POST_CHUNKS; ++k)
-      coop_load(T.base + (size_t)src.off[k] * TB, static_cast<const char*>(src.ptr[k]) + (size_t)e0 * src.rowb[k],
-                (uint32_t)(n_tile * src.rowb[k]));
+      if (!FUSED || (k != C_ACT && k != C_TORQUES))
+        coop_load(T.base + (size_t)src.off[k] * TB, static_cast<const char*>(src.ptr[k]) + (size_t)e0 * src.rowb[k],
+                  (uint32_t)(n_tile * src.rowb[k]));
 #pragma unroll 1
     for (int t = 0; t < TI5_NUM_TERMS; ++t)
       if (mask & (1u << t)) coop_load(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(n_tile * 4));
   }
   __syncthreads();
-  if (n_tile == TB) {
+  if (FUSED) {
+    if (role >= POST_ROLES) {
+      // ======== substep workers: one thread per (env, four DOFs), coalesced over the CTA's 3 x TB groups ========
+      const int item = tid - POST_ROLES * TB, wl = item / 3, gq = item - wl * 3;
+      if (e0 + wl < N) {
+        float* ta = T.at<float>(C_ACT) + wl * D;
+        float* tt = T.at<float>(C_TORQUES) + wl * D;
+        if (p.decimation == 10) substep_worker<10>(p, b, r, actions_in, step, e0 * 3 + item, e0 + wl, gq, ta, tt);
+        else substep_worker<0>(p, b, r, actions_in, step, e0 * 3 + item, e0 + wl, gq, ta, tt);
+      }
+      bar_arrive(BAR_TORQUES, (POST_ROLES + 1) * TB);   // role 1 may read the two tile rows (stores above are ordered by it)
+    }
+    // a preceding ti5_sample_heights (chained launch) must have completed before this grid does: ti5_reset_observe,
+    // which reads the heights, only waits for THIS grid
+    if (options & TI5_FUSED_CHAINED) chain_wait();
+  }
+  if (n_tile == TB && role < POST_ROLES) {
     mbar_wait(T.bar, 0);
-    if (!early) mbar_wait(T.bar + 1, 0);
+    if (late_by_tma) mbar_wait(T.bar + 1, 0);
   }
   // typed views of the tile
   const float* t_root = T.at<float>(C_ROOT);
@@ -301,7 +455,16 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       b.projected_gravity[e * 3 + 0] = grav.x; b.projected_gravity[e * 3 + 1] = grav.y; b.projected_gravity[e * 3 + 2] = grav.z;
 #pragma unroll
       for (int i = 0; i < 3; ++i) b.base_euler_xyz[e * 3 + i] = eul[i];
-      if (push_last && (p.flags & TI5_F_ADD_IMU_LAG)) {                      // fused IMU-lag push of the last substep
+      if (FUSED && (p.flags & TI5_F_ADD_IMU_LAG)) {
+        // lr:428-434 for every substep: without a simulator in between the base does not move, so each push is the
+        // derived state of this step (same quaternion, same arithmetic as the substep kernel's pieces)
+        const int s0 = (int)(((step - 1) * p.decimation) % p.imu_lag_len);
+#pragma unroll 1
+        for (int k = 0; k < p.decimation; ++k) {
+          float* row = b.imu_ring + ((size_t)((s0 + k) % p.imu_lag_len) * N + e) * 6;
+          row[0] = ang.x; row[1] = ang.y; row[2] = ang.z; row[3] = eul[0]; row[4] = eul[1]; row[5] = eul[2];
+        }
+      } else if (push_last && (p.flags & TI5_F_ADD_IMU_LAG)) {               // fused IMU-lag push of the last substep
         const int64_t j = (step - 1) * p.decimation + (p.decimation - 1);
         float* row = b.imu_ring + ((size_t)ring_slot(j, p.imu_lag_len) * N + e) * 6;
         row[0] = ang.x; row[1] = ang.y; row[2] = ang.z; row[3] = eul[0]; row[4] = eul[1]; row[5] = eul[2];
@@ -408,17 +571,13 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       }
     } else if (role == 1) {
       // ================================ role 1: the joints =============================================
-      if (push_last && (p.flags & TI5_F_ADD_DOF_LAG)) {                      // fused DOF-lag push of the last substep
+      if (!FUSED && push_last && (p.flags & TI5_F_ADD_DOF_LAG)) {            // fused DOF-lag push of the last substep
         const int64_t j = (step - 1) * p.decimation + (p.decimation - 1);
         float* row = b.dof_ring + ((size_t)ring_slot(j, p.dof_lag_len) * N + e) * (2 * D);
 #pragma unroll 1
         for (int i = 0; i < D; ++i) { row[i] = qrow[2 * i]; row[D + i] = qrow[2 * i + 1]; }
       }
-      const float* act = t_act + le * D;
-      const float* la = t_last_act + le * D;
-      const float* lla = t_last_last_act + le * D;
       const float* ldv = t_last_dof_vel + le * D;
-      const float* tau = t_torques + le * D;
       const float* ref = t_ref + le * D;
       // one pass over the 12 DOFs feeds every per-DOF reduction that needs joint state only (each sum keeps its own
       // DOF order); the sums over `actions` and `torques` follow below, behind the grid wait in early mode
@@ -465,31 +624,6 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
         put(T_FEET_DISTANCE, pair_distance_reward(f0[0], f0[1], f1[0], f1[1], p.foot_min_dist, p.foot_max_dist));
       if (mask & (1u << T_KNEE_DISTANCE))                   // t1:615-628
         put(T_KNEE_DISTANCE, pair_distance_reward(k0[0], k0[1], k1[0], k1[1], p.knee_min_dist, p.knee_max_dist));
-      // ---- the two terms over this step's actions and torques -------------------------------------------
-      if (early) {
-        chain_wait();                                       // the substep kernels are done
-        // the two late rows of this env, straight from the L2 into the env's own tile rows (shorter than a bulk-copy
-        // round trip for 96 bytes per thread)
-        const float4* ga = reinterpret_cast<const float4*>(b.actions + (size_t)e * D);
-        const float4* gt = reinterpret_cast<const float4*>(b.torques + (size_t)e * D);
-        const float4 a0 = ga[0], a1 = ga[1], a2 = ga[2], t0 = gt[0], t1 = gt[1], t2 = gt[2];
-        float4* sa = reinterpret_cast<float4*>(const_cast<float*>(act));
-        float4* st = reinterpret_cast<float4*>(const_cast<float*>(tau));
-        sa[0] = a0; sa[1] = a1; sa[2] = a2; st[0] = t0; st[1] = t1; st[2] = t2;
-      }
-      float s_d1 = 0.0f, s_d2 = 0.0f, s_abs = 0.0f, s_tau = 0.0f;
-#pragma unroll 1
-      for (int i = 0; i < D; ++i) {
-        const float a = act[i], l = la[i];
-        const float d1 = (l - a) * 1.0f;
-        const float d2 = ((a + lla[i]) - 2.0f * l) * 1.0f;
-        s_d1 += d1 * d1;
-        s_d2 += d2 * d2;
-        s_abs += fabsf(a * 1.0f);
-        s_tau += tau[i] * tau[i];
-      }
-      if (mask & (1u << T_ACTION_SMOOTHNESS)) put(T_ACTION_SMOOTHNESS, (s_d1 + s_d2) + 0.05f * s_abs);   // t1:877-892
-      if (mask & (1u << T_TORQUES)) put(T_TORQUES, s_tau);       // t1:849-854
     } else {
       // ================================ role 2: the feet ===============================================
       FootState foot[2];
@@ -601,6 +735,40 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       }
     }
   }
+  // ---- role 1, last: the two terms over this step's actions and torques ---------------------------------------
+  if (role == 1) {
+    if (FUSED) bar_sync(BAR_TORQUES, (POST_ROLES + 1) * TB);     // the CTA's substep workers have left both rows in the tile
+    if (live) {
+      const float* act = t_act + le * D;
+      const float* la = t_last_act + le * D;
+      const float* lla = t_last_last_act + le * D;
+      const float* tau = t_torques + le * D;
+      if (early) {
+        chain_wait();                                       // the substep kernels are done
+        // the two late rows of this env, straight from the L2 into the env's own tile rows (shorter than a bulk-copy
+        // round trip for 96 bytes per thread)
+        const float4* ga = reinterpret_cast<const float4*>(b.actions + (size_t)e * D);
+        const float4* gt = reinterpret_cast<const float4*>(b.torques + (size_t)e * D);
+        const float4 a0 = ga[0], a1 = ga[1], a2 = ga[2], t0 = gt[0], t1 = gt[1], t2 = gt[2];
+        float4* sa = reinterpret_cast<float4*>(const_cast<float*>(act));
+        float4* st = reinterpret_cast<float4*>(const_cast<float*>(tau));
+        sa[0] = a0; sa[1] = a1; sa[2] = a2; st[0] = t0; st[1] = t1; st[2] = t2;
+      }
+      float s_d1 = 0.0f, s_d2 = 0.0f, s_abs = 0.0f, s_tau = 0.0f;
+#pragma unroll 1
+      for (int i = 0; i < D; ++i) {
+        const float a = act[i], l = la[i];
+        const float d1 = (l - a) * 1.0f;
+        const float d2 = ((a + lla[i]) - 2.0f * l) * 1.0f;
+        s_d1 += d1 * d1;
+        s_d2 += d2 * d2;
+        s_abs += fabsf(a * 1.0f);
+        s_tau += tau[i] * tau[i];
+      }
+      if (mask & (1u << T_ACTION_SMOOTHNESS)) put(T_ACTION_SMOOTHNESS, (s_d1 + s_d2) + 0.05f * s_abs);   // t1:877-892
+      if (mask & (1u << T_TORQUES)) put(T_TORQUES, s_tau);       // t1:849-854
+    }
+  }
   probe(b.debug_ts, 0, 2);
   probe(b.debug_ts, 0, 6, TB);          // role 1 done
   probe(b.debug_ts, 0, 7, 2 * TB);      // role 2 done
@@ -646,9 +814,10 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
   // t1:205-215: `is_first_add_force` of the next step (double-buffered by step parity: no CTA of this grid reads it)
   if (blockIdx.x == 0 && tid == 0) {
     g->step_now = step;                              // read by ti5_reset_observe (nobody in this grid reads it)
+    g->n_listed[(step + 1) & 1] = 0;                 // the next step's work-list counter (this grid fills [step & 1])
     if (p.flags & TI5_F_ADD_EXT_FORCE) g->is_first_add_force[(step + 1) & 1] = force_window ? 0 : 1;
   }
-  reset_bookkeeping(p, b, reset, e, le, T.sums, TB);
+  reset_bookkeeping(p, b, reset, e, le, T.sums, TB, step);
   probe(b.debug_ts, 0, 5);
 }
 
@@ -660,8 +829,9 @@ reset_bookkeeping_kernel(const __grid_constant__ Ti5Params p, const __grid_const
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const bool reset = e < N && b.reset_buf[e] != 0;
   // an explicit reset happens between steps: the scatter that follows works at the count of completed steps
-  if (e == 0) b.globals->step_now = b.globals->step_index;
-  reset_bookkeeping(p, b, reset, e, threadIdx.x, nullptr, 0);
+  const int64_t step = b.globals->step_index;
+  if (e == 0) b.globals->step_now = step;
+  reset_bookkeeping(p, b, reset, e, threadIdx.x, nullptr, 0, step);
 }
 
 }  // namespace ti5
@@ -672,14 +842,15 @@ extern "C" int ti5_reset_bookkeeping(const Ti5Params* p, const Ti5Buffers* b, vo
   TI5_CHECK_ARGS(p && b && p->num_envs > 0);
   TI5_CHECK_ARGS(p->env_block == 32 || p->env_block == 64 || p->env_block == 128);
   const int blocks = (p->num_envs + p->env_block - 1) / p->env_block;
-  cudaMemsetAsync(reinterpret_cast<char*>(b->globals) + offsetof(Ti5Globals, n_listed), 0, sizeof(int32_t), (cudaStream_t)stream);
+  cudaMemsetAsync(reinterpret_cast<char*>(b->globals) + offsetof(Ti5Globals, n_listed), 0, 2 * sizeof(int32_t), (cudaStream_t)stream);
   reset_bookkeeping_kernel<<<blocks, p->env_block, 0, (cudaStream_t)stream>>>(*p, *b);
   return ti5_check_launch("ti5_reset_bookkeeping");
 }
 
-extern "C" int ti5_post_physics(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, int options, void* stream) {
+static int launch_post(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, const float* actions_in, int options,
+                       bool fused, void* stream, const char* what) {
   TI5_CHECK_ARGS(p && b && p->num_envs > 0 && (options & ~3) == 0);
-  TI5_CHECK_ARGS(p->env_block == 32 || p->env_block == 64 || p->env_block == 128);
+  TI5_CHECK_ARGS(p->env_block == 32 || p->env_block == 64 || (!fused && p->env_block == 128));
   TI5_CHECK_ARGS(p->rng_mode == TI5_RNG_PHILOX || (r && r->cmd));
   TI5_CHECK_ARGS((p->term_mask & (1u << T_DOF_VEL_LIMITS)) == 0);   // the reference term reads a cfg field t1 lacks
   TI5_CHECK_ARGS(!(p->flags & TI5_F_ADD_EXT_FORCE) || p->applied_stride >= 3);
@@ -687,17 +858,26 @@ extern "C" int ti5_post_physics(const Ti5Params* p, const Ti5Buffers* b, const T
   const int blocks = (p->num_envs + p->env_block - 1) / p->env_block;
   const PostSrc src = make_post_src(*p, *b);
   const size_t smem = post_tile_bytes(p->env_block, src.off[POST_CHUNKS]);
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(post_physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-      ti5_set_error("ti5_post_physics: %zu bytes of shared memory per CTA not available", smem);
-      cudaGetLastError();
-      return TI5_ECUDA;
-    }
-    configured = smem;
+  auto kernel = fused ? post_physics_kernel<true> : post_physics_kernel<false>;
+  if (!ti5_ensure_smem(kernel, smem)) {
+    ti5_set_error("%s: %zu bytes of shared memory per CTA not available", what, smem);
+    return TI5_ECUDA;
   }
-  ti5_set_carveout(post_physics_kernel, ti5_small_grid(p));
-  (void)ti5_launch(post_physics_kernel, dim3(blocks), dim3(POST_ROLES * p->env_block), smem, stream,
-                   (options & TI5_POST_CHAINED) != 0, *p, *b, rr, src, options);
-  return ti5_check_launch("ti5_post_physics");
+  ti5_set_carveout(kernel, ti5_small_grid(p));
+  const int threads = (fused ? 2 : 1) * POST_ROLES * p->env_block;
+  (void)ti5_launch(kernel, dim3(blocks), dim3(threads), smem, stream, (options & TI5_POST_CHAINED) != 0, *p, *b, rr, src,
+                   actions_in, options);
+  return ti5_check_launch(what);
+}
+
+extern "C" int ti5_post_physics(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, int options, void* stream) {
+  return launch_post(p, b, r, nullptr, options, false, stream, "ti5_post_physics");
+}
+
+extern "C" int ti5_fused_step(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r, const float* actions_in, int options,
+                              void* stream) {
+  TI5_CHECK_ARGS(actions_in != nullptr && (options & ~TI5_FUSED_CHAINED) == 0);
+  TI5_CHECK_ARGS(p && p->decimation >= 1 && p->decimation <= 16);       // Philox sites S_TORQUE + k stay below S_CMD
+  TI5_CHECK_ARGS(p->rng_mode == TI5_RNG_PHILOX || !(p->flags & TI5_F_RAND_TORQUE) || (r && r->torque));
+  return launch_post(p, b, r, actions_in, options, true, stream, "ti5_fused_step");
 }

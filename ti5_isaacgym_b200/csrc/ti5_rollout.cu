@@ -217,7 +217,7 @@ extern "C" int ti5_gather_minibatch(const Ti5Rollout* ro, const int64_t* idx, co
   const int wpb = 8;
   // enough warps to fill the machine several times over, capped so each keeps a few samples
   int blocks = (B + wpb - 1) / wpb;
-  const int cap = 148 * 8 * 4;
+  const int cap = ti5_sm_count() * 8 * 4;
   if (blocks > cap) blocks = cap;
   cudaStream_t st = (cudaStream_t)stream;
   if (ro->num_single_obs == 47 && ro->priv_frame == 73)

@@ -15,7 +15,7 @@ namespace ti5 {
 __global__ void __launch_bounds__(256) begin_step_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
                                                         const float* __restrict__ actions_in) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx == 0) b.globals->n_listed = 0;      // work list of the history clear, refilled by ti5_post_physics
+  if (idx == 0) b.globals->n_listed[(b.globals->step_index + 1) & 1] = 0;      // work list of the history clear, refilled by ti5_post_physics
   if (idx >= p.num_envs * D) return;
   b.actions[idx] = clampf(actions_in[idx], -p.clip_actions, p.clip_actions);
 }
@@ -66,7 +66,7 @@ substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5B
       a4 = make_float4(clampf(a4.x, -p.clip_actions, p.clip_actions), clampf(a4.y, -p.clip_actions, p.clip_actions),
                        clampf(a4.z, -p.clip_actions, p.clip_actions), clampf(a4.w, -p.clip_actions, p.clip_actions));
       reinterpret_cast<float4*>(b.actions)[idx] = a4;
-      if (idx == 0) b.globals->n_listed = 0;
+      if (idx == 0) b.globals->n_listed[step & 1] = 0;
     } else if (!late_actions) {
       a4 = ld4(b.actions);
     }
@@ -188,6 +188,7 @@ static int launch_substep(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng*
                           void* stream) {
   TI5_CHECK_ARGS(p && b && p->num_envs > 0 && k >= 0 && k <= p->decimation && (phases & 3) != 0 && (phases & ~7) == 0);
   TI5_CHECK_ARGS(!(phases & TI5_SUB_TORQUE) || k < p->decimation);
+  TI5_CHECK_ARGS(p->decimation <= 16);       // Philox sites S_TORQUE + k must stay below S_CMD
   TI5_CHECK_ARGS(!(phases & TI5_SUB_TORQUE) || p->rng_mode == TI5_RNG_PHILOX || !(p->flags & TI5_F_RAND_TORQUE) ||
                  (r && r->torque));
   Ti5Rng rr = r ? *r : Ti5Rng{};

@@ -83,7 +83,8 @@ class EpisodeInfo(dict):
 
 class LeggedRobot(BaseTask):
     def __init__(self, cfg, sim_params, physics_engine, sim_device, headless, gym=None, rng_mode="philox",
-                 div_mode="reciprocal", use_cuda_graph=True, materialize_obs=False, seed=None, chain_launches=None):
+                 div_mode="reciprocal", use_cuda_graph=True, materialize_obs=False, seed=None, chain_launches=None,
+                 fused_step=None):
         """Args as the reference (lr:57).  Extra keyword options:
         rng_mode        "philox" (in-kernel Philox4x32-10) or "pools" (uniforms supplied per step via
                         `set_rng_pools`, the parity mode of SURVEY.md section 7)
@@ -93,7 +94,10 @@ class LeggedRobot(BaseTask):
                         (t1:477-481), instead of views into the history rings that are valid until the next step
         chain_launches  launch the kernels of a fused step (no simulator in between) as programmatic dependents of one
                         another: each becomes resident while its predecessor still runs and waits for it only where
-                        it needs its results (default on; env var TI5_CHAIN=0 turns it off)"""
+                        it needs its results (default on; env var TI5_CHAIN=0 turns it off)
+        fused_step      with no simulator between the substeps, run the action clip, the DEC substeps and the post-physics
+                        phase as ONE launch (ti5_fused_step) followed by ti5_reset_observe: 2 launches per step instead of
+                        12, bit-identical results (default on; env var TI5_FUSED=0 selects the 12-launch sequence)"""
         self.cfg = cfg
         self.sim_params = sim_params
         self.height_samples = None
@@ -105,6 +109,7 @@ class LeggedRobot(BaseTask):
         self._use_graph = bool(use_cuda_graph) and rng_mode == "philox"
         self._materialize = bool(materialize_obs)
         self._chain_launches = (os.environ.get("TI5_CHAIN", "1") != "0") if chain_launches is None else bool(chain_launches)
+        self._fused_step = (os.environ.get("TI5_FUSED", "1") != "0") if fused_step is None else bool(fused_step)
         self._seed = int(getattr(cfg, "seed", 0) if seed is None else seed)
         self._parse_cfg(self.cfg)
         super().__init__(self.cfg, sim_params, physics_engine, sim_device, headless, gym=gym)
@@ -589,6 +594,18 @@ class LeggedRobot(BaseTask):
 
     def _launch_step(self, actions_ptr, with_physics, notify=False):
         """Enqueue the kernels of one policy step on the current stream."""
+        if self._fused_step and not with_physics and self._params.env_block <= 64:
+            # no simulator between the substeps: [heights] -> clip + DEC substeps + post-physics -> resets + observations
+            lib, p, b, r, st = self._lib, self._p_ref, self._b_ref, self._rng_ref(), self._stream()
+            opt = 0
+            if self._params.num_height_points:
+                _lib.check(lib.ti5_sample_heights(p, b, st))
+                opt = self._chain("TI5_FUSED_CHAINED")
+            _lib.check(lib.ti5_fused_step(p, b, r, actions_ptr, opt, st))
+            if notify:
+                self._notify_simulator_of_disturbances()
+            self._launch_post(with_physics, part=2, notify=notify)
+            return
         self._launch_substeps(actions_ptr, with_physics)
         self._launch_post(with_physics, notify=notify)
 
@@ -607,7 +624,8 @@ class LeggedRobot(BaseTask):
 
     @property
     def launches_per_step(self):
-        return self._params.decimation + 2 + (1 if self._params.num_height_points else 0) + (1 if self._materialize else 0)
+        step = 2 if (self._fused_step and self._params.env_block <= 64) else self._params.decimation + 2
+        return step + (1 if self._params.num_height_points else 0) + (1 if self._materialize else 0)
 
     def step(self, actions):
         with_physics = getattr(self.gym, "physics", None) is not None or not hasattr(self.gym, "physics")
