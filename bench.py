@@ -45,7 +45,8 @@ def ncu_traffic(kernel):
     path = os.path.join(ROOT, "profiles", "r01c_ncu_full_summary_8192.json")
     if not os.path.exists(path):
         return None
-    want = {"substep": "substep_kernel", "post_physics": "post_physics_kernel", "reset_observe": "reset_observe_kernel"}[kernel]
+    want = {"substep": "substep_kernel", "post_physics": "post_physics_kernel", "reset_observe": "reset_observe_kernel",
+            "fused_step": "post_physics_kernelILb1", "heights": "heights_kernel"}[kernel]
     table = json.load(open(path))
     rows = next((v for k, v in table.items() if want in k), None)
     if not rows:
@@ -306,7 +307,7 @@ def cuda_arm(args):
         dom = max(kt, key=lambda k: kt[k]["share_ms"])
         # algorithmic bytes of one launch of the dominant family (SURVEY 8d figure x envs per launch);
         # the post phase's 2412 B/env are spread over its two launches
-        bytes_per_launch = KERNEL_BYTES[dom] * N
+        bytes_per_launch = kt[dom]["bytes_per_launch"]
         ach = bytes_per_launch / (kt[dom]["ms_per_launch"] * 1e-3) / 1e9
         launches_per_step = env.launches_per_step
         cpu = torch_gpu = None
@@ -362,7 +363,8 @@ def sweep_point(N, dev, steps=48, warmup=12):
     from ti5_isaacgym_b200.envs import T1DHStandEnv
     from ti5_isaacgym_b200.sim.synthetic import SimParams, fill_synthetic_state, synthetic_actions
     cfg = make_cfg(N)
-    env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, dev, True, rng_mode="philox", div_mode="reciprocal", use_cuda_graph=True)
+    env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, dev, True, rng_mode="philox", div_mode="reciprocal", use_cuda_graph=True,
+                       materialize_obs=False)
     gen = torch.Generator(device=dev).manual_seed(4321)
     fill_synthetic_state(env.gym.tensors, env.env_origins, gen)
     env.reset()
@@ -393,11 +395,9 @@ def sweep_point(N, dev, steps=48, warmup=12):
     ms = sum(a.elapsed_time(b) for a, b in marks) / steps
     kt = kernel_times(env, actions, steps=24)
     peak, _ = peaks()
-    sub_ms = kt["substep"]["ms_per_launch"]
     out = {"envs_per_gpu": N, "value": N / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms,
-           "substep": {"ms_per_launch": sub_ms, "achieved": BYTES_SUBSTEP * N / (sub_ms * 1e-3) / 1e9,
-                       "frac": BYTES_SUBSTEP * N / (sub_ms * 1e-3) / 1e9 / peak},
-           "post_physics_ms": kt["post_physics"]["phase_ms"], "reset_observe_ms": kt["reset_observe"]["phase_ms"],
+           "kernels": {k: {"ms_per_launch": v["ms_per_launch"], "achieved": v["achieved_GBps"], "frac": v["achieved_GBps"] / peak}
+                       for k, v in kt.items()},
            "whole_step": {"bytes": BYTES_ENV_STEP * N, "achieved": BYTES_ENV_STEP * N / (ms * 1e-3) / 1e9,
                           "frac": BYTES_ENV_STEP * N / (ms * 1e-3) / 1e9 / peak}}
     del env, flush
@@ -491,46 +491,47 @@ def rollout_bench(env, gen, actions):
 # pose (264 B) — its re-reads of what ti5_post_physics produced are not counted.
 BYTES_POST_PHYSICS = 922 + 266
 BYTES_RESET_OBSERVE = BYTES_POST - BYTES_POST_PHYSICS
-KERNEL_BYTES = {"substep": BYTES_SUBSTEP, "post_physics": BYTES_POST_PHYSICS, "reset_observe": BYTES_RESET_OBSERVE}
+# ti5_fused_step (clip + 10 substeps + post-physics in one launch): what has to move once the substeps share one pass
+# over an env — reads: actions 48, five actuator arrays 240, lag index + stamp 12, on average 8.2
+# lagged action rows that predate the step 394, the post-physics inputs 922 (joint state included); writes: ten action /
+# DOF / IMU ring rows 1680, actions + final torques + multipliers 144, the post-physics outputs 266.
+BYTES_FUSED_STEP = (48 + 240 + 12 + 394 + 922) + (1680 + 144 + 266)
+BYTES_HEIGHTS = 1122 + 748          # 3 x 187 int16 gathers + (N,187) fp32 out
+KERNEL_BYTES = {"substep": BYTES_SUBSTEP, "post_physics": BYTES_POST_PHYSICS, "reset_observe": BYTES_RESET_OBSERVE,
+                "fused_step": BYTES_FUSED_STEP, "heights": BYTES_HEIGHTS}
 
 
 def kernel_times(env, actions, steps):
-    """Average device time of the three kernel families of a step, CUDA events on the launching stream around
-    the replay of one CUDA graph per family (a single whole-step graph cannot be bracketed inside; the event
-    records also cut the programmatic launch chain at the two family boundaries, so the three times add up to
-    a little more than the whole-step time).  The substep family is DEC launches of the fused substep kernel
-    (the action clip rides in the first); its per-launch time is family time / DEC."""
-    g_sub, g_post, g_obs = env.capture_phase_graphs()
-    dec = env._params.decimation
+    """Average device time of the kernel families of a step, CUDA events on the launching stream around the replay of
+    one CUDA graph per family (a single whole-step graph cannot be bracketed inside; the event records also cut the
+    programmatic launch chain at the family boundaries, so the times add up to a little more than the whole-step
+    time).  Per-launch time = family time / launches in the family."""
+    graphs = env.capture_phase_graphs()
     ev = lambda: torch.cuda.Event(enable_timing=True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=env.device)
     env._actions_in.copy_(actions)
-    names = ("substep", "post_physics", "reset_observe")
-    acc = {n: [] for n in names}
+    acc = {name: [] for name, _, _ in graphs}
     marks = []
     for i in range(steps):
         flush.fill_(i & 0xFF)
-        e = [ev() for _ in range(4)]
+        e = [ev() for _ in range(len(graphs) + 1)]
         e[0].record()
-        g_sub.replay()
-        e[1].record()
-        g_post.replay()
-        e[2].record()
-        g_obs.replay()
-        e[3].record()
+        for k, (_, g, _) in enumerate(graphs):
+            g.replay()
+            e[k + 1].record()
         env._finish_step()
         marks.append(e)
     torch.cuda.synchronize()
     for e in marks:
-        for k, n in enumerate(names):
-            acc[n].append(e[k].elapsed_time(e[k + 1]))
+        for k, (name, _, _) in enumerate(graphs):
+            acc[name].append(e[k].elapsed_time(e[k + 1]))
     out = {}
-    for name, v in acc.items():
-        n = dec if name == "substep" else 1
-        phase = statistics.mean(v)
+    for name, _, n in graphs:
+        phase = statistics.mean(acc[name])
+        extra = env._params.priv_frame - 73 if name == "reset_observe" else 0       # measured heights ride in the critic frame
+        nbytes = (KERNEL_BYTES[name] + 4 * 3 * extra) * env.num_envs
         out[name] = {"phase_ms": phase, "launches": n, "ms_per_launch": phase / n, "share_ms": phase,
-                     "bytes_per_launch": KERNEL_BYTES[name] * env.num_envs,
-                     "achieved_GBps": KERNEL_BYTES[name] * env.num_envs / (phase / n * 1e-3) / 1e9}
+                     "bytes_per_launch": nbytes, "achieved_GBps": nbytes / (phase / n * 1e-3) / 1e9}
     del flush
     return out
 

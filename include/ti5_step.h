@@ -183,7 +183,9 @@ typedef struct Ti5Buffers {
   float* rigid_state;      /* (N,13,13) */
   /* actuation */
   float* actions;          /* (N,12) clipped actions of this step */
-  float* torques;          /* (N,12) */
+  float* torques;          /* (N,12) torques of the last substep evaluated (lr:401) */
+  float* torques_substeps; /* optional (DEC,N,12), or NULL: ti5_fused_step leaves the torques of EVERY substep here — what
+                              set_dof_actuation_force_tensor is handed DEC times per step (lr:403) */
   float* torque_multi;     /* (N,12) */
   float* p_gains_r;        /* (N,12) randomized_p_gains */
   float* d_gains_r;        /* (N,12) */

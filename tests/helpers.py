@@ -53,6 +53,7 @@ def gym_calls_of(out):
 
 def make_env(cfg, rng_mode="pools", div_mode="ieee", **kw):
     from ti5_isaacgym_b200.envs import T1DHStandEnv
+    kw.setdefault("materialize_obs", False)         # most tests read the ring views right after the step
     from ti5_isaacgym_b200.sim.synthetic import SimParams
     return T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, "cuda:0", True, rng_mode=rng_mode, div_mode=div_mode,
                         use_cuda_graph=False, **kw)

@@ -71,6 +71,7 @@ def _production_env(N, name="plane_default", **kw):
     from ti5_isaacgym_b200.envs import T1DHStandEnv
     from ti5_isaacgym_b200.sim.synthetic import SimParams, fill_synthetic_state
     cfg = scenario_cfg(name, N)
+    kw.setdefault("materialize_obs", False)
     env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, "cuda:0", True, seed=11, **kw)
     gen = torch.Generator(device="cuda").manual_seed(5)
     fill_synthetic_state(env.gym.tensors, env.env_origins, gen, base_contact_rate=0.03)

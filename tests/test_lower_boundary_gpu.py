@@ -16,7 +16,7 @@ def _env(name, N, gym_cls):
     from ti5_isaacgym_b200.sim.synthetic import SimParams
     cfg = scenario_cfg(name, N)
     return T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, "cuda:0", True, gym=gym_cls(N, "cuda:0"), rng_mode="pools",
-                        div_mode="ieee", use_cuda_graph=False)
+                        div_mode="ieee", use_cuda_graph=False, materialize_obs=False)
 
 
 @pytest.mark.parametrize("name", ["plane_windows", "trimesh_windows", "plane_events"])

@@ -83,6 +83,8 @@ class RolloutStorage:
         if self.step >= self.num_transitions_per_env:
             raise AssertionError("Rollout buffer overflow")
         s = self.step
+        check_not_stale_ring_view(tr.observations, "observations")
+        check_not_stale_ring_view(tr.critic_observations, "critic_observations")
         self.observations[s].copy_(tr.observations)
         if self.privileged_observations is not None:
             self.privileged_observations[s].copy_(tr.critic_observations)
@@ -310,6 +312,18 @@ class FrameLogRolloutStorage(RolloutStorage):
         return self._all_rows("critic_obs")
 
 
+def check_not_stale_ring_view(t, what="observations"):
+    """An env built with `materialize_obs=False` returns views into its history rings that the NEXT `step()` overwrites
+    (oldest slot reused, re-spawned envs cleared).  The reference's runner stores the observation one step after the
+    policy saw it (dh_ppo.py:88 -> rs:62): copying such a view then would silently store the wrong window.  The env
+    tags its views with the step they belong to; a copy-late storage calls this and fails loudly instead."""
+    tag = getattr(t, "ti5_ring_view", None)
+    if tag is not None and tag[0][0] != tag[1]:
+        raise _lib.Ti5Error(f"{what}: a view into the env's history ring taken at step {tag[1]}, but the env has stepped "
+                            f"to {tag[0][0]} since — the window it showed is gone.  Build the env with materialize_obs=True "
+                            "(the default), or use FrameLogRolloutStorage (task_registry.make_alg_runner does).")
+
+
 def install_frame_log_storage(alg, env, group=None, num_transitions_per_env=None):
     """Swap a `FrameLogRolloutStorage` into a PPO object built by the reference's runner (`alg.storage`,
     dh_ppo.py:67-70) and fuse its `process_env_step` (dh_ppo.py:93-103) into the single store launch."""
@@ -331,6 +345,14 @@ def install_frame_log_storage(alg, env, group=None, num_transitions_per_env=None
 
 def patch_compute_returns(storage_cls, group=None):
     """Swap the GPU GAE into an existing storage class (e.g. the reference's own RolloutStorage)."""
+    add_plain = storage_cls.add_transitions
+
+    def add_transitions(self, transition):
+        check_not_stale_ring_view(transition.observations, "observations")
+        check_not_stale_ring_view(getattr(transition, "critic_observations", None), "critic_observations")
+        return add_plain(self, transition)
+    storage_cls.add_transitions = add_transitions
+
     def compute_returns(self, last_values, gamma, lam):
         if getattr(self, "_ti5_scratch", None) is None:
             self._ti5_scratch = make_gae_scratch(self.rewards.shape[1], self.rewards.device)

@@ -220,6 +220,16 @@ __device__ __forceinline__ void coop_load(void* dst, const void* src, uint32_t b
     reinterpret_cast<uint8_t*>(dst)[(words << 2) + threadIdx.x] = reinterpret_cast<const uint8_t*>(src)[(words << 2) + threadIdx.x];
 }
 
+// the same by a subset of the CTA: threads 0 .. nthreads-1, `t` = the caller's index among them
+__device__ __forceinline__ void coop_load_n(void* dst, const void* src, uint32_t bytes, int t, int nthreads) {
+  const uint32_t words = bytes >> 2;
+  for (uint32_t i = t; i < words; i += nthreads)
+    reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+  const uint32_t tail = bytes & 3u;
+  if ((uint32_t)t < tail)
+    reinterpret_cast<uint8_t*>(dst)[(words << 2) + t] = reinterpret_cast<const uint8_t*>(src)[(words << 2) + t];
+}
+
 static __device__ __noinline__ void coop_load_call(void* dst, const void* src, uint32_t bytes) { coop_load(dst, src, bytes); }
 
 // ---------------------------------------------------------------------------------------------
@@ -246,8 +256,20 @@ __device__ __forceinline__ void probe(uint64_t* ts, int kernel, int k, int threa
   }
 }
 
+// 64-bit step counters divided by run-time divisors: a 64-bit division is a ~100-instruction subroutine with a long
+// dependent chain, and the kernels are bound by exactly that (one warp runs the whole program once).  Counters fit
+// 31 bits for any realistic run (2^31 steps = 8 months at 100 steps/s): one 32-bit division then; the 64-bit path stays
+// for correctness beyond.
+__device__ __forceinline__ int64_t fast_mod(int64_t x, int64_t m) {
+  if ((((uint64_t)x | (uint64_t)m) >> 31) == 0) return (int64_t)((uint32_t)x % (uint32_t)m);
+  return x % m;
+}
+__device__ __forceinline__ int64_t fast_div(int64_t x, int64_t m) {
+  if ((((uint64_t)x | (uint64_t)m) >> 31) == 0) return (int64_t)((uint32_t)x / (uint32_t)m);
+  return x / m;
+}
 // ring slot of push index j (j >= 0)
-__device__ __forceinline__ int ring_slot(int64_t j, int len) { return (int)(j % len); }
+__device__ __forceinline__ int ring_slot(int64_t j, int len) { return (int)fast_mod(j, len); }
 
 // block-wide exclusive scan helper result for compaction
 struct BlockRank {

@@ -252,7 +252,12 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
   // complete there) it takes a ticket, and the CTA that draws the last one — every CTA of the grid has read by then —
   // publishes the new count.
   __shared__ int64_t s_step;
-  if (tid == 0) s_step = (phases & TI5_RO_CHAINED) ? g->step_index + 1 : g->step_now;
+  __shared__ bool s_new_step;
+  if (tid == 0) {
+    const int64_t done = g->step_index;
+    s_step = (phases & TI5_RO_CHAINED) ? done + 1 : g->step_now;
+    s_new_step = s_step != done;       // false: compute_observations() called again on a completed step (same slots)
+  }
   __syncthreads();
   const int64_t step = s_step;
   const int64_t pushes = step * p.decimation;            // lag pushes completed after this step
@@ -353,7 +358,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
   }
   int n_reset = 0, id_offset = 0;
   const int64_t counter = step + g->common_step_offset;
-  const bool curriculum_due = do_reset && (p.flags & TI5_F_COMMAND_CURRICULUM) && (counter % p.max_episode_length == 0);
+  const bool curriculum_due = do_reset && (p.flags & TI5_F_COMMAND_CURRICULUM) && (fast_mod(counter, p.max_episode_length) == 0);
   if (do_reset) {
     int tot = 0, bef = 0;
     double trk = 0.0;
@@ -649,13 +654,13 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
   // ---- history rings: append this step's frames; clear the rows of re-spawned envs ------------
   const size_t obs_row = (size_t)2 * H * K, priv_row = (size_t)2 * CH * P;
   const int warp_env0 = blockIdx.x * TB + tile_warp * 32;
-  const int hs = (int)((step - 1) % H), cs = (int)((step - 1) % CH);       // slot of this step's frame
+  const int hs = (int)fast_mod(step - 1, H), cs = (int)fast_mod(step - 1, CH);       // slot of this step's frame
   __syncthreads();       // both frames of every env of the CTA are staged
   probe(b.debug_ts, 1, 7);
   if (do_obs && blockIdx.x < env_blocks && warp_env0 < N) {
     const int n_here = min(32, N - warp_env0);
     const float lim = p.clip_obs;
-    const int L = p.log_len, ls = L > 0 ? (int)((step - 1) % L) : 0;      // frame-log row of this step
+    const int L = p.log_len, ls = L > 0 ? (int)fast_mod(step - 1, L) : 0;      // frame-log row of this step
     // the tile's warps (frame builders and writers alike) stride over the staged obs elements, then the priv ones;
     // small loop bodies on purpose (32-bit offsets from a uniform base, no unrolling): this is the stretch of the
     // kernel with the most instructions per warp, and it is bound by instruction fetch / issue, not by memory
@@ -689,8 +694,8 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
     int hv = b.hist_valid[e];
     if (do_reset && reset) hv = 0;
     if (do_obs) {
-      hv = min(hv + 1, H);
-      b.valid_log[(size_t)((step - 1) % p.log_len) * N + e] = (int16_t)hv;
+      if (s_new_step) hv = min(hv + 1, H);      // a re-observation rewrites the slot of the step: no frame is added
+      b.valid_log[(size_t)fast_mod(step - 1, p.log_len) * N + e] = (int16_t)hv;
     }
     b.hist_valid[e] = hv;
   }
@@ -827,7 +832,7 @@ __global__ void __launch_bounds__(256) materialize_kernel(const __grid_constant_
   const int N = p.num_envs, K = p.num_single_obs, P = p.priv_frame, H = p.frame_stack, CH = p.c_frame_stack;
   const int64_t step = b.globals->step_index;            // runs after the step has been completed
   const size_t ow = (size_t)H * K, pw = (size_t)CH * P;
-  const size_t o_off = (size_t)(((step - 1) % H) + 1) * K, p_off = (size_t)(((step - 1) % CH) + 1) * P;
+  const size_t o_off = (size_t)(fast_mod(step - 1, H) + 1) * K, p_off = (size_t)(fast_mod(step - 1, CH) + 1) * P;
   const size_t total_o = (size_t)N * ow, total_p = (size_t)N * pw;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_o + total_p; i += stride) {

@@ -39,7 +39,7 @@ static __device__ __noinline__ float pair_distance_reward(float ax, float ay, fl
 static __device__ __noinline__ void reset_bookkeeping(const Ti5Params& p, const Ti5Buffers& b, bool reset, int e, int le,
                                                       const float* sums, int tb, int64_t step) {
   __shared__ int s_warp[32];
-  __shared__ float s_red[12][TI5_NUM_TERMS];
+  __shared__ float s_red[32][TI5_NUM_TERMS];
   const int N = p.num_envs, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   if (reset) b.reset_list[atomicAdd(&b.globals->n_listed[step & 1], 1)] = e;
   const BlockRank br = block_rank(reset, s_warp);
@@ -100,41 +100,23 @@ struct PostTile {
   template <class T> __device__ __forceinline__ T* at(int chunk) const { return reinterpret_cast<T*>(base + (size_t)src->off[chunk] * tb); }
 };
 
+constexpr int FOOT_PARTS = 9;        // FootPart entries handed from one foot role to the other (post_physics_kernel)
 __host__ __device__ inline size_t post_tile_bytes(int tb, int per_env_bytes) {
-  return (size_t)tb * per_env_bytes + 2 * (size_t)TI5_NUM_TERMS * tb * 4 + 16;
+  return (size_t)tb * per_env_bytes + 2 * (size_t)TI5_NUM_TERMS * tb * 4 + 16 + (size_t)FOOT_PARTS * tb * 4;
 }
 
-// The CTA owns TB = env_block consecutive envs and runs POST_ROLES x TB threads: every env is worked on by
-// three threads ("roles"), each evaluating a third of the step — at 8192 envs the kernel is bound by the
-// length of one thread's dependent instruction chain, not by bandwidth, so the chain is cut in three.
-//   role 0 (base):   counters, derived base state, push / external-force windows, termination, base terms
-//   role 1 (joints): the per-DOF reductions and the joint / distance terms, DOF-lag push
-//   role 2 (feet):   feet Euler angles, contact bookkeeping (air time, clearance) and the feet terms
-// The unscaled terms meet in shared memory; role 0 then forms the reward sum in the reference's
-// (alphabetical) order and all threads share the reset bookkeeping.
-constexpr int POST_ROLES = 3;
-
-// named barrier between the substep workers (arrive) and role 1 (sync) of the fused kernel
-constexpr int BAR_TORQUES = 1;
-__device__ __forceinline__ void bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
-__device__ __forceinline__ void bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
-// a store the compiler may not drop although the same address is stored again later in the kernel: every substep's
-// torques land in memory in turn, as they do when the substeps are separate launches (lr:401-403)
-__device__ __forceinline__ void store4_kept(float* ptr, float4 v) {
-  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
-// lr:393-434 for one (env, group of four DOFs) when no simulator runs between the substeps: the action clip, then DEC x
-// [_compute_torques, DOF-lag push] with the joint state, gains and offsets read once.  Same arithmetic, same Philox
-// counters and the same stores as DEC launches of substep_kernel (ti5_substep.cu); the IMU-lag pushes, whose values equal
-// the derived base state, are left to role 0.  DEC > 0: unrolled, all lagged rows in flight together; DEC == 0: any
-// decimation, one row at a time.  Leaves the clipped actions and the last substep's torques in the CTA's tile.
-template <int DEC>
+// lr:393-434 when no simulator runs between the substeps, for one (env, group of four DOFs): the action clip, then
+// [_compute_torques, DOF-lag push] for the substeps k = kh, kh + WORKER_SPLIT, ... with the joint state, gains and offsets
+// read once.  Same arithmetic and the same Philox counters as DEC launches of substep_kernel (ti5_substep.cu); every
+// substep's torques are stored (torques_substeps[k]), the last substep's also where the unfused kernels leave them.
+// The IMU-lag pushes, whose values equal the derived base state, are left to role 0.  The loop is rolled on purpose:
+// a warp runs it once, so every instruction of an unrolled body would be a cold instruction-cache line.
+constexpr int WORKER_SPLIT = 2;      // threads per (env, four DOFs): the substeps are dealt out round-robin
+constexpr int WORKER_THREADS_PER_ENV = 3 * WORKER_SPLIT;
 __device__ __forceinline__ void substep_worker(const Ti5Params& p, const Ti5Buffers& b, const Ti5Rng& r,
                                                const float* __restrict__ actions_in, int64_t step, int idx, int e, int gq,
-                                               float* tile_act, float* tile_tau) {
-  const int N = p.num_envs, d0 = 4 * gq;
-  const int dec = DEC > 0 ? DEC : p.decimation;
+                                               int kh, float* tile_act, float* tile_tau) {
+  const int N = p.num_envs, d0 = 4 * gq, dec = p.decimation;
   const bool rg = p.flags & TI5_F_RAND_GAINS, fric = p.flags & TI5_F_RAND_COULOMB, rt = p.flags & TI5_F_RAND_TORQUE;
   const bool lagged = p.flags & TI5_F_ADD_LAG, philox = p.rng_mode == TI5_RNG_PHILOX;
   auto ld4 = [&](const float* base_ptr) { return reinterpret_cast<const float4*>(base_ptr)[idx]; };
@@ -150,28 +132,44 @@ __device__ __forceinline__ void substep_worker(const Ti5Params& p, const Ti5Buff
   if (lagged) { lag = b.lag_timestep[e * 3 + 0]; stamp = b.ring_stamp[e]; }
   if (rg) { kp4 = ld4(b.p_gains_r); kd4 = ld4(b.d_gains_r); }
   if (fric) { vis4 = ld4(b.viscous); cou4 = ld4(b.coulomb); }
-  const int64_t base = (step - 1) * p.decimation;          // pushes completed before this step
+  const int64_t base = (step - 1) * dec;                   // pushes completed before this step
   float4* ring = reinterpret_cast<float4*>(b.act_ring);
   const size_t ring_row = (size_t)N * 3;
-  // ring slots of this step's pushes: one 64-bit remainder per ring, then 32-bit wrap-arounds
-  const int as0 = (int)(base % p.lag_len), ds0 = (int)(base % p.dof_lag_len);
-  auto wrap = [](int s, int len) { return s % len; };
-  // the lagged action rows of the substeps that look back past the start of this step (lr:1045); rows pushed before the
-  // env's last reset read as zero (lr:606).  Read before any row of this step is pushed: a slot this step overwrites
-  // is only ever read by an EARLIER substep than the one that overwrites it (slot(base + k') == slot(base + k - lag)
-  // needs k' = k + len - lag > k).
-  float4 old_row[DEC > 0 ? DEC : 1];
-  if (DEC > 0) {
-#pragma unroll
-    for (int k = 0; k < DEC; ++k) {
-      const int64_t jj = base + k - lag;
-      old_row[k] = zero4;
-      if (lagged && lag > k && jj >= stamp && jj >= 0) old_row[k] = ring[(size_t)ring_slot(jj, p.lag_len) * ring_row + idx];
+  // ring slots: one remainder per ring, then increments
+  const int alen = p.lag_len, dlen = p.dof_lag_len;
+  int ws = (int)fast_mod(base + kh, alen);                 // slot the action of substep k is pushed to
+  int dsl = (int)fast_mod(base + kh, dlen);                // slot of the DOF-lag push after substep k
+  int rs = ws - lag % alen;                                // slot of the lagged row substep k looks at
+  if (rs < 0) rs += alen;
+  auto adv = [](int s, int len) { s += WORKER_SPLIT; return s >= len ? s % len : s; };
+  // the lagged action row of a substep that looks back past the start of this step (lr:1045); rows pushed before the
+  // env's last reset read as zero (lr:606).  Loaded one turn ahead, while no ordering with this step's own pushes is
+  // needed: push k' of this step lands in the slot substep k reads only if k' - k + lag is a multiple of the ring
+  // length, and with 0 < lag < len that means k' = k + len - lag > k — a slot is overwritten only AFTER its last reader,
+  // in whatever order the earlier pushes (k' <= k, by this thread or its twin) and this load are performed.
+  auto load_old = [&](int k, int slot) {
+    const int64_t jj = base + k - lag;
+    float4 v = zero4;
+    if (lagged && lag > k && jj >= stamp && jj >= 0) v = ring[(size_t)slot * ring_row + idx];
+    return v;
+  };
+  // start fetching every old row this thread will read (evicted from the L2 since they were pushed): the loop below then
+  // finds them one short L2 hit apart instead of one DRAM round trip apart
+  if (lagged) {
+    int slot = rs;
+#pragma unroll 1
+    for (int k = kh; k < dec && k < lag; k += WORKER_SPLIT) {
+      prefetch_l2(ring + (size_t)slot * ring_row + idx);
+      slot = adv(slot, alen);
     }
   }
+  float4 nxt = kh < dec ? load_old(kh, rs) : zero4;
   a4 = make_float4(clampf(a4.x, -p.clip_actions, p.clip_actions), clampf(a4.y, -p.clip_actions, p.clip_actions),
                    clampf(a4.z, -p.clip_actions, p.clip_actions), clampf(a4.w, -p.clip_actions, p.clip_actions));   // lr:393-394
-  reinterpret_cast<float4*>(b.actions)[idx] = a4;
+  if (kh == 0) {
+    reinterpret_cast<float4*>(b.actions)[idx] = a4;
+    *reinterpret_cast<float4*>(tile_act + d0) = a4;
+  }
   const float q[4] = {s0.x, s0.z, s1.x, s1.z}, qd[4] = {s0.y, s0.w, s1.y, s1.w};
   const float a[4] = {a4.x * p.action_scale, a4.y * p.action_scale, a4.z * p.action_scale, a4.w * p.action_scale};
   const float4 as4 = make_float4(a[0], a[1], a[2], a[3]);
@@ -183,15 +181,19 @@ __device__ __forceinline__ void substep_worker(const Ti5Params& p, const Ti5Buff
   const float off[4] = {off4.x, off4.y, off4.z, off4.w};
   const float vis[4] = {vis4.x, vis4.y, vis4.z, vis4.w}, cou[4] = {cou4.x, cou4.y, cou4.z, cou4.w};
   const float4 q4 = make_float4(q[0], q[1], q[2], q[3]), qd4 = make_float4(qd[0], qd[1], qd[2], qd[3]);
-  float tau[4] = {0.f, 0.f, 0.f, 0.f};
-  auto substep = [&](int k, float4 t4) {
+  const bool from_ring = lagged && lag > 0;
+#pragma unroll 1
+  for (int k = kh; k < dec; k += WORKER_SPLIT) {
+    const float4 t4 = lag <= k ? as4 : nxt;                // a row this step pushed itself: from registers
+    const int rs_next = adv(rs, alen);
+    if (k + WORKER_SPLIT < dec) nxt = load_old(k + WORKER_SPLIT, rs_next);
     // lr:1019-1074 torque of substep k
     float4 u4 = zero4;
     if (rt) u4 = philox ? philox_u4(p.seed, (uint64_t)step, S_TORQUE + k, idx)
                         : reinterpret_cast<const float4*>(r.torque)[(size_t)k * ring_row + idx];
-    if (lagged) ring[(size_t)wrap(as0 + k, p.lag_len) * ring_row + idx] = as4;
-    const bool from_ring = lagged && lag > 0;
+    if (lagged) ring[(size_t)ws * ring_row + idx] = as4;
     const float target[4] = {from_ring ? t4.x : a[0], from_ring ? t4.y : a[1], from_ring ? t4.z : a[2], from_ring ? t4.w : a[3]};
+    float tau[4], m[4] = {1.f, 1.f, 1.f, 1.f};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float err = ((target[i] + p.default_dof_pos[d0 + i]) - q[i]) + off[i];
@@ -206,49 +208,86 @@ __device__ __forceinline__ void substep_worker(const Ti5Params& p, const Ti5Buff
     }
     if (rt) {
       const float u[4] = {u4.x, u4.y, u4.z, u4.w};
-      float m[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         m[i] = affine(p.torque_multi_w, p.torque_multi_lo, u[i]);
         tau[i] = tau[i] * m[i];
       }
-      store4_kept(b.torque_multi + (size_t)idx * 4, make_float4(m[0], m[1], m[2], m[3]));
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float lim = p.torque_limits[d0 + i];
       tau[i] = clampf(tau[i], -lim, lim);
     }
-    store4_kept(b.torques + (size_t)idx * 4, make_float4(tau[0], tau[1], tau[2], tau[3]));
+    const float4 tau4 = make_float4(tau[0], tau[1], tau[2], tau[3]);
+    if (b.torques_substeps) reinterpret_cast<float4*>(b.torques_substeps)[(size_t)k * ring_row + idx] = tau4;
+    if (k == dec - 1) {                                    // what the unfused sequence leaves behind (lr:401, 1072)
+      reinterpret_cast<float4*>(b.torques)[idx] = tau4;
+      if (rt) reinterpret_cast<float4*>(b.torque_multi)[idx] = make_float4(m[0], m[1], m[2], m[3]);
+      *reinterpret_cast<float4*>(tile_tau + d0) = tau4;
+    }
     // lr:412-418 DOF-lag push after (what would be) simulator substep k
     if (p.flags & TI5_F_ADD_DOF_LAG) {
-      float* row = b.dof_ring + ((size_t)wrap(ds0 + k, p.dof_lag_len) * N + e) * (2 * D);
+      float* row = b.dof_ring + ((size_t)dsl * N + e) * (2 * D);
       *reinterpret_cast<float4*>(row + d0) = q4;
       *reinterpret_cast<float4*>(row + D + d0) = qd4;
     }
-  };
-  if (DEC > 0) {
-#pragma unroll
-    for (int k = 0; k < DEC; ++k) substep(k, lag <= k ? as4 : old_row[k]);       // rows this step pushed: from registers
-  } else {
-#pragma unroll 1
-    for (int k = 0; k < dec; ++k) {
-      const int64_t jj = base + k - lag;
-      float4 t4 = lag <= k ? as4 : zero4;
-      if (lagged && lag > k && jj >= stamp && jj >= 0) t4 = ring[(size_t)ring_slot(jj, p.lag_len) * ring_row + idx];
-      substep(k, t4);
-    }
+    ws = adv(ws, alen);
+    dsl = adv(dsl, dlen);
+    rs = rs_next;
   }
-  // what role 1 needs of this phase
-  *reinterpret_cast<float4*>(tile_act + d0) = a4;
-  *reinterpret_cast<float4*>(tile_tau + d0) = make_float4(tau[0], tau[1], tau[2], tau[3]);
 }
 
+// The CTA owns TB = env_block consecutive envs.  At the sizes this task runs at the kernel is bound by the length of
+// one thread's dependent instruction chain (a warp runs the program exactly once; there are only a few warps per
+// scheduler), not by bandwidth, so every env is worked on by POST_ROLES threads ("roles"), each a warp-uniform slice of
+// the step:
+//   R_BASE     counters, command schedule, derived base state (+ IMU-lag pushes), push / external-force windows,
+//              termination, collision                                                    lr:464-481, 509-517; t1:179-247
+//   R_BASE_A   base_acc, low_speed, orientation                                          t1:717, 816, 670
+//   R_BASE_B   track_vel_hard, tracking_ang_vel, tracking_lin_vel, vel_mismatch_exp      t1:738-790, 726
+//   R_JOINT_A  the per-DOF reductions: default_joint_pos, dof_acc, dof_vel, joint_pos, stand_sysmetry
+//   R_JOINT_B  feet_distance, knee_distance, and — last, behind the substeps — action_smoothness, torques
+//   R_FOOT0/1  one foot each: Euler angles, contact bookkeeping (air time, clearance) and its share of every feet
+//              term; foot 1 hands its partial results to foot 0, which adds them in the reference's order
+// A role recomputes what it needs of another role's intermediate results (a quaternion rotation is cheaper than a
+// barrier).  The unscaled terms meet in shared memory; R_BASE then forms the reward sum in the reference's
+// (alphabetical) order while the other roles update the per-term episode sums, and all threads share the reset
+// bookkeeping.
 // FUSED: the kernel also carries the CTA's envs through the DEC substeps that precede the post-physics phase
-// (ti5_fused_step): 3 x TB further threads, one per (env, four DOFs), run them while the roles work; they meet role 1
-// on a named barrier in front of the two terms over this step's actions and torques.
-template <bool FUSED>
-__global__ void __launch_bounds__(POST_ROLES * 128)
+// (ti5_fused_step): 3 x WORKER_SPLIT x TB further threads, WORKER_SPLIT per (env, four DOFs), run them while the roles
+// work; they meet R_JOINT_B on a named barrier in front of the two terms over this step's actions and torques.
+constexpr int POST_ROLES = 7;
+enum PostRole { R_BASE = 0, R_BASE_A, R_BASE_B, R_JOINT_A, R_JOINT_B, R_FOOT0, R_FOOT1 };
+// named barriers (0 is __syncthreads)
+constexpr int BAR_TORQUES = 1;      // substep workers arrive, R_JOINT_B waits
+constexpr int BAR_ROLES = 2;        // the role threads among themselves while the workers run (FUSED)
+constexpr int BAR_FEET = 3;         // R_FOOT1 arrives, R_FOOT0 waits
+__device__ __forceinline__ void bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// t1:223-226 the base velocities a push sets: drawn by R_BASE (which applies them) and again, identically, by R_BASE_A
+// (whose base_acc term sees the pushed velocities)
+struct PushDraw { float fx, fy, tq[3]; };
+static __device__ __noinline__ PushDraw push_draw(const Ti5Params& p, const Ti5Rng& r, int64_t step, int e) {
+  float u[5];
+#pragma unroll
+  for (int c = 0; c < 5; ++c)
+    u[c] = p.rng_mode == TI5_RNG_PHILOX ? philox_u(p.seed, (uint64_t)step, S_PUSH, e * 5 + c) : r.push[(size_t)e * 5 + c];
+  PushDraw d;
+  d.fx = affine(p.push_vel_w, p.push_vel_lo, u[0]);
+  d.fy = affine(p.push_vel_w, p.push_vel_lo, u[1]);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) d.tq[c] = affine(p.push_ang_w, p.push_ang_lo, u[2 + c]);
+  return d;
+}
+
+// what one foot contributes to the feet terms (R_FOOT1 -> R_FOOT0 through shared memory)
+enum FootPart { FP_Z = 0, FP_AIR, FP_CLEAR, FP_FORCE, FP_NUMBER, FP_PITCH, FP_STUMBLE, FP_SLIP, FP_STILL, FP_COUNT };
+static_assert(FP_COUNT == FOOT_PARTS, "post_tile_bytes reserves FOOT_PARTS floats per env");
+
+template <bool FUSED, int MAXTB>
+__global__ void __launch_bounds__((POST_ROLES + (FUSED ? WORKER_THREADS_PER_ENV : 0)) * MAXTB, MAXTB == 32 ? 2 : 1)
 post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
                     const __grid_constant__ Ti5Rng r, const __grid_constant__ PostSrc src,
                     const float* __restrict__ actions_in, int options) {
@@ -258,30 +297,11 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
   const int TB = p.env_block, tid = threadIdx.x;
   const int role = tid / TB, le = tid - role * TB;
   const int e0 = blockIdx.x * TB, e = e0 + le, n_tile = min(TB, N - e0);
-  const bool live = e < N && role < POST_ROLES;
+  const bool is_role = role < POST_ROLES;
+  const bool live = e < N && is_role;
+  const int role_threads = POST_ROLES * TB;
   Ti5Globals* g = b.globals;
-  const int64_t step = g->step_index + 1;                 // index of the step in progress
-  const int64_t counter = step + g->common_step_offset;   // common_step_counter after lr:471
-  const bool first_force = g->is_first_add_force[step & 1] != 0;
-  const bool philox = p.rng_mode == TI5_RNG_PHILOX;
-  const int dm = p.div_mode;
   const uint32_t mask = p.term_mask;
-
-  // window predicates are uniform over the grid (t1:193-215)
-  bool push_window = false, force_window = false;
-  if (p.flags & TI5_F_PUSH_ROBOTS) {
-    int64_t i = counter / p.push_update_step;
-    if (i >= p.n_push_dur) i = p.n_push_dur - 1;
-    push_window = (double)(counter % p.push_interval) <= p.push_duration[i];
-  }
-  if (p.flags & TI5_F_ADD_EXT_FORCE) {
-    int64_t i = counter / p.add_update_step;
-    if (i >= p.n_add_dur) i = p.n_add_dur - 1;
-    force_window = (double)(counter % p.ext_force_interval) <= p.add_duration[i];
-  }
-
-  probe(b.debug_ts, 0, 0);
-  // ---- stage the CTA's tile of inputs: one TMA bulk copy per array, all in flight together ----------
   extern __shared__ __align__(128) unsigned char post_smem[];
   PostTile T;
   T.base = post_smem;
@@ -290,83 +310,114 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
   T.sums = reinterpret_cast<float*>(post_smem + (size_t)src.off[POST_CHUNKS] * TB);
   T.vals = T.sums + TI5_NUM_TERMS * TB;
   T.bar = reinterpret_cast<uint64_t*>(T.vals + TI5_NUM_TERMS * TB);
-  // Early mode (chained launch, full tile): of everything this kernel reads, only `actions` and `torques` come from the
-  // substep kernels of this step — every other array is simulator state (untouched while no simulator runs between
-  // the kernels) or was last written by the previous step.  Roles 0 and 2 and most of role 1 therefore run BEFORE the
-  // grid wait, on the first mbarrier; role 1 then waits for the substeps, pulls the two late arrays on the second
-  // mbarrier and finishes the two terms that need them.  Nothing stored in front of the wait is read or written by a
-  // substep kernel (root_states is: with push_robots the kernel keeps the plain order).
-  // Small grids only (<= 12288 envs): there the CTAs are resident long before the substeps finish (common
-  // carve-out, ti5_host.h) and the work in front of the wait is free; on large grids the plain order measured no worse.
+  float* s_foot = reinterpret_cast<float*>(T.bar + 2);    // [FP_COUNT][TB] partial results of foot 1
+  // the role threads synchronise among themselves; with substep workers in the CTA (FUSED) those run on undisturbed
+  auto roles_sync = [&]() {
+    if (FUSED) bar_sync(BAR_ROLES, role_threads);
+    else __syncthreads();
+  };
+
+  if (FUSED && !is_role) {
+    // ======== substep workers: WORKER_SPLIT threads per (env, four DOFs), coalesced over the CTA's 3 x TB groups; the
+    // split index is warp-uniform: the first 3 x TB workers take the substeps 0, WORKER_SPLIT, ..., the next 1, ... ========
+    const int64_t step = g->step_index + 1;
+    const int item0 = tid - role_threads, kh = item0 / (3 * TB), item = item0 - kh * 3 * TB;
+    const int wl = item / 3, gq = item - wl * 3;
+    probe(b.debug_ts, 2, 0, role_threads);
+    if (e0 + wl < N)
+      substep_worker(p, b, r, actions_in, step, e0 * 3 + item, e0 + wl, gq, kh, T.at<float>(C_ACT) + wl * D,
+                     T.at<float>(C_TORQUES) + wl * D);
+    probe(b.debug_ts, 2, 1, role_threads);
+    bar_arrive(BAR_TORQUES, WORKER_THREADS_PER_ENV * TB + TB);   // R_JOINT_B may read the two tile rows
+  }
+
+  // Early mode (chained launch after the substep kernels, full tile): of everything this kernel reads, only `actions`
+  // and `torques` come from the substep kernels of this step — every other array is simulator state (untouched while no
+  // simulator runs between the kernels) or was last written by the previous step.  All roles but the tail of R_JOINT_B
+  // therefore run BEFORE the grid wait; R_JOINT_B then waits for the substeps and pulls the two late arrays.  Nothing
+  // stored in front of the wait is read or written by a substep kernel (root_states is: with push_robots the kernel
+  // keeps the plain order).  Small grids only (<= 12288 envs): there the CTAs are resident long before the substeps
+  // finish (common carve-out, ti5_host.h); on large grids the plain order measured no worse.
   const bool early = !FUSED && (options & TI5_POST_CHAINED) && n_tile == TB && N <= TI5_SMALL_GRID_ENVS && !(p.flags & TI5_F_PUSH_ROBOTS);
-  // FUSED: the two arrays come from this CTA's own substep workers (below), never from memory
+  // FUSED: the two arrays come from this CTA's own substep workers, never from memory
   const bool late_by_tma = !FUSED && !early;
   const uint32_t late_bytes = (uint32_t)TB * (uint32_t)(src.rowb[C_ACT] + src.rowb[C_TORQUES]);
-  auto issue_late = [&]() {      // one thread: arm the second barrier and start the two copies
-    mbar_expect_tx(T.bar + 1, late_bytes);
-    tma_load_1d(T.base + (size_t)src.off[C_ACT] * TB, static_cast<const char*>(src.ptr[C_ACT]) + (size_t)e0 * src.rowb[C_ACT],
-                (uint32_t)(TB * src.rowb[C_ACT]), T.bar + 1);
-    tma_load_1d(T.base + (size_t)src.off[C_TORQUES] * TB, static_cast<const char*>(src.ptr[C_TORQUES]) + (size_t)e0 * src.rowb[C_TORQUES],
-                (uint32_t)(TB * src.rowb[C_TORQUES]), T.bar + 1);
-  };
-  if (n_tile == TB) {
-    if (tid == 0) { mbar_init(T.bar, 1); mbar_init(T.bar + 1, 1); }
-    __syncthreads();
-    // thread k issues bulk copy k of the table; threads 32..59 one episode-sum column each; thread 0 arms the
-    // barrier with the byte total (arrival order between the copies and the arm does not matter)
-    // (the (TERMS, N) episode-sum columns start 16-byte aligned only when N is a multiple of 4)
-    const bool sums_by_tma = (N & 3) == 0;
-    if (tid < POST_CHUNKS) {
-      if (tid != C_ACT && tid != C_TORQUES)
-        tma_load_1d(T.base + (size_t)src.off[tid] * TB, static_cast<const char*>(src.ptr[tid]) + (size_t)e0 * src.rowb[tid],
-                    (uint32_t)(TB * src.rowb[tid]), T.bar);
-    } else if (sums_by_tma && tid >= 32 && tid < 32 + TI5_NUM_TERMS && (mask & (1u << (tid - 32)))) {
-      const int t = tid - 32;
-      tma_load_1d(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(TB * 4), T.bar);
-    }
-    if (tid == 0)
-      mbar_expect_tx(T.bar, (uint32_t)TB * (uint32_t)(src.off[POST_CHUNKS] + (sums_by_tma ? 4 * __popc(mask) : 0)) - late_bytes);
-    if (!sums_by_tma) {
+  int64_t step = 0, counter = 0;
+  bool first_force = false, push_window = false, force_window = false;
+  if (is_role) {
+    probe(b.debug_ts, 0, 0);
+    // ---- stage the CTA's tile of inputs, FIRST: one TMA bulk copy per array, all in flight together ----------
+    if (n_tile == TB) {
+      if (tid == 0) { mbar_init(T.bar, 1); mbar_init(T.bar + 1, 1); }
+      roles_sync();
+      // thread k issues bulk copy k of the table; threads 32..59 one episode-sum column each; thread 0 arms the
+      // barrier with the byte total (arrival order between the copies and the arm does not matter)
+      // (the (TERMS, N) episode-sum columns start 16-byte aligned only when N is a multiple of 4)
+      const bool sums_by_tma = (N & 3) == 0;
+      if (tid < POST_CHUNKS) {
+        if (tid != C_ACT && tid != C_TORQUES)
+          tma_load_1d(T.base + (size_t)src.off[tid] * TB, static_cast<const char*>(src.ptr[tid]) + (size_t)e0 * src.rowb[tid],
+                      (uint32_t)(TB * src.rowb[tid]), T.bar);
+      } else if (sums_by_tma && tid >= 32 && tid < 32 + TI5_NUM_TERMS && (mask & (1u << (tid - 32)))) {
+        const int t = tid - 32;
+        tma_load_1d(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(TB * 4), T.bar);
+      }
+      if (tid == 0)
+        mbar_expect_tx(T.bar, (uint32_t)TB * (uint32_t)(src.off[POST_CHUNKS] + (sums_by_tma ? 4 * __popc(mask) : 0)) - late_bytes);
+      if (!sums_by_tma) {
+#pragma unroll 1
+        for (int t = 0; t < TI5_NUM_TERMS; ++t)
+          if (mask & (1u << t))
+            coop_load_n(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(TB * 4), tid, role_threads);
+      }
+      if (late_by_tma) {
+        chain_wait();                                     // the substep kernels are done
+        if (tid == TB) {                                  // one thread: arm the second barrier and start the two copies
+          mbar_expect_tx(T.bar + 1, late_bytes);
+          tma_load_1d(T.base + (size_t)src.off[C_ACT] * TB, static_cast<const char*>(src.ptr[C_ACT]) + (size_t)e0 * src.rowb[C_ACT],
+                      (uint32_t)(TB * src.rowb[C_ACT]), T.bar + 1);
+          tma_load_1d(T.base + (size_t)src.off[C_TORQUES] * TB,
+                      static_cast<const char*>(src.ptr[C_TORQUES]) + (size_t)e0 * src.rowb[C_TORQUES],
+                      (uint32_t)(TB * src.rowb[C_TORQUES]), T.bar + 1);
+        }
+      }
+    } else {      // partial last tile: byte counts need not be multiples of 16, copy word by word
+      if (!FUSED) chain_wait();
+#pragma unroll 1
+      for (int k = 0; k < POST_CHUNKS; ++k)
+        if (!FUSED || (k != C_ACT && k != C_TORQUES))
+          coop_load_n(T.base + (size_t)src.off[k] * TB, static_cast<const char*>(src.ptr[k]) + (size_t)e0 * src.rowb[k],
+                      (uint32_t)(n_tile * src.rowb[k]), tid, role_threads);
 #pragma unroll 1
       for (int t = 0; t < TI5_NUM_TERMS; ++t)
-        if (mask & (1u << t)) coop_load(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(TB * 4));
+        if (mask & (1u << t))
+          coop_load_n(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(n_tile * 4), tid, role_threads);
     }
-    if (late_by_tma) {
-      chain_wait();                                       // the substep kernels are done
-      if (tid == TB) issue_late();
+    // ---- while the tile is in flight: the step counters and the window predicates (uniform over the grid, t1:193-215)
+    step = g->step_index + 1;                             // index of the step in progress
+    counter = step + g->common_step_offset;               // common_step_counter after lr:471
+    first_force = g->is_first_add_force[step & 1] != 0;
+    if (p.flags & TI5_F_PUSH_ROBOTS) {
+      int64_t i = fast_div(counter, p.push_update_step);
+      if (i >= p.n_push_dur) i = p.n_push_dur - 1;
+      push_window = (double)fast_mod(counter, p.push_interval) <= p.push_duration[i];
     }
-  } else {      // partial last tile: byte counts need not be multiples of 16, copy word by word
-    if (!FUSED) chain_wait();
-#pragma unroll 1
-    for (int k = 0; k < POST_CHUNKS; ++k)
-      if (!FUSED || (k != C_ACT && k != C_TORQUES))
-        coop_load(T.base + (size_t)src.off[k] * TB, static_cast<const char*>(src.ptr[k]) + (size_t)e0 * src.rowb[k],
-                  (uint32_t)(n_tile * src.rowb[k]));
-#pragma unroll 1
-    for (int t = 0; t < TI5_NUM_TERMS; ++t)
-      if (mask & (1u << t)) coop_load(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(n_tile * 4));
-  }
-  __syncthreads();
-  if (FUSED) {
-    if (role >= POST_ROLES) {
-      // ======== substep workers: one thread per (env, four DOFs), coalesced over the CTA's 3 x TB groups ========
-      const int item = tid - POST_ROLES * TB, wl = item / 3, gq = item - wl * 3;
-      if (e0 + wl < N) {
-        float* ta = T.at<float>(C_ACT) + wl * D;
-        float* tt = T.at<float>(C_TORQUES) + wl * D;
-        if (p.decimation == 10) substep_worker<10>(p, b, r, actions_in, step, e0 * 3 + item, e0 + wl, gq, ta, tt);
-        else substep_worker<0>(p, b, r, actions_in, step, e0 * 3 + item, e0 + wl, gq, ta, tt);
-      }
-      bar_arrive(BAR_TORQUES, (POST_ROLES + 1) * TB);   // role 1 may read the two tile rows (stores above are ordered by it)
+    if (p.flags & TI5_F_ADD_EXT_FORCE) {
+      int64_t i = fast_div(counter, p.add_update_step);
+      if (i >= p.n_add_dur) i = p.n_add_dur - 1;
+      force_window = (double)fast_mod(counter, p.ext_force_interval) <= p.add_duration[i];
     }
     // a preceding ti5_sample_heights (chained launch) must have completed before this grid does: ti5_reset_observe,
     // which reads the heights, only waits for THIS grid
-    if (options & TI5_FUSED_CHAINED) chain_wait();
+    if (FUSED && (options & TI5_FUSED_CHAINED)) chain_wait();
+    roles_sync();
+    if (n_tile == TB) {
+      mbar_wait(T.bar, 0);
+      if (late_by_tma) mbar_wait(T.bar + 1, 0);
+    }
   }
-  if (n_tile == TB && role < POST_ROLES) {
-    mbar_wait(T.bar, 0);
-    if (late_by_tma) mbar_wait(T.bar + 1, 0);
-  }
+  const bool philox = p.rng_mode == TI5_RNG_PHILOX;
+  const int dm = p.div_mode;
   // typed views of the tile
   const float* t_root = T.at<float>(C_ROOT);
   const float* t_dof = T.at<float>(C_DOF);
@@ -391,9 +442,12 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
   probe(b.debug_ts, 0, 1);
   bool reset = false, time_out = false;
   auto put = [&](int t, float v) { T.vals[t * TB + le] = v; };
+  // what the two foot roles carry across their barrier
+  float part[FP_COUNT], stance[2] = {0.0f, 0.0f};
+  bool stand_foot = false;
 
   if (live) {
-    // ======== common prologue (every role, same values): command schedule, gait phase, contacts ==========
+    // ======== common prologue (every role, same values): command schedule, stand flag =====================
     // t1:183-184 phase counter and gait-schedule command resampling (pass 0)
     const int64_t ep_len = t_ep_len[le] + 1;                                  // lr:469
     int64_t phase_len = t_phase_len[le] + 1;
@@ -419,19 +473,12 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
     }
     const float cmd_norm = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y + cmd.z * cmd.z);
     const bool stand = cmd_norm <= p.stand_threshold;
-    // gait phase and stance mask (t1:80-107).  Side effect: standing envs restart the phase.
-    if (stand) phase_len = 0;
-    const float phase = (py_mod1(sdiv((float)phase_len * p.dt, p.cycle_time, dm)) + t_gait_start[le]) * (stand ? 0.0f : 1.0f);
-    const float sin_pos = sinf(TWO_PI_F * phase);
-    float stance[2] = {sin_pos >= 0.0f ? 1.0f : 0.0f, sin_pos < 0.0f ? 1.0f : 0.0f};
-    if (fabsf(sin_pos) < 0.1f) stance[0] = stance[1] = 1.0f;
-    const float* cf0 = t_contact + ((size_t)le * NB + p.feet[0]) * 3;
-    const float* cf1 = t_contact + ((size_t)le * NB + p.feet[1]) * 3;
-    const bool contact[2] = {cf0[2] > 5.0f, cf1[2] > 5.0f};
+    if (stand) phase_len = 0;                             // t1:86 side effect: standing envs restart the phase
     const float* qrow = t_dof + (size_t)le * 2 * D;                           // interleaved (q, qd)
+    const float bq[4] = {t_root[le * RB + 3], t_root[le * RB + 4], t_root[le * RB + 5], t_root[le * RB + 6]};
 
-    if (role == 0) {
-      // ================================ role 0: the base ===============================================
+    if (role == R_BASE) {
+      // ================================ the base: state ================================================
       float root[RB];
 #pragma unroll
       for (int i = 0; i < RB; ++i) root[i] = t_root[le * RB + i];
@@ -443,7 +490,6 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       b.phase_length_buf[e] = phase_len;
       reinterpret_cast<float4*>(b.commands)[e] = cmd;
       // lr:475-479 derived base state
-      const float bq[4] = {root[3], root[4], root[5], root[6]};
       const V3 lin = quat_rotate_inverse(bq, V3{root[7], root[8], root[9]});
       const V3 ang = quat_rotate_inverse(bq, V3{root[10], root[11], root[12]});
       const V3 grav = quat_rotate_inverse(bq, V3{0.0f, 0.0f, -1.0f});
@@ -458,11 +504,12 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       if (FUSED && (p.flags & TI5_F_ADD_IMU_LAG)) {
         // lr:428-434 for every substep: without a simulator in between the base does not move, so each push is the
         // derived state of this step (same quaternion, same arithmetic as the substep kernel's pieces)
-        const int s0 = (int)(((step - 1) * p.decimation) % p.imu_lag_len);
+        int slot = (int)fast_mod((step - 1) * p.decimation, p.imu_lag_len);
 #pragma unroll 1
         for (int k = 0; k < p.decimation; ++k) {
-          float* row = b.imu_ring + ((size_t)((s0 + k) % p.imu_lag_len) * N + e) * 6;
+          float* row = b.imu_ring + ((size_t)slot * N + e) * 6;
           row[0] = ang.x; row[1] = ang.y; row[2] = ang.z; row[3] = eul[0]; row[4] = eul[1]; row[5] = eul[2];
+          slot = slot + 1 == p.imu_lag_len ? 0 : slot + 1;
         }
       } else if (push_last && (p.flags & TI5_F_ADD_IMU_LAG)) {               // fused IMU-lag push of the last substep
         const int64_t j = (step - 1) * p.decimation + (p.decimation - 1);
@@ -471,21 +518,14 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       }
       // t1:193-203, 217-231 push window: overwrite the base velocity
       if (p.flags & TI5_F_PUSH_ROBOTS) {
-        float fx = 0.0f, fy = 0.0f, tq[3] = {0.0f, 0.0f, 0.0f};
+        float tq[3] = {0.0f, 0.0f, 0.0f};
         if (push_window) {
-          float u[5];
-#pragma unroll
-          for (int c = 0; c < 5; ++c)
-            u[c] = philox ? philox_u(p.seed, (uint64_t)step, S_PUSH, e * 5 + c) : r.push[(size_t)e * 5 + c];
-          fx = affine(p.push_vel_w, p.push_vel_lo, u[0]);
-          fy = affine(p.push_vel_w, p.push_vel_lo, u[1]);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) tq[c] = affine(p.push_ang_w, p.push_ang_lo, u[2 + c]);
-          root[7] = fx; root[8] = fy; root[10] = tq[0]; root[11] = tq[1]; root[12] = tq[2];
+          const PushDraw d = push_draw(p, r, step, e);
           float* rw = b.root_states + (size_t)e * RB;
-          rw[7] = fx; rw[8] = fy; rw[10] = tq[0]; rw[11] = tq[1]; rw[12] = tq[2];
-          b.rand_push_force[e * 3 + 0] = fx;
-          b.rand_push_force[e * 3 + 1] = fy;
+          rw[7] = d.fx; rw[8] = d.fy; rw[10] = d.tq[0]; rw[11] = d.tq[1]; rw[12] = d.tq[2];
+          b.rand_push_force[e * 3 + 0] = d.fx;
+          b.rand_push_force[e * 3 + 1] = d.fy;
+          tq[0] = d.tq[0]; tq[1] = d.tq[1]; tq[2] = d.tq[2];
         } else {
           b.rand_push_force[e * 3 + 0] = 0.0f; b.rand_push_force[e * 3 + 1] = 0.0f; b.rand_push_force[e * 3 + 2] = 0.0f;
         }
@@ -527,18 +567,27 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       reset = (term_force > 1.0f) || time_out;
       b.time_out_buf[e] = time_out ? 1 : 0;
       b.reset_buf[e] = reset ? 1 : 0;
-      // ---- base terms
-      if (mask & (1u << T_BASE_ACC)) {                      // t1:717-724
+      if (mask & (1u << T_COLLISION)) put(T_COLLISION, 1.0f * (pen_force > 0.1f ? 1.0f : 0.0f));   // t1:870-875
+    } else if (role == R_BASE_A) {
+      // ================================ the base: acceleration, speed, orientation ====================
+      if (mask & (1u << T_BASE_ACC)) {                      // t1:717-724, on the velocities a push may just have set
+        float v[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) v[i] = t_root[le * RB + 7 + i];
+        if ((p.flags & TI5_F_PUSH_ROBOTS) && push_window) {
+          const PushDraw d = push_draw(p, r, step, e);
+          v[0] = d.fx; v[1] = d.fy; v[3] = d.tq[0]; v[4] = d.tq[1]; v[5] = d.tq[2];
+        }
         float sq = 0.0f;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-          const float d = t_last_root_vel[le * 6 + i] - root[7 + i];
+          const float d = t_last_root_vel[le * 6 + i] - v[i];
           sq += d * d;
         }
         put(T_BASE_ACC, expf_call(-sqrtf(sq) * 3.0f));
       }
-      if (mask & (1u << T_COLLISION)) put(T_COLLISION, 1.0f * (pen_force > 0.1f ? 1.0f : 0.0f));   // t1:870-875
       if (mask & (1u << T_LOW_SPEED)) {                     // t1:816-847 (appendix A13)
+        const V3 lin = quat_rotate_inverse(bq, V3{t_root[le * RB + 7], t_root[le * RB + 8], t_root[le * RB + 9]});
         const float av = fabsf(lin.x), ac = fabsf(cmd.x);
         const bool slow = av < 0.5f * ac, fast = av > 1.2f * ac;
         float v = 0.0f;
@@ -549,10 +598,15 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
         put(T_LOW_SPEED, v * (ac > 0.05f ? 1.0f : 0.0f));
       }
       if (mask & (1u << T_ORIENTATION)) {                   // t1:670-677
-        const float a = expf_call(-(fabsf(eul[0]) + fabsf(eul[1])) * 10.0f);
+        const V3 grav = quat_rotate_inverse(bq, V3{0.0f, 0.0f, -1.0f});
+        const float a = expf_call(-(fabsf(euler_roll(bq)) + fabsf(euler_pitch(bq))) * 10.0f);
         const float bb = expf_call(-sqrtf(grav.x * grav.x + grav.y * grav.y) * 20.0f);
         put(T_ORIENTATION, (a + bb) / 2.0f);
       }
+    } else if (role == R_BASE_B) {
+      // ================================ the base: velocity tracking ====================================
+      const V3 lin = quat_rotate_inverse(bq, V3{t_root[le * RB + 7], t_root[le * RB + 8], t_root[le * RB + 9]});
+      const V3 ang = quat_rotate_inverse(bq, V3{t_root[le * RB + 10], t_root[le * RB + 11], t_root[le * RB + 12]});
       const float ex = cmd.x - lin.x, ey = cmd.y - lin.y, ew = cmd.z - ang.z;
       if (mask & (1u << T_TRACK_VEL_HARD)) {                // t1:738-758
         const float le_ = sqrtf(ex * ex + ey * ey);
@@ -569,8 +623,8 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
         const float bb = expf_call(-sqrtf(ang.x * ang.x + ang.y * ang.y) * 5.0f);
         put(T_VEL_MISMATCH_EXP, (a + bb) / 2.0f);
       }
-    } else if (role == 1) {
-      // ================================ role 1: the joints =============================================
+    } else if (role == R_JOINT_A) {
+      // ================================ the joints: per-DOF reductions =================================
       if (!FUSED && push_last && (p.flags & TI5_F_ADD_DOF_LAG)) {            // fused DOF-lag push of the last substep
         const int64_t j = (step - 1) * p.decimation + (p.decimation - 1);
         float* row = b.dof_ring + ((size_t)ring_slot(j, p.dof_lag_len) * N + e) * (2 * D);
@@ -580,7 +634,7 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       const float* ldv = t_last_dof_vel + le * D;
       const float* ref = t_ref + le * D;
       // one pass over the 12 DOFs feeds every per-DOF reduction that needs joint state only (each sum keeps its own
-      // DOF order); the sums over `actions` and `torques` follow below, behind the grid wait in early mode
+      // DOF order)
       float s_dq = 0.0f, s_acc = 0.0f, s_vel = 0.0f, s_jp = 0.0f;
 #pragma unroll 1
       for (int i = 0; i < D; ++i) {
@@ -616,6 +670,8 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
         }
         put(T_STAND_SYSMETRY, stand ? expf_call(-sq) : 0.0f);
       }
+    } else if (role == R_JOINT_B) {
+      // ================================ the joints: distances (actions and torques follow below) ======
       const float* f0 = t_rigid + ((size_t)le * NB + p.feet[0]) * RB;
       const float* f1 = t_rigid + ((size_t)le * NB + p.feet[1]) * RB;
       const float* k0 = t_rigid + ((size_t)le * NB + p.knees[0]) * RB;
@@ -625,119 +681,116 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       if (mask & (1u << T_KNEE_DISTANCE))                   // t1:615-628
         put(T_KNEE_DISTANCE, pair_distance_reward(k0[0], k0[1], k1[0], k1[1], p.knee_min_dist, p.knee_max_dist));
     } else {
-      // ================================ role 2: the feet ===============================================
-      FootState foot[2];
+      // ================================ one foot (f = 0: R_FOOT0, f = 1: R_FOOT1) =====================
+      const int f = role - R_FOOT0;
+      // gait phase and stance mask (t1:80-107)
+      const float phase = (py_mod1(sdiv((float)phase_len * p.dt, p.cycle_time, dm)) + t_gait_start[le]) * (stand ? 0.0f : 1.0f);
+      const float sin_pos = sinf(TWO_PI_F * phase);
+      stance[0] = sin_pos >= 0.0f ? 1.0f : 0.0f;
+      stance[1] = sin_pos < 0.0f ? 1.0f : 0.0f;
+      if (fabsf(sin_pos) < 0.1f) stance[0] = stance[1] = 1.0f;
+      stand_foot = stand;
+      const float* cf = t_contact + ((size_t)le * NB + p.feet[f]) * 3;
+      const bool contact = cf[2] > 5.0f;
+      const float* rs = t_rigid + ((size_t)le * NB + p.feet[f]) * RB;
+      const float fq[4] = {rs[3], rs[4], rs[5], rs[6]};
+      float fe[3];
+      euler_xyz(fq, fe);                                                       // lr:480-481
 #pragma unroll
-      for (int f = 0; f < 2; ++f) {
-        const float* rs = t_rigid + ((size_t)le * NB + p.feet[f]) * RB;
-        foot[f].pos[0] = rs[0]; foot[f].pos[1] = rs[1]; foot[f].pos[2] = rs[2];
-        foot[f].quat[0] = rs[3]; foot[f].quat[1] = rs[4]; foot[f].quat[2] = rs[5]; foot[f].quat[3] = rs[6];
-        foot[f].wxy[0] = rs[10]; foot[f].wxy[1] = rs[11];
-        const float* cf = f == 0 ? cf0 : cf1;
-        foot[f].force[0] = cf[0]; foot[f].force[1] = cf[1]; foot[f].force[2] = cf[2];
-        float fe[3];
-        euler_xyz(foot[f].quat, fe);                                           // lr:480-481
-        foot[f].pitch = fe[1];
+      for (int i = 0; i < 3; ++i) b.feet_euler_xyz[e * 6 + 3 * f + i] = fe[i];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) b.feet_euler_xyz[e * 6 + 3 * f + i] = fe[i];
+      for (int i = 0; i < FP_COUNT; ++i) part[i] = 0.0f;
+      part[FP_Z] = rs[2];
+      part[FP_PITCH] = fe[1];
+      if (mask & (1u << T_FEET_AIR_TIME)) {                 // t1:642-657 (appendix A6, A8)
+        const bool tiny = cmd_norm < 0.05f;
+        const float st = tiny ? 1.0f : stance[f];
+        const bool filt = contact || (st != 0.0f) || (t_last_contacts[le * 2 + f] != 0);
+        b.contact_filt[e * 2 + f] = filt ? 1 : 0;
+        b.last_contacts[e * 2 + f] = contact ? 1 : 0;
+        float air = t_air[le * 2 + f];
+        const float first = (air > 0.0f && filt) ? 1.0f : 0.0f;
+        air += p.dt;
+        part[FP_AIR] = clampf(air, 0.0f, 0.5f) * first;
+        b.feet_air_time[e * 2 + f] = air * (filt ? 0.0f : 1.0f);
       }
-      if (mask & (1u << T_BASE_HEIGHT)) {                   // t1:706-715
-        const float ground = (foot[0].pos[2] * stance[0] + foot[1].pos[2] * stance[1]) / (stance[0] + stance[1]);
+      if (mask & (1u << T_FEET_CLEARANCE)) {                // t1:793-814 (appendix A9)
+        const float z = rs[2];
+        const float h = t_feet_h[le * 2 + f] + (z - t_last_z[le * 2 + f]);
+        b.last_feet_z[e * 2 + f] = z;
+        const float swing = 1.0f - stance[f];
+        const float hit = (h > p.target_feet_height && h < p.target_feet_height_max) ? 1.0f : 0.0f;
+        part[FP_CLEAR] = hit * swing;
+        b.feet_height[e * 2 + f] = h * (contact ? 0.0f : 1.0f);
+      }
+      if (mask & (1u << T_FEET_CONTACT_FORCES)) {           // t1:679-684
+        const float n = sqrtf((cf[0] * cf[0] + cf[1] * cf[1]) + cf[2] * cf[2]);
+        part[FP_FORCE] = clampf(n - p.max_contact_force, 0.0f, 400.0f);
+      }
+      if (mask & (1u << T_FEET_CONTACT_NUMBER)) {           // t1:659-668 (appendix A14)
+        const float st = stand ? 1.0f : stance[f];
+        part[FP_NUMBER] = ((contact ? 1.0f : 0.0f) == st) ? 1.0f : -0.3f;
+      }
+      if (mask & (1u << T_FEET_STUMBLE))                    // t1:937-940
+        part[FP_STUMBLE] = sqrtf(cf[0] * cf[0] + cf[1] * cf[1]) > 5.0f * fabsf(cf[2]) ? 1.0f : 0.0f;
+      if (mask & (1u << T_FOOT_SLIP))                       // t1:630-640 (appendix A10): rigid_state[..., 10:12]
+        part[FP_SLIP] = sqrtf(sqrtf(rs[10] * rs[10] + rs[11] * rs[11])) * (contact ? 1.0f : 0.0f);
+      if (f == 1) {
+        if (mask & (1u << T_STAND_STILL)) {                 // t1:899-915 (appendix A12), the joint part:
+          // dof_idx [0,1,2,3,5,6,7,8] with weights [2,2,1,1,1,2,2,1]; foot 0 adds the two foot pitches with weight 1
+          float sq = 0.0f;
+#pragma unroll 1
+          for (int i = 0; i < 8; ++i) {
+            const int j = i < 4 ? i : i + 1;
+            const float w = (i < 2 || i == 5 || i == 6) ? 2.0f : 1.0f;
+            const float er = (qrow[2 * j] - p.default_dof_pos[j]) * w;
+            sq += er * er;
+          }
+          part[FP_STILL] = sq;
+        }
+#pragma unroll
+        for (int i = 0; i < FP_COUNT; ++i) s_foot[i * TB + le] = part[i];
+      }
+    }
+  }
+  // ---- foot 0 adds up both feet, in the reference's order (0 + foot 0 + foot 1).  The barrier instructions sit outside
+  // every `live` branch: a warp executes them as a whole (partial tiles have idle lanes) -------------------------
+  if (is_role && role == R_FOOT1) bar_arrive(BAR_FEET, 2 * TB);
+  if (is_role && role == R_FOOT0) {
+    bar_sync(BAR_FEET, 2 * TB);
+    if (live) {
+      const bool stand = stand_foot;
+      float o[FP_COUNT];
+#pragma unroll
+      for (int i = 0; i < FP_COUNT; ++i) o[i] = s_foot[i * TB + le];
+      if (mask & (1u << T_BASE_HEIGHT)) {                 // t1:706-715
+        const float ground = (part[FP_Z] * stance[0] + o[FP_Z] * stance[1]) / (stance[0] + stance[1]);
         const float h = t_root[le * RB + 2] - (ground - 0.05f);
         put(T_BASE_HEIGHT, expf_call(-fabsf(h - p.base_height_target) * 100.0f));
       }
-      if (mask & (1u << T_FEET_AIR_TIME)) {                 // t1:642-657 (appendix A6, A8)
-        const bool tiny = cmd_norm < 0.05f;
-        float air_sum = 0.0f;
-#pragma unroll
-        for (int f = 0; f < 2; ++f) {
-          const float st = tiny ? 1.0f : stance[f];
-          const bool filt = contact[f] || (st != 0.0f) || (t_last_contacts[le * 2 + f] != 0);
-          b.contact_filt[e * 2 + f] = filt ? 1 : 0;
-          b.last_contacts[e * 2 + f] = contact[f] ? 1 : 0;
-          float air = t_air[le * 2 + f];
-          const float first = (air > 0.0f && filt) ? 1.0f : 0.0f;
-          air += p.dt;
-          air_sum += clampf(air, 0.0f, 0.5f) * first;
-          b.feet_air_time[e * 2 + f] = air * (filt ? 0.0f : 1.0f);
-        }
-        put(T_FEET_AIR_TIME, air_sum);
-      }
-      if (mask & (1u << T_FEET_CLEARANCE)) {                // t1:793-814 (appendix A9)
-        float sw = 0.0f;
-#pragma unroll
-        for (int f = 0; f < 2; ++f) {
-          const float z = foot[f].pos[2];
-          const float h = t_feet_h[le * 2 + f] + (z - t_last_z[le * 2 + f]);
-          b.last_feet_z[e * 2 + f] = z;
-          const float swing = 1.0f - stance[f];
-          const float hit = (h > p.target_feet_height && h < p.target_feet_height_max) ? 1.0f : 0.0f;
-          sw += hit * swing;
-          b.feet_height[e * 2 + f] = h * (contact[f] ? 0.0f : 1.0f);
-        }
-        put(T_FEET_CLEARANCE, sw);
-      }
-      if (mask & (1u << T_FEET_CONTACT_FORCES)) {           // t1:679-684
-        float sq = 0.0f;
-#pragma unroll
-        for (int f = 0; f < 2; ++f) {
-          const float n = sqrtf((foot[f].force[0] * foot[f].force[0] + foot[f].force[1] * foot[f].force[1]) +
-                                foot[f].force[2] * foot[f].force[2]);
-          sq += clampf(n - p.max_contact_force, 0.0f, 400.0f);
-        }
-        put(T_FEET_CONTACT_FORCES, sq);
-      }
-      if (mask & (1u << T_FEET_CONTACT_NUMBER)) {           // t1:659-668 (appendix A14)
-        float sq = 0.0f;
-#pragma unroll
-        for (int f = 0; f < 2; ++f) {
-          const float st = stand ? 1.0f : stance[f];
-          sq += ((contact[f] ? 1.0f : 0.0f) == st) ? 1.0f : -0.3f;
-        }
-        put(T_FEET_CONTACT_NUMBER, sq / 2.0f);
-      }
-      if (mask & (1u << T_FEET_ROTATION)) {                 // t1:926-935 (appendix A11)
-        const float rot = foot[0].pitch * foot[0].pitch + foot[1].pitch * foot[1].pitch;
+      if (mask & (1u << T_FEET_AIR_TIME)) put(T_FEET_AIR_TIME, (0.0f + part[FP_AIR]) + o[FP_AIR]);
+      if (mask & (1u << T_FEET_CLEARANCE)) put(T_FEET_CLEARANCE, (0.0f + part[FP_CLEAR]) + o[FP_CLEAR]);
+      if (mask & (1u << T_FEET_CONTACT_FORCES)) put(T_FEET_CONTACT_FORCES, (0.0f + part[FP_FORCE]) + o[FP_FORCE]);
+      if (mask & (1u << T_FEET_CONTACT_NUMBER)) put(T_FEET_CONTACT_NUMBER, ((0.0f + part[FP_NUMBER]) + o[FP_NUMBER]) / 2.0f);
+      if (mask & (1u << T_FEET_ROTATION)) {               // t1:926-935 (appendix A11)
+        const float rot = part[FP_PITCH] * part[FP_PITCH] + o[FP_PITCH] * o[FP_PITCH];
         const float x = rot / 1.0f;
         put(T_FEET_ROTATION, 1.0f * expf_call(-(x * x)));
       }
-      if (mask & (1u << T_FEET_STUMBLE)) {                  // t1:937-940
-        bool any = false;
-#pragma unroll
-        for (int f = 0; f < 2; ++f)
-          any = any || (sqrtf(foot[f].force[0] * foot[f].force[0] + foot[f].force[1] * foot[f].force[1]) >
-                        5.0f * fabsf(foot[f].force[2]));
-        put(T_FEET_STUMBLE, any ? 1.0f : 0.0f);
-      }
-      if (mask & (1u << T_FOOT_SLIP)) {                     // t1:630-640 (appendix A10)
-        float sq = 0.0f;
-#pragma unroll
-        for (int f = 0; f < 2; ++f)
-          sq += sqrtf(sqrtf(foot[f].wxy[0] * foot[f].wxy[0] + foot[f].wxy[1] * foot[f].wxy[1])) * (contact[f] ? 1.0f : 0.0f);
-        put(T_FOOT_SLIP, sq);
-      }
-      if (mask & (1u << T_STAND_STILL)) {                   // t1:899-915 (appendix A12)
-        // dof_idx [0,1,2,3,5,6,7,8] with weights [2,2,1,1,1,2,2,1], then the two foot pitches with weight 1
-        float sq = 0.0f;
-#pragma unroll 1
-        for (int i = 0; i < 8; ++i) {
-          const int j = i < 4 ? i : i + 1;
-          const float w = (i < 2 || i == 5 || i == 6) ? 2.0f : 1.0f;
-          const float er = (qrow[2 * j] - p.default_dof_pos[j]) * w;
-          sq += er * er;
-        }
-#pragma unroll
-        for (int f = 0; f < 2; ++f) {
-          const float er = foot[f].pitch * 1.0f;
-          sq += er * er;
-        }
+      if (mask & (1u << T_FEET_STUMBLE)) put(T_FEET_STUMBLE, (part[FP_STUMBLE] != 0.0f || o[FP_STUMBLE] != 0.0f) ? 1.0f : 0.0f);
+      if (mask & (1u << T_FOOT_SLIP)) put(T_FOOT_SLIP, (0.0f + part[FP_SLIP]) + o[FP_SLIP]);
+      if (mask & (1u << T_STAND_STILL)) {
+        float sq = o[FP_STILL];
+        const float e0p = part[FP_PITCH] * 1.0f, e1p = o[FP_PITCH] * 1.0f;
+        sq += e0p * e0p;
+        sq += e1p * e1p;
         put(T_STAND_STILL, stand ? expf_call(-sq) : 0.0f);
       }
     }
   }
-  // ---- role 1, last: the two terms over this step's actions and torques ---------------------------------------
-  if (role == 1) {
-    if (FUSED) bar_sync(BAR_TORQUES, (POST_ROLES + 1) * TB);     // the CTA's substep workers have left both rows in the tile
+  // ---- R_JOINT_B, last: the two terms over this step's actions and torques ---------------------------------------
+  if (is_role && role == R_JOINT_B) {
+    if (FUSED) bar_sync(BAR_TORQUES, WORKER_THREADS_PER_ENV * TB + TB);     // the CTA's substep workers have left both rows in the tile
     if (live) {
       const float* act = t_act + le * D;
       const float* la = t_last_act + le * D;
@@ -770,13 +823,13 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
     }
   }
   probe(b.debug_ts, 0, 2);
-  probe(b.debug_ts, 0, 6, TB);          // role 1 done
-  probe(b.debug_ts, 0, 7, 2 * TB);      // role 2 done
+  probe(b.debug_ts, 0, 6, R_JOINT_B * TB);      // R_JOINT_B done
+  probe(b.debug_ts, 0, 7, R_FOOT0 * TB);        // R_FOOT0 done
   __syncthreads();
   probe(b.debug_ts, 0, 3);
 
   // ---- lr:654-680: reward sum in alphabetical term order, per-term episode sums, clip at zero -----------
-  // The per-term episode sums are independent of one another: roles 1 and 2 take every other term while role 0
+  // The per-term episode sums are independent of one another: the other roles take every sixth term each while R_BASE
   // runs the ordered sum (the scaled term is recomputed there: same product, same bits).
   if (live && role > 0) {
 #pragma unroll 1
@@ -817,6 +870,7 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
     g->n_listed[(step + 1) & 1] = 0;                 // the next step's work-list counter (this grid fills [step & 1])
     if (p.flags & TI5_F_ADD_EXT_FORCE) g->is_first_add_force[(step + 1) & 1] = force_window ? 0 : 1;
   }
+  // (every thread of the CTA calls the bookkeeping; `step` is only used by the threads that hold a flag: role 0)
   reset_bookkeeping(p, b, reset, e, le, T.sums, TB, step);
   probe(b.debug_ts, 0, 5);
 }
@@ -851,6 +905,7 @@ static int launch_post(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r,
                        bool fused, void* stream, const char* what) {
   TI5_CHECK_ARGS(p && b && p->num_envs > 0 && (options & ~3) == 0);
   TI5_CHECK_ARGS(p->env_block == 32 || p->env_block == 64 || (!fused && p->env_block == 128));
+  TI5_CHECK_ARGS(p->num_gaits >= 0 && p->num_gaits <= TI5_MAX_GAITS);
   TI5_CHECK_ARGS(p->rng_mode == TI5_RNG_PHILOX || (r && r->cmd));
   TI5_CHECK_ARGS((p->term_mask & (1u << T_DOF_VEL_LIMITS)) == 0);   // the reference term reads a cfg field t1 lacks
   TI5_CHECK_ARGS(!(p->flags & TI5_F_ADD_EXT_FORCE) || p->applied_stride >= 3);
@@ -858,13 +913,15 @@ static int launch_post(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r,
   const int blocks = (p->num_envs + p->env_block - 1) / p->env_block;
   const PostSrc src = make_post_src(*p, *b);
   const size_t smem = post_tile_bytes(p->env_block, src.off[POST_CHUNKS]);
-  auto kernel = fused ? post_physics_kernel<true> : post_physics_kernel<false>;
+  auto kernel = fused ? (p->env_block == 32 ? post_physics_kernel<true, 32> : post_physics_kernel<true, 64>)
+                      : (p->env_block == 32 ? post_physics_kernel<false, 32>
+                                            : p->env_block == 64 ? post_physics_kernel<false, 64> : post_physics_kernel<false, 128>);
   if (!ti5_ensure_smem(kernel, smem)) {
     ti5_set_error("%s: %zu bytes of shared memory per CTA not available", what, smem);
     return TI5_ECUDA;
   }
   ti5_set_carveout(kernel, ti5_small_grid(p));
-  const int threads = (fused ? 2 : 1) * POST_ROLES * p->env_block;
+  const int threads = (POST_ROLES + (fused ? WORKER_THREADS_PER_ENV : 0)) * p->env_block;
   (void)ti5_launch(kernel, dim3(blocks), dim3(threads), smem, stream, (options & TI5_POST_CHAINED) != 0, *p, *b, rr, src,
                    actions_in, options);
   return ti5_check_launch(what);

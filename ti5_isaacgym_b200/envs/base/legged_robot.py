@@ -83,15 +83,19 @@ class EpisodeInfo(dict):
 
 class LeggedRobot(BaseTask):
     def __init__(self, cfg, sim_params, physics_engine, sim_device, headless, gym=None, rng_mode="philox",
-                 div_mode="reciprocal", use_cuda_graph=True, materialize_obs=False, seed=None, chain_launches=None,
+                 div_mode="reciprocal", use_cuda_graph=True, materialize_obs=True, seed=None, chain_launches=None,
                  fused_step=None):
         """Args as the reference (lr:57).  Extra keyword options:
         rng_mode        "philox" (in-kernel Philox4x32-10) or "pools" (uniforms supplied per step via
                         `set_rng_pools`, the parity mode of SURVEY.md section 7)
         div_mode        "reciprocal" = torch-on-GPU rounding of tensor/scalar, "ieee" = torch-on-CPU
         use_cuda_graph  capture the whole step into one CUDA graph (philox mode, synthetic sim only)
-        materialize_obs return fresh contiguous (N, H*47) / (N, CH*P) tensors every step, as the reference does
-                        (t1:477-481), instead of views into the history rings that are valid until the next step
+        materialize_obs True (default): `step` returns FRESH contiguous (N, H*47) / (N, CH*P) tensors, as the reference
+                        does (t1:477-481) — a caller may hold them across later steps, which the reference's runner does
+                        (dh_ppo.py:88 -> rs:62).  False: zero-copy views into the history rings, valid ONLY until the
+                        next `step()` (+25 KB/env/step saved); for callers that consume the observation at once, or
+                        that use `FrameLogRolloutStorage` (`task_registry.make_alg_runner` switches the env to views
+                        when it installs that storage)
         chain_launches  launch the kernels of a fused step (no simulator in between) as programmatic dependents of one
                         another: each becomes resident while its predecessor still runs and waits for it only where
                         it needs its results (default on; env var TI5_CHAIN=0 turns it off)
@@ -214,6 +218,7 @@ class LeggedRobot(BaseTask):
         self.base_init_state = torch.tensor(list(p.base_init_state), device=dev)
         # per-env state, names as in the reference
         self.torques, self.torque_multi = f32(N, D), torch.ones(N, D, device=dev)
+        self.torques_substeps = f32(p.decimation, N, D)      # lr:401-403: the torques of every substep of the last step
         self.actions, self.last_actions, self.last_last_actions = f32(N, D), f32(N, D), f32(N, D)
         self._actions_in = f32(N, D)
         self.last_dof_vel, self.last_root_vel = f32(N, D), f32(N, 6)
@@ -284,6 +289,7 @@ class LeggedRobot(BaseTask):
         self._write_globals()
         self._bind_buffers()
         self._graph = self._graph_host = None
+        self._view_epoch = [STEP_INDEX0]            # mutable cell shared with the ring-view tags: [current step index]
         self._graphs, self._max_graphs = {}, 8      # captured steps keyed by the address of the action buffer
         self.host_actions = None                                  # enable_host_io()
         self._rng = None
@@ -354,7 +360,8 @@ class LeggedRobot(BaseTask):
         b.globals = ptr(self._globals)
         pairs = dict(
             root_states=self.root_states, dof_state=self.dof_state, contact_forces=self.contact_forces,
-            rigid_state=self.rigid_state, actions=self.actions, torques=self.torques, torque_multi=self.torque_multi,
+            rigid_state=self.rigid_state, actions=self.actions, torques=self.torques, torques_substeps=self.torques_substeps,
+            torque_multi=self.torque_multi,
             p_gains_r=self.randomized_p_gains, d_gains_r=self.randomized_d_gains, motor_offsets=self.motor_offsets,
             coulomb=self.randomized_joint_coulomb, viscous=self.randomized_joint_viscous,
             joint_armatures=self.joint_armatures, act_ring=self._act_ring, dof_ring=self._dof_ring,
@@ -594,7 +601,7 @@ class LeggedRobot(BaseTask):
 
     def _launch_step(self, actions_ptr, with_physics, notify=False):
         """Enqueue the kernels of one policy step on the current stream."""
-        if self._fused_step and not with_physics and self._params.env_block <= 64:
+        if self._uses_fused_step(with_physics):
             # no simulator between the substeps: [heights] -> clip + DEC substeps + post-physics -> resets + observations
             lib, p, b, r, st = self._lib, self._p_ref, self._b_ref, self._rng_ref(), self._stream()
             opt = 0
@@ -609,22 +616,36 @@ class LeggedRobot(BaseTask):
         self._launch_substeps(actions_ptr, with_physics)
         self._launch_post(with_physics, notify=notify)
 
+    def _uses_fused_step(self, with_physics=False):
+        return self._fused_step and not with_physics and self._params.env_block <= 64
+
     def capture_phase_graphs(self):
-        """Three CUDA graphs (substep phase, ti5_post_physics, ti5_reset_observe) instead of one, so that a benchmark
-        can bracket each kernel family with CUDA events.  Replay all three in order, then call `_finish_step()`."""
+        """One CUDA graph per kernel family of the step instead of one for the whole step, so that a benchmark can
+        bracket each family with CUDA events: [(name, graph, launches)].  Replay all in order, then `_finish_step()`."""
         torch.cuda.synchronize(self.device)
+        lib, p, b, r = self._lib, self._p_ref, self._b_ref, self._rng_ref()
+        a_ptr = ctypes.c_void_p(self._actions_in.data_ptr())
+        phases = []
+        if self._params.num_height_points:
+            phases.append(("heights", lambda: _lib.check(lib.ti5_sample_heights(p, b, self._stream())), 1))
+        if self._uses_fused_step():
+            phases.append(("fused_step", lambda: _lib.check(lib.ti5_fused_step(p, b, r, a_ptr, 0, self._stream())), 1))
+        else:
+            phases.append(("substep", lambda: self._launch_substeps(a_ptr, False), self._params.decimation))
+            phases.append(("post_physics", lambda: _lib.check(lib.ti5_post_physics(
+                p, b, r, C["TI5_POST_PUSH_LAST"] | self._chain("TI5_POST_CHAINED"), self._stream())), 1))
+        phases.append(("reset_observe", lambda: self._launch_post(False, 2), 1))
         graphs = []
-        for fn in (lambda: self._launch_substeps(ctypes.c_void_p(self._actions_in.data_ptr()), False),
-                   lambda: self._launch_post(False, 1), lambda: self._launch_post(False, 2)):
+        for name, fn, n in phases:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=torch.cuda.Stream(self.device)):
                 fn()
-            graphs.append(g)
+            graphs.append((name, g, n))
         return graphs
 
     @property
     def launches_per_step(self):
-        step = 2 if (self._fused_step and self._params.env_block <= 64) else self._params.decimation + 2
+        step = 2 if self._uses_fused_step() else self._params.decimation + 2
         return step + (1 if self._params.num_height_points else 0) + (1 if self._materialize else 0)
 
     def step(self, actions):
@@ -710,6 +731,7 @@ class LeggedRobot(BaseTask):
     def _finish_step(self):
         """Host-side epilogue: counters, output views, extras (all without a device sync)."""
         self._step_index += 1
+        self._view_epoch[0] = self._step_index
         self.common_step_counter += 1
         if hasattr(self.gym, "substep"):
             self.gym.substep = 0
@@ -718,11 +740,17 @@ class LeggedRobot(BaseTask):
             self.obs_buf, self.privileged_obs_buf = self._obs_out, self._priv_out
         else:
             self.obs_buf, self.privileged_obs_buf = self._history_views()
+            # ring views die at the next step(): tag them, so that a storage that copies them late can tell
+            # (`check_not_stale_ring_view`; the reference's runner holds the observation across a step, dh_ppo.py:88)
+            self.obs_buf.ti5_ring_view = self.privileged_obs_buf.ti5_ring_view = (self._view_epoch, self._step_index)
         if self._params.log_len:
             # a fresh tensor object per step, tagged with the log row of its newest frame: the rollout storage
             # receives it one env step later (dh_ppo.py:88 -> rs:62) and must know which window it was
+            tag = getattr(self.obs_buf, "ti5_ring_view", None)
             self.obs_buf = self.obs_buf.view_as(self.obs_buf)
             self.obs_buf.ti5_frame_row = self.frame_log_row
+            if tag is not None:
+                self.obs_buf.ti5_ring_view = tag
         self._publish_extras()
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
 

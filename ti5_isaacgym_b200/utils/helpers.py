@@ -57,3 +57,22 @@ def update_cfg_from_args(env_cfg, cfg_train, args):
         if getattr(args, "resume", False):
             cfg_train.runner.resume = True
     return env_cfg, cfg_train
+
+
+def get_load_path(root, load_run=-1, checkpoint=-1):
+    """helpers.py:94-123: newest run directory under `root` (lexicographic order, "exported" skipped) unless `load_run`
+    names one; in it the newest `model_<it>.pt` (zero-padded name order) unless `checkpoint` names the iteration."""
+    try:
+        runs = sorted(os.listdir(root))
+        if "exported" in runs:
+            runs.remove("exported")
+        last_run = os.path.join(root, runs[-1])
+    except (OSError, IndexError):
+        raise ValueError("No runs in this directory: " + root)
+    load_run = last_run if load_run == -1 else os.path.join(root, load_run)
+    if checkpoint == -1:
+        models = sorted((f for f in os.listdir(load_run) if "model" in f), key=lambda m: "{0:0>15}".format(m))
+        model = models[-1]
+    else:
+        model = "model_{}.pt".format(checkpoint)
+    return os.path.join(load_run, model)

@@ -10,7 +10,7 @@ from types import SimpleNamespace
 
 from .. import LEGGED_GYM_ROOT_DIR
 from ..sim.synthetic import SimParams
-from .helpers import class_to_dict, set_seed, update_cfg_from_args
+from .helpers import class_to_dict, get_load_path, set_seed, update_cfg_from_args
 
 
 def default_args(**over):
@@ -86,6 +86,11 @@ class TaskRegistry:
         if storage == "frame_log":
             from ..algo.rollout_storage import install_frame_log_storage
             install_frame_log_storage(runner.alg, env)
+            env._materialize = False       # this storage never reads the held observation: ring views are enough
+        if train_cfg.runner.resume:        # task_registry.py:137-143
+            resume_path = get_load_path(log_root, load_run=train_cfg.runner.load_run, checkpoint=train_cfg.runner.checkpoint)
+            print(f"Loading model from: {resume_path}")
+            runner.load(resume_path, load_optimizer=False)
         return runner, train_cfg, log_dir
 
 

@@ -9,7 +9,7 @@ from ti5_isaacgym_b200.envs import T1DHStandEnv
 from ti5_isaacgym_b200.sim.synthetic import SimParams, fill_synthetic_state, synthetic_actions
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 cfg = make_cfg(N)
-env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, 'cuda:0', True, use_cuda_graph=True)
+env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, 'cuda:0', True, use_cuda_graph=True, materialize_obs=False)
 gen = torch.Generator(device='cuda').manual_seed(1)
 fill_synthetic_state(env.gym.tensors, env.env_origins, gen)
 env.reset()

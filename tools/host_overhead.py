@@ -8,7 +8,7 @@ from ti5_isaacgym_b200.envs import T1DHStandEnv, make_t1_cfg
 from ti5_isaacgym_b200.sim.synthetic import SimParams, fill_synthetic_state, synthetic_actions
 N = 8192
 cfg = make_t1_cfg()(); cfg.env.num_envs = N; cfg.terrain.mesh_type = "plane"
-env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, "cuda:0", True, rng_mode="philox", div_mode="reciprocal")
+env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, "cuda:0", True, rng_mode="philox", div_mode="reciprocal", materialize_obs=False)
 gen = torch.Generator(device="cuda").manual_seed(1)
 fill_synthetic_state(env.gym.tensors, env.env_origins, gen)
 env.reset()

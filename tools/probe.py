@@ -7,7 +7,7 @@ from ti5_isaacgym_b200.envs import T1DHStandEnv
 from ti5_isaacgym_b200.sim.synthetic import SimParams, fill_synthetic_state, synthetic_actions
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 cfg = make_cfg(N)
-env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, 'cuda:0', True, use_cuda_graph=True)
+env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, 'cuda:0', True, use_cuda_graph=True, materialize_obs=False)
 gen = torch.Generator(device='cuda').manual_seed(1)
 fill_synthetic_state(env.gym.tensors, env.env_origins, gen)
 env.reset()
@@ -22,11 +22,13 @@ for i in range(20):
     env.step(act)
 torch.cuda.synchronize()
 ts = env._debug_ts.cpu().double()
-for kern, name, nprobe in ((0, 'post_physics', 8), (1, 'reset_observe', 8)):
+for kern, name, nprobe in ((0, 'post_physics / fused_step', 8), (2, 'substep workers', 2), (1, 'reset_observe', 8)):
     t = ts[kern]
     used = t[:, 0] > 0
     t = t[used]
-    t0 = t[:, 0].min()
+    if not len(t):
+        continue
+    t0 = ts[0][:, 0][ts[0][:, 0] > 0].min()          # everything relative to the first CTA of the step's first per-env kernel
     print(name, 'CTAs', int(used.sum()))
     for k in range(nprobe):
         col = t[:, k]; col = col[col > 0]
@@ -35,7 +37,7 @@ for kern, name, nprobe in ((0, 'post_physics', 8), (1, 'reset_observe', 8)):
 counts = env._block_counts.cpu()[:(N + env._params.env_block - 1) // env._params.env_block]
 t = ts[1]
 nb = len(counts)
-t0 = t[:, 0][t[:, 0] > 0].min()
+t0 = ts[0][:, 0][ts[0][:, 0] > 0].min()
 for label, rows in (("env CTAs with a reset", (counts > 0).nonzero().flatten()), ("env CTAs without", (counts == 0).nonzero().flatten()),
                     ("helper CTAs", torch.arange(nb, int((t[:, 0] > 0).sum())))):
     print(label, len(rows))

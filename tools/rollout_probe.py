@@ -15,7 +15,7 @@ T, NMB = 24, 4
 cfg = make_t1_cfg()()
 cfg.env.num_envs = N
 cfg.terrain.mesh_type = "plane"
-env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, "cuda:0", True, rng_mode="philox", div_mode="reciprocal")
+env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, "cuda:0", True, rng_mode="philox", div_mode="reciprocal", materialize_obs=False)
 gen = torch.Generator(device="cuda").manual_seed(1)
 fill_synthetic_state(env.gym.tensors, env.env_origins, gen)
 obs, priv = env.reset()
