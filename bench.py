@@ -2,19 +2,25 @@
 """Benchmark of the t1_dh_stand hot path (BASELINE.json metric: env-steps/sec, step math + reward + obs,
 8192 envs/GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
-    python bench.py --impl reference [--steps K] [--warmup W]      # the reference's algorithm on the host CPU
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path, BASELINE config 2
+    python bench.py --config 3 ...                                  # trimesh + measured heights + pushes + 5 % resets
+    python bench.py --impl reference [--config 2|3] ...             # the reference's algorithm on the host CPU
+    python bench.py --ppo-iter [--gpus N]                           # BASELINE config 4: a whole PPO iteration with the
+                                                                    # gradient all-reduce (one JSON line of its own)
     torchrun --nproc-per-node N bench.py --gpus N ...               # one rank per GPU, envs sharded 8192/rank
 
-One "step" = one policy step of every env of the rank: 10 x (PD torque + lag push) + post-physics
-(derived state, command schedule, termination, 24 reward terms, reset scatter, observation frames +
-history rings), plus the GAE reverse scan over the 24-step rollout every 24th step.  Physics is not
-part of the metric: the simulator tensors hold one draw of the synthetic near-nominal state
- and `simulate` is a no-op, exactly like the fake gym the reference baseline runs on.
+One "step" = one policy step of every env of the rank: action clip + 10 x (PD torque + lag pushes) + post-physics
+(derived state, command schedule, termination, 24 reward terms, reset scatter, observation frames + history rings),
+plus the GAE reverse scan over the 24-step rollout on every 24th step (the step counter runs through warm-up, so the
+cadence does not depend on --steps).  Physics is not part of the metric: the simulator tensors hold one draw of the
+synthetic near-nominal state and `simulate` is a no-op, exactly like the fake gym the reference baseline
+runs on.
 
-Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM and the L2
-flushed between timed steps; `e2e` goes through the public `env.step()` with pinned HOST buffers
-(H2D of the actions, D2H of reward / reset / time-out flags, a stream sync per step).
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM and the L2 flushed between timed
+steps; `e2e` goes through the public `env.step_host()` with pinned HOST buffers (actions in, reward / reset / time-out
+flags out, a stream sync per step).  The benchmarked mode (in-kernel Philox, CUDA graph, chained launches, fused step)
+is checked in tests/ against itself (graph == direct launches, fused == 12 launches, chained == plain, bit-exact) and
+statistically; parity with the reference is established in pools mode on the same kernels.
 """
 import argparse
 import json
@@ -33,31 +39,42 @@ sys.path.insert(0, ROOT)
 ENVS_PER_GPU = 8192
 ROLLOUT = 24
 GAMMA, LAM = 0.994, 0.9
-# algorithmic bytes per env per launch (fp32, D=12, K=47, P=73)
-BYTES_SUBSTEP = 584 + 244          # fused torque + lag push of one substep
+# ---- algorithmic bytes per env (fp32, D=12, K=47, P=73, DEC=10), SURVEY.md 8(d) / DESIGN.md section 4 ------------
+BYTES_SUBSTEP = 584 + 244          # torque + lag push of one substep as separate launches (12-launch sequence)
 BYTES_POST = 2412                  # post-physics + reset/observe, ring-view variant
-BYTES_ENV_STEP = 10 * BYTES_SUBSTEP + BYTES_POST
+BYTES_ENV_STEP = 10 * BYTES_SUBSTEP + BYTES_POST        # 10 692 B per env-step
+# SURVEY 8(d) row B (2412 B per env-step for the whole post phase) split over its two kernels: ti5_post_physics reads
+# every input of the phase once (922 B) and writes the derived state, counters, reward and episode sums (266 B);
+# ti5_reset_observe writes both frames into both mirrored ring slots (960 B), the last_* copies and the reference
+# pose (264 B) — its re-reads of what ti5_post_physics produced are not counted.
+BYTES_POST_PHYSICS = 922 + 266
+BYTES_RESET_OBSERVE = BYTES_POST - BYTES_POST_PHYSICS
+# ti5_fused_step (clip + 10 substeps + post-physics in ONE launch): what has to move once the substeps share one pass
+# over an env — reads: actions 48, five actuator arrays 240, lag index + stamp 12, on average 8.2 lagged action rows
+# that predate the step 394, the post-physics inputs 922 (joint state included); writes: ten action / DOF / IMU ring
+# rows 1680, the ten substeps' torques 480, actions + final torques + multipliers 144, the post-physics outputs 266.
+# (SURVEY's per-launch figures would credit this kernel with 10 x 828 + 1188 = 9468 B; the smaller number is used.)
+BYTES_FUSED_STEP = (48 + 240 + 12 + 394 + 922) + (1680 + 480 + 144 + 266)
+BYTES_HEIGHTS = 1122 + 748         # 3 x 187 int16 gathers + (N,187) fp32 out
+BYTES_ENV_STEP_FUSED = BYTES_FUSED_STEP + BYTES_RESET_OBSERVE
+KERNEL_BYTES = {"substep": BYTES_SUBSTEP, "post_physics": BYTES_POST_PHYSICS, "reset_observe": BYTES_RESET_OBSERVE,
+                "fused_step": BYTES_FUSED_STEP, "heights": BYTES_HEIGHTS}
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r02_ncu_full_summary_8192.json")
 
 
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel family, from the committed
-    `ncu --set full` capture of this same command (profiles/r01c_ncu_full_summary_8192.json); None if absent."""
-    path = os.path.join(ROOT, "profiles", "r01c_ncu_full_summary_8192.json")
-    if not os.path.exists(path):
+    `ncu --set full` capture of this same step (profiles/r02_ncu_full_summary_8192.json); None if absent."""
+    if not os.path.exists(NCU_SUMMARY):
         return None
-    want = {"substep": "substep_kernel", "post_physics": "post_physics_kernel", "reset_observe": "reset_observe_kernel",
-            "fused_step": "post_physics_kernelILb1", "heights": "heights_kernel"}[kernel]
-    table = json.load(open(path))
-    rows = next((v for k, v in table.items() if want in k), None)
+    want = {"substep": "substep_kernel", "post_physics": "post_physics_kernel<0", "reset_observe": "reset_observe_kernel",
+            "fused_step": "post_physics_kernel<1", "heights": "heights_kernel"}[kernel]
+    table = json.load(open(NCU_SUMMARY))
+    rows = next((v for k, v in table.items() if want in k.replace("(bool)", "").replace("(int)", "")), None)
     if not rows:
         return None
-    unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-
-    def to_bytes(s):
-        v, u = s.split()
-        return float(v) * unit[u]
     r = rows[len(rows) // 2]
-    return to_bytes(r["dram__bytes_read.sum"]) + to_bytes(r["dram__bytes_write.sum"])
+    return float(r["dram_bytes_read"]) + float(r["dram_bytes_write"])
 
 
 def peaks():
@@ -65,6 +82,16 @@ def peaks():
     if os.path.exists(path):
         return json.load(open(path))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 class ClockSampler(threading.Thread):
@@ -123,33 +150,119 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "via": "nvml" if self.nvml else "nvidia-smi"}
 
 
-def make_cfg(num_envs):
-    from ti5_isaacgym_b200.envs import DHT1StandCfg
-    cfg = DHT1StandCfg()
+# ---------------------------------------------------------------------------------------------
+# workloads: BASELINE.json configs 2 (plane) and 3 (trimesh + measured heights + pushes + frequent resets)
+# ---------------------------------------------------------------------------------------------
+CONFIG_NOTE = {2: "flat plane", 3: "trimesh terrain, measured heights (187 points, 260-float privileged frame), "
+                                   "push_robots, 5 % base-contact terminations per step"}
+CONTACT_RATE = {2: 0.01, 3: 0.05}
+COUNTER0 = {2: 0, 3: 240000}        # config 3: common_step_counter where the push window is 20 of 600 steps (t1_cfg:190-192)
+
+
+def make_cfg(num_envs, config=2, frame_stack=66):
+    from ti5_isaacgym_b200.envs import make_t1_cfg
+    cfg = make_t1_cfg(frame_stack=frame_stack)()
     cfg.env.num_envs = num_envs
-    cfg.terrain.mesh_type = "plane"         # BASELINE config 2: flat plane
+    cfg.terrain.mesh_type = "plane"
+    if config == 3:
+        cfg.terrain.mesh_type = "trimesh"
+        cfg.terrain.measure_heights = True
+        cfg.env.num_privileged_obs = cfg.env.c_frame_stack * (cfg.env.single_num_privileged_obs + cfg.terrain.num_height)
+        cfg.domain_rand.push_robots = True
     cfg.seed = 5
     return cfg
+
+
+def workload_name(N, config, H):
+    return (f"t1_dh_stand {N} envs/GPU, {CONFIG_NOTE[config]}, frame_stack {H}, full step + 24-step rollout GAE "
+            "(every 24th step)")
+
+
+class StepLoop:
+    """The env, its inputs, and the GAE tensors of one rank; `one()` is one step of the metric."""
+
+    def __init__(self, N, dev, config=2, frame_stack=66, rank=0, graph=True, materialize=False, group=None, seed=1234):
+        from ti5_isaacgym_b200.algo.rollout_storage import make_gae_scratch
+        from ti5_isaacgym_b200.envs import T1DHStandEnv
+        from ti5_isaacgym_b200.sim.synthetic import SimParams, fill_synthetic_state, synthetic_actions
+        self.cfg = cfg = make_cfg(N, config, frame_stack)
+        cfg.seed = 5 + rank
+        self.N, self.dev, self.group, self.config = N, dev, group, config
+        self.env = env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, dev, True, rng_mode="philox", div_mode="reciprocal",
+                                      use_cuda_graph=graph, materialize_obs=materialize)
+        gen = self.gen = torch.Generator(device=dev).manual_seed(seed + rank)
+        fill_synthetic_state(env.gym.tensors, env.env_origins, gen, base_contact_rate=CONTACT_RATE[config])
+        env.reset()
+        env.episode_length_buf = torch.randint(1, 2000, (N,), generator=gen, device=dev)
+        if COUNTER0[config]:
+            env.set_common_step_counter(COUNTER0[config])
+        self.actions = synthetic_actions(N, gen, dev)
+        T = ROLLOUT
+        self.rew = torch.randn(T, N, 1, generator=gen, device=dev)
+        self.val = torch.randn(T, N, 1, generator=gen, device=dev)
+        self.done = (torch.rand(T, N, 1, generator=gen, device=dev) < 0.02).byte()
+        self.last = torch.randn(N, 1, generator=gen, device=dev)
+        self.ret, self.adv = torch.empty_like(self.rew), torch.empty_like(self.rew)
+        self.scratch = make_gae_scratch(N, dev)
+        self.count = 0          # env steps taken so far: the GAE cadence runs through warm-up and every timed region
+        self.gae_calls = 0
+
+    def gae(self):
+        from ti5_isaacgym_b200.algo.rollout_storage import gae_returns_
+        gae_returns_(self.rew, self.val, self.done, self.last, self.ret, self.adv, GAMMA, LAM, self.scratch, self.group)
+        self.gae_calls += 1
+
+    def one(self, host=False):
+        self.env.step_host() if host else self.env.step(self.actions)
+        self.count += 1
+        if self.count % ROLLOUT == 0:
+            self.gae()
+
+    def timed(self, steps, flush):
+        """K steps, device-timed: CUDA events on the launching stream around every step, the L2 flushed (256 MiB write)
+        outside the brackets before each.  Returns (total ms, GAE calls inside)."""
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        g0 = self.gae_calls
+        for i in range(steps):
+            flush.fill_(i & 0xFF)
+            starts[i].record()
+            self.one()
+            ends[i].record()
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in zip(starts, ends)), self.gae_calls - g0
 
 
 # ---------------------------------------------------------------------------------------------
 # the reference arm / CPU baseline: the oracle port of the reference's torch algorithm on host cores
 # ---------------------------------------------------------------------------------------------
 
-def run_cpu_port(num_envs, steps, warmup, seed=1234, device="cpu"):
+def run_cpu_port(num_envs, steps, warmup, seed=1234, device="cpu", config=2):
     from types import SimpleNamespace
     from oracle import t1_oracle as O
     from ti5_isaacgym_b200.envs.t1.t1_robot import robot_constants
-    from ti5_isaacgym_b200.sim.synthetic import alloc_sim_tensors, fill_synthetic_state, synthetic_actions
-    cfg = make_cfg(num_envs)
-    C = O.make_consts(cfg, cfg.sim.dt, robot_constants(cfg), device=device)
+    from ti5_isaacgym_b200.sim.synthetic import (SyntheticTerrain, alloc_sim_tensors, fill_synthetic_state, synthetic_actions,
+                                                 synthetic_height_field)
+    cfg = make_cfg(num_envs, config)
+    terrain = heights = None
+    if config == 3:
+        st = SyntheticTerrain(cfg.terrain, num_envs)
+        terrain = SimpleNamespace(env_length=st.env_length, max_level=cfg.terrain.num_rows,
+                                  origins=torch.from_numpy(st.env_origins).float().to(device))
+        heights = synthetic_height_field(st.tot_rows, st.tot_cols, seed=7).to(device)
+    C = O.make_consts(cfg, cfg.sim.dt, robot_constants(cfg), device=device, terrain=terrain)
     S = O.new_state(C, num_envs)
     gen = torch.Generator().manual_seed(seed)
+    if terrain is not None:
+        S.terrain_levels[:] = torch.randint(0, 6, (num_envs,), generator=gen).to(device)
+        S.terrain_types[:] = torch.div(torch.arange(num_envs), num_envs / cfg.terrain.num_cols, rounding_mode="floor").long().to(device)
+        S.env_origins[:] = terrain.origins[S.terrain_levels, S.terrain_types]
     sim = alloc_sim_tensors(num_envs, "cpu")
-    fill_synthetic_state(sim, S.env_origins.cpu(), gen)
+    fill_synthetic_state(sim, S.env_origins.cpu(), gen, base_contact_rate=CONTACT_RATE[config])
     sim = SimpleNamespace(**{k: v.to(device) for k, v in vars(sim).items()})
     S.episode_length_buf[:] = torch.randint(1, 2000, (num_envs,), generator=gen).to(device)
     S.gait_time[:, 1], S.gait_time[:, 2] = 900, 1500
+    S.common_step_counter = COUNTER0[config]
     actions = synthetic_actions(num_envs, gen, "cpu").to(device)
     pools = {k: v.to(device) for k, v in O.draw_pools(C, num_envs, gen).items()}
     rew = torch.randn(ROLLOUT, num_envs, 1, generator=gen).to(device)
@@ -157,22 +270,31 @@ def run_cpu_port(num_envs, steps, warmup, seed=1234, device="cpu"):
     done = (torch.rand(ROLLOUT, num_envs, 1, generator=gen) < 0.02).byte().to(device)
     last = torch.randn(num_envs, 1, generator=gen).to(device)
     sync = torch.cuda.synchronize if device != "cpu" else (lambda: None)
+    count = [0]
 
-    def one(i):
-        O.step(C, S, sim, actions, pools)
-        if (i + 1) % ROLLOUT == 0:
+    def one():
+        O.step(C, S, sim, actions, pools, terrain=terrain, height_samples=heights)
+        count[0] += 1
+        if count[0] % ROLLOUT == 0:
             O.gae_returns(rew, val, done, last, GAMMA, LAM)
 
     with torch.inference_mode():
-        for i in range(warmup):
-            one(i)
+        for _ in range(warmup):
+            one()
         sync()
         t0 = time.perf_counter()
-        for i in range(steps):
-            one(i)
+        for _ in range(steps):
+            one()
         sync()
         dt = time.perf_counter() - t0
     return num_envs * steps / dt, dt / steps * 1e3
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
 
 
 def reference_arm(args):
@@ -181,25 +303,26 @@ def reference_arm(args):
         return
     # torchrun exports OMP_NUM_THREADS=1 for N > 1: the CPU arm runs alone on rank 0 and takes every host core it may use
     try:
-        torch.set_num_threads(len(os.sched_getaffinity(0)))
-    except (AttributeError, RuntimeError):
+        torch.set_num_threads(host_threads())
+    except RuntimeError:
         pass
     cores = torch.get_num_threads()
     # bounded sample: the whole run should end within ~2 minutes on the host cores (~30 us per env-step with all
     # threads), so large --steps shrink the number of envs stepped per step (never below 256, at most the workload's 8192)
-    budget_env_steps = 3.0e6
-    sample_envs = ENVS_PER_GPU
+    budget_env_steps = 3.0e6 if args.config == 2 else 1.5e6
+    sample_envs = args.envs
     while sample_envs > 256 and sample_envs * (args.steps + args.warmup) > budget_env_steps:
         sample_envs //= 2
-    value, ms = run_cpu_port(sample_envs, args.steps, args.warmup)
+    value, ms = run_cpu_port(sample_envs, args.steps, args.warmup, config=args.config)
     line = {"impl": "reference", "metric": "env-steps/sec (step math + reward + obs)", "value": value,
             "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": "t1_dh_stand 8192 envs, flat plane, full step + 24-step rollout GAE",
-                                            "device": "host CPU", "physics": "no-op (fake gym)"},
-            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} steps x {sample_envs} envs of the oracle port (torch CPU, "
-                                       "the reference's op chains), all host threads"},
+            "data": "synthetic", "config": {"workload": workload_name(args.envs, args.config, 66), "baseline_config": args.config,
+                                            "device": "host CPU", "cpu_model": cpu_model(), "physics": "no-op (fake gym)",
+                                            "sample_envs": sample_envs},
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(),
+                             "sample": f"{args.steps} steps x {sample_envs} envs of the oracle port (torch CPU, the reference's "
+                                       "op chains, pinned bit-equal to the unmodified reference), all host threads"},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -209,12 +332,8 @@ def reference_arm(args):
 # this repo's arm
 # ---------------------------------------------------------------------------------------------
 
-def cuda_arm(args):
+def dist_setup():
     import torch.distributed as dist
-    from ti5_isaacgym_b200.algo.rollout_storage import gae_returns_, make_gae_scratch
-    from ti5_isaacgym_b200.envs import T1DHStandEnv
-    from ti5_isaacgym_b200.sim.synthetic import SimParams, fill_synthetic_state, synthetic_actions
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -226,23 +345,22 @@ def cuda_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
         group = dist.group.WORLD
-    N = args.envs
-    cfg = make_cfg(N)
-    cfg.seed = 5 + rank
-    env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, dev, True, rng_mode="philox", div_mode="reciprocal",
-                       use_cuda_graph=True, materialize_obs=args.materialize)
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    fill_synthetic_state(env.gym.tensors, env.env_origins, gen)
-    env.reset()
-    env.episode_length_buf = torch.randint(1, 2000, (N,), generator=gen, device=dev)
-    actions = synthetic_actions(N, gen, dev)
-    T = ROLLOUT
-    rew = torch.randn(T, N, 1, generator=gen, device=dev)
-    val = torch.randn(T, N, 1, generator=gen, device=dev)
-    done = (torch.rand(T, N, 1, generator=gen, device=dev) < 0.02).byte()
-    last = torch.randn(N, 1, generator=gen, device=dev)
-    ret, adv = torch.empty_like(rew), torch.empty_like(rew)
-    scratch = make_gae_scratch(N, dev)
+    return dist, world, rank, local, dev, group
+
+
+def max_over_ranks(x, dev, world, dist):
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def cuda_arm(args):
+    dist, world, rank, local, dev, group = dist_setup()
+    N, H = args.envs, args.frame_stack
+    loop = StepLoop(N, dev, args.config, H, rank, graph=os.environ.get("TI5_BENCH_GRAPH", "1") != "0",
+                    materialize=args.materialize, group=group)
+    env = loop.env
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     def barrier():
@@ -250,102 +368,109 @@ def cuda_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one(i):
-        env.step(actions)
-        if (i + 1) % T == 0:
-            gae_returns_(rew, val, done, last, ret, adv, GAMMA, LAM, scratch, group)
-
-    for i in range(max(args.warmup, 3)):
-        one(i)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        loop.one()
     # ---- device-timed region: K steps, L2 flushed (outside the event brackets) between steps ----
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)
-        starts[i].record()
-        one(i)
-        ends[i].record()
+    dev_ms, gae_in_region = loop.timed(args.steps, flush)
     barrier()
-    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
+    dev_ms = max_over_ranks(dev_ms, dev, world, dist)
     value = world * N * args.steps / (dev_ms * 1e-3)
 
-    # ---- per-launch duration of the dominant kernel family (events on the launching stream) -------
-    kt = kernel_times(env, actions, steps=min(args.steps, 48))
+    # ---- per-launch duration of the kernel families (events on the launching stream) -------
+    kt = kernel_times(env, loop.actions, steps=min(args.steps, 48))
 
-    # ---- end to end through env.step() with pinned host buffers ------------------------------------
+    # ---- end to end through env.step_host() with pinned host buffers ------------------------------------
     # pinned, device-mapped host buffers wired into the step's CUDA graph (LeggedRobot.enable_host_io): every
-    # step_host() has the first substep kernel read the actions from host memory, runs the step, has the observation
+    # step_host() has the first kernel of the step read the actions from host memory, runs the step, has the observation
     # kernel store [rew | reset | time_outs] into host memory, and waits for the stream
-    h_act, h_out = env.enable_host_io()
-    h_act.copy_(actions.cpu())
-    for i in range(3):
-        env.step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        env.step_host()
-        if (i + 1) % T == 0:
-            gae_returns_(rew, val, done, last, ret, adv, GAMMA, LAM, scratch, group)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * N * args.steps / float(t.item())
+    e2e = None
+    if env._use_graph:
+        h_act, h_out = env.enable_host_io()
+        h_act.copy_(loop.actions.cpu())
+        for _ in range(3):
+            env.step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            loop.one(host=True)
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0, dev, world, dist)
+        e2e = {"value": world * N * args.steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h_act.numel() * 4 * world,
+               "d2h_bytes_per_step": h_out.numel() * world,
+               "note": "env.step_host(): actions read from pinned host memory by the first kernel of the step, reward/reset/"
+                       "time-out flags stored into pinned host memory by the last one (mapped pages, no copy-engine hop), "
+                       "stream sync every step; L2 not flushed"}
     clocks = sampler.summary() if sampler else None      # sampled across the device-timed, per-phase and e2e regions
+
+    # ---- BASELINE config 5: num_envs and frame-stack sweeps, every rank its own shard (same code path as above) ----
+    sweep = None
+    if not args.no_sweep and N == ENVS_PER_GPU and H == 66 and not args.materialize:
+        del flush
+        torch.cuda.empty_cache()
+        points = [(1024, 66), (16384, 66), (65536, 66), (8192, 16), (8192, 100)] if args.config == 2 else [(65536, 66)]
+        sweep = [sweep_point(n, h, dev, args.config, rank, world, dist, group) for n, h in points]
 
     if rank == 0:
         peak, peak_src = peaks()
         dom = max(kt, key=lambda k: kt[k]["share_ms"])
-        # algorithmic bytes of one launch of the dominant family (SURVEY 8d figure x envs per launch);
-        # the post phase's 2412 B/env are spread over its two launches
         bytes_per_launch = kt[dom]["bytes_per_launch"]
         ach = bytes_per_launch / (kt[dom]["ms_per_launch"] * 1e-3) / 1e9
         launches_per_step = env.launches_per_step
+        fused = env._uses_fused_step()
+        step_bytes = (BYTES_ENV_STEP_FUSED if fused else BYTES_ENV_STEP) + (BYTES_HEIGHTS + 12 * 187 if args.config == 3 else 0)
         cpu = torch_gpu = None
         if world == 1 and not args.no_cpu_baseline:
-            v, ms = run_cpu_port(4096, 40, 3)
-            cpu = {"value": v, "unit": "env-steps/s", "cores": torch.get_num_threads(), "kind": "port",
-                   "sample": "40 steps x 4096 envs (BASELINE config 1) of the oracle port, torch CPU, all host threads, "
-                             f"{ms:.1f} ms/step"}
+            torch.set_num_threads(host_threads())
+            v, ms = run_cpu_port(4096, 30, 3, config=args.config)
+            cores = torch.get_num_threads()
+            torch.set_num_threads(1)
+            v1, ms1 = run_cpu_port(1024, 12, 2, config=args.config)
+            torch.set_num_threads(cores)
+            cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(),
+                   "sample": f"30 steps x 4096 envs (BASELINE config 1 size) of the oracle port, torch CPU, all {cores} host "
+                             f"threads, {ms:.1f} ms/step",
+                   "single_thread": {"value": v1, "cores": 1,
+                                     "sample": f"12 steps x 1024 envs, torch.set_num_threads(1), {ms1:.1f} ms/step"}}
             # the reference's eager-torch algorithm on THIS GPU (the north_star's 20x denominator); context only
-            v, ms = run_cpu_port(N, 24, 3, device=dev)
+            v, ms = run_cpu_port(N, 24, 3, device=dev, config=args.config)
             torch_gpu = {"value": v, "unit": "env-steps/s", "ms_per_step": ms,
                          "sample": f"24 steps x {N} envs of the oracle port in eager torch on the same B200"}
-        rollout = rollout_bench(env, gen, actions) if world == 1 and not args.no_rollout and not args.materialize else None
-        sweep = None
-        if world == 1 and not args.no_sweep and N == ENVS_PER_GPU and not args.materialize:
-            del flush
-            sweep = [sweep_point(n, dev) for n in (1024, 16384, 65536)]
+        rollout = None
+        if world == 1 and not args.no_rollout and not args.materialize and args.config == 2:
+            rollout = rollout_bench(env, loop.gen, loop.actions)
         line = {
             "metric": "env-steps/sec (step math + reward + obs)", "value": value, "unit": "env-steps/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+            "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"t1_dh_stand {N} envs/GPU, flat plane, full fused step + 24-step rollout GAE",
-                       "envs_per_gpu": N, "frame_stack": cfg.env.frame_stack, "obs": "materialised" if args.materialize else "ring view",
+            "config": {"workload": workload_name(N, args.config, H), "baseline_config": args.config,
+                       "envs_per_gpu": N, "frame_stack": H, "obs": "materialised" if args.materialize else "ring view",
                        "rng": "in-kernel Philox4x32-10", "physics": "no-op (synthetic state, SURVEY 8d)",
+                       "gae_calls_in_timed_region": gae_in_region,
                        "l2": "flushed between timed steps (256 MiB write outside the event brackets)",
-                       "launch": f"one CUDA graph per step ({env.launches_per_step} kernels"
+                       "launch": (f"one CUDA graph per step ({launches_per_step} kernels" if env._use_graph
+                                  else f"direct launches ({launches_per_step} kernels")
                                  + (", programmatic dependent launches)" if env._chain_launches else ")")},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h_act.numel() * 4 * world,
-                    "d2h_bytes_per_step": h_out.numel() * world,
-                    "note": "env.step_host(): actions read from pinned host memory by the first kernel of the step, reward/reset/time-out flags stored into pinned host memory by the last one (mapped pages, no copy-engine hop), stream sync every step; L2 not flushed"},
-            "gpu_launches": launches_per_step * args.steps + 2 * (args.steps // T),
+            "e2e": e2e,
+            "gpu_launches": launches_per_step * args.steps + 2 * gae_in_region,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": ncu_traffic(dom) if N == ENVS_PER_GPU else None, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch,
+                         "traffic": ncu_traffic(dom) if N == ENVS_PER_GPU and args.config == 2 else None,
+                         "peak_source": peak_src, "bytes_per_launch": bytes_per_launch,
                          "ms_per_launch": kt[dom]["ms_per_launch"],
-                         "whole_step": {"bytes": BYTES_ENV_STEP * N, "achieved": BYTES_ENV_STEP * N * args.steps / (dev_ms * 1e-3) / 1e9},
+                         "whole_step": {"bytes": step_bytes * N, "achieved": step_bytes * N * args.steps / (dev_ms * 1e-3) / 1e9,
+                                        "frac": step_bytes * N * args.steps / (dev_ms * 1e-3) / 1e9 / peak,
+                                        "survey_8d_bytes": BYTES_ENV_STEP * N,
+                                        "survey_8d_frac": BYTES_ENV_STEP * N * args.steps / (dev_ms * 1e-3) / 1e9 / peak},
                          "kernels": kt,
-                         "how": "CUDA events on the launching stream around one CUDA graph per kernel family (L2 flushed before each step); per-launch = family time / launches in the family; algorithmic bytes = SURVEY 8d per-env figure x envs (post phase split over its two kernels, see bench.py)"},
+                         "how": "CUDA events on the launching stream around each kernel family of the step (L2 flushed before "
+                                "each step); per-launch = family time / launches in the family; algorithmic bytes = DESIGN.md "
+                                "section 4 per-env figure x envs.  At 8192 envs every kernel is latency-bound (13 us of HBM time "
+                                "per step): see `sweep` for the sizes where bandwidth is the bound"},
             "cpu_baseline": cpu,
             "reference_torch_gpu": torch_gpu,
             "rollout_storage": rollout,
@@ -356,51 +481,30 @@ def cuda_arm(args):
         dist.destroy_process_group()
 
 
-def sweep_point(N, dev, steps=48, warmup=12):
-    """One point of BASELINE config 5 (num_envs sweep): the same device-timed step (L2 flushed before every step, GAE
-    every 24th) and per-phase graph timing as the main line, on a fresh env of N envs."""
-    from ti5_isaacgym_b200.algo.rollout_storage import gae_returns_, make_gae_scratch
-    from ti5_isaacgym_b200.envs import T1DHStandEnv
-    from ti5_isaacgym_b200.sim.synthetic import SimParams, fill_synthetic_state, synthetic_actions
-    cfg = make_cfg(N)
-    env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, dev, True, rng_mode="philox", div_mode="reciprocal", use_cuda_graph=True,
-                       materialize_obs=False)
-    gen = torch.Generator(device=dev).manual_seed(4321)
-    fill_synthetic_state(env.gym.tensors, env.env_origins, gen)
-    env.reset()
-    env.episode_length_buf = torch.randint(1, 2000, (N,), generator=gen, device=dev)
-    actions = synthetic_actions(N, gen, dev)
-    T = ROLLOUT
-    rew = torch.randn(T, N, 1, generator=gen, device=dev)
-    val = torch.randn(T, N, 1, generator=gen, device=dev)
-    done = (torch.rand(T, N, 1, generator=gen, device=dev) < 0.02).byte()
-    last = torch.randn(N, 1, generator=gen, device=dev)
-    ret, adv = torch.empty_like(rew), torch.empty_like(rew)
-    scratch = make_gae_scratch(N, dev)
+def sweep_point(N, H, dev, config, rank, world, dist, group, steps=48, warmup=12):
+    """One point of BASELINE config 5 (num_envs / frame_stack sweep): the same device-timed step (L2 flushed before every
+    step, GAE every 24th) and per-family timing as the main line, on a fresh env of N envs per GPU; under torchrun every
+    rank steps its own shard and the time is the max over ranks."""
+    loop = StepLoop(N, dev, config, H, rank, group=group, seed=4321)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def one(i):
-        env.step(actions)
-        if (i + 1) % T == 0:
-            gae_returns_(rew, val, done, last, ret, adv, GAMMA, LAM, scratch, None)
-    for i in range(warmup):
-        one(i)
-    marks = []
-    for i in range(steps):
-        flush.fill_(i & 0xFF)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); one(i); b.record()
-        marks.append((a, b))
+    for _ in range(warmup):
+        loop.one()
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
-    ms = sum(a.elapsed_time(b) for a, b in marks) / steps
-    kt = kernel_times(env, actions, steps=24)
+    ms, _ = loop.timed(steps, flush)
+    ms = max_over_ranks(ms, dev, world, dist) / steps
+    kt = kernel_times(loop.env, loop.actions, steps=24)
     peak, _ = peaks()
-    out = {"envs_per_gpu": N, "value": N / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms,
+    step_bytes = BYTES_ENV_STEP_FUSED if loop.env._uses_fused_step() else BYTES_ENV_STEP     # the frames written do not depend on H
+    out = {"envs_per_gpu": N, "frame_stack": H, "n_gpus": world, "value": world * N / (ms * 1e-3), "unit": "env-steps/s",
+           "ms_per_step": ms,
            "kernels": {k: {"ms_per_launch": v["ms_per_launch"], "achieved": v["achieved_GBps"], "frac": v["achieved_GBps"] / peak}
                        for k, v in kt.items()},
-           "whole_step": {"bytes": BYTES_ENV_STEP * N, "achieved": BYTES_ENV_STEP * N / (ms * 1e-3) / 1e9,
-                          "frac": BYTES_ENV_STEP * N / (ms * 1e-3) / 1e9 / peak}}
-    del env, flush
+           "whole_step": {"bytes": step_bytes * N, "achieved": step_bytes * N / (ms * 1e-3) / 1e9,
+                          "frac": step_bytes * N / (ms * 1e-3) / 1e9 / peak,
+                          "survey_8d_frac": BYTES_ENV_STEP * N / (ms * 1e-3) / 1e9 / peak}}
+    del loop, flush
     torch.cuda.empty_cache()
     return out
 
@@ -485,48 +589,33 @@ def rollout_bench(env, gen, actions):
     }
 
 
-# SURVEY 8(d) row B (2412 B per env-step for the whole post phase) split over its two kernels: ti5_post_physics reads
-# every input of the phase once (922 B) and writes the derived state, counters, reward and episode sums (266 B);
-# ti5_reset_observe writes both frames into both mirrored ring slots (960 B), the last_* copies and the reference
-# pose (264 B) — its re-reads of what ti5_post_physics produced are not counted.
-BYTES_POST_PHYSICS = 922 + 266
-BYTES_RESET_OBSERVE = BYTES_POST - BYTES_POST_PHYSICS
-# ti5_fused_step (clip + 10 substeps + post-physics in one launch): what has to move once the substeps share one pass
-# over an env — reads: actions 48, five actuator arrays 240, lag index + stamp 12, on average 8.2
-# lagged action rows that predate the step 394, the post-physics inputs 922 (joint state included); writes: ten action /
-# DOF / IMU ring rows 1680, actions + final torques + multipliers 144, the post-physics outputs 266.
-BYTES_FUSED_STEP = (48 + 240 + 12 + 394 + 922) + (1680 + 144 + 266)
-BYTES_HEIGHTS = 1122 + 748          # 3 x 187 int16 gathers + (N,187) fp32 out
-KERNEL_BYTES = {"substep": BYTES_SUBSTEP, "post_physics": BYTES_POST_PHYSICS, "reset_observe": BYTES_RESET_OBSERVE,
-                "fused_step": BYTES_FUSED_STEP, "heights": BYTES_HEIGHTS}
-
-
 def kernel_times(env, actions, steps):
-    """Average device time of the kernel families of a step, CUDA events on the launching stream around the replay of
-    one CUDA graph per family (a single whole-step graph cannot be bracketed inside; the event records also cut the
-    programmatic launch chain at the family boundaries, so the times add up to a little more than the whole-step
-    time).  Per-launch time = family time / launches in the family."""
-    graphs = env.capture_phase_graphs()
+    """Average device time of the kernel families of a step: CUDA events on the launching stream around each family
+    (direct launches, L2 flushed before every step).  A single whole-step graph cannot be bracketed inside, and the
+    event records cut the programmatic launch chain at the family boundaries, so the times add up to more than the
+    whole-step time.  Per-launch time = family time / launches in the family."""
+    phases = env.phase_launchers()
     ev = lambda: torch.cuda.Event(enable_timing=True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=env.device)
     env._actions_in.copy_(actions)
-    acc = {name: [] for name, _, _ in graphs}
+    acc = {name: [] for name, _, _ in phases}
     marks = []
-    for i in range(steps):
+    for i in range(steps + 4):
         flush.fill_(i & 0xFF)
-        e = [ev() for _ in range(len(graphs) + 1)]
+        e = [ev() for _ in range(len(phases) + 1)]
         e[0].record()
-        for k, (_, g, _) in enumerate(graphs):
-            g.replay()
+        for k, (_, fn, _) in enumerate(phases):
+            fn()
             e[k + 1].record()
         env._finish_step()
-        marks.append(e)
+        if i >= 4:
+            marks.append(e)
     torch.cuda.synchronize()
     for e in marks:
-        for k, (name, _, _) in enumerate(graphs):
+        for k, (name, _, _) in enumerate(phases):
             acc[name].append(e[k].elapsed_time(e[k + 1]))
     out = {}
-    for name, _, n in graphs:
+    for name, _, n in phases:
         phase = statistics.mean(acc[name])
         extra = env._params.priv_frame - 73 if name == "reset_observe" else 0       # measured heights ride in the critic frame
         nbytes = (KERNEL_BYTES[name] + 4 * 3 * extra) * env.num_envs
@@ -536,6 +625,118 @@ def kernel_times(env, actions, steps):
     return out
 
 
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 4 as written: envs sharded 8192/GPU WITH the PPO gradient all-reduce — a whole PPO iteration
+# ---------------------------------------------------------------------------------------------
+
+def ppo_iter_arm(args):
+    """One PPO iteration as `DHOnPolicyRunner.learn` runs it (dh_on_policy_runner.py:125-187) on every rank's shard:
+    24 x [policy forward -> env.step -> ti5_store_transition], GAE with the 3-double all-reduce of the advantage
+    statistics, then 2 epochs x 4 mini-batches (t1_cfg:455-468) of: ti5_gather_minibatch -> forward/backward of a
+    stand-in actor-critic with ActorCriticDH's parameter count -> ONE flat-bucket gradient all-reduce
+    (FlatGradAllReduce) -> clip -> Adam.  The actor-critic itself is out of scope (it stays plain PyTorch); the point is
+    where the collective sits and what it costs next to the env steps.  Device-timed, max over ranks."""
+    dist, world, rank, local, dev, group = dist_setup()
+    from ti5_isaacgym_b200.algo.rollout_storage import FrameLogRolloutStorage, RolloutStorage
+    from ti5_isaacgym_b200.distributed import FlatGradAllReduce, all_reduce_mean
+    N, T, EPOCHS, NMB = args.envs, ROLLOUT, 2, 4
+    loop = StepLoop(N, dev, 2, 66, rank, group=group)
+    env = loop.env
+    storage = FrameLogRolloutStorage(env, T, group=group)
+    torch.manual_seed(0)
+    P = env.num_privileged_obs
+
+    class ActorCritic(torch.nn.Module):          # stand-in with ActorCriticDH's size (~0.86 M parameters, actor_critic_dh.py:31-117)
+        def __init__(self):
+            super().__init__()
+            mlp = lambda i, o: torch.nn.Sequential(torch.nn.Linear(i, 512), torch.nn.ELU(), torch.nn.Linear(512, 256), torch.nn.ELU(),
+                                                   torch.nn.Linear(256, 128), torch.nn.ELU(), torch.nn.Linear(128, o))
+            self.hist = torch.nn.Conv1d(66, 32, 6, stride=3)          # long-history encoder over (N, 66, 47)
+            self.actor, self.critic = mlp(235 + 32 * 14, 12), mlp(P, 1)
+            self.std = torch.nn.Parameter(torch.ones(12))
+
+        def forward(self, obs, critic_obs):
+            h = self.hist(obs.view(-1, 66, 47)).flatten(1)
+            return self.actor(torch.cat((obs[..., -235:], h), -1)), self.critic(critic_obs)
+
+    net = ActorCritic().to(dev)
+    n_params = sum(p.numel() for p in net.parameters())
+    opt = torch.optim.Adam(net.parameters(), lr=1e-5)
+    sync = FlatGradAllReduce(net, group)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    phases = {"collect": [], "gae": [], "update": [], "allreduce": [], "iteration": []}
+
+    def iteration(record):
+        e = [ev() for _ in range(4)]
+        e[0].record()
+        storage.clear()
+        obs, priv = env.get_observations(), env.get_privileged_observations()
+        with torch.inference_mode():
+            for _ in range(T):
+                mu, v = net(obs, priv)
+                act = mu + net.std * torch.randn_like(mu)
+                tr = RolloutStorage.Transition()
+                tr.actions, tr.values, tr.action_mean, tr.action_sigma = act, v, mu, net.std.expand_as(mu).contiguous()
+                tr.actions_log_prob = -0.5 * ((act - mu) / net.std).square().sum(-1)
+                tr.observations, tr.critic_observations = obs, priv
+                obs, priv, rew, dones, infos = env.step(act)
+                storage.store_step(tr, rew, dones, infos["time_outs"], GAMMA)
+            e[1].record()
+            storage.compute_returns(net(obs, priv)[1], GAMMA, LAM)       # advantage statistics all-reduced over the ranks
+        e[2].record()
+        ar = []
+        for _ in range(EPOCHS):
+            perm = torch.randperm(T * N, device=dev)
+            for i in range(NMB):
+                b = storage.gather(perm[i * (T * N // NMB):(i + 1) * (T * N // NMB)])
+                mu, v = net(b["obs"], b["critic_obs"])
+                logp = -0.5 * ((b["actions"] - mu) / net.std).square().sum(-1, keepdim=True)
+                ratio = torch.exp(logp - b["actions_log_prob"])
+                adv = b["advantages"]
+                loss = torch.max(-adv * ratio, -adv * ratio.clamp(0.8, 1.2)).mean() + (b["returns"] - v).square().mean()
+                all_reduce_mean((logp - b["actions_log_prob"]).mean().detach().reshape(1), group)      # KL, dh_ppo.py:139-151
+                opt.zero_grad(set_to_none=False)
+                loss.backward()
+                a, z = ev(), ev()
+                a.record(); sync.reduce(); z.record()          # dh_ppo.py:180-181: between backward and the clip
+                ar.append((a, z))
+                torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+                opt.step()
+        e[3].record()
+        if record:
+            torch.cuda.synchronize()
+            phases["collect"].append(e[0].elapsed_time(e[1])); phases["gae"].append(e[1].elapsed_time(e[2]))
+            phases["update"].append(e[2].elapsed_time(e[3])); phases["iteration"].append(e[0].elapsed_time(e[3]))
+            phases["allreduce"].append(sum(a.elapsed_time(z) for a, z in ar))
+
+    iters = max(2, min(args.steps, 6))
+    for _ in range(2):
+        iteration(False)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for _ in range(iters):
+        iteration(True)
+    mean = {k: max_over_ranks(statistics.mean(v), dev, world, dist) for k, v in phases.items()}
+    if rank == 0:
+        it_ms = mean["iteration"]
+        line = {"metric": "PPO iteration (24 env steps + GAE + 8 mini-batch updates) env-steps/sec", "mode": "ppo-iter",
+                "value": world * N * T / (it_ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": iters, "warmup": 2,
+                "ms_per_step": it_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"BASELINE config 4: {world * N} envs sharded {N}/GPU over {world} GPU(s), whole PPO iteration "
+                                       "with the gradient all-reduce", "envs_per_gpu": N, "rollout": T, "epochs": EPOCHS,
+                           "mini_batches": NMB, "stand_in_parameters": n_params},
+                "iteration_ms": it_ms, "collect_ms": mean["collect"], "gae_ms": mean["gae"], "update_ms": mean["update"],
+                "grad_allreduce": {"calls_per_iteration": EPOCHS * NMB, "us_per_call": 1e3 * mean["allreduce"] / (EPOCHS * NMB),
+                                   "bytes_per_call": 4 * n_params, "share_of_iteration": mean["allreduce"] / it_ms,
+                                   "how": "CUDA events around FlatGradAllReduce.reduce() (bucket copy + NCCL all-reduce, AVG)"},
+                "env_steps_share_of_iteration": mean["collect"] / it_ms}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -543,13 +744,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=24)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU (BASELINE metric: 8192)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3],
+                    help="BASELINE.json config: 2 = plane, 3 = trimesh + heights + pushes + 5 %% resets")
+    ap.add_argument("--frame-stack", type=int, default=66, help="observation history length H (BASELINE config 5 sweeps it)")
     ap.add_argument("--materialize", action="store_true", help="also write contiguous (N,3102)/(N,219) observations")
+    ap.add_argument("--ppo-iter", action="store_true", help="BASELINE config 4: a whole PPO iteration with the gradient all-reduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rollout", action="store_true", help="skip the rollout-storage measurement (SURVEY 8f rows 1-2)")
-    ap.add_argument("--no-sweep", action="store_true", help="skip the num_envs sweep points (BASELINE config 5)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the num_envs / frame_stack sweep points (BASELINE config 5)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
+    elif args.ppo_iter:
+        ppo_iter_arm(args)
     else:
         cuda_arm(args)
 

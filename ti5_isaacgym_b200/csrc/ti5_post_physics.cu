@@ -141,7 +141,11 @@ __device__ __forceinline__ void substep_worker(const Ti5Params& p, const Ti5Buff
   int dsl = (int)fast_mod(base + kh, dlen);                // slot of the DOF-lag push after substep k
   int rs = ws - lag % alen;                                // slot of the lagged row substep k looks at
   if (rs < 0) rs += alen;
-  auto adv = [](int s, int len) { s += WORKER_SPLIT; return s >= len ? s % len : s; };
+  auto adv = [](int s, int len) {          // (s + WORKER_SPLIT) mod len without a division (len >= 1)
+    s += WORKER_SPLIT;
+    while (s >= len) s -= len;
+    return s;
+  };
   // the lagged action row of a substep that looks back past the start of this step (lr:1045); rows pushed before the
   // env's last reset read as zero (lr:606).  Loaded one turn ahead, while no ordering with this step's own pushes is
   // needed: push k' of this step lands in the slot substep k reads only if k' - k + lag is a multiple of the ring
@@ -294,7 +298,8 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
   chain_trigger();                                        // ti5_reset_observe may become resident
   const int push_last = options & TI5_POST_PUSH_LAST;
   const int N = p.num_envs;
-  const int TB = p.env_block, tid = threadIdx.x;
+  constexpr int TB = MAXTB;                               // == p.env_block (checked at launch): divisions become shifts
+  const int tid = threadIdx.x;
   const int role = tid / TB, le = tid - role * TB;
   const int e0 = blockIdx.x * TB, e = e0 + le, n_tile = min(TB, N - e0);
   const bool is_role = role < POST_ROLES;

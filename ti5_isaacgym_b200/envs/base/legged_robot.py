@@ -619,10 +619,10 @@ class LeggedRobot(BaseTask):
     def _uses_fused_step(self, with_physics=False):
         return self._fused_step and not with_physics and self._params.env_block <= 64
 
-    def capture_phase_graphs(self):
-        """One CUDA graph per kernel family of the step instead of one for the whole step, so that a benchmark can
-        bracket each family with CUDA events: [(name, graph, launches)].  Replay all in order, then `_finish_step()`."""
-        torch.cuda.synchronize(self.device)
+    def phase_launchers(self):
+        """The kernel families of a fused step as [(name, launch, launches)], for a benchmark that brackets each family
+        with CUDA events on the current stream (direct launches: the event records cut the programmatic chain anyway).
+        Call all in order, then `_finish_step()`."""
         lib, p, b, r = self._lib, self._p_ref, self._b_ref, self._rng_ref()
         a_ptr = ctypes.c_void_p(self._actions_in.data_ptr())
         phases = []
@@ -635,6 +635,13 @@ class LeggedRobot(BaseTask):
             phases.append(("post_physics", lambda: _lib.check(lib.ti5_post_physics(
                 p, b, r, C["TI5_POST_PUSH_LAST"] | self._chain("TI5_POST_CHAINED"), self._stream())), 1))
         phases.append(("reset_observe", lambda: self._launch_post(False, 2), 1))
+        return phases
+
+    def capture_phase_graphs(self):
+        """One CUDA graph per kernel family of the step instead of one for the whole step, so that a benchmark can
+        bracket each family with CUDA events: [(name, graph, launches)].  Replay all in order, then `_finish_step()`."""
+        torch.cuda.synchronize(self.device)
+        phases = self.phase_launchers()
         graphs = []
         for name, fn, n in phases:
             g = torch.cuda.CUDAGraph()
