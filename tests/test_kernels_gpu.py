@@ -179,6 +179,29 @@ def test_fused_step_equals_the_twelve_launch_sequence(N, graph, name, chain):
     assert int(a.sync_from_device().step_index) == int(b.sync_from_device().step_index)
 
 
+def test_use_ref_actions_offsets_the_policy_output():
+    """t1:360-366 `env.use_ref_actions`: the step runs on actions + ref_action (added in place, as the reference does)."""
+    from ti5_isaacgym_b200.sim.synthetic import synthetic_actions
+    N = 512
+    envs = []
+    for flag in (True, False):
+        torch.manual_seed(0)
+        env, gen = _production_env(N, use_cuda_graph=False)
+        env.cfg.env.use_ref_actions = flag
+        env.reset()
+        envs.append(env)
+    a, b = envs
+    for t in range(6):
+        act = synthetic_actions(N, gen, "cuda")
+        want = act + b.ref_action
+        given = act.clone()
+        oa, _, ra, da, _ = a.step(given)
+        ob, _, rb, db, _ = b.step(want.clone())
+        exact(given, want, f"step {t}: the caller's tensor carries the offset")
+        exact(oa, ob, f"step {t}: obs"); exact(ra, rb, f"step {t}: rewards"); exact(da, db, f"step {t}: resets")
+        exact(a.ref_action, b.ref_action, f"step {t}: reference action")
+
+
 def test_graph_cache_follows_the_action_buffer():
     """The captured step reads the caller's action tensor in place (one graph per buffer address, at most 8); beyond
     that, and for host / strided inputs, it goes through the static copy.  Same results as direct launches."""

@@ -290,6 +290,10 @@ class LeggedRobot(BaseTask):
         self._bind_buffers()
         self._graph = self._graph_host = None
         self._view_epoch = [STEP_INDEX0]            # mutable cell shared with the ring-view tags: [current step index]
+        self._view_cache = ({}, {})                 # ring-window views by slot (`_window_views`)
+        self._extras_rows = [self._extras_log[i] for i in range(C["TI5_LOG_ROWS"])]
+        self._extras_args = (list(reward_scales(cfg, self.dt)), cfg.terrain.mesh_type == "trimesh", bool(cfg.commands.curriculum),
+                             bool(cfg.env.send_timeouts))
         self._graphs, self._max_graphs = {}, 8      # captured steps keyed by the address of the action buffer
         self.host_actions = None                                  # enable_host_io()
         self._rng = None
@@ -447,7 +451,8 @@ class LeggedRobot(BaseTask):
         return self._ring_as_shifted(self._imu_ring, self._params.imu_lag_len)
 
     def _history_views(self):
-        """The current H-frame / CH-frame windows as (N, H*K) / (N, CH*P) views into the mirrored rings."""
+        """The current H-frame / CH-frame windows as (N, H*K) / (N, CH*P) views into the mirrored rings (fresh tensor
+        objects; the per-step path takes them from `_window_views`)."""
         p = self._params
         H, CH, K, P = p.frame_stack, p.c_frame_stack, p.num_single_obs, p.priv_frame
         s = self._step_index
@@ -455,6 +460,22 @@ class LeggedRobot(BaseTask):
         c_off = (((s - 1) % CH) + 1) * P
         obs = self._obs_ring.view(self.num_envs, -1)[:, o_off:o_off + H * K]
         priv = self._priv_ring.view(self.num_envs, -1)[:, c_off:c_off + CH * P]
+        return obs, priv
+
+    def _window_views(self):
+        """The same windows from a per-slot cache: the window of step s starts at ring slot s % H, so there are only H
+        (CH) distinct views; building them once keeps four tensor ops out of every step."""
+        p = self._params
+        H, CH, K, P = p.frame_stack, p.c_frame_stack, p.num_single_obs, p.priv_frame
+        s = self._step_index
+        cache = self._view_cache
+        ko, kc = (s - 1) % H, (s - 1) % CH
+        obs = cache[0].get(ko)
+        if obs is None:
+            obs = cache[0][ko] = self._obs_ring.view(self.num_envs, -1)[:, (ko + 1) * K:(ko + 1) * K + H * K]
+        priv = cache[1].get(kc)
+        if priv is None:
+            priv = cache[1][kc] = self._priv_ring.view(self.num_envs, -1)[:, (kc + 1) * P:(kc + 1) * P + CH * P]
         return obs, priv
 
     @property
@@ -746,7 +767,7 @@ class LeggedRobot(BaseTask):
             self._materialize_windows()
             self.obs_buf, self.privileged_obs_buf = self._obs_out, self._priv_out
         else:
-            self.obs_buf, self.privileged_obs_buf = self._history_views()
+            self.obs_buf, self.privileged_obs_buf = self._window_views()
             # ring views die at the next step(): tag them, so that a storage that copies them late can tell
             # (`check_not_stale_ring_view`; the reference's runner holds the observation across a step, dh_ppo.py:88)
             self.obs_buf.ti5_ring_view = self.privileged_obs_buf.ti5_ring_view = (self._view_epoch, self._step_index)
@@ -762,10 +783,9 @@ class LeggedRobot(BaseTask):
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
 
     def _publish_extras(self):
-        row = self._extras_log[self._step_index % C["TI5_LOG_ROWS"]]
-        self.extras["episode"] = EpisodeInfo(row, list(self.reward_scales), self.cfg.terrain.mesh_type == "trimesh",
-                                             self.cfg.commands.curriculum)
-        if self.cfg.env.send_timeouts:
+        names, trimesh, curriculum, timeouts = self._extras_args
+        self.extras["episode"] = EpisodeInfo(self._extras_rows[self._step_index % len(self._extras_rows)], names, trimesh, curriculum)
+        if timeouts:
             self.extras["time_outs"] = self._time_outs_latched
 
     # ------------------------------------------------------------------ pieces, with the reference's names
@@ -803,28 +823,9 @@ class LeggedRobot(BaseTask):
         self._publish_extras()
 
     # ------------------------------------------------------------------ lower boundary: what the simulator is told
-    def _disturbance_windows(self, counter):
-        """t1:193-215: the push / external-force window predicates of the step whose `common_step_counter` (after
-        lr:471) is `counter` — a host-side integer schedule, the same arithmetic ti5_post_physics does on the device."""
-        p = self._params
-        push = force = False
-        if p.flags & C["TI5_F_PUSH_ROBOTS"]:
-            i = min(int(counter / p.push_update_step), p.n_push_dur - 1)
-            push = counter % p.push_interval <= p.push_duration[i]
-        if p.flags & C["TI5_F_ADD_EXT_FORCE"]:
-            i = min(int(counter / p.add_update_step), p.n_add_dur - 1)
-            force = counter % p.ext_force_interval <= p.add_duration[i]
-        return push, force
-
     def _notify_simulator_of_disturbances(self):
-        """t1:230 / t1:247, where `_post_physics_step_callback` issues them: the pushed base velocities (written into
-        `root_states` by ti5_post_physics) go back to the simulator as the whole root tensor; the external force /
-        torque on the base as (N, NB, 3) tensors in env space.  Stream-ordered behind the kernel, no host wait."""
-        push, force = self._disturbance_windows(self.common_step_counter + 1)
-        if push:
-            self.gym.set_actor_root_state_tensor(self.sim, self.root_states)
-        if force:
-            self.gym.apply_rigid_body_force_tensors(self.sim, self._apply_forces, self._apply_torques, 0)   # gymapi.ENV_SPACE
+        """Hook of the task class: hand the disturbances of `_post_physics_step_callback` to the simulator (the base
+        callback of the reference, lr:520-560 region, has none that touch the simulator in t1's configuration)."""
 
     def _notify_simulator_of_resets(self):
         """lr:1087-1090, 1117-1120, 915-939 for the envs ti5_reset_observe re-spawned: joint state, root state and the

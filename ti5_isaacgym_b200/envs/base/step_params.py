@@ -44,8 +44,8 @@ def build_params(cfg, sim_dt, robot, terrain=None, height_shape=(0, 0), div_mode
     for f in UNSUPPORTED_FLAGS:
         if getattr(dr, f, False):
             raise NotImplementedError(f"domain_rand.{f}=True is not exercised by t1_dh_stand (t1_cfg:290-312)")
-    if cm.heading_command or not cm.sw_switch or getattr(cfg.env, "use_ref_actions", False):
-        raise NotImplementedError("heading_command / sw_switch=False / use_ref_actions are disabled in t1_dh_stand")
+    if cm.heading_command or not cm.sw_switch:
+        raise NotImplementedError("heading_command / sw_switch=False are disabled in t1_dh_stand (t1_cfg:322-340)")
     p = _lib.Ti5Params()
     dt = cfg.control.decimation * sim_dt
     N = cfg.env.num_envs
