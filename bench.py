@@ -64,17 +64,23 @@ NCU_SUMMARY = os.path.join(ROOT, "profiles", "r02_ncu_full_summary_8192.json")
 
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel family, from the committed
-    `ncu --set full` capture of this same step (profiles/r02_ncu_full_summary_8192.json); None if absent."""
+    `ncu --set full` capture of this same step (profiles/r02_ncu_full_summary_8192.json, written by
+    tools/ncu_summary.py); None if absent."""
     if not os.path.exists(NCU_SUMMARY):
         return None
-    want = {"substep": "substep_kernel", "post_physics": "post_physics_kernel<0", "reset_observe": "reset_observe_kernel",
-            "fused_step": "post_physics_kernel<1", "heights": "heights_kernel"}[kernel]
+    want = {"substep": "substep_kernel", "post_physics": "post_physics_kernel", "reset_observe": "reset_observe_kernel",
+            "fused_step": "post_physics_kernel", "heights": "heights_kernel"}[kernel]
     table = json.load(open(NCU_SUMMARY))
-    rows = next((v for k, v in table.items() if want in k.replace("(bool)", "").replace("(int)", "")), None)
+    rows = next((v for k, v in table.items() if want in k), None)
     if not rows:
         return None
+    unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+    def to_bytes(s):
+        v, u = s.split()
+        return float(v) * unit[u]
     r = rows[len(rows) // 2]
-    return float(r["dram_bytes_read"]) + float(r["dram_bytes_write"])
+    return to_bytes(r["dram__bytes_read.sum"]) + to_bytes(r["dram__bytes_write.sum"])
 
 
 def peaks():

@@ -29,5 +29,13 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for i in range(int(os.environ.get("STEPS", 8))):
     flush.fill_(i)
     env.step(act)
+# the GAE kernels on a 24-step rollout of the same size (rs:97-119)
+from ti5_isaacgym_b200.algo.rollout_storage import gae_returns_
+rew, val = torch.randn(24, N, 1, device="cuda"), torch.randn(24, N, 1, device="cuda")
+done, last = (torch.rand(24, N, 1, device="cuda") < 0.02).byte(), torch.randn(N, 1, device="cuda")
+ret, adv = torch.empty_like(rew), torch.empty_like(rew)
+for i in range(2):
+    flush.fill_(i)
+    gae_returns_(rew, val, done, last, ret, adv, 0.994, 0.9)
 torch.cuda.synchronize()
 print("done", env.launches_per_step, "launches per step")
