@@ -210,6 +210,14 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// one 4-byte asynchronous copy global -> shared (LDGSTS): for rows the bulk engine cannot take (52-byte rows of an
+// AoS tensor are neither 16-byte aligned nor a multiple of 16 long); the issuing thread does not wait for the data
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
 // fallback for a partial tile (byte count not a multiple of 16): the CTA's threads copy word by word
 __device__ __forceinline__ void coop_load(void* dst, const void* src, uint32_t bytes) {
   const uint32_t words = bytes >> 2;

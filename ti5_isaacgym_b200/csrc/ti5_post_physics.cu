@@ -71,6 +71,8 @@ constexpr int POST_CHUNKS = 20;
 enum PostChunk { C_ROOT = 0, C_DOF, C_CONTACT, C_RIGID, C_ACT, C_LAST_ACT, C_LAST_LAST_ACT, C_LAST_DOF_VEL, C_TORQUES, C_REF,
                  C_LAST_ROOT_VEL, C_CMD, C_GAIT_START, C_AIR, C_FEET_H, C_LAST_Z, C_EP_LEN, C_PHASE_LEN, C_GAIT_TIME,
                  C_LAST_CONTACTS };
+constexpr int STAGED_BODIES = 4;     // contact tile rows: [termination, penalised, foot 0, foot 1]; rigid tile rows: [foot 0, foot 1, knee 0, knee 1]
+constexpr int CON_STRIDE = STAGED_BODIES * 3 + 1, RIG_STRIDE = STAGED_BODIES * RB + 1;   // floats per env in the tile: odd, conflict-free by env
 struct PostSrc {
   const void* ptr[POST_CHUNKS];
   int32_t rowb[POST_CHUNKS];          // bytes per env
@@ -83,8 +85,11 @@ static PostSrc make_post_src(const Ti5Params& p, const Ti5Buffers& b) {
                                   b.last_last_actions, b.last_dof_vel, b.torques, b.ref_dof_pos, b.last_root_vel, b.commands,
                                   b.gait_start, b.feet_air_time, b.feet_height, b.last_feet_z, b.episode_length_buf,
                                   b.phase_length_buf, b.gait_time, b.last_contacts};
-  const int rowb[POST_CHUNKS] = {RB * 4, 2 * D * 4, NB * 3 * 4, NB * RB * 4, D * 4, D * 4, D * 4, D * 4, D * 4, D * 4, 6 * 4, 4 * 4,
-                                 4, 2 * 4, 2 * 4, 2 * 4, 8, 8, p.num_gaits * 4, 2};
+  // C_CONTACT and C_RIGID are NOT copied whole: of the 13 bodies the phase reads the contact force of the termination /
+  // penalised body and the two feet, and the state of the two feet and the two knees — STAGED_BODIES rows each, gathered
+  // with 4-byte asynchronous copies (stage_body_rows)
+  const int rowb[POST_CHUNKS] = {RB * 4, 2 * D * 4, CON_STRIDE * 4, RIG_STRIDE * 4, D * 4, D * 4, D * 4, D * 4, D * 4, D * 4,
+                                 6 * 4, 4 * 4, 4, 2 * 4, 2 * 4, 2 * 4, 8, 8, p.num_gaits * 4, 2};
   int o = 0;
   for (int k = 0; k < POST_CHUNKS; ++k) { s.ptr[k] = ptr[k]; s.rowb[k] = rowb[k]; s.off[k] = o; o += rowb[k]; }
   s.off[POST_CHUNKS] = o;
@@ -101,6 +106,24 @@ struct PostTile {
 };
 
 constexpr int FOOT_PARTS = 9;        // FootPart entries handed from one foot role to the other (post_physics_kernel)
+// The rows of the AoS contact-force (N,13,3) and rigid-body (N,13,13) tensors the phase uses, into the tile: 4-byte
+// asynchronous copies (a 12- or 52-byte row at a 4-byte-aligned address is nothing the bulk engine takes), issued by
+// `nthreads` threads together with the bulk copies of the other arrays; 244 of 832 bytes per env are fetched.
+__device__ __forceinline__ void stage_body_rows(const Ti5Params& p, const Ti5Buffers& b, float* t_contact, float* t_rigid,
+                                                int e0, int n_tile, int t, int nthreads) {
+  constexpr int CW = STAGED_BODIES * 3, RW = STAGED_BODIES * RB;
+  for (int i = t; i < n_tile * CW; i += nthreads) {
+    const int en = i / CW, j = i - en * CW, r = j / 3, c = j - r * 3;
+    const int body = r == 0 ? p.term_body : r == 1 ? p.pen_body : p.feet[r - 2];
+    cp_async4(t_contact + en * CON_STRIDE + j, b.contact_forces + ((size_t)(e0 + en) * NB + body) * 3 + c);
+  }
+  for (int i = t; i < n_tile * RW; i += nthreads) {
+    const int en = i / RW, j = i - en * RW, r = j / RB, c = j - r * RB;
+    const int body = r < 2 ? p.feet[r] : p.knees[r - 2];
+    cp_async4(t_rigid + en * RIG_STRIDE + j, b.rigid_state + ((size_t)(e0 + en) * NB + body) * RB + c);
+  }
+}
+
 __host__ __device__ inline size_t post_tile_bytes(int tb, int per_env_bytes) {
   return (size_t)tb * per_env_bytes + 2 * (size_t)TI5_NUM_TERMS * tb * 4 + 16 + (size_t)FOOT_PARTS * tb * 4;
 }
@@ -360,7 +383,7 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       // (the (TERMS, N) episode-sum columns start 16-byte aligned only when N is a multiple of 4)
       const bool sums_by_tma = (N & 3) == 0;
       if (tid < POST_CHUNKS) {
-        if (tid != C_ACT && tid != C_TORQUES)
+        if (tid != C_ACT && tid != C_TORQUES && tid != C_CONTACT && tid != C_RIGID)
           tma_load_1d(T.base + (size_t)src.off[tid] * TB, static_cast<const char*>(src.ptr[tid]) + (size_t)e0 * src.rowb[tid],
                       (uint32_t)(TB * src.rowb[tid]), T.bar);
       } else if (sums_by_tma && tid >= 32 && tid < 32 + TI5_NUM_TERMS && (mask & (1u << (tid - 32)))) {
@@ -368,7 +391,8 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
         tma_load_1d(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(TB * 4), T.bar);
       }
       if (tid == 0)
-        mbar_expect_tx(T.bar, (uint32_t)TB * (uint32_t)(src.off[POST_CHUNKS] + (sums_by_tma ? 4 * __popc(mask) : 0)) - late_bytes);
+        mbar_expect_tx(T.bar, (uint32_t)TB * (uint32_t)(src.off[POST_CHUNKS] - src.rowb[C_CONTACT] - src.rowb[C_RIGID] +
+                                                        (sums_by_tma ? 4 * __popc(mask) : 0)) - late_bytes);
       if (!sums_by_tma) {
 #pragma unroll 1
         for (int t = 0; t < TI5_NUM_TERMS; ++t)
@@ -390,7 +414,7 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       if (!FUSED) chain_wait();
 #pragma unroll 1
       for (int k = 0; k < POST_CHUNKS; ++k)
-        if (!FUSED || (k != C_ACT && k != C_TORQUES))
+        if (k != C_CONTACT && k != C_RIGID && (!FUSED || (k != C_ACT && k != C_TORQUES)))
           coop_load_n(T.base + (size_t)src.off[k] * TB, static_cast<const char*>(src.ptr[k]) + (size_t)e0 * src.rowb[k],
                       (uint32_t)(n_tile * src.rowb[k]), tid, role_threads);
 #pragma unroll 1
@@ -398,6 +422,7 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
         if (mask & (1u << t))
           coop_load_n(T.sums + (size_t)t * TB, b.episode_sums + (size_t)t * N + e0, (uint32_t)(n_tile * 4), tid, role_threads);
     }
+    stage_body_rows(p, b, T.at<float>(C_CONTACT), T.at<float>(C_RIGID), e0, n_tile, tid, role_threads);
     // ---- while the tile is in flight: the step counters and the window predicates (uniform over the grid, t1:193-215)
     step = g->step_index + 1;                             // index of the step in progress
     counter = step + g->common_step_offset;               // common_step_counter after lr:471
@@ -415,6 +440,7 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
     // a preceding ti5_sample_heights (chained launch) must have completed before this grid does: ti5_reset_observe,
     // which reads the heights, only waits for THIS grid
     if (FUSED && (options & TI5_FUSED_CHAINED)) chain_wait();
+    cp_async_wait_all();                                  // this thread's share of the body rows has landed
     roles_sync();
     if (n_tile == TB) {
       mbar_wait(T.bar, 0);
@@ -487,9 +513,9 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       float root[RB];
 #pragma unroll
       for (int i = 0; i < RB; ++i) root[i] = t_root[le * RB + i];
-      const float* tf = t_contact + ((size_t)le * NB + p.term_body) * 3;
+      const float* tf = t_contact + le * CON_STRIDE + 0;
       const float term_force = sqrtf(tf[0] * tf[0] + tf[1] * tf[1] + tf[2] * tf[2]);
-      const float* pf = t_contact + ((size_t)le * NB + p.pen_body) * 3;
+      const float* pf = t_contact + le * CON_STRIDE + 3;
       const float pen_force = sqrtf(pf[0] * pf[0] + pf[1] * pf[1] + pf[2] * pf[2]);
       b.episode_length_buf[e] = ep_len;
       b.phase_length_buf[e] = phase_len;
@@ -677,10 +703,10 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       }
     } else if (role == R_JOINT_B) {
       // ================================ the joints: distances (actions and torques follow below) ======
-      const float* f0 = t_rigid + ((size_t)le * NB + p.feet[0]) * RB;
-      const float* f1 = t_rigid + ((size_t)le * NB + p.feet[1]) * RB;
-      const float* k0 = t_rigid + ((size_t)le * NB + p.knees[0]) * RB;
-      const float* k1 = t_rigid + ((size_t)le * NB + p.knees[1]) * RB;
+      const float* f0 = t_rigid + le * RIG_STRIDE + 0 * RB;
+      const float* f1 = t_rigid + le * RIG_STRIDE + 1 * RB;
+      const float* k0 = t_rigid + le * RIG_STRIDE + 2 * RB;
+      const float* k1 = t_rigid + le * RIG_STRIDE + 3 * RB;
       if (mask & (1u << T_FEET_DISTANCE))                   // t1:599-612
         put(T_FEET_DISTANCE, pair_distance_reward(f0[0], f0[1], f1[0], f1[1], p.foot_min_dist, p.foot_max_dist));
       if (mask & (1u << T_KNEE_DISTANCE))                   // t1:615-628
@@ -695,9 +721,9 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       stance[1] = sin_pos < 0.0f ? 1.0f : 0.0f;
       if (fabsf(sin_pos) < 0.1f) stance[0] = stance[1] = 1.0f;
       stand_foot = stand;
-      const float* cf = t_contact + ((size_t)le * NB + p.feet[f]) * 3;
+      const float* cf = t_contact + le * CON_STRIDE + (2 + f) * 3;
       const bool contact = cf[2] > 5.0f;
-      const float* rs = t_rigid + ((size_t)le * NB + p.feet[f]) * RB;
+      const float* rs = t_rigid + le * RIG_STRIDE + f * RB;
       const float fq[4] = {rs[3], rs[4], rs[5], rs[6]};
       float fe[3];
       euler_xyz(fq, fe);                                                       // lr:480-481
