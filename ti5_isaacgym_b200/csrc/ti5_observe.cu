@@ -271,7 +271,14 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
   __shared__ double s_trk[16];
   __shared__ double s_range[3][2];
   const ObsRng rng{p, r, (uint64_t)step, p.rng_mode == TI5_RNG_PHILOX};
-  const int Kp = K | 1, Pp = P | 1;                      // odd row strides: conflict-free staging
+  // staged frames: odd row strides (conflict-free).  With measured heights the privileged frame's 187 height entries are
+  // NOT staged per env: the tile's rows of `measured_heights` are one contiguous block and arrive by a single bulk copy
+  // into `s_h`, behind the frames of all the tile's envs
+  const int npts_h = (p.flags & TI5_F_MEASURE_HEIGHTS) ? p.num_height_points : 0, P0 = P - npts_h;
+  const int Kp = K | 1, Pp = P0 | 1;
+  float* s_h = smem + (size_t)TB * (Kp + Pp);            // [TB][npts_h] raw heights (16-byte aligned: Kp + Pp is even... see host)
+  __shared__ __align__(8) uint64_t s_hbar;
+  __shared__ float s_zref[128];                          // base height - 0.5 of the tile's envs (t1:466)
   float* s_obs = smem + (size_t)tile_warp * 32 * (Kp + Pp);
   float* s_priv = s_obs + 32 * Kp;
   // t1:471-472 observation noise: needs nothing from the other kernels of the step, so a chained launch draws it
@@ -296,7 +303,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
 #else
   const bool pre_draws = false;
 #endif
-  float* s_draw = smem + (size_t)TB * (Kp + Pp) + (size_t)(tile_warp * 32 + lane) * DRAW_STRIDE;   // this lane's env
+  float* s_draw = smem + (size_t)TB * (Kp + Pp + npts_h) + (size_t)(tile_warp * 32 + lane) * DRAW_STRIDE;   // this lane's env
   if (pre_draws && role >= OBS_ROLES && e < N && blockIdx.x < env_blocks) {
     const int half = role - OBS_ROLES;                   // role 2: DOFs 0-5, role 3: DOFs 6-11 and the schedule
 #pragma unroll 1
@@ -357,6 +364,16 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
     }
   }
   chain_wait();                                          // ti5_post_physics is done
+  // t1:466-468: this tile's rows of measured_heights (written by ti5_sample_heights, complete behind the wait): one bulk
+  // copy, in flight while the resets and the frames are worked on
+  const int h_env0 = blockIdx.x * TB, h_n = min(TB, N - h_env0);
+  const bool h_tile = do_obs && npts_h > 0 && blockIdx.x < env_blocks;
+  const bool h_bulk = h_tile && ((h_n * npts_h) & 3) == 0 && (((size_t)h_env0 * npts_h) & 3) == 0;
+  if (h_bulk && tid == 0) {
+    mbar_init(&s_hbar, 1);
+    mbar_expect_tx(&s_hbar, (uint32_t)(h_n * npts_h * 4));
+    tma_load_1d(s_h, b.measured_heights + (size_t)h_env0 * npts_h, (uint32_t)(h_n * npts_h * 4), &s_hbar);
+  }
   if (tid == 0 && atomicAdd(&g->tickets[0], step == INT64_MIN ? 2 : 1) == (int)gridDim.x - 1) {
     g->tickets[0] = 0;
     if (do_obs) g->step_index = step;                    // the step counts as completed: nobody in this grid reads it any more
@@ -644,25 +661,16 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
         po[67] = fric;
         po[68] = sdiv(mass, 30.0f, dm);
         po[71] = fz0 > 5.0f ? 1.0f : 0.0f; po[72] = fz1 > 5.0f ? 1.0f : 0.0f;
-        // (t1:466-468: the measured heights are staged below, by all lanes of the tile)
+        if (npts_h) s_zref[le] = root[2] - 0.5f;                               // t1:466-468: used by the ring writers
 #pragma unroll
         for (int i = 0; i < 6; ++i) b.last_root_vel[e * 6 + i] = root[7 + i];  // lr:499
       }
     }
   }
 
-  // t1:466-468 with measured heights: the 187 height entries of every privileged frame of the tile, by all of the tile's
-  // warps (lanes over scan points: coalesced reads of measured_heights, dozens of independent loads in flight per lane)
-  if (do_obs && (p.flags & TI5_F_MEASURE_HEIGHTS) && blockIdx.x < env_blocks) {
-    const int npts = p.num_height_points, nw = (int)(blockDim.x / TB), env0 = blockIdx.x * TB + tile_warp * 32;
-#pragma unroll 1
-    for (int en = role; en < 32 && env0 + en < N; en += nw) {
-      const float zref = b.root_states[(size_t)(env0 + en) * RB + 2] - 0.5f;      // the (re-spawned) base height
-      const float* mh = b.measured_heights + (size_t)(env0 + en) * npts;
-      float* po = s_priv + en * Pp + (P - npts);
-#pragma unroll 4
-      for (int k = lane; k < npts; k += 32) po[k] = clampf(zref - mh[k], -1.0f, 1.0f) * p.obs_height;
-    }
+  // partial last tile whose byte count the bulk engine does not take: the tile's threads copy the raw heights
+  if (h_tile && !h_bulk) {
+    for (int i = tid; i < h_n * npts_h; i += blockDim.x) s_h[i] = b.measured_heights[(size_t)h_env0 * npts_h + i];
   }
   probe(b.debug_ts, 1, 3);
   // ---- history rings: append this step's frames; clear the rows of re-spawned envs ------------
@@ -670,6 +678,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
   const int warp_env0 = blockIdx.x * TB + tile_warp * 32;
   const int hs = (int)fast_mod(step - 1, H), cs = (int)fast_mod(step - 1, CH);       // slot of this step's frame
   __syncthreads();       // both frames of every env of the CTA are staged
+  if (h_bulk) mbar_wait(&s_hbar, 0);                     // ... and the tile's raw heights have landed
   probe(b.debug_ts, 1, 7);
   if (do_obs && blockIdx.x < env_blocks && warp_env0 < N) {
     const int n_here = min(32, N - warp_env0);
@@ -694,14 +703,35 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
       dst[omir] = v;
       if (L > 0) ol[(uint32_t)en * (uint32_t)(L * K) + (uint32_t)k] = v;
     }
+    auto priv_entry = [&](int en, int k) {      // entry k of env en's privileged frame, clipped
+      float raw;
+      if (k < P0) raw = s_priv[en * Pp + k];
+      else raw = clampf(s_zref[tile_warp * 32 + en] - s_h[(tile_warp * 32 + en) * npts_h + (k - P0)], -1.0f, 1.0f) * p.obs_height;
+      return clampf(raw, -lim, lim);
+    };
+    if (PC > 0 && (PC & 3) == 0) {
+      // a frame width that is a multiple of four floats (260 with measured heights) makes every frame of the critic ring
+      // start 16-byte aligned (row 2*CH*P, slot P, mirror CH*P, log L*P floats): one 128-bit store per four entries
+      constexpr int P4 = PC > 0 ? PC / 4 : 1;
 #pragma unroll 1
-    for (int i = role * 32 + lane; i < n_priv; i += stride) {
-      const int en = i / P, k = i - en * P;
-      const float v = clampf(s_priv[en * Pp + k], -lim, lim);
-      float* dst = pb + (uint32_t)en * prow + (uint32_t)k;
-      dst[0] = v;
-      dst[pmir] = v;
-      if (L > 0) pl[(uint32_t)en * (uint32_t)(L * P) + (uint32_t)k] = v;
+      for (int i = role * 32 + lane; i < n_here * P4; i += stride) {
+        const int en = i / P4, k = (i - en * P4) * 4;
+        const float4 v = make_float4(priv_entry(en, k), priv_entry(en, k + 1), priv_entry(en, k + 2), priv_entry(en, k + 3));
+        float* dst = pb + (uint32_t)en * prow + (uint32_t)k;
+        *reinterpret_cast<float4*>(dst) = v;
+        *reinterpret_cast<float4*>(dst + pmir) = v;
+        if (L > 0) *reinterpret_cast<float4*>(pl + (uint32_t)en * (uint32_t)(L * P) + (uint32_t)k) = v;
+      }
+    } else {
+#pragma unroll 1
+      for (int i = role * 32 + lane; i < n_priv; i += stride) {
+        const int en = i / P, k = i - en * P;
+        const float v = priv_entry(en, k);
+        float* dst = pb + (uint32_t)en * prow + (uint32_t)k;
+        dst[0] = v;
+        dst[pmir] = v;
+        if (L > 0) pl[(uint32_t)en * (uint32_t)(L * P) + (uint32_t)k] = v;
+      }
     }
   }
   // frames of the env's window that no reset has cleared: 0 after reset_idx, +1 per appended frame
@@ -882,7 +912,11 @@ extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const 
 #else
   const int draw_floats = 0;
 #endif
-  const size_t smem = (size_t)p->env_block * ((p->num_single_obs | 1) + (p->priv_frame | 1) + draw_floats) * sizeof(float);
+  const int npts_h = (p->flags & TI5_F_MEASURE_HEIGHTS) ? p->num_height_points : 0;
+  TI5_CHECK_ARGS(npts_h == 0 || p->priv_frame - npts_h == 73);
+  // per env: 47 (+0: odd) observation floats, 73 privileged floats staged per env, the raw heights of the tile behind them
+  // ((47 | 1) + (73 | 1) = 120 floats = 480 bytes per env: the heights block starts 16-byte aligned)
+  const size_t smem = (size_t)p->env_block * ((p->num_single_obs | 1) + ((p->priv_frame - npts_h) | 1) + npts_h + draw_floats) * sizeof(float);
   const bool big = p->num_envs >= 32768;
   auto kernel = p->priv_frame == 73 ? (big ? reset_observe_kernel<47, 73, 2> : reset_observe_kernel<47, 73, 1>)
                 : p->priv_frame == 260 ? (big ? reset_observe_kernel<47, 260, 2> : reset_observe_kernel<47, 260, 1>)

@@ -17,8 +17,11 @@ env._bind_buffers(); env._drop_graphs()
 act = synthetic_actions(N, gen, 'cuda')
 flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 NOFLUSH = os.environ.get('NOFLUSH') == '1'
+CLEAN = os.environ.get('CLEANFLUSH') == '1'          # write the flush buffer, then read a second one: the L2 ends up full of CLEAN lines
+flush2 = torch.zeros(256 << 18, dtype=torch.int32, device='cuda') if CLEAN else None
 for i in range(20):
     if not NOFLUSH: flush.fill_(i)
+    if CLEAN: sink = flush2.sum()
     env.step(act)
 torch.cuda.synchronize()
 ts = env._debug_ts.cpu().double()
