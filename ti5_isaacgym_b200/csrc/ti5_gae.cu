@@ -23,19 +23,34 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
   if (n < N) {
     float adv = 0.0f;
     float nxt = last_values[n];
-    for (int t = T - 1; t >= 0; --t) {
-      const size_t i = (size_t)t * N + n;
-      const float v = values[i];
-      const float alive = 1.0f - (float)dones[i];
-      const float delta = (rewards[i] + (alive * gamma) * nxt) - v;
-      adv = delta + ((alive * gamma) * lam) * adv;
-      const float ret = adv + v;
-      returns[i] = ret;
-      const float a = ret - v;
-      advantages[i] = a;
-      sum += (double)a;
-      sq += (double)a * (double)a;
-      nxt = v;
+    // the scan is a dependent chain, its inputs are not: GC steps' worth of loads are issued before the chain consumes
+    // them (a rolled load-compute loop pays one memory round trip per step: 17.7 us for T = 24 at 8192 envs, ncu)
+    constexpr int GC = 8;
+    for (int t1 = T; t1 > 0; t1 -= GC) {
+      float rv[GC], vv[GC], dv[GC];
+#pragma unroll
+      for (int j = 0; j < GC; ++j) {
+        const int t = t1 - 1 - j;
+        const size_t i = (size_t)(t < 0 ? 0 : t) * N + n;
+        rv[j] = rewards[i]; vv[j] = values[i]; dv[j] = (float)dones[i];
+      }
+#pragma unroll
+      for (int j = 0; j < GC; ++j) {
+        const int t = t1 - 1 - j;
+        if (t < 0) break;
+        const size_t i = (size_t)t * N + n;
+        const float v = vv[j];
+        const float alive = 1.0f - dv[j];
+        const float delta = (rv[j] + (alive * gamma) * nxt) - v;
+        adv = delta + ((alive * gamma) * lam) * adv;
+        const float ret = adv + v;
+        returns[i] = ret;
+        const float a = ret - v;
+        advantages[i] = a;
+        sum += (double)a;
+        sq += (double)a * (double)a;
+        nxt = v;
+      }
     }
   }
 #pragma unroll
