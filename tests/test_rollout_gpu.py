@@ -247,9 +247,18 @@ def test_collector_runs_the_runner_loop_without_per_step_syncs():
         def compute_returns(self, last_critic_obs):
             self.storage.compute_returns(last_critic_obs[:, :1] * 0.5, self.gamma, 0.9)
 
+    # the stand-in answers to the signatures of the reference's DHPPO (recorded from the unmodified tree by
+    # oracle/pin_signatures.py; the GPU box has no reference)
+    import inspect
+    import json
+    import os
+    ref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_signatures.json")))
+    for meth in ("act", "compute_returns"):
+        assert list(inspect.signature(getattr(Alg, meth)).parameters) == ref[f"DHPPO.{meth}"], meth
     env.reset()
     alg = Alg()
     col = RolloutCollector(env, alg, T)
+    assert list(inspect.signature(alg.process_env_step).parameters) == ref["DHPPO.process_env_step"][1:]
     want_rb, want_lb = [], []
     cs, cl = torch.zeros(N), torch.zeros(N)
     for rollout in range(2):
