@@ -45,6 +45,17 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(out_path, extra_flags):
+    """An experimental / instrumented build next to the product library (e.g. `-DTI5_PROBES` for tools/probe.py);
+    load it with TI5_LIB=<out_path>."""
+    cmd = [_nvcc(), *[f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")], *extra_flags, "-shared", "-o", out_path] + \
+          [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return out_path
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
     print("built", LIB)

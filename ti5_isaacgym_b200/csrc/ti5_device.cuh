@@ -215,6 +215,10 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+// one 16-byte asynchronous copy global -> shared (both addresses 16-byte aligned), L2 only
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
@@ -256,6 +260,9 @@ __device__ __forceinline__ void chain_trigger() { asm volatile("griddepcontrol.l
 __device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // profiling aid: nanosecond timestamp probe `k` of this CTA (thread 0 only), when a probe buffer is bound
+// (compiled in with -DTI5_PROBES only — tools/probe.py builds its own library: ten predicated probe sites were 2.4 % of
+// the fused kernel's executed instructions)
+#ifdef TI5_PROBES
 __device__ __forceinline__ void probe(uint64_t* ts, int kernel, int k, int thread = 0) {
   if (ts != nullptr && (int)threadIdx.x == thread) {
     uint64_t t;
@@ -263,6 +270,9 @@ __device__ __forceinline__ void probe(uint64_t* ts, int kernel, int k, int threa
     ts[((size_t)kernel * 4096 + blockIdx.x) * 8 + k] = t;
   }
 }
+#else
+__device__ __forceinline__ void probe(uint64_t*, int, int, int = 0) {}
+#endif
 
 // 64-bit step counters divided by run-time divisors: a 64-bit division is a ~100-instruction subroutine with a long
 // dependent chain, and the kernels are bound by exactly that (one warp runs the whole program once).  Counters fit

@@ -124,8 +124,12 @@ __device__ __forceinline__ void stage_body_rows(const Ti5Params& p, const Ti5Buf
   }
 }
 
-__host__ __device__ inline size_t post_tile_bytes(int tb, int per_env_bytes) {
-  return (size_t)tb * per_env_bytes + 2 * (size_t)TI5_NUM_TERMS * tb * 4 + 16 + (size_t)FOOT_PARTS * tb * 4;
+// `fused_dec` > 0 (ti5_fused_step): behind the tile, per (substep, env, four DOFs) item one float4 of torque-multiplier
+// uniforms (drawn by the role threads while the tile is in flight) and one float4 for the lagged action row a substep
+// reads (fetched by 16-byte asynchronous copies before the substep loop starts)
+__host__ __device__ inline size_t post_tile_bytes(int tb, int per_env_bytes, int fused_dec = 0) {
+  return (size_t)tb * per_env_bytes + 2 * (size_t)TI5_NUM_TERMS * tb * 4 + 16 + (size_t)FOOT_PARTS * tb * 4 +
+         2 * (size_t)fused_dec * 3 * tb * 16;
 }
 
 // lr:393-434 when no simulator runs between the substeps, for one (env, group of four DOFs): the action clip, then
@@ -136,132 +140,196 @@ __host__ __device__ inline size_t post_tile_bytes(int tb, int per_env_bytes) {
 // a warp runs it once, so every instruction of an unrolled body would be a cold instruction-cache line.
 constexpr int WORKER_SPLIT = 2;      // threads per (env, four DOFs): the substeps are dealt out round-robin
 constexpr int WORKER_THREADS_PER_ENV = 3 * WORKER_SPLIT;
-__device__ __forceinline__ void substep_worker(const Ti5Params& p, const Ti5Buffers& b, const Ti5Rng& r,
-                                               const float* __restrict__ actions_in, int64_t step, int idx, int e, int gq,
-                                               int kh, float* tile_act, float* tile_tau) {
-  const int N = p.num_envs, d0 = 4 * gq, dec = p.decimation;
-  const bool rg = p.flags & TI5_F_RAND_GAINS, fric = p.flags & TI5_F_RAND_COULOMB, rt = p.flags & TI5_F_RAND_TORQUE;
-  const bool lagged = p.flags & TI5_F_ADD_LAG, philox = p.rng_mode == TI5_RNG_PHILOX;
-  auto ld4 = [&](const float* base_ptr) { return reinterpret_cast<const float4*>(base_ptr)[idx]; };
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  // ---- loads, all independent ----------------------------------------------------------------------
-  const float4* ds = reinterpret_cast<const float4*>(b.dof_state);
-  const float4 s0 = ds[2 * idx], s1 = ds[2 * idx + 1];
-  float4 a4 = ld4(actions_in);
-  const float4 off4 = ld4(b.motor_offsets);
-  float4 kp4 = zero4, kd4 = zero4, vis4 = zero4, cou4 = zero4;
-  int lag = 0;
-  int64_t stamp = 0;
-  if (lagged) { lag = b.lag_timestep[e * 3 + 0]; stamp = b.ring_stamp[e]; }
-  if (rg) { kp4 = ld4(b.p_gains_r); kd4 = ld4(b.d_gains_r); }
-  if (fric) { vis4 = ld4(b.viscous); cou4 = ld4(b.coulomb); }
-  const int64_t base = (step - 1) * dec;                   // pushes completed before this step
-  float4* ring = reinterpret_cast<float4*>(b.act_ring);
-  const size_t ring_row = (size_t)N * 3;
-  // ring slots: one remainder per ring, then increments
-  const int alen = p.lag_len, dlen = p.dof_lag_len;
-  int ws = (int)fast_mod(base + kh, alen);                 // slot the action of substep k is pushed to
-  int dsl = (int)fast_mod(base + kh, dlen);                // slot of the DOF-lag push after substep k
-  int rs = ws - lag % alen;                                // slot of the lagged row substep k looks at
-  if (rs < 0) rs += alen;
-  auto adv = [](int s, int len) {          // (s + WORKER_SPLIT) mod len without a division (len >= 1)
-    s += WORKER_SPLIT;
-    while (s >= len) s -= len;
-    return s;
-  };
-  // the lagged action row of a substep that looks back past the start of this step (lr:1045); rows pushed before the
-  // env's last reset read as zero (lr:606).  Loaded one turn ahead, while no ordering with this step's own pushes is
-  // needed: push k' of this step lands in the slot substep k reads only if k' - k + lag is a multiple of the ring
-  // length, and with 0 < lag < len that means k' = k + len - lag > k — a slot is overwritten only AFTER its last reader,
-  // in whatever order the earlier pushes (k' <= k, by this thread or its twin) and this load are performed.
-  auto load_old = [&](int k, int slot) {
-    const int64_t jj = base + k - lag;
-    float4 v = zero4;
-    if (lagged && lag > k && jj >= stamp && jj >= 0) v = ring[(size_t)slot * ring_row + idx];
-    return v;
-  };
-  // start fetching every old row this thread will read (evicted from the L2 since they were pushed): the loop below then
-  // finds them one short L2 hit apart instead of one DRAM round trip apart
-  if (lagged) {
-    int slot = rs;
+// named barriers (0 is __syncthreads)
+constexpr int BAR_TORQUES = 1;      // substep workers arrive, R_JOINT_B waits
+constexpr int BAR_ROLES = 2;        // the role threads among themselves while the workers run (FUSED)
+constexpr int BAR_FEET = 3;         // R_FOOT1 arrives, R_FOOT0 waits
+constexpr int BAR_DRAWS = 4;        // the role threads arrive (torque-multiplier uniforms staged), the substep workers wait (FUSED)
+__device__ __forceinline__ void bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// Two halves around the CTA's BAR_DRAWS barrier: setup() issues every load of the item (joint state, actuator arrays,
+// and — by 16-byte asynchronous copies into `s_old` — all lagged action rows this thread will read); run() is the
+// substep loop, which takes the torque-multiplier uniforms of (substep, item) from `s_u4`, where the role threads
+// staged them (same Philox counters / pool entries) while the tile was in flight.
+struct SubstepWorker {
+  float4 q4, qd4, as4, kp4, kd4, off4, vis4, cou4;
+  int lag, ws, dsl;
+
+  __device__ __forceinline__ void setup(const Ti5Params& p, const Ti5Buffers& b, const float* __restrict__ actions_in, int64_t step,
+                                        int idx, int e, int gq, int kh, float* tile_act, float4* s_old, int item, int items) {
+    const int N = p.num_envs, d0 = 4 * gq, dec = p.decimation;
+    const bool rg = p.flags & TI5_F_RAND_GAINS, fric = p.flags & TI5_F_RAND_COULOMB, lagged = p.flags & TI5_F_ADD_LAG;
+    auto ld4 = [&](const float* base_ptr) { return reinterpret_cast<const float4*>(base_ptr)[idx]; };
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // ---- loads, all independent ----------------------------------------------------------------------
+    const float4* ds = reinterpret_cast<const float4*>(b.dof_state);
+    const float4 s0 = ds[2 * idx], s1 = ds[2 * idx + 1];
+    float4 a4 = ld4(actions_in);
+    off4 = ld4(b.motor_offsets);
+    kp4 = kd4 = vis4 = cou4 = zero4;
+    lag = 0;
+    int64_t stamp = 0;
+    if (lagged) { lag = b.lag_timestep[e * 3 + 0]; stamp = b.ring_stamp[e]; }
+    if (rg) { kp4 = ld4(b.p_gains_r); kd4 = ld4(b.d_gains_r); }
+    else { kp4 = make_float4(p.p_gains[d0], p.p_gains[d0 + 1], p.p_gains[d0 + 2], p.p_gains[d0 + 3]);
+           kd4 = make_float4(p.d_gains[d0], p.d_gains[d0 + 1], p.d_gains[d0 + 2], p.d_gains[d0 + 3]); }
+    if (fric) { vis4 = ld4(b.viscous); cou4 = ld4(b.coulomb); }
+    const int64_t base = (step - 1) * dec;                   // pushes completed before this step
+    const float4* ring = reinterpret_cast<const float4*>(b.act_ring);
+    const size_t ring_row = (size_t)N * 3;
+    // ring slots: one remainder per ring, then increments
+    const int alen = p.lag_len, dlen = p.dof_lag_len;
+    ws = (int)fast_mod(base + kh, alen);                     // slot the action of substep k is pushed to
+    dsl = (int)fast_mod(base + kh, dlen);                    // slot of the DOF-lag push after substep k
+    // the lagged action row of a substep that looks back past the start of this step (lr:1045); rows pushed before the
+    // env's last reset read as zero (lr:606).  All of this thread's old rows (pushed up to three steps ago, evicted
+    // from the L2 since) are fetched up front; every copy of every worker of the CTA is complete before the barrier,
+    // i.e. before any push of this step, so no slot is overwritten in front of its reader.
+    if (lagged) {
+      int slot = ws - lag % alen;                            // slot of the lagged row substep kh looks at
+      if (slot < 0) slot += alen;
+      // row j = base + k - lag is live iff j >= max(stamp, 0), i.e. k >= kmin
+      const int64_t first_live = (stamp > 0 ? stamp : 0) - (base - lag);
+      const int kmin = first_live <= 0 ? 0 : (first_live >= dec ? dec : (int)first_live);
 #pragma unroll 1
-    for (int k = kh; k < dec && k < lag; k += WORKER_SPLIT) {
-      prefetch_l2(ring + (size_t)slot * ring_row + idx);
-      slot = adv(slot, alen);
-    }
-  }
-  float4 nxt = kh < dec ? load_old(kh, rs) : zero4;
-  a4 = make_float4(clampf(a4.x, -p.clip_actions, p.clip_actions), clampf(a4.y, -p.clip_actions, p.clip_actions),
-                   clampf(a4.z, -p.clip_actions, p.clip_actions), clampf(a4.w, -p.clip_actions, p.clip_actions));   // lr:393-394
-  if (kh == 0) {
-    reinterpret_cast<float4*>(b.actions)[idx] = a4;
-    *reinterpret_cast<float4*>(tile_act + d0) = a4;
-  }
-  const float q[4] = {s0.x, s0.z, s1.x, s1.z}, qd[4] = {s0.y, s0.w, s1.y, s1.w};
-  const float a[4] = {a4.x * p.action_scale, a4.y * p.action_scale, a4.z * p.action_scale, a4.w * p.action_scale};
-  const float4 as4 = make_float4(a[0], a[1], a[2], a[3]);
-  float kp[4] = {kp4.x, kp4.y, kp4.z, kp4.w}, kd[4] = {kd4.x, kd4.y, kd4.z, kd4.w};
-  if (!rg) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { kp[i] = p.p_gains[d0 + i]; kd[i] = p.d_gains[d0 + i]; }
-  }
-  const float off[4] = {off4.x, off4.y, off4.z, off4.w};
-  const float vis[4] = {vis4.x, vis4.y, vis4.z, vis4.w}, cou[4] = {cou4.x, cou4.y, cou4.z, cou4.w};
-  const float4 q4 = make_float4(q[0], q[1], q[2], q[3]), qd4 = make_float4(qd[0], qd[1], qd[2], qd[3]);
-  const bool from_ring = lagged && lag > 0;
-#pragma unroll 1
-  for (int k = kh; k < dec; k += WORKER_SPLIT) {
-    const float4 t4 = lag <= k ? as4 : nxt;                // a row this step pushed itself: from registers
-    const int rs_next = adv(rs, alen);
-    if (k + WORKER_SPLIT < dec) nxt = load_old(k + WORKER_SPLIT, rs_next);
-    // lr:1019-1074 torque of substep k
-    float4 u4 = zero4;
-    if (rt) u4 = philox ? philox_u4(p.seed, (uint64_t)step, S_TORQUE + k, idx)
-                        : reinterpret_cast<const float4*>(r.torque)[(size_t)k * ring_row + idx];
-    if (lagged) ring[(size_t)ws * ring_row + idx] = as4;
-    const float target[4] = {from_ring ? t4.x : a[0], from_ring ? t4.y : a[1], from_ring ? t4.z : a[2], from_ring ? t4.w : a[3]};
-    float tau[4], m[4] = {1.f, 1.f, 1.f, 1.f};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float err = ((target[i] + p.default_dof_pos[d0 + i]) - q[i]) + off[i];
-      tau[i] = kp[i] * err - kd[i] * qd[i];
-    }
-    if (fric) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        tau[i] = tau[i] - vis[i] * qd[i];
-        tau[i] = tau[i] - cou[i] * signf(qd[i]);
+      for (int k = kh; k < dec && k < lag; k += WORKER_SPLIT) {
+        float4* dst = s_old + k * items + item;
+        if (k >= kmin) cp_async16(dst, ring + (size_t)slot * ring_row + idx);
+        else *dst = zero4;
+        slot += WORKER_SPLIT;
+        while (slot >= alen) slot -= alen;
       }
     }
-    if (rt) {
-      const float u[4] = {u4.x, u4.y, u4.z, u4.w};
+    a4 = make_float4(clampf(a4.x, -p.clip_actions, p.clip_actions), clampf(a4.y, -p.clip_actions, p.clip_actions),
+                     clampf(a4.z, -p.clip_actions, p.clip_actions), clampf(a4.w, -p.clip_actions, p.clip_actions));   // lr:393-394
+    if (kh == 0) {
+      reinterpret_cast<float4*>(b.actions)[idx] = a4;
+      *reinterpret_cast<float4*>(tile_act + d0) = a4;
+    }
+    q4 = make_float4(s0.x, s0.z, s1.x, s1.z);
+    qd4 = make_float4(s0.y, s0.w, s1.y, s1.w);
+    as4 = make_float4(a4.x * p.action_scale, a4.y * p.action_scale, a4.z * p.action_scale, a4.w * p.action_scale);
+    cp_async_wait_all();                                     // this thread's old rows are in shared memory
+  }
+
+  __device__ __forceinline__ void run(const Ti5Params& p, const Ti5Buffers& b, const Ti5Rng& r, int64_t step, int idx, int e,
+                                      int gq, int kh, float* tile_tau, const float4* s_u4, const float4* s_old, int item,
+                                      int items) {
+    const int N = p.num_envs, d0 = 4 * gq, dec = p.decimation;
+    const bool fric = p.flags & TI5_F_RAND_COULOMB, rt = p.flags & TI5_F_RAND_TORQUE, lagged = p.flags & TI5_F_ADD_LAG;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* ring = reinterpret_cast<float4*>(b.act_ring);
+    const size_t ring_row = (size_t)N * 3;
+    const int alen = p.lag_len, dlen = p.dof_lag_len;
+    auto adv = [](int s, int len) {          // (s + WORKER_SPLIT) mod len without a division (len >= 1)
+      s += WORKER_SPLIT;
+      while (s >= len) s -= len;
+      return s;
+    };
+    const float q[4] = {q4.x, q4.y, q4.z, q4.w}, qd[4] = {qd4.x, qd4.y, qd4.z, qd4.w};
+    const float a[4] = {as4.x, as4.y, as4.z, as4.w};
+    const float kp[4] = {kp4.x, kp4.y, kp4.z, kp4.w}, kd[4] = {kd4.x, kd4.y, kd4.z, kd4.w};
+    const float off[4] = {off4.x, off4.y, off4.z, off4.w};
+    const float vis[4] = {vis4.x, vis4.y, vis4.z, vis4.w}, cou[4] = {cou4.x, cou4.y, cou4.z, cou4.w};
+    const bool from_ring = lagged && lag > 0;
+#pragma unroll 1
+    for (int k = kh; k < dec; k += WORKER_SPLIT) {
+      const float4 t4 = lag <= k ? as4 : s_old[k * items + item];      // a row this step pushed itself: from registers
+      // lr:1019-1074 torque of substep k
+      const float4 u4 = rt ? s_u4[k * items + item] : zero4;
+      if (lagged) ring[(size_t)ws * ring_row + idx] = as4;
+      const float target[4] = {from_ring ? t4.x : a[0], from_ring ? t4.y : a[1], from_ring ? t4.z : a[2], from_ring ? t4.w : a[3]};
+      float tau[4], m[4] = {1.f, 1.f, 1.f, 1.f};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        m[i] = affine(p.torque_multi_w, p.torque_multi_lo, u[i]);
-        tau[i] = tau[i] * m[i];
+        const float err = ((target[i] + p.default_dof_pos[d0 + i]) - q[i]) + off[i];
+        tau[i] = kp[i] * err - kd[i] * qd[i];
       }
+      if (fric) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          tau[i] = tau[i] - vis[i] * qd[i];
+          tau[i] = tau[i] - cou[i] * signf(qd[i]);
+        }
+      }
+      if (rt) {
+        const float u[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          m[i] = affine(p.torque_multi_w, p.torque_multi_lo, u[i]);
+          tau[i] = tau[i] * m[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float lim = p.torque_limits[d0 + i];
+        tau[i] = clampf(tau[i], -lim, lim);
+      }
+      const float4 tau4 = make_float4(tau[0], tau[1], tau[2], tau[3]);
+      if (b.torques_substeps) reinterpret_cast<float4*>(b.torques_substeps)[(size_t)k * ring_row + idx] = tau4;
+      if (k == dec - 1) {                                    // what the unfused sequence leaves behind (lr:401, 1072)
+        reinterpret_cast<float4*>(b.torques)[idx] = tau4;
+        if (rt) reinterpret_cast<float4*>(b.torque_multi)[idx] = make_float4(m[0], m[1], m[2], m[3]);
+        *reinterpret_cast<float4*>(tile_tau + d0) = tau4;
+      }
+      // lr:412-418 DOF-lag push after (what would be) simulator substep k
+      if (p.flags & TI5_F_ADD_DOF_LAG) {
+        float* row = b.dof_ring + ((size_t)dsl * N + e) * (2 * D);
+        *reinterpret_cast<float4*>(row + d0) = q4;
+        *reinterpret_cast<float4*>(row + D + d0) = qd4;
+      }
+      ws = adv(ws, alen);
+      dsl = adv(dsl, dlen);
+    }
+  }
+};
+
+// The torque-multiplier uniforms of all (substep, item) pairs of the CTA (lr:1065-1068; one float4 = the four DOFs of
+// an item), staged by `nthreads` role threads while the tile is in flight: NCH Philox chains per thread side by side
+// (a single chain is a ~500-cycle dependent sequence; in the substep loop it was the largest part of a worker's time).
+__device__ __forceinline__ void stage_torque_uniforms(const Ti5Params& p, const Ti5Rng& r, int64_t step, int e0, int items,
+                                                      float4* s_u4, int t, int nthreads) {
+  constexpr int NCH = 5;
+  const int total = p.decimation * items;
+  if (p.rng_mode != TI5_RNG_PHILOX) {
+    const size_t ring_row = (size_t)p.num_envs * 3;
+    for (int j = t; j < total; j += nthreads) {
+      const int k = j / items, item = j - k * items;
+      const size_t idx = (size_t)e0 * 3 + item;
+      s_u4[j] = idx < ring_row ? reinterpret_cast<const float4*>(r.torque)[(size_t)k * ring_row + idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
+  const uint32_t key0 = (uint32_t)p.seed, key1 = (uint32_t)(p.seed >> 32);
+#pragma unroll 1
+  for (int j0 = t; j0 < total; j0 += NCH * nthreads) {
+    uint32_t c0[NCH], c1[NCH], c2[NCH], c3[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int j = j0 + c * nthreads, k = j / items, item = j - k * items;
+      c0[c] = (uint32_t)(e0 * 3 + item); c1[c] = (uint32_t)(S_TORQUE + k); c2[c] = (uint32_t)step; c3[c] = (uint32_t)((uint64_t)step >> 32);
+    }
+    uint32_t k0 = key0, k1 = key1;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0[c]), lo0 = 0xD2511F53u * c0[c];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2[c]), lo1 = 0xCD9E8D57u * c2[c];
+        c0[c] = hi1 ^ c1[c] ^ k0;
+        c1[c] = lo1;
+        c2[c] = hi0 ^ c3[c] ^ k1;
+        c3[c] = lo0;
+      }
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float lim = p.torque_limits[d0 + i];
-      tau[i] = clampf(tau[i], -lim, lim);
+    for (int c = 0; c < NCH; ++c) {
+      const int j = j0 + c * nthreads;
+      if (j < total) s_u4[j] = make_float4(u01(c0[c]), u01(c1[c]), u01(c2[c]), u01(c3[c]));
     }
-    const float4 tau4 = make_float4(tau[0], tau[1], tau[2], tau[3]);
-    if (b.torques_substeps) reinterpret_cast<float4*>(b.torques_substeps)[(size_t)k * ring_row + idx] = tau4;
-    if (k == dec - 1) {                                    // what the unfused sequence leaves behind (lr:401, 1072)
-      reinterpret_cast<float4*>(b.torques)[idx] = tau4;
-      if (rt) reinterpret_cast<float4*>(b.torque_multi)[idx] = make_float4(m[0], m[1], m[2], m[3]);
-      *reinterpret_cast<float4*>(tile_tau + d0) = tau4;
-    }
-    // lr:412-418 DOF-lag push after (what would be) simulator substep k
-    if (p.flags & TI5_F_ADD_DOF_LAG) {
-      float* row = b.dof_ring + ((size_t)dsl * N + e) * (2 * D);
-      *reinterpret_cast<float4*>(row + d0) = q4;
-      *reinterpret_cast<float4*>(row + D + d0) = qd4;
-    }
-    ws = adv(ws, alen);
-    dsl = adv(dsl, dlen);
-    rs = rs_next;
   }
 }
 
@@ -286,12 +354,6 @@ __device__ __forceinline__ void substep_worker(const Ti5Params& p, const Ti5Buff
 // work; they meet R_JOINT_B on a named barrier in front of the two terms over this step's actions and torques.
 constexpr int POST_ROLES = 7;
 enum PostRole { R_BASE = 0, R_BASE_A, R_BASE_B, R_JOINT_A, R_JOINT_B, R_FOOT0, R_FOOT1 };
-// named barriers (0 is __syncthreads)
-constexpr int BAR_TORQUES = 1;      // substep workers arrive, R_JOINT_B waits
-constexpr int BAR_ROLES = 2;        // the role threads among themselves while the workers run (FUSED)
-constexpr int BAR_FEET = 3;         // R_FOOT1 arrives, R_FOOT0 waits
-__device__ __forceinline__ void bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
-__device__ __forceinline__ void bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 // t1:223-226 the base velocities a push sets: drawn by R_BASE (which applies them) and again, identically, by R_BASE_A
 // (whose base_acc term sees the pushed velocities)
@@ -345,16 +407,22 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
     else __syncthreads();
   };
 
+  // FUSED: [DEC][3 TB] torque-multiplier uniforms, then [DEC][3 TB] lagged action rows, behind the tile
+  float4* s_u4 = reinterpret_cast<float4*>(s_foot + FP_COUNT * TB);
+  float4* s_old = s_u4 + p.decimation * 3 * TB;
+  constexpr int WORKER_THREADS = FUSED ? WORKER_THREADS_PER_ENV * TB : 0;
   if (FUSED && !is_role) {
     // ======== substep workers: WORKER_SPLIT threads per (env, four DOFs), coalesced over the CTA's 3 x TB groups; the
     // split index is warp-uniform: the first 3 x TB workers take the substeps 0, WORKER_SPLIT, ..., the next 1, ... ========
     const int64_t step = g->step_index + 1;
     const int item0 = tid - role_threads, kh = item0 / (3 * TB), item = item0 - kh * 3 * TB;
     const int wl = item / 3, gq = item - wl * 3;
+    const bool active = e0 + wl < N;
     probe(b.debug_ts, 2, 0, role_threads);
-    if (e0 + wl < N)
-      substep_worker(p, b, r, actions_in, step, e0 * 3 + item, e0 + wl, gq, kh, T.at<float>(C_ACT) + wl * D,
-                     T.at<float>(C_TORQUES) + wl * D);
+    SubstepWorker w;
+    if (active) w.setup(p, b, actions_in, step, e0 * 3 + item, e0 + wl, gq, kh, T.at<float>(C_ACT) + wl * D, s_old, item, 3 * TB);
+    bar_sync(BAR_DRAWS, role_threads + WORKER_THREADS);    // the uniforms are staged; every worker's old rows are in
+    if (active) w.run(p, b, r, step, e0 * 3 + item, e0 + wl, gq, kh, T.at<float>(C_TORQUES) + wl * D, s_u4, s_old, item, 3 * TB);
     probe(b.debug_ts, 2, 1, role_threads);
     bar_arrive(BAR_TORQUES, WORKER_THREADS_PER_ENV * TB + TB);   // R_JOINT_B may read the two tile rows
   }
@@ -436,6 +504,11 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       int64_t i = fast_div(counter, p.add_update_step);
       if (i >= p.n_add_dur) i = p.n_add_dur - 1;
       force_window = (double)fast_mod(counter, p.ext_force_interval) <= p.add_duration[i];
+    }
+    if (FUSED) {
+      // the substep workers' torque-multiplier uniforms, while the tile is in flight
+      if (p.flags & TI5_F_RAND_TORQUE) stage_torque_uniforms(p, r, step, e0, 3 * TB, s_u4, tid, role_threads);
+      bar_arrive(BAR_DRAWS, role_threads + WORKER_THREADS);
     }
     // a preceding ti5_sample_heights (chained launch) must have completed before this grid does: ti5_reset_observe,
     // which reads the heights, only waits for THIS grid
@@ -943,7 +1016,7 @@ static int launch_post(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r,
   Ti5Rng rr = r ? *r : Ti5Rng{};
   const int blocks = (p->num_envs + p->env_block - 1) / p->env_block;
   const PostSrc src = make_post_src(*p, *b);
-  const size_t smem = post_tile_bytes(p->env_block, src.off[POST_CHUNKS]);
+  const size_t smem = post_tile_bytes(p->env_block, src.off[POST_CHUNKS], fused ? p->decimation : 0);
   auto kernel = fused ? (p->env_block == 32 ? post_physics_kernel<true, 32> : post_physics_kernel<true, 64>)
                       : (p->env_block == 32 ? post_physics_kernel<false, 32>
                                             : p->env_block == 64 ? post_physics_kernel<false, 64> : post_physics_kernel<false, 128>);

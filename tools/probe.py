@@ -1,6 +1,13 @@
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+# the probe sites are compiled in with -DTI5_PROBES only: an instrumented library next to the product one
+PROBE_LIB = os.path.join(ROOT, "tools", "exp", "libti5_probes.so")
+if not os.path.exists(PROBE_LIB) or os.environ.get("REBUILD_PROBES") == "1":
+    from ti5_isaacgym_b200.build import build_variant
+    os.makedirs(os.path.dirname(PROBE_LIB), exist_ok=True)
+    build_variant(PROBE_LIB, ["-DTI5_PROBES"])
+os.environ["TI5_LIB"] = PROBE_LIB
 import torch, sys
 from bench import make_cfg
 from ti5_isaacgym_b200.envs import T1DHStandEnv
