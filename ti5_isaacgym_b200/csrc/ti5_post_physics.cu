@@ -38,13 +38,12 @@ static __device__ __noinline__ float pair_distance_reward(float ax, float ay, fl
 // `sums` is the CTA's shared tile [term][tb] (post-physics) or null (read episode_sums from memory).
 static __device__ __noinline__ void reset_bookkeeping(const Ti5Params& p, const Ti5Buffers& b, bool reset, int e, int le,
                                                       const float* sums, int tb, int64_t step) {
-  __shared__ int s_warp[32];
   __shared__ float s_red[32][TI5_NUM_TERMS];
   const int N = p.num_envs, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   if (reset) b.reset_list[atomicAdd(&b.globals->n_listed[step & 1], 1)] = e;
-  const BlockRank br = block_rank(reset, s_warp);
-  if (tid == 0) b.block_counts[blockIdx.x] = br.total;
-  if (br.total == 0) return;
+  const int total = __syncthreads_count(reset);          // one barrier: only the count is needed here
+  if (tid == 0) b.block_counts[blockIdx.x] = total;
+  if (total == 0) return;
   // lanes over terms: lane t adds up term t of the warp's flagged envs (a handful), then the warps are folded
   const unsigned flagged = __ballot_sync(0xffffffffu, reset);
   float acc = 0.0f;
@@ -111,16 +110,31 @@ constexpr int FOOT_PARTS = 9;        // FootPart entries handed from one foot ro
 // `nthreads` threads together with the bulk copies of the other arrays; 244 of 832 bytes per env are fetched.
 __device__ __forceinline__ void stage_body_rows(const Ti5Params& p, const Ti5Buffers& b, float* t_contact, float* t_rigid,
                                                 int e0, int n_tile, int t, int nthreads) {
-  constexpr int CW = STAGED_BODIES * 3, RW = STAGED_BODIES * RB;
-  for (int i = t; i < n_tile * CW; i += nthreads) {
-    const int en = i / CW, j = i - en * CW, r = j / 3, c = j - r * 3;
-    const int body = r == 0 ? p.term_body : r == 1 ? p.pen_body : p.feet[r - 2];
-    cp_async4(t_contact + en * CON_STRIDE + j, b.contact_forces + ((size_t)(e0 + en) * NB + body) * 3 + c);
-  }
-  for (int i = t; i < n_tile * RW; i += nthreads) {
-    const int en = i / RW, j = i - en * RW, r = j / RB, c = j - r * RB;
-    const int body = r < 2 ? p.feet[r] : p.knees[r - 2];
-    cp_async4(t_rigid + en * RIG_STRIDE + j, b.rigid_state + ((size_t)(e0 + en) * NB + body) * RB + c);
+  // twelve work items per env — four 3-float contact rows, four 13-float rigid-body rows as halves of 7 + 6 floats — so
+  // that a thread forms one row address and then issues its copies at immediate offsets (the first form, one item per
+  // FLOAT with two divisions each, was 10 % of the kernel's executed instructions, in front of the tile wait)
+  constexpr int ITEMS = 3 * STAGED_BODIES;
+#pragma unroll 1
+  for (int it = t; it < n_tile * ITEMS; it += nthreads) {
+    const int en = it / ITEMS, r = it - en * ITEMS;
+    const float* src;
+    float* dst;
+    int n;
+    if (r < STAGED_BODIES) {
+      const int body = r == 0 ? p.term_body : r == 1 ? p.pen_body : p.feet[r - 2];
+      src = b.contact_forces + ((size_t)(e0 + en) * NB + body) * 3;
+      dst = t_contact + en * CON_STRIDE + r * 3;
+      n = 3;
+    } else {
+      const int rr = (r - STAGED_BODIES) >> 1, half = (r - STAGED_BODIES) & 1;
+      const int body = rr < 2 ? p.feet[rr] : p.knees[rr - 2];
+      src = b.rigid_state + ((size_t)(e0 + en) * NB + body) * RB + half * 7;
+      dst = t_rigid + en * RIG_STRIDE + rr * RB + half * 7;
+      n = half ? RB - 7 : 7;
+    }
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+      if (j < n) cp_async4(dst + j, src + j);
   }
 }
 
