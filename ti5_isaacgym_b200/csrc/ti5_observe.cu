@@ -906,7 +906,8 @@ extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const 
   TI5_CHECK_ARGS(p->rng_mode == TI5_RNG_PHILOX || (r && r->cmd && r->dofs && r->dr && r->gait_time && r->noise));
   Ti5Rng rr = r ? *r : Ti5Rng{};
   const int blocks = (p->num_envs + p->env_block - 1) / p->env_block;
-  const bool writers = p->env_block == 32;
+  static const int forced_writers = getenv("TI5_RO_WRITERS") ? atoi(getenv("TI5_RO_WRITERS")) : -1;
+  const bool writers = forced_writers >= 0 ? forced_writers != 0 : p->env_block == 32;
 #ifdef TI5_PRE_DRAWS
   const int draw_floats = writers ? DRAW_STRIDE : 0;
 #else

@@ -152,8 +152,9 @@ __host__ __device__ inline size_t post_tile_bytes(int tb, int per_env_bytes, int
 // substep's torques are stored (torques_substeps[k]), the last substep's also where the unfused kernels leave them.
 // The IMU-lag pushes, whose values equal the derived base state, are left to role 0.  The loop is rolled on purpose:
 // a warp runs it once, so every instruction of an unrolled body would be a cold instruction-cache line.
-constexpr int WORKER_SPLIT = 2;      // threads per (env, four DOFs): the substeps are dealt out round-robin
-constexpr int WORKER_THREADS_PER_ENV = 3 * WORKER_SPLIT;
+// WS = threads per (env, four DOFs): the substeps are dealt out round-robin.  2 on small grids (the kernel is bound by
+// the length of a thread's chain there), 1 on large ones (by the number of instructions: half as many worker set-ups,
+// and a CTA small enough for three per SM)
 // named barriers (0 is __syncthreads)
 constexpr int BAR_TORQUES = 1;      // substep workers arrive, R_JOINT_B waits
 constexpr int BAR_ROLES = 2;        // the role threads among themselves while the workers run (FUSED)
@@ -166,6 +167,7 @@ __device__ __forceinline__ void bar_sync(int id, int threads) { asm volatile("ba
 // and — by 16-byte asynchronous copies into `s_old` — all lagged action rows this thread will read); run() is the
 // substep loop, which takes the torque-multiplier uniforms of (substep, item) from `s_u4`, where the role threads
 // staged them (same Philox counters / pool entries) while the tile was in flight.
+template <int WORKER_SPLIT>
 struct SubstepWorker {
   float4 q4, qd4, as4, kp4, kd4, off4, vis4, cou4;
   int lag, ws, dsl;
@@ -364,7 +366,7 @@ __device__ __forceinline__ void stage_torque_uniforms(const Ti5Params& p, const 
 // (alphabetical) order while the other roles update the per-term episode sums, and all threads share the reset
 // bookkeeping.
 // FUSED: the kernel also carries the CTA's envs through the DEC substeps that precede the post-physics phase
-// (ti5_fused_step): 3 x WORKER_SPLIT x TB further threads, WORKER_SPLIT per (env, four DOFs), run them while the roles
+// (ti5_fused_step): 3 x WS x TB further threads, WS per (env, four DOFs), run them while the roles
 // work; they meet R_JOINT_B on a named barrier in front of the two terms over this step's actions and torques.
 constexpr int POST_ROLES = 7;
 enum PostRole { R_BASE = 0, R_BASE_A, R_BASE_B, R_JOINT_A, R_JOINT_B, R_FOOT0, R_FOOT1 };
@@ -389,8 +391,8 @@ static __device__ __noinline__ PushDraw push_draw(const Ti5Params& p, const Ti5R
 enum FootPart { FP_Z = 0, FP_AIR, FP_CLEAR, FP_FORCE, FP_NUMBER, FP_PITCH, FP_STUMBLE, FP_SLIP, FP_STILL, FP_COUNT };
 static_assert(FP_COUNT == FOOT_PARTS, "post_tile_bytes reserves FOOT_PARTS floats per env");
 
-template <bool FUSED, int MAXTB>
-__global__ void __launch_bounds__((POST_ROLES + (FUSED ? WORKER_THREADS_PER_ENV : 0)) * MAXTB, MAXTB == 32 ? 2 : 1)
+template <bool FUSED, int MAXTB, int WS = 2>
+__global__ void __launch_bounds__((POST_ROLES + (FUSED ? 3 * WS : 0)) * MAXTB, MAXTB == 32 ? (FUSED && WS == 1 ? 3 : 2) : 1)
 post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
                     const __grid_constant__ Ti5Rng r, const __grid_constant__ PostSrc src,
                     const float* __restrict__ actions_in, int options) {
@@ -424,16 +426,17 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
   // FUSED: [DEC][3 TB] torque-multiplier uniforms, then [DEC][3 TB] lagged action rows, behind the tile
   float4* s_u4 = reinterpret_cast<float4*>(s_foot + FP_COUNT * TB);
   float4* s_old = s_u4 + p.decimation * 3 * TB;
+  constexpr int WORKER_THREADS_PER_ENV = 3 * WS;
   constexpr int WORKER_THREADS = FUSED ? WORKER_THREADS_PER_ENV * TB : 0;
   if (FUSED && !is_role) {
-    // ======== substep workers: WORKER_SPLIT threads per (env, four DOFs), coalesced over the CTA's 3 x TB groups; the
-    // split index is warp-uniform: the first 3 x TB workers take the substeps 0, WORKER_SPLIT, ..., the next 1, ... ========
+    // ======== substep workers: WS threads per (env, four DOFs), coalesced over the CTA's 3 x TB groups; the
+    // split index is warp-uniform: the first 3 x TB workers take the substeps 0, WS, ..., the next 1, ... ========
     const int64_t step = g->step_index + 1;
     const int item0 = tid - role_threads, kh = item0 / (3 * TB), item = item0 - kh * 3 * TB;
     const int wl = item / 3, gq = item - wl * 3;
     const bool active = e0 + wl < N;
     probe(b.debug_ts, 2, 0, role_threads);
-    SubstepWorker w;
+    SubstepWorker<WS> w;
     if (active) w.setup(p, b, actions_in, step, e0 * 3 + item, e0 + wl, gq, kh, T.at<float>(C_ACT) + wl * D, s_old, item, 3 * TB);
     bar_sync(BAR_DRAWS, role_threads + WORKER_THREADS);    // the uniforms are staged; every worker's old rows are in
     if (active) w.run(p, b, r, step, e0 * 3 + item, e0 + wl, gq, kh, T.at<float>(C_TORQUES) + wl * D, s_u4, s_old, item, 3 * TB);
@@ -1031,7 +1034,11 @@ static int launch_post(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r,
   const int blocks = (p->num_envs + p->env_block - 1) / p->env_block;
   const PostSrc src = make_post_src(*p, *b);
   const size_t smem = post_tile_bytes(p->env_block, src.off[POST_CHUNKS], fused ? p->decimation : 0);
-  auto kernel = fused ? (p->env_block == 32 ? post_physics_kernel<true, 32> : post_physics_kernel<true, 64>)
+  // large grids: one worker thread per (env, four DOFs) (see WS); TI5_WORKER_SPLIT=1|2 overrides
+  static const int forced_ws = getenv("TI5_WORKER_SPLIT") ? atoi(getenv("TI5_WORKER_SPLIT")) : 0;
+  const int ws = !fused ? 2 : forced_ws ? forced_ws : (ti5_small_grid(p) ? 2 : 1);
+  auto kernel = fused ? (p->env_block == 32 ? (ws == 1 ? post_physics_kernel<true, 32, 1> : post_physics_kernel<true, 32, 2>)
+                                            : (ws == 1 ? post_physics_kernel<true, 64, 1> : post_physics_kernel<true, 64, 2>))
                       : (p->env_block == 32 ? post_physics_kernel<false, 32>
                                             : p->env_block == 64 ? post_physics_kernel<false, 64> : post_physics_kernel<false, 128>);
   if (!ti5_ensure_smem(kernel, smem)) {
@@ -1039,7 +1046,7 @@ static int launch_post(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r,
     return TI5_ECUDA;
   }
   ti5_set_carveout(kernel, ti5_small_grid(p));
-  const int threads = (POST_ROLES + (fused ? WORKER_THREADS_PER_ENV : 0)) * p->env_block;
+  const int threads = (POST_ROLES + (fused ? 3 * ws : 0)) * p->env_block;
   (void)ti5_launch(kernel, dim3(blocks), dim3(threads), smem, stream, (options & TI5_POST_CHAINED) != 0, *p, *b, rr, src,
                    actions_in, options);
   return ti5_check_launch(what);
