@@ -36,11 +36,13 @@ static __device__ __noinline__ float pair_distance_reward(float ax, float ay, fl
 // sums of their episode sums (t1:531-533).  Nothing here waits on another CTA: ti5_reset_observe, which runs
 // after this grid has completed, turns the per-CTA counts into offsets / totals itself.
 // `sums` is the CTA's shared tile [term][tb] (post-physics) or null (read episode_sums from memory).
+// `listed`: the caller has already put its flagged envs on the work list (post_physics_kernel does so the moment the
+// flag is known: the returning atomic is a ~1 us round trip, and the CTAs that hold a flagged env finish last).
 static __device__ __noinline__ void reset_bookkeeping(const Ti5Params& p, const Ti5Buffers& b, bool reset, int e, int le,
-                                                      const float* sums, int tb, int64_t step) {
+                                                      const float* sums, int tb, int64_t step, bool listed) {
   __shared__ float s_red[32][TI5_NUM_TERMS];
   const int N = p.num_envs, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  if (reset) b.reset_list[atomicAdd(&b.globals->n_listed[step & 1], 1)] = e;
+  if (reset && !listed) b.reset_list[atomicAdd(&b.globals->n_listed[step & 1], 1)] = e;
   const int total = __syncthreads_count(reset);          // one barrier: only the count is needed here
   if (tid == 0) b.block_counts[blockIdx.x] = total;
   if (total == 0) return;
@@ -688,6 +690,8 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       reset = (term_force > 1.0f) || time_out;
       b.time_out_buf[e] = time_out ? 1 : 0;
       b.reset_buf[e] = reset ? 1 : 0;
+      // the arrival-order work list for the history clear (ti5_reset_observe), here rather than in the epilogue
+      if (reset) b.reset_list[atomicAdd(&g->n_listed[step & 1], 1)] = e;
       if (mask & (1u << T_COLLISION)) put(T_COLLISION, 1.0f * (pen_force > 0.1f ? 1.0f : 0.0f));   // t1:870-875
     } else if (role == R_BASE_A) {
       // ================================ the base: acceleration, speed, orientation ====================
@@ -992,7 +996,7 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
     if (p.flags & TI5_F_ADD_EXT_FORCE) g->is_first_add_force[(step + 1) & 1] = force_window ? 0 : 1;
   }
   // (every thread of the CTA calls the bookkeeping; `step` is only used by the threads that hold a flag: role 0)
-  reset_bookkeeping(p, b, reset, e, le, T.sums, TB, step);
+  reset_bookkeeping(p, b, reset, e, le, T.sums, TB, step, true);
   probe(b.debug_ts, 0, 5);
 }
 
@@ -1006,7 +1010,7 @@ reset_bookkeeping_kernel(const __grid_constant__ Ti5Params p, const __grid_const
   // an explicit reset happens between steps: the scatter that follows works at the count of completed steps
   const int64_t step = b.globals->step_index;
   if (e == 0) b.globals->step_now = step;
-  reset_bookkeeping(p, b, reset, e, threadIdx.x, nullptr, 0, step);
+  reset_bookkeeping(p, b, reset, e, threadIdx.x, nullptr, 0, step, false);
 }
 
 }  // namespace ti5
