@@ -778,6 +778,23 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
       float* row = is_obs ? b.obs_ring + (size_t)en * obs_row : b.priv_ring + (size_t)en * priv_row;
       const int len = (int)(is_obs ? obs_row : priv_row), width = is_obs ? K : P;
       const int s0 = (is_obs ? hs : cs) * width, s1 = (is_obs ? hs + H : cs + CH) * width;
+      // a chunk clear of this step's two frame slots, in a row whose length is a multiple of four floats (every chunk
+      // then starts 16-byte aligned): four 128-bit read-modify-writes per lane, no per-element predicates
+      const int c0 = c * CHUNK, c1 = min(c0 + CHUNK, len);
+      const bool touches_frame = do_obs && ((c0 < s0 + width && c1 > s0) || (c0 < s1 + width && c1 > s1));
+      if ((len & 3) == 0 && !touches_frame) {
+        float4* r4 = reinterpret_cast<float4*>(row + c0);
+        const int n4 = (c1 - c0) >> 2;
+        constexpr int U4 = CHUNK / 4 / 32;
+        float4 q4[U4];
+#pragma unroll
+        for (int j = 0; j < U4; ++j)
+          if (j * 32 + lane < n4) q4[j] = r4[j * 32 + lane];
+#pragma unroll
+        for (int j = 0; j < U4; ++j)
+          if (j * 32 + lane < n4) r4[j * 32 + lane] = make_float4(q4[j].x * 0.0f, q4[j].y * 0.0f, q4[j].z * 0.0f, q4[j].w * 0.0f);
+        continue;
+      }
       float v[U];
       bool ok[U];
 #pragma unroll
