@@ -778,34 +778,26 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
       float* row = is_obs ? b.obs_ring + (size_t)en * obs_row : b.priv_ring + (size_t)en * priv_row;
       const int len = (int)(is_obs ? obs_row : priv_row), width = is_obs ? K : P;
       const int s0 = (is_obs ? hs : cs) * width, s1 = (is_obs ? hs + H : cs + CH) * width;
-      // a chunk clear of this step's two frame slots, in a row whose length is a multiple of four floats (every chunk
-      // then starts 16-byte aligned): four 128-bit read-modify-writes per lane, no per-element predicates
+      // `x *= 0` is stored as +0 without reading x back (the product of a finite x is +-0, equal to it in every
+      // comparison and in every sum the policy forms; the read-modify-write cost a DRAM round trip per chunk on the
+      // critical path of every CTA of a large grid: 7.4 us per CTA at 65536 envs).  A chunk clear of this step's two
+      // frame slots, in a row whose length is a multiple of four floats (every chunk then starts 16-byte aligned), is
+      // four 128-bit stores per lane; the chunks that hold the frame slots go element by element.
       const int c0 = c * CHUNK, c1 = min(c0 + CHUNK, len);
       const bool touches_frame = do_obs && ((c0 < s0 + width && c1 > s0) || (c0 < s1 + width && c1 > s1));
       if ((len & 3) == 0 && !touches_frame) {
         float4* r4 = reinterpret_cast<float4*>(row + c0);
         const int n4 = (c1 - c0) >> 2;
-        constexpr int U4 = CHUNK / 4 / 32;
-        float4 q4[U4];
 #pragma unroll
-        for (int j = 0; j < U4; ++j)
-          if (j * 32 + lane < n4) q4[j] = r4[j * 32 + lane];
-#pragma unroll
-        for (int j = 0; j < U4; ++j)
-          if (j * 32 + lane < n4) r4[j * 32 + lane] = make_float4(q4[j].x * 0.0f, q4[j].y * 0.0f, q4[j].z * 0.0f, q4[j].w * 0.0f);
+        for (int j = 0; j < CHUNK / 4 / 32; ++j)
+          if (j * 32 + lane < n4) r4[j * 32 + lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         continue;
       }
-      float v[U];
-      bool ok[U];
 #pragma unroll
       for (int j = 0; j < U; ++j) {
-        const int i = c * CHUNK + j * 32 + lane;
-        ok[j] = i < len && !(do_obs && ((i >= s0 && i < s0 + width) || (i >= s1 && i < s1 + width)));
-        if (ok[j]) v[j] = row[i];
+        const int i = c0 + j * 32 + lane;
+        if (i < len && !(do_obs && ((i >= s0 && i < s0 + width) || (i >= s1 && i < s1 + width)))) row[i] = 0.0f;
       }
-#pragma unroll
-      for (int j = 0; j < U; ++j)
-        if (ok[j]) row[c * CHUNK + j * 32 + lane] = v[j] * 0.0f;
     }
   }
   probe(b.debug_ts, 1, 5);

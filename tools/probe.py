@@ -56,3 +56,15 @@ for label, rows in (("env CTAs with a reset", (counts > 0).nonzero().flatten()),
         if len(col): print('  probe %d: median %7.2f  max %7.2f us' % (k, (col.median()-t0)/1e3, (col.max()-t0)/1e3))
 b1_end = ts[0][:, 5].max(); b2_start = ts[1][:, 0][ts[1][:, 0] > 0].min()
 print('gap B1 end -> B2 start: %.2f us' % ((b2_start - b1_end) / 1e3))
+# per-CTA stretches (probe k minus the same CTA's probe 0): meaningful on grids of several waves, where the absolute
+# times above mix the waves
+for kern, name in ((0, 'post_physics / fused_step'), (1, 'reset_observe')):
+    t = ts[kern]
+    t = t[t[:, 0] > 0]
+    if kern == 1: t = t[:nb]
+    print(name, 'per-CTA time since its probe 0 (env CTAs)')
+    for k in range(1, 8):
+        ok = t[:, k] > 0
+        if ok.any():
+            d = (t[ok, k] - t[ok, 0]) / 1e3
+            print('  probe %d: n=%4d  median %7.2f  p90 %7.2f  max %7.2f us' % (k, int(ok.sum()), d.median(), d.quantile(0.9), d.max()))
