@@ -432,6 +432,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
     s_range[tid >> 1][tid & 1] = g->cmd_range[step & 1][tid >> 1][tid & 1];
   }
   const bool any_reset = n_reset > 0;
+  probe(b.debug_ts, 2, 7);
 
   const bool flagged = live && do_reset && b.reset_buf[e] != 0;   // both roles see the flag
   const bool reset = flagged && role == 0;                          // ... role 0 accounts for it
@@ -540,6 +541,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
     }
     if (role == 0 && (p.flags & TI5_F_TRIMESH)) level_f = (float)b.terrain_levels[e];
 
+    probe(b.debug_ts, 2, 2);        // (builder probes: kernel row 2, slots 2-7; obs A = thread 0)
     // =========================== observations (t1:368-481) =================================
     if (do_obs) {
       float s = 0.0f, ci[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -585,6 +587,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
         store12(b.last_last_actions, e, last_act);
         store12(b.last_actions, e, act);
         store12(b.last_dof_vel, e, qd);
+        probe(b.debug_ts, 2, 3);
       }
       if (obsB) {
         // ---------------- obs B: lagged joint state; rows pushed before the env's last reset read as zero ------
@@ -606,6 +609,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
           put(5 + i, (lq[i] - p.default_dof_pos[i]) * p.obs_dof_pos);
           put(17 + i, lqd[i] * p.obs_dof_vel);
         }
+        probe(b.debug_ts, 2, 4, nparts >= 4 ? 2 * TB : 0);
       }
       if (privA) {
         // ---------------- priv A: command input, reference pose (t1:250-274), stance -------------------------
@@ -634,6 +638,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < D; ++i) po[41 + i] = q[i] - ref[i];
         po[69] = stance[0]; po[70] = stance[1];
+        probe(b.debug_ts, 2, 5, TB);
       }
       if (privB) {
         // ---------------- priv B: plain functions of the loaded state ---------------------------------------
@@ -664,6 +669,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
         if (npts_h) s_zref[le] = root[2] - 0.5f;                               // t1:466-468: used by the ring writers
 #pragma unroll
         for (int i = 0; i < 6; ++i) b.last_root_vel[e * 6 + i] = root[7 + i];  // lr:499
+        probe(b.debug_ts, 2, 6, nparts >= 4 ? 3 * TB : TB);
       }
     }
   }

@@ -68,3 +68,12 @@ for kern, name in ((0, 'post_physics / fused_step'), (1, 'reset_observe')):
         if ok.any():
             d = (t[ok, k] - t[ok, 0]) / 1e3
             print('  probe %d: n=%4d  median %7.2f  p90 %7.2f  max %7.2f us' % (k, int(ok.sum()), d.median(), d.quantile(0.9), d.max()))
+# builder probes of reset_observe (kernel row 2, slots 2-7), relative to the CTA's probe 0 (behind the grid wait)
+t2, t1 = ts[2][:nb], ts[1][:nb]
+names = {7: 'counts folded', 2: 'obs A: loads issued, second command pass done', 3: 'obs A done', 4: 'obs B done', 5: 'priv A done', 6: 'priv B done'}
+print('reset_observe builders, per-CTA time since probe 0')
+for k in (7, 2, 3, 4, 5, 6):
+    ok = (t2[:, k] > 0) & (t1[:, 0] > 0)
+    if ok.any():
+        d = (t2[ok, k] - t1[ok, 0]) / 1e3
+        print('  %-48s median %6.2f  p90 %6.2f  max %6.2f us' % (names[k], d.median(), d.quantile(0.9), d.max()))
