@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TI5_ABI_VERSION 6
+#define TI5_ABI_VERSION 7
 
 #define TI5_NUM_DOF 12      /* leg_l1..l6, leg_r1..r6 */
 #define TI5_NUM_BODIES 13   /* base_link + 12 leg links after collapse_fixed_joints */
@@ -66,7 +66,9 @@ enum {
   TI5_F_RAND_LAG_STEPS = 1 << 17,    /* randomize_lag_timesteps */
   TI5_F_RAND_DOF_LAG_STEPS = 1 << 18,
   TI5_F_RAND_IMU_LAG_STEPS = 1 << 19,
-  TI5_F_PLANE = 1 << 20              /* heights are identically zero on a plane (lr:1564) */
+  TI5_F_PLANE = 1 << 20,             /* heights are identically zero on a plane (lr:1564) */
+  TI5_F_HEADING_COMMAND = 1 << 21    /* commands.heading_command: the schedule draws a heading target (column 3), the yaw
+                                        rate (column 2) follows the heading error on every step (t1:141-176, 185-188) */
 };
 
 /* gait kinds of cfg.commands.gait (t1:138-177) */
@@ -135,6 +137,7 @@ typedef struct Ti5Params {
   float noise_level;
   float obs_lin_vel, obs_ang_vel, obs_dof_pos, obs_dof_vel, obs_quat, obs_height;
   float cmd_scale[3];
+  float heading_w, heading_lo;            /* command_ranges["heading"] as (hi - lo, lo) */
   float base_init_state[13];
   /* reward constants (t1_cfg:360-381) */
   float base_height_target, foot_min_dist, foot_max_dist, knee_min_dist, knee_max_dist;

@@ -86,6 +86,10 @@ SCENARIOS = {
                             edit=lambda c: (setattr(c.terrain, "measure_heights", True),
                                             setattr(c.env, "num_privileged_obs", 3 * (73 + 187)),
                                             setattr(c.domain_rand, "push_robots", True))),
+    # heading mode (t1:141-176, 185-188; off in t1_cfg): the gait schedule draws a heading target, the yaw-rate command is
+    # recomputed from the heading error for every env on every step
+    "plane_heading": dict(N=24, steps=30, mesh="plane", contact_rate=0.05, events=True,
+                          edit=lambda c: setattr(c.commands, "heading_command", True)),
     "big_plane": dict(N=512, steps=12, mesh="plane", contact_rate=0.03, events=True, golden=False),
     # the reward terms the task defines but t1_cfg leaves at zero scale (t1:894-896, 917-925, 937-940)
     "plane_extra_terms": dict(N=16, steps=12, mesh="plane", contact_rate=0.08, events=True,

@@ -54,6 +54,8 @@ _RAND_FLOAT_SITES = {
     ("_resample_walk_omnidirectional_command", 171): ("cmd", 0),
     ("_resample_walk_omnidirectional_command", 172): ("cmd", 1),
     ("_resample_walk_omnidirectional_command", 176): ("cmd", 2),
+    # heading mode (t1:165-174): the third draw of the gait slot is the heading target
+    ("_resample_rotate_command", 166): ("cmd", 2), ("_resample_walk_omnidirectional_command", 174): ("cmd", 2),
     ("generate_gait_time", 116): ("gait_time", None),
     ("_push_robots", 223): ("push", (0, 2)), ("_push_robots", 225): ("push", (2, 5)),
     ("_add_ext_force", 237): ("ext", (0, 1)), ("_add_ext_force", 238): ("ext", (1, 2)),

@@ -144,7 +144,9 @@ def make_consts(cfg, sim_dt, robot, device="cpu", terrain=None):
     for flag in ("randomize_lag_timesteps_perstep", "randomize_dof_lag_timesteps_perstep",
                  "randomize_imu_lag_timesteps_perstep", "add_dof_pos_vel_lag"):
         assert not getattr(dr, flag), "not exercised by t1_dh_stand (t1_cfg:290-312)"
-    assert not cfg.commands.heading_command and cfg.commands.sw_switch
+    assert cfg.commands.sw_switch
+    C.heading_command = bool(cfg.commands.heading_command)
+    C.forward_vec = torch.tensor([1., 0., 0.], **f32)                                         # lr:170
     C.custom_origins = cfg.terrain.mesh_type in ("heightfield", "trimesh")                   # lr:1481
     C.curriculum = cfg.terrain.curriculum and C.custom_origins                                 # lr:104-105
     if cfg.terrain.measure_heights:                                                            # lr:1535-1549
@@ -372,7 +374,26 @@ def resample_commands(C, S, u_cmd):
         assert kind in GAIT_KINDS
         S.commands[ids, 0] = draw("lin_vel_x", 0) if kind in ("walk_sagittal", "walk_omnidirectional") else zero
         S.commands[ids, 1] = draw("lin_vel_y", 1) if kind in ("walk_lateral", "walk_omnidirectional") else zero
-        S.commands[ids, 2] = draw("ang_vel_yaw", 2) if kind in ("rotate", "walk_omnidirectional") else zero
+        # t1:141-176: in heading mode the third draw is the heading target (column 3); the yaw rate (column 2) is then
+        # not touched here but recomputed from the heading error for every env, every step (t1:185-188)
+        if C.heading_command:
+            S.commands[ids, 3] = draw("heading", 2) if kind in ("rotate", "walk_omnidirectional") else zero
+        else:
+            S.commands[ids, 2] = draw("ang_vel_yaw", 2) if kind in ("rotate", "walk_omnidirectional") else zero
+
+
+def wrap_to_pi(angles):
+    """humanoid/utils/math.py:15-18 (in place on its argument, like the reference)."""
+    angles %= 2 * np.pi
+    angles -= 2 * np.pi * (angles > np.pi)
+    return angles
+
+
+def heading_to_yaw_rate(C, S):
+    """t1:185-188."""
+    forward = quat_apply(S.base_quat, C.forward_vec.expand(S.N, 3))
+    heading = torch.atan2(forward[:, 1], forward[:, 0])
+    S.commands[:, 2] = torch.clip(0.5 * wrap_to_pi(S.commands[:, 3] - heading), -1., 1.)
 
 
 def generate_gait_time(C, S, ids, u_gait):
@@ -824,6 +845,8 @@ def post_physics(C, S, sim, R, terrain=None, height_samples=None):
     S.feet_euler_xyz = euler_xyz(rs[:, C.feet, 3:7])
     S.phase_length_buf += 1                                                # t1:183-215
     resample_commands(C, S, R["cmd"][0])
+    if C.heading_command:
+        heading_to_yaw_rate(C, S)
     if cfg.terrain.measure_heights:
         S.measured_heights = sample_heights(C, S, sim, height_samples)
     if dr.push_robots:

@@ -39,11 +39,13 @@ def scenario_cfg(name, num_envs, frame_stack=66):
         cfg.domain_rand.push_robots = True
     if name == "plane_windows":
         cfg.domain_rand.push_robots = True
+    if name == "plane_heading":
+        cfg.commands.heading_command = True
     return cfg
 
 
 GOLDEN_SCENARIOS = ["plane_default", "plane_events", "trimesh_heights_push", "plane_extra_terms", "plane_windows",
-                    "trimesh_windows"]
+                    "trimesh_windows", "plane_heading"]
 
 
 def gym_calls_of(out):

@@ -113,6 +113,24 @@ __device__ __forceinline__ float euler_yaw(const float q[4]) {
   const float x = q[0], y = q[1], z = q[2], w = q[3];
   return wrap_angle(atan2f(2.0f * (w * z + x * y), ((w * w + x * x) - y * y) - z * z));
 }
+// t1:185-188 (heading mode): forward = quat_apply(base_quat, (1, 0, 0)) as isaacgym.torch_utils writes it
+// (t = 2 * cross(q.xyz, v); v + w * t + cross(q.xyz, t), every product formed: signed zeros come out as in torch),
+// heading = atan2(forward.y, forward.x), yaw rate = clip(0.5 * wrap_to_pi(target - heading), -1, 1) with
+// wrap_to_pi of humanoid/utils/math.py:15-18: torch's `%` (fmod, then + b when the signs differ), then
+// `-= float32(2 pi) * (angle > float32(pi))`.  Out of line: off in t1_cfg, never on the hot path's instruction stream.
+static __device__ __noinline__ float heading_yaw_rate(const float q[4], float target) {
+  const float x = q[0], y = q[1], z = q[2], w = q[3];
+  const float vx = 1.0f, vy = 0.0f, vz = 0.0f;
+  const float tx = (y * vz - z * vy) * 2.0f, ty = (z * vx - x * vz) * 2.0f, tz = (x * vy - y * vx) * 2.0f;
+  const float fx = (vx + w * tx) + (y * tz - z * ty);
+  const float fy = (vy + w * ty) + (z * tx - x * tz);
+  const float heading = atan2f(fy, fx);
+  float m = fmodf(target - heading, TWO_PI_F);
+  if (m != 0.0f && m < 0.0f) m += TWO_PI_F;
+  m -= TWO_PI_F * (m > PI_F ? 1.0f : 0.0f);
+  return clampf(0.5f * m, -1.0f, 1.0f);
+}
+
 // expf as a real call: ~25 call sites share one copy of the libdevice body (and its I-cache lines)
 static __device__ __noinline__ float expf_call(float x) { return expf(x); }
 

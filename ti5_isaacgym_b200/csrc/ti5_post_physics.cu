@@ -592,13 +592,16 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       const double (*cr)[2] = g->cmd_range[step & 1];    // ranges before this step's curriculum update (lr:537 runs later)
       cmd.x = mx ? affine((float)(cr[0][1] - cr[0][0]), (float)cr[0][0], u[0]) : 0.0f;
       cmd.y = my ? affine((float)(cr[1][1] - cr[1][0]), (float)cr[1][0], u[1]) : 0.0f;
-      cmd.z = mz ? affine((float)(cr[2][1] - cr[2][0]), (float)cr[2][0], u[2]) : 0.0f;
+      // heading mode (t1:141-176): the third draw is the heading target; the yaw rate follows below
+      if (p.flags & TI5_F_HEADING_COMMAND) cmd.w = mz ? affine(p.heading_w, p.heading_lo, u[2]) : 0.0f;
+      else cmd.z = mz ? affine((float)(cr[2][1] - cr[2][0]), (float)cr[2][0], u[2]) : 0.0f;
     }
+    const float bq[4] = {t_root[le * RB + 3], t_root[le * RB + 4], t_root[le * RB + 5], t_root[le * RB + 6]};
+    if (p.flags & TI5_F_HEADING_COMMAND) cmd.z = heading_yaw_rate(bq, cmd.w);       // t1:185-188, every env, every step
     const float cmd_norm = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y + cmd.z * cmd.z);
     const bool stand = cmd_norm <= p.stand_threshold;
     if (stand) phase_len = 0;                             // t1:86 side effect: standing envs restart the phase
     const float* qrow = t_dof + (size_t)le * 2 * D;                           // interleaved (q, qd)
-    const float bq[4] = {t_root[le * RB + 3], t_root[le * RB + 4], t_root[le * RB + 5], t_root[le * RB + 6]};
 
     if (role == R_BASE) {
       // ================================ the base: state ================================================

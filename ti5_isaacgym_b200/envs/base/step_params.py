@@ -44,8 +44,8 @@ def build_params(cfg, sim_dt, robot, terrain=None, height_shape=(0, 0), div_mode
     for f in UNSUPPORTED_FLAGS:
         if getattr(dr, f, False):
             raise NotImplementedError(f"domain_rand.{f}=True is not exercised by t1_dh_stand (t1_cfg:290-312)")
-    if cm.heading_command or not cm.sw_switch:
-        raise NotImplementedError("heading_command / sw_switch=False are disabled in t1_dh_stand (t1_cfg:322-340)")
+    if not cm.sw_switch:
+        raise NotImplementedError("sw_switch=False is disabled in t1_dh_stand (t1_cfg:322-340)")
     p = _lib.Ti5Params()
     dt = cfg.control.decimation * sim_dt
     N = cfg.env.num_envs
@@ -69,7 +69,8 @@ def build_params(cfg, sim_dt, robot, terrain=None, height_shape=(0, 0), div_mode
         "TI5_F_TERRAIN_CURRICULUM": curriculum, "TI5_F_COMMAND_CURRICULUM": cm.curriculum,
         "TI5_F_TRIMESH": cfg.terrain.mesh_type == "trimesh", "TI5_F_RAND_LAG_STEPS": dr.randomize_lag_timesteps,
         "TI5_F_RAND_DOF_LAG_STEPS": dr.randomize_dof_lag_timesteps,
-        "TI5_F_RAND_IMU_LAG_STEPS": dr.randomize_imu_lag_timesteps, "TI5_F_PLANE": cfg.terrain.mesh_type == "plane"}
+        "TI5_F_RAND_IMU_LAG_STEPS": dr.randomize_imu_lag_timesteps, "TI5_F_PLANE": cfg.terrain.mesh_type == "plane",
+        "TI5_F_HEADING_COMMAND": cm.heading_command}
     p.flags = sum(C[k] for k, on in flag_src.items() if on)
     if dr.randomize_joint_armature and not dr.randomize_joint_armature_each_joint:
         raise NotImplementedError("randomize_joint_armature without _each_joint is not used by t1_dh_stand")
@@ -109,6 +110,7 @@ def build_params(cfg, sim_dt, robot, terrain=None, height_shape=(0, 0), div_mode
     p.cycle_time, p.action_scale = rw.cycle_time, cfg.control.action_scale
     p.clip_actions, p.clip_obs = nz.clip_actions, nz.clip_observations
     p.stand_threshold = cm.stand_com_threshold
+    p.heading_w, p.heading_lo = cm.ranges.heading[1] - cm.ranges.heading[0], cm.ranges.heading[0]
     # robot (lr:216-234, 843-849)
     for i, name in enumerate(robot.dof_names):
         p.default_dof_pos[i] = cfg.init_state.default_joint_angles[name]
