@@ -46,6 +46,8 @@ def _build(name, N, device, seed=3, frame_stack=66, counter=2397):
     S.commands[:, :3] = -0.5 + r(N, 3)
     S.commands[S.episode_length_buf > S.gait_time[:, 1], :3] = 0
     S.commands[S.episode_length_buf > S.gait_time[:, 2], :3] = -0.5 + r(int((S.episode_length_buf > S.gait_time[:, 2]).sum()), 3)
+    if cfg.commands.heading_command:
+        S.commands[:, 3] = -3.0 + 6.0 * r(N)                      # heading targets of a schedule in progress
     S.env_frictions[:] = 0.2 + 1.1 * r(N, 1)
     S.body_mass[:] = 10 + 5 * r(N, 1)
     S.common_step_counter = counter                               # curriculum check + ext-force window at step 3
@@ -78,6 +80,9 @@ MASS = (1.0, 0.0, 0.04, 0.0, 1.0, 1.0)
     # window exit, and a command-curriculum change; in both rounding modes
     ("plane_windows", 1024, 30, "cuda", 66, None), ("plane_windows", 256, 30, "cpu", 66, None),
     ("trimesh_windows", 512, 26, "cuda", 66, None),
+    # heading mode (commands.heading_command, off in t1_cfg): heading target drawn by the schedule, yaw rate from the
+    # heading error on every step; in both rounding modes
+    ("plane_heading", 1024, 40, "cuda", 66, None), ("plane_heading", 256, 20, "cpu", 66, None),
     # BASELINE config 3 at its own size, and the plane step at the sizes where env_block, early mode, the carve-out and
     # the 128-register build switch
     ("trimesh_heights_push", 8192, 5, "cuda", 66, None),
@@ -158,7 +163,8 @@ def test_env_follows_oracle(name, N, steps, where, H, rates, fused=True):
         assert list(S.command_ranges["lin_vel_x"]) != range0, "the command curriculum must change the range"
 
 
-@pytest.mark.parametrize("name,N,steps", [("plane_events", 1024, 20), ("trimesh_windows", 200, 26), ("plane_events", 65536, 3)])
+@pytest.mark.parametrize("name,N,steps", [("plane_events", 1024, 20), ("trimesh_windows", 200, 26), ("plane_events", 65536, 3),
+                                          ("plane_heading", 512, 12)])
 def test_twelve_launch_sequence_follows_oracle(name, N, steps):
     """The unfused kernels of a step without a simulator (ti5_first_substep, ti5_substep, ti5_post_physics) against the
     oracle: the default path of the tests above is ti5_fused_step."""
