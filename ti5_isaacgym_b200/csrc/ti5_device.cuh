@@ -118,6 +118,11 @@ __device__ __forceinline__ float euler_yaw(const float q[4]) {
 // heading = atan2(forward.y, forward.x), yaw rate = clip(0.5 * wrap_to_pi(target - heading), -1, 1) with
 // wrap_to_pi of humanoid/utils/math.py:15-18: torch's `%` (fmod, then + b when the signs differ), then
 // `-= float32(2 pi) * (angle > float32(pi))`.  Out of line: off in t1_cfg, never on the hot path's instruction stream.
+#ifdef TI5_NO_HEADING                  // A/B builds only: what the (uniform, never taken in t1_cfg) heading branches cost
+#define TI5_HEADING(p) false
+#else
+#define TI5_HEADING(p) (((p).flags & TI5_F_HEADING_COMMAND) != 0)
+#endif
 static __device__ __noinline__ float heading_yaw_rate(const float q[4], float target) {
   const float x = q[0], y = q[1], z = q[2], w = q[3];
   const float vx = 1.0f, vy = 0.0f, vz = 0.0f;

@@ -534,7 +534,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
         cmd.y = my ? affine((float)(s_range[1][1] - s_range[1][0]), (float)s_range[1][0], cu[1]) : 0.0f;
         // heading mode: the heading target is re-drawn; the yaw rate keeps the value of this step's callback (t1:185-188
         // runs before the resets)
-        if (p.flags & TI5_F_HEADING_COMMAND) cmd.w = mz ? affine(p.heading_w, p.heading_lo, cu[2]) : 0.0f;
+        if (TI5_HEADING(p)) cmd.w = mz ? affine(p.heading_w, p.heading_lo, cu[2]) : 0.0f;
         else cmd.z = mz ? affine((float)(s_range[2][1] - s_range[2][0]), (float)s_range[2][0], cu[2]) : 0.0f;
       }
       if (obsA) {
