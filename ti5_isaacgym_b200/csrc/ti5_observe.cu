@@ -349,11 +349,15 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
       prefetch_l2(b.contact_forces + ((size_t)e * NB + p.feet[1]) * 3);
     }
   }
+  // (dealt over all warps of the tile: while ti5_fused_step fills the register file of an SM, this kernel's CTAs only
+  // become resident as its CTAs retire, and whatever stands in front of the wait is then on the critical path — twelve
+  // Philox calls on one warp were 1.5 us of it with a warm L2)
   const bool noisy = do_obs && (p.flags & TI5_F_ADD_NOISE);
-  if (noisy && live && role == 0) {
+  if (noisy && e < N && blockIdx.x < env_blocks) {
     float* oo = s_obs + lane * Kp;
-#pragma unroll 4
-    for (int g4 = 0; 4 * g4 < K; ++g4) {
+    const int nroles = (int)blockDim.x / TB;
+#pragma unroll 3
+    for (int g4 = role; 4 * g4 < K; g4 += nroles) {
       const float4 u = rng.noise4(e, g4, K);
       const float uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
