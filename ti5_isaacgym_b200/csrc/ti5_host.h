@@ -47,6 +47,7 @@ inline cudaError_t ti5_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#include <tuple>
 #define TI5_SMALL_GRID_ENVS 12288    /* measured: early mode + carve-out 58.8 vs 60.2 us at 12288 envs, 67.2 vs 66.5 at 16384 */
 inline bool ti5_small_grid(const Ti5Params* p) { return p->num_envs <= TI5_SMALL_GRID_ENVS; }
 
@@ -57,6 +58,7 @@ struct Ti5AttrCache {
   std::map<std::pair<int, const void*>, int> carveout;
   std::map<std::pair<int, const void*>, size_t> smem;
   std::map<int, int> sms;
+  std::map<std::tuple<int, const void*, int, size_t>, int> occupancy;
 };
 inline Ti5AttrCache& ti5_attr_cache() {
   static Ti5AttrCache c;
@@ -97,6 +99,22 @@ inline bool ti5_ensure_smem(K kernel, size_t bytes) {
   return true;
 }
 // SM count of the current device (148 on a B200)
+// resident CTAs per SM of `kernel` launched with `threads` threads and `smem` bytes of dynamic shared memory (cached)
+template <class K>
+inline int ti5_ctas_per_sm(K kernel, int threads, size_t smem) {
+  Ti5AttrCache& c = ti5_attr_cache();
+  const auto key = std::make_tuple(ti5_current_device(), reinterpret_cast<const void*>(kernel), threads, smem);
+  std::lock_guard<std::mutex> lock(c.mu);
+  auto it = c.occupancy.find(key);
+  if (it != c.occupancy.end()) return it->second;
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = 1;
+  }
+  c.occupancy[key] = n;
+  return n;
+}
 inline int ti5_sm_count() {
   Ti5AttrCache& c = ti5_attr_cache();
   const int dev = ti5_current_device();
