@@ -109,6 +109,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.sm, self.reasons, self.sm_max, self.stop_flag = index, [], set(), None, threading.Event()
+        self.interval = 0.005          # seconds between NVML samples (the wall-clock e2e region widens it, see cuda_arm)
         self.nvml = None
         try:
             import pynvml
@@ -145,7 +146,7 @@ class ClockSampler(threading.Thread):
                 self._sample_nvml() if self.nvml else self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.005 if self.nvml else 0.2)
+            self.stop_flag.wait(self.interval if self.nvml else 0.2)
 
     def summary(self):
         self.stop_flag.set()
@@ -398,15 +399,22 @@ def cuda_arm(args):
     if env._use_graph:
         h_act, h_out = env.enable_host_io()
         h_act.copy_(loop.actions.cpu())
-        for _ in range(3):
+        for _ in range(20):
             env.step_host()
+        # wall-clock region: at least 2000 steps (0.1 s) — K = 240 steps are 12 ms, at the mercy of one scheduler hiccup —
+        # and the clock sampler slowed to one NVML query per 50 ms (a query takes driver locks the launch path needs:
+        # at 5 ms the same loop measured 139-165 M env-steps/s from run to run, 166-168 M without)
+        e2e_steps = max(args.steps, 2000)
+        if sampler:
+            sampler.interval = 0.05
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(e2e_steps):
             loop.one(host=True)
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0, dev, world, dist)
-        e2e = {"value": world * N * args.steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h_act.numel() * 4 * world,
+        e2e = {"value": world * N * e2e_steps / e2e_s, "unit": "env-steps/s", "steps": e2e_steps,
+               "h2d_bytes_per_step": h_act.numel() * 4 * world,
                "d2h_bytes_per_step": h_out.numel() * world,
                "note": "env.step_host(): actions read from pinned host memory by the first kernel of the step, reward/reset/"
                        "time-out flags stored into pinned host memory by the last one (mapped pages, no copy-engine hop), "

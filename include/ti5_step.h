@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TI5_ABI_VERSION 7
+#define TI5_ABI_VERSION 8
 
 #define TI5_NUM_DOF 12      /* leg_l1..l6, leg_r1..r6 */
 #define TI5_NUM_BODIES 13   /* base_link + 12 leg links after collapse_fixed_joints */
@@ -67,8 +67,10 @@ enum {
   TI5_F_RAND_DOF_LAG_STEPS = 1 << 18,
   TI5_F_RAND_IMU_LAG_STEPS = 1 << 19,
   TI5_F_PLANE = 1 << 20,             /* heights are identically zero on a plane (lr:1564) */
-  TI5_F_HEADING_COMMAND = 1 << 21    /* commands.heading_command: the schedule draws a heading target (column 3), the yaw
+  TI5_F_HEADING_COMMAND = 1 << 21,   /* commands.heading_command: the schedule draws a heading target (column 3), the yaw
                                         rate (column 2) follows the heading error on every step (t1:141-176, 185-188) */
+  TI5_F_NO_SW_SWITCH = 1 << 22       /* commands.sw_switch == False: the gait phase follows episode_length_buf and standing
+                                        envs keep cycling (t1:89-90) */
 };
 
 /* gait kinds of cfg.commands.gait (t1:138-177) */

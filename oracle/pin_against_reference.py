@@ -90,6 +90,9 @@ SCENARIOS = {
     # recomputed from the heading error for every env on every step
     "plane_heading": dict(N=24, steps=30, mesh="plane", contact_rate=0.05, events=True,
                           edit=lambda c: setattr(c.commands, "heading_command", True)),
+    # commands.sw_switch = False (t1:89-90): the gait phase follows the episode counter, standing envs keep cycling
+    "plane_no_sw": dict(N=24, steps=20, mesh="plane", contact_rate=0.05, events=True,
+                        edit=lambda c: setattr(c.commands, "sw_switch", False)),
     "big_plane": dict(N=512, steps=12, mesh="plane", contact_rate=0.03, events=True, golden=False),
     # the reward terms the task defines but t1_cfg leaves at zero scale (t1:894-896, 917-925, 937-940)
     "plane_extra_terms": dict(N=16, steps=12, mesh="plane", contact_rate=0.08, events=True,

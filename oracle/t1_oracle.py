@@ -144,7 +144,6 @@ def make_consts(cfg, sim_dt, robot, device="cpu", terrain=None):
     for flag in ("randomize_lag_timesteps_perstep", "randomize_dof_lag_timesteps_perstep",
                  "randomize_imu_lag_timesteps_perstep", "add_dof_pos_vel_lag"):
         assert not getattr(dr, flag), "not exercised by t1_dh_stand (t1_cfg:290-312)"
-    assert cfg.commands.sw_switch
     C.heading_command = bool(cfg.commands.heading_command)
     C.forward_vec = torch.tensor([1., 0., 0.], **f32)                                         # lr:170
     C.custom_origins = cfg.terrain.mesh_type in ("heightfield", "trimesh")                   # lr:1481
@@ -325,6 +324,8 @@ def stand_command(C, S):
 
 def gait_phase(C, S):
     """t1:80-92.  Side effect kept: standing envs get `phase_length_buf = 0` (A4)."""
+    if not C.cfg.commands.sw_switch:                                           # t1:89-90
+        return (S.episode_length_buf * C.dt / C.cfg.rewards.cycle_time) % 1.0 + S.gait_start
     stand = stand_command(C, S)
     S.phase_length_buf[stand] = 0
     return ((S.phase_length_buf * C.dt / C.cfg.rewards.cycle_time) % 1.0 + S.gait_start) * (~stand)

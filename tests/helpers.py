@@ -41,11 +41,13 @@ def scenario_cfg(name, num_envs, frame_stack=66):
         cfg.domain_rand.push_robots = True
     if name == "plane_heading":
         cfg.commands.heading_command = True
+    if name == "plane_no_sw":
+        cfg.commands.sw_switch = False
     return cfg
 
 
 GOLDEN_SCENARIOS = ["plane_default", "plane_events", "trimesh_heights_push", "plane_extra_terms", "plane_windows",
-                    "trimesh_windows", "plane_heading"]
+                    "trimesh_windows", "plane_heading", "plane_no_sw"]
 
 
 def gym_calls_of(out):

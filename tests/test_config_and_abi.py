@@ -144,10 +144,6 @@ def test_unsupported_options_raise():
     from ti5_isaacgym_b200.envs.base.step_params import build_params
     from ti5_isaacgym_b200.envs.t1.t1_robot import robot_constants
     cfg = DHT1StandCfg()
-    cfg.commands.sw_switch = False
-    with pytest.raises(NotImplementedError):
-        build_params(cfg, 0.001, robot_constants(cfg))
-    cfg = DHT1StandCfg()
     cfg.domain_rand.randomize_lag_timesteps_perstep = True
     with pytest.raises(NotImplementedError):
         build_params(cfg, 0.001, robot_constants(cfg))
@@ -156,6 +152,9 @@ def test_unsupported_options_raise():
     p = build_params(cfg, 0.001, robot_constants(cfg))
     from ti5_isaacgym_b200._lib import CONSTS
     assert p.flags & CONSTS["TI5_F_HEADING_COMMAND"] and abs(p.heading_w - 6.28) < 1e-6 and abs(p.heading_lo + 3.14) < 1e-6
+    assert not p.flags & CONSTS["TI5_F_NO_SW_SWITCH"]
+    cfg.commands.sw_switch = False                      # t1:89-90
+    assert build_params(cfg, 0.001, robot_constants(cfg)).flags & CONSTS["TI5_F_NO_SW_SWITCH"]
     cfg = DHT1StandCfg()
     cfg.rewards.scales.dof_vel_limits = -1.0
     with pytest.raises(NotImplementedError):

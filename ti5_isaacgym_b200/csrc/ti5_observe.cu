@@ -554,9 +554,10 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
     if (do_obs) {
       float s = 0.0f, ci[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
       if (pA1 || pPA) {
-        const bool stand = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y + cmd.z * cmd.z) <= p.stand_threshold;
+        const bool no_sw = (p.flags & TI5_F_NO_SW_SWITCH) != 0;                 // t1:89-90: phase from the episode counter
+        const bool stand = !no_sw && sqrtf(cmd.x * cmd.x + cmd.y * cmd.y + cmd.z * cmd.z) <= p.stand_threshold;
         if (stand) phase_len = 0;                                               // t1:86 side effect
-        const float phase = (py_mod1(sdiv((float)phase_len * p.dt, p.cycle_time, dm)) + gait_start) * (stand ? 0.0f : 1.0f);
+        const float phase = (py_mod1(sdiv((float)(no_sw ? ep_len : phase_len) * p.dt, p.cycle_time, dm)) + gait_start) * (stand ? 0.0f : 1.0f);
         const float ang_ph = TWO_PI_F * phase;
         s = sinf(ang_ph);
         ci[0] = s; ci[1] = cosf(ang_ph);

@@ -393,10 +393,10 @@ static __device__ __noinline__ PushDraw push_draw(const Ti5Params& p, const Ti5R
 enum FootPart { FP_Z = 0, FP_AIR, FP_CLEAR, FP_FORCE, FP_NUMBER, FP_PITCH, FP_STUMBLE, FP_SLIP, FP_STILL, FP_COUNT };
 static_assert(FP_COUNT == FOOT_PARTS, "post_tile_bytes reserves FOOT_PARTS floats per env");
 
-// HEADING: commands.heading_command (t1:141-176, 185-188; off in t1_cfg) as a compile-time switch — as run-time branches
-// in the common prologue of the seven roles the option cost the t1 configuration 0.5 us per step (38.3 -> 38.8 us at
-// 8192 envs) without ever being taken.
-template <bool FUSED, int MAXTB, int WS = 2, bool HEADING = false>
+// RARE: the options t1_cfg leaves off — commands.heading_command (t1:141-176, 185-188) and commands.sw_switch = False
+// (t1:89-90) — behind a compile-time switch: as never-taken run-time branches in the common prologue of the seven roles
+// heading_command alone cost the t1 configuration 0.5 us per step (38.3 -> 38.8 us at 8192 envs).
+template <bool FUSED, int MAXTB, int WS = 2, bool RARE = false>
 __global__ void __launch_bounds__((POST_ROLES + (FUSED ? 3 * WS : 0)) * MAXTB, MAXTB == 32 ? (FUSED && WS == 1 ? 3 : 2) : 1)
 post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
                     const __grid_constant__ Ti5Rng r, const __grid_constant__ PostSrc src,
@@ -596,14 +596,15 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       cmd.x = mx ? affine((float)(cr[0][1] - cr[0][0]), (float)cr[0][0], u[0]) : 0.0f;
       cmd.y = my ? affine((float)(cr[1][1] - cr[1][0]), (float)cr[1][0], u[1]) : 0.0f;
       // heading mode (t1:141-176): the third draw is the heading target; the yaw rate follows below
-      if (HEADING) cmd.w = mz ? affine(p.heading_w, p.heading_lo, u[2]) : 0.0f;
+      if (RARE && (p.flags & TI5_F_HEADING_COMMAND)) cmd.w = mz ? affine(p.heading_w, p.heading_lo, u[2]) : 0.0f;
       else cmd.z = mz ? affine((float)(cr[2][1] - cr[2][0]), (float)cr[2][0], u[2]) : 0.0f;
     }
     const float bq[4] = {t_root[le * RB + 3], t_root[le * RB + 4], t_root[le * RB + 5], t_root[le * RB + 6]};
-    if (HEADING) cmd.z = heading_yaw_rate(bq, cmd.w);       // t1:185-188, every env, every step
+    if (RARE && (p.flags & TI5_F_HEADING_COMMAND)) cmd.z = heading_yaw_rate(bq, cmd.w);       // t1:185-188, every env, every step
     const float cmd_norm = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y + cmd.z * cmd.z);
     const bool stand = cmd_norm <= p.stand_threshold;
-    if (stand) phase_len = 0;                             // t1:86 side effect: standing envs restart the phase
+    const bool no_sw = RARE && (p.flags & TI5_F_NO_SW_SWITCH);                 // t1:89-90: phase from the episode counter
+    if (stand && !no_sw) phase_len = 0;                   // t1:86 side effect: standing envs restart the phase
     const float* qrow = t_dof + (size_t)le * 2 * D;                           // interleaved (q, qd)
 
     if (role == R_BASE) {
@@ -815,7 +816,8 @@ post_physics_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__
       // ================================ one foot (f = 0: R_FOOT0, f = 1: R_FOOT1) =====================
       const int f = role - R_FOOT0;
       // gait phase and stance mask (t1:80-107)
-      const float phase = (py_mod1(sdiv((float)phase_len * p.dt, p.cycle_time, dm)) + t_gait_start[le]) * (stand ? 0.0f : 1.0f);
+      const float phase = (py_mod1(sdiv((float)(no_sw ? ep_len : phase_len) * p.dt, p.cycle_time, dm)) + t_gait_start[le]) *
+                          (stand && !no_sw ? 0.0f : 1.0f);
       const float sin_pos = sinf(TWO_PI_F * phase);
       stance[0] = sin_pos >= 0.0f ? 1.0f : 0.0f;
       stance[1] = sin_pos < 0.0f ? 1.0f : 0.0f;
@@ -1046,13 +1048,13 @@ static int launch_post(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r,
   const size_t smem = post_tile_bytes(p->env_block, src.off[POST_CHUNKS], fused ? p->decimation : 0);
   // large grids: one worker thread per (env, four DOFs) (see WS); TI5_WORKER_SPLIT=1|2 overrides
   static const int forced_ws = getenv("TI5_WORKER_SPLIT") ? atoi(getenv("TI5_WORKER_SPLIT")) : 0;
-  const bool heading = (p->flags & TI5_F_HEADING_COMMAND) != 0;       // heading builds exist with two workers only
-  const int ws = !fused || heading ? 2 : forced_ws ? forced_ws : (ti5_small_grid(p) ? 2 : 1);
+  const bool rare = (p->flags & (TI5_F_HEADING_COMMAND | TI5_F_NO_SW_SWITCH)) != 0;     // RARE builds exist with two workers only
+  const int ws = !fused || rare ? 2 : forced_ws ? forced_ws : (ti5_small_grid(p) ? 2 : 1);
   auto kernel = fused ? (p->env_block == 32 ? (ws == 1 ? post_physics_kernel<true, 32, 1> : post_physics_kernel<true, 32, 2>)
                                             : (ws == 1 ? post_physics_kernel<true, 64, 1> : post_physics_kernel<true, 64, 2>))
                       : (p->env_block == 32 ? post_physics_kernel<false, 32>
                                             : p->env_block == 64 ? post_physics_kernel<false, 64> : post_physics_kernel<false, 128>);
-  if (heading)
+  if (rare)
     kernel = fused ? (p->env_block == 32 ? post_physics_kernel<true, 32, 2, true> : post_physics_kernel<true, 64, 2, true>)
                    : (p->env_block == 32 ? post_physics_kernel<false, 32, 2, true>
                                          : p->env_block == 64 ? post_physics_kernel<false, 64, 2, true> : post_physics_kernel<false, 128, 2, true>);

@@ -44,8 +44,6 @@ def build_params(cfg, sim_dt, robot, terrain=None, height_shape=(0, 0), div_mode
     for f in UNSUPPORTED_FLAGS:
         if getattr(dr, f, False):
             raise NotImplementedError(f"domain_rand.{f}=True is not exercised by t1_dh_stand (t1_cfg:290-312)")
-    if not cm.sw_switch:
-        raise NotImplementedError("sw_switch=False is disabled in t1_dh_stand (t1_cfg:322-340)")
     p = _lib.Ti5Params()
     dt = cfg.control.decimation * sim_dt
     N = cfg.env.num_envs
@@ -70,7 +68,7 @@ def build_params(cfg, sim_dt, robot, terrain=None, height_shape=(0, 0), div_mode
         "TI5_F_TRIMESH": cfg.terrain.mesh_type == "trimesh", "TI5_F_RAND_LAG_STEPS": dr.randomize_lag_timesteps,
         "TI5_F_RAND_DOF_LAG_STEPS": dr.randomize_dof_lag_timesteps,
         "TI5_F_RAND_IMU_LAG_STEPS": dr.randomize_imu_lag_timesteps, "TI5_F_PLANE": cfg.terrain.mesh_type == "plane",
-        "TI5_F_HEADING_COMMAND": cm.heading_command}
+        "TI5_F_HEADING_COMMAND": cm.heading_command, "TI5_F_NO_SW_SWITCH": not cm.sw_switch}
     p.flags = sum(C[k] for k, on in flag_src.items() if on)
     if dr.randomize_joint_armature and not dr.randomize_joint_armature_each_joint:
         raise NotImplementedError("randomize_joint_armature without _each_joint is not used by t1_dh_stand")

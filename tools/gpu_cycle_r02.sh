@@ -9,6 +9,9 @@ python bench.py --impl reference --steps 20 --warmup 5 2>/dev/null | tail -1 > $
 python bench.py --impl reference --config 3 --steps 20 --warmup 5 2>/dev/null | tail -1 > $o/${tag}_bench_reference_arm_config3.json
 python tools/probe.py 8192 > $o/${tag}_probes_8192.txt 2>&1
 NOFLUSH=1 python tools/probe.py 8192 > $o/${tag}_probes_8192_noflush.txt 2>&1
+python tools/probe.py 65536 > $o/${tag}_probes_65536.txt 2>&1
+python tools/e2e_probe.py 8192 2000 2>&1 | tail -3 > $o/${tag}_e2e_breakdown.txt
+python tools/sustained.py 8192 6 2>&1 | tail -4 > $o/${tag}_sustained_8192.txt
 # ncu: launch list of the bench command, then full captures of one step (never a bench number under ncu)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/${tag}_ncu_launches_8192.csv \
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-rollout --no-sweep > $o/ncu_launches.log 2>&1
