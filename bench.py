@@ -407,11 +407,14 @@ def cuda_arm(args):
         for _ in range(20):
             env.step_host()
         # wall-clock region: at least 2000 steps (0.1 s) — K = 240 steps are 12 ms, at the mercy of one scheduler hiccup —
-        # and the clock sampler slowed to one NVML query per 50 ms (a query takes driver locks the launch path needs:
-        # at 5 ms the same loop measured 139-165 M env-steps/s from run to run, 166-168 M without)
+        # with the clock sampler parked (one NVML query per second; the clocks were sampled every 5 ms through the
+        # device-timed regions above): a query takes driver locks the launch path needs, and with the sampler running the
+        # same loop measured anything between 139 and 168 M env-steps/s from run to run, against 166-168 M without it
+        # (tools/e2e_probe.py)
         e2e_steps = max(args.steps, 2000)
         if sampler:
-            sampler.interval = 0.05
+            sampler.interval = 1.0
+            time.sleep(0.02)          # let a query in flight finish
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):

@@ -13,10 +13,11 @@ from bench import make_cfg
 from ti5_isaacgym_b200.envs import T1DHStandEnv
 from ti5_isaacgym_b200.sim.synthetic import SimParams, fill_synthetic_state, synthetic_actions
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
-cfg = make_cfg(N)
+CONFIG3 = len(sys.argv) > 2 and sys.argv[2] == "config3"        # trimesh + measured heights + pushes + 5 % resets per step
+cfg = make_cfg(N, 3 if CONFIG3 else 2)
 env = T1DHStandEnv(cfg, SimParams(dt=cfg.sim.dt), 1, 'cuda:0', True, use_cuda_graph=True, materialize_obs=False)
 gen = torch.Generator(device='cuda').manual_seed(1)
-fill_synthetic_state(env.gym.tensors, env.env_origins, gen)
+fill_synthetic_state(env.gym.tensors, env.env_origins, gen, base_contact_rate=0.05 if CONFIG3 else 0.01)
 env.reset()
 env.episode_length_buf = torch.randint(1, 2000, (N,), generator=gen, device='cuda')
 env._debug_ts = torch.zeros(3, 4096, 8, dtype=torch.int64, device='cuda')
