@@ -395,6 +395,7 @@ def cuda_arm(args):
 
     # ---- per-launch duration of the kernel families (events on the launching stream) -------
     kt = kernel_times(env, loop.actions, steps=min(args.steps, 48))
+    bracket_ms = bracket_overhead_ms(dev)
 
     # ---- end to end through env.step_host() with pinned host buffers ------------------------------------
     # pinned, device-mapped host buffers wired into the step's CUDA graph (LeggedRobot.enable_host_io): every
@@ -485,6 +486,7 @@ def cuda_arm(args):
                          "traffic": ncu_traffic(dom) if N == ENVS_PER_GPU and args.config == 2 else None,
                          "peak_source": peak_src, "bytes_per_launch": bytes_per_launch,
                          "ms_per_launch": kt[dom]["ms_per_launch"],
+                         "empty_bracket_ms": bracket_ms,
                          "whole_step": {"bytes": step_bytes * N, "achieved": step_bytes * N * args.steps / (dev_ms * 1e-3) / 1e9,
                                         "frac": step_bytes * N * args.steps / (dev_ms * 1e-3) / 1e9 / peak,
                                         "survey_8d_bytes": BYTES_ENV_STEP * N,
@@ -493,7 +495,8 @@ def cuda_arm(args):
                          "how": "CUDA events on the launching stream around each kernel family of the step (L2 flushed before "
                                 "each step); per-launch = family time / launches in the family; algorithmic bytes = DESIGN.md "
                                 "section 4 per-env figure x envs.  At 8192 envs every kernel is latency-bound (13 us of HBM time "
-                                "per step): see `sweep` for the sizes where bandwidth is the bound"},
+                                "per step): see `sweep` for the sizes where bandwidth is the bound.  `empty_bracket_ms` = what the same event "
+                                "bracket reads around one empty kernel (launch / event latency inside every per-family time)"},
             "cpu_baseline": cpu,
             "reference_torch_gpu": torch_gpu,
             "rollout_storage": rollout,
@@ -610,6 +613,26 @@ def rollout_bench(env, gen, actions):
         "observation_storage_bytes": {"ours_frame_logs": kept,
                                       "reference": 4 * T * N * (env.num_obs + env.num_privileged_obs)},
     }
+
+
+def bracket_overhead_ms(dev, reps=48):
+    """What a CUDA-event bracket around ONE (almost) empty kernel reads, after the same L2 flush: the share of every
+    per-family time below that is launch / event latency, not kernel execution (calibration only: a torch fill of one
+    element, none of this library's kernels)."""
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    x = torch.zeros(1, device=dev)
+    ts = []
+    for i in range(reps + 4):
+        flush.fill_(i & 0xFF)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        x.fill_(1.0)
+        b.record()
+        if i >= 4:
+            ts.append((a, b))
+    torch.cuda.synchronize()
+    del flush
+    return statistics.mean(a.elapsed_time(b) for a, b in ts)
 
 
 def kernel_times(env, actions, steps):
