@@ -67,6 +67,26 @@ def snapshot_state(S, C):
     return out
 
 
+def _flags_off(c):
+    """Every optional branch of the path switched the other way from t1_cfg."""
+    dr = c.domain_rand
+    for f in ("add_lag", "add_dof_lag", "add_imu_lag", "randomize_gains", "randomize_coulomb_friction", "randomize_torque",
+              "randomize_motor_offset", "randomize_joint_armature", "add_ext_force"):
+        setattr(dr, f, False)
+    c.noise.add_noise = False
+    c.rewards.only_positive_rewards = False
+    c.commands.curriculum = False
+
+
+def _flags_mixed(c):
+    """Lags on but with fixed (maximal) indices, half of the actuator randomisation off, pushes on."""
+    dr = c.domain_rand
+    for f in ("randomize_lag_timesteps", "randomize_dof_lag_timesteps", "randomize_imu_lag_timesteps", "randomize_gains",
+              "randomize_torque", "randomize_joint_armature", "add_ext_force"):
+        setattr(dr, f, False)
+    dr.push_robots = True
+
+
 SCENARIOS = {
     # name: (num_envs, steps, mesh_type, cfg edits, base-contact rate, forced events)
     "plane_default": dict(N=16, steps=28, mesh="plane"),
@@ -93,6 +113,10 @@ SCENARIOS = {
     # commands.sw_switch = False (t1:89-90): the gait phase follows the episode counter, standing envs keep cycling
     "plane_no_sw": dict(N=24, steps=20, mesh="plane", contact_rate=0.05, events=True,
                         edit=lambda c: setattr(c.commands, "sw_switch", False)),
+    # the optional branches of the path the other way round (no lags / actuator randomisation / noise / external force, raw
+    # reward sum, fixed command ranges), and a mix (lags with fixed maximal indices, part of the randomisation off)
+    "plane_flags_off": dict(N=24, steps=20, mesh="plane", contact_rate=0.05, events=True, edit=_flags_off),
+    "plane_flags_mixed": dict(N=24, steps=20, mesh="plane", contact_rate=0.05, events=True, edit=_flags_mixed),
     "big_plane": dict(N=512, steps=12, mesh="plane", contact_rate=0.03, events=True, golden=False),
     # the reward terms the task defines but t1_cfg leaves at zero scale (t1:894-896, 917-925, 937-940)
     "plane_extra_terms": dict(N=16, steps=12, mesh="plane", contact_rate=0.08, events=True,
@@ -173,7 +197,7 @@ def run_scenario(name, spec, write_dir=None, verbose=True):
             if not same(a, b):
                 bad.append(key)
         for key in STATE_KEYS:
-            if not same(getattr(S, key), getattr(env, key)):
+            if hasattr(env, key) and not same(getattr(S, key), getattr(env, key)):
                 bad.append(key)
         if not same(S.last_feet_z, env.last_feet_z):
             bad.append("last_feet_z")

@@ -183,7 +183,8 @@ def adopt_reference_state(S, env):
             "dof_lag_timestep imu_lag_timestep episode_length_buf phase_length_buf rew_buf reset_buf "
             "time_out_buf").split()
     for name in same:
-        setattr(S, name, getattr(env, name).clone())
+        if hasattr(env, name):          # the reference allocates some buffers only when their option is on (lr:251-349)
+            setattr(S, name, getattr(env, name).clone())
     S.last_feet_z = env.last_feet_z if isinstance(env.last_feet_z, int) else env.last_feet_z.clone()
     S.contact_filt = getattr(env, "contact_filt", S.contact_filt).clone()
     S.common_step_counter = env.common_step_counter

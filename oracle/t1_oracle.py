@@ -735,16 +735,17 @@ def reset_envs(C, S, sim, ids, R, terrain=None):
         for j in range(D):
             S.joint_armatures[ids, j] = _affine(*getattr(dr, f"joint_{j + 1}_armature_range"), u[:, 6, j:j + 1]).reshape(-1)
     # lr:604-633 lag buffers and indices
+    # (without randomize_*_lag_timesteps the index is the range maximum, and the reference keeps it as a float tensor)
     li = R["lag_idx"][ids]
     if dr.add_lag:
         S.lag_buffer[ids, :, :] = 0.0
-        S.lag_timestep[ids] = li[:, 0]
+        S.lag_timestep[ids] = li[:, 0] if dr.randomize_lag_timesteps else dr.lag_timesteps_range[1]
     if dr.add_dof_lag:
         S.dof_lag_buffer[ids, :, :] = 0.0
-        S.dof_lag_timestep[ids] = li[:, 1]
+        S.dof_lag_timestep[ids] = li[:, 1] if dr.randomize_dof_lag_timesteps else dr.dof_lag_timesteps_range[1]
     if dr.add_imu_lag:
         S.imu_lag_buffer[ids, :, :] = 0.0
-        S.imu_lag_timestep[ids] = li[:, 2]
+        S.imu_lag_timestep[ids] = li[:, 2] if dr.randomize_imu_lag_timesteps else dr.imu_lag_timesteps_range[1]
     # t1:513-523
     for name in ("last_last_actions", "actions", "last_actions", "last_dof_vel", "last_root_vel", "feet_air_time"):
         getattr(S, name)[ids] = 0.

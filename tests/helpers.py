@@ -43,11 +43,24 @@ def scenario_cfg(name, num_envs, frame_stack=66):
         cfg.commands.heading_command = True
     if name == "plane_no_sw":
         cfg.commands.sw_switch = False
+    dr = cfg.domain_rand
+    if name == "plane_flags_off":         # like oracle/pin_against_reference.py _flags_off
+        for f in ("add_lag", "add_dof_lag", "add_imu_lag", "randomize_gains", "randomize_coulomb_friction", "randomize_torque",
+                  "randomize_motor_offset", "randomize_joint_armature", "add_ext_force"):
+            setattr(dr, f, False)
+        cfg.noise.add_noise = False
+        cfg.rewards.only_positive_rewards = False
+        cfg.commands.curriculum = False
+    if name == "plane_flags_mixed":       # _flags_mixed
+        for f in ("randomize_lag_timesteps", "randomize_dof_lag_timesteps", "randomize_imu_lag_timesteps", "randomize_gains",
+                  "randomize_torque", "randomize_joint_armature", "add_ext_force"):
+            setattr(dr, f, False)
+        dr.push_robots = True
     return cfg
 
 
 GOLDEN_SCENARIOS = ["plane_default", "plane_events", "trimesh_heights_push", "plane_extra_terms", "plane_windows",
-                    "trimesh_windows", "plane_heading", "plane_no_sw"]
+                    "trimesh_windows", "plane_heading", "plane_no_sw", "plane_flags_off", "plane_flags_mixed"]
 
 
 def gym_calls_of(out):

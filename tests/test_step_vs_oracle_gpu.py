@@ -84,6 +84,9 @@ MASS = (1.0, 0.0, 0.04, 0.0, 1.0, 1.0)
     # heading error on every step; in both rounding modes
     ("plane_heading", 1024, 40, "cuda", 66, None), ("plane_heading", 256, 20, "cpu", 66, None),
     ("plane_no_sw", 1024, 20, "cuda", 66, None),      # commands.sw_switch = False: phase from the episode counter
+    # the optional branches the other way round from t1_cfg (no lags / randomisation / noise / force; fixed lag indices)
+    ("plane_flags_off", 1024, 20, "cuda", 66, None), ("plane_flags_mixed", 1024, 20, "cuda", 66, None),
+    ("plane_flags_off", 200, 12, "cpu", 66, MASS),
     # BASELINE config 3 at its own size, and the plane step at the sizes where env_block, early mode, the carve-out and
     # the 128-register build switch
     ("trimesh_heights_push", 8192, 5, "cuda", 66, None),
@@ -165,7 +168,8 @@ def test_env_follows_oracle(name, N, steps, where, H, rates, fused=True):
 
 
 @pytest.mark.parametrize("name,N,steps", [("plane_events", 1024, 20), ("trimesh_windows", 200, 26), ("plane_events", 65536, 3),
-                                          ("plane_heading", 512, 12), ("plane_no_sw", 512, 12)])
+                                          ("plane_heading", 512, 12), ("plane_no_sw", 512, 12),
+                                          ("plane_flags_off", 512, 12), ("plane_flags_mixed", 512, 12)])
 def test_twelve_launch_sequence_follows_oracle(name, N, steps):
     """The unfused kernels of a step without a simulator (ti5_first_substep, ti5_substep, ti5_post_physics) against the
     oracle: the default path of the tests above is ti5_fused_step."""
