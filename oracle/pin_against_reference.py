@@ -117,6 +117,16 @@ SCENARIOS = {
     # reward sum, fixed command ranges), and a mix (lags with fixed maximal indices, part of the randomisation off)
     "plane_flags_off": dict(N=24, steps=20, mesh="plane", contact_rate=0.05, events=True, edit=_flags_off),
     "plane_flags_mixed": dict(N=24, steps=20, mesh="plane", contact_rate=0.05, events=True, edit=_flags_mixed),
+    # terrain variants: measured heights on a plane (identically zero, lr:1564), trimesh without heights, trimesh with
+    # heights but without the terrain curriculum
+    "plane_heights": dict(N=16, steps=12, mesh="plane", contact_rate=0.05, events=True,
+                          edit=lambda c: (setattr(c.terrain, "measure_heights", True),
+                                          setattr(c.env, "num_privileged_obs", 3 * (73 + 187)))),
+    "trimesh_plain": dict(N=16, steps=12, mesh="trimesh", contact_rate=0.05, events=True),
+    "trimesh_no_curriculum": dict(N=16, steps=12, mesh="trimesh", contact_rate=0.05, events=True,
+                                  edit=lambda c: (setattr(c.terrain, "measure_heights", True),
+                                                  setattr(c.env, "num_privileged_obs", 3 * (73 + 187)),
+                                                  setattr(c.terrain, "curriculum", False))),
     "big_plane": dict(N=512, steps=12, mesh="plane", contact_rate=0.03, events=True, golden=False),
     # the reward terms the task defines but t1_cfg leaves at zero scale (t1:894-896, 917-925, 937-940)
     "plane_extra_terms": dict(N=16, steps=12, mesh="plane", contact_rate=0.08, events=True,

@@ -37,6 +37,11 @@ def scenario_cfg(name, num_envs, frame_stack=66):
         cfg.terrain.measure_heights = True
         cfg.env.num_privileged_obs = 3 * (73 + 187)
         cfg.domain_rand.push_robots = True
+    if name in ("plane_heights", "trimesh_no_curriculum"):
+        cfg.terrain.measure_heights = True
+        cfg.env.num_privileged_obs = 3 * (73 + 187)
+    if name == "trimesh_no_curriculum":
+        cfg.terrain.curriculum = False
     if name == "plane_windows":
         cfg.domain_rand.push_robots = True
     if name == "plane_heading":
@@ -60,7 +65,8 @@ def scenario_cfg(name, num_envs, frame_stack=66):
 
 
 GOLDEN_SCENARIOS = ["plane_default", "plane_events", "trimesh_heights_push", "plane_extra_terms", "plane_windows",
-                    "trimesh_windows", "plane_heading", "plane_no_sw", "plane_flags_off", "plane_flags_mixed"]
+                    "trimesh_windows", "plane_heading", "plane_no_sw", "plane_flags_off", "plane_flags_mixed",
+                    "plane_heights", "trimesh_plain", "trimesh_no_curriculum"]
 
 
 def gym_calls_of(out):
