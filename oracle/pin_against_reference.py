@@ -27,7 +27,7 @@ from ti5_isaacgym_b200.sim.synthetic import fill_synthetic_state, synthetic_acti
 
 STATE_KEYS = ("torques actions last_actions last_last_actions last_dof_vel last_root_vel commands feet_air_time "
               "feet_height last_contacts contact_filt base_quat base_lin_vel base_ang_vel projected_gravity "
-              "base_euler_xyz feet_euler_xyz ext_forces ext_torques rand_push_force rand_push_torque ref_dof_pos "
+              "base_euler_xyz feet_euler_xyz ext_forces ext_torques rand_push_force rand_push_torque ref_dof_pos ref_action "
               "gait_time gait_start torque_multi motor_offsets randomized_p_gains randomized_d_gains "
               "randomized_joint_coulomb randomized_joint_viscous joint_armatures lag_buffer dof_lag_buffer "
               "imu_lag_buffer lag_timestep dof_lag_timestep imu_lag_timestep episode_length_buf phase_length_buf "
@@ -127,6 +127,13 @@ SCENARIOS = {
                                   edit=lambda c: (setattr(c.terrain, "measure_heights", True),
                                                   setattr(c.env, "num_privileged_obs", 3 * (73 + 187)),
                                                   setattr(c.terrain, "curriculum", False))),
+    # env.use_ref_actions (t1:360-366): the policy output is an offset on the gait's reference action
+    # (switched on after reset(): the reference's own reset() steps once before `ref_action` exists and raises with it)
+    "plane_ref_actions": dict(N=16, steps=14, mesh="plane", contact_rate=0.05, events=True,
+                              after_reset=lambda c: setattr(c.env, "use_ref_actions", True)),
+    # a shorter observation history (BASELINE config 5: frame_stack sweep)
+    "plane_h15": dict(N=16, steps=20, mesh="plane", contact_rate=0.05, events=True,
+                      edit=lambda c: (setattr(c.env, "frame_stack", 15), setattr(c.env, "num_observations", 15 * 47))),
     "big_plane": dict(N=512, steps=12, mesh="plane", contact_rate=0.03, events=True, golden=False),
     # the reward terms the task defines but t1_cfg leaves at zero scale (t1:894-896, 917-925, 937-940)
     "plane_extra_terms": dict(N=16, steps=12, mesh="plane", contact_rate=0.08, events=True,
@@ -163,6 +170,8 @@ def run_scenario(name, spec, write_dir=None, verbose=True):
         env.common_step_counter = spec.get("counter", 2397)   # command-curriculum check at step 3, ext-force window
     if spec.get("track_sums"):        # tracking reward above 80 % of its maximum: the curriculum widens lin_vel_x
         env.episode_sums["tracking_lin_vel"][:] = 0.9 * env.reward_scales["tracking_lin_vel"] * float(env.max_episode_length)
+    if spec.get("after_reset"):
+        spec["after_reset"](env.cfg)
     env.gym.log_calls = True
     S = adopt_reference_state(O.new_state(C, N), env)
     state0 = snapshot_state(S, C)
@@ -178,7 +187,7 @@ def run_scenario(name, spec, write_dir=None, verbose=True):
         pools = O.draw_pools(C, N, gen)
         # oracle on a private copy of the simulator tensors
         osim = SimpleNamespace(**{k: v.clone() for k, v in sim0.items()})
-        o_obs, o_priv, o_rew, o_reset, o_extras = O.step(C, S, osim, actions, pools, terrain=terrain, height_samples=heights)
+        o_obs, o_priv, o_rew, o_reset, o_extras = O.step(C, S, osim, actions.clone(), pools, terrain=terrain, height_samples=heights)
         env.gym.calls.clear()
         ranges_before = {k: list(v) for k, v in env.command_ranges.items()}
         r_obs, r_priv, r_rew, r_reset, r_extras = drv.step(actions, pools)

@@ -177,7 +177,7 @@ def adopt_reference_state(S, env):
     same = ("torques actions last_actions last_last_actions last_dof_vel last_root_vel commands "
             "feet_air_time feet_height last_contacts base_quat base_lin_vel base_ang_vel "
             "projected_gravity base_euler_xyz feet_euler_xyz rand_push_force rand_push_torque "
-            "ext_forces ext_torques ref_dof_pos gait_time gait_start env_frictions body_mass env_origins "
+            "ext_forces ext_torques ref_dof_pos ref_action gait_time gait_start env_frictions body_mass env_origins "
             "torque_multi motor_offsets randomized_p_gains randomized_d_gains randomized_joint_coulomb "
             "randomized_joint_viscous joint_armatures lag_buffer dof_lag_buffer imu_lag_buffer lag_timestep "
             "dof_lag_timestep imu_lag_timestep episode_length_buf phase_length_buf rew_buf reset_buf "

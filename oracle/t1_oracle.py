@@ -872,6 +872,8 @@ def post_physics(C, S, sim, R, terrain=None, height_samples=None):
 def step(C, S, sim, actions, R, terrain=None, height_samples=None, physics=None):
     """One policy step.  `physics(substep)` stands in for gym.simulate + refresh."""
     clip_a = C.cfg.normalization.clip_actions
+    if getattr(C.cfg.env, "use_ref_actions", False):                        # t1:360-366 (in place on the caller's tensor)
+        actions += S.ref_action
     S.actions = torch.clip(actions, -clip_a, clip_a).to(C.device)
     for k in range(C.decimation):
         S.torques = torque_substep(C, S, sim, S.actions, R["torque"][k]).view(S.torques.shape)
@@ -923,6 +925,8 @@ def load_state(C, S, state):
     """Adopt a flat state dict (the `state0.*` entries of tests/golden/*.npz)."""
     for k in _PLAIN_STATE:
         setattr(S, k, torch.as_tensor(state[k]).clone().to(C.device))
+    if "ref_action" in state:          # fixtures written since env.use_ref_actions is pinned carry it
+        S.ref_action = torch.as_tensor(state["ref_action"]).clone().to(C.device)
     S.last_feet_z = torch.as_tensor(state["last_feet_z"]).clone().to(C.device)
     S.obs_history = torch.as_tensor(state["obs_history"]).clone().to(C.device)
     S.critic_history = torch.as_tensor(state["critic_history"]).clone().to(C.device)

@@ -48,6 +48,10 @@ def scenario_cfg(name, num_envs, frame_stack=66):
         cfg.commands.heading_command = True
     if name == "plane_no_sw":
         cfg.commands.sw_switch = False
+    if name == "plane_ref_actions":
+        cfg.env.use_ref_actions = True
+    if name == "plane_h15":
+        cfg = scenario_cfg("plane_default", num_envs, frame_stack=15)
     dr = cfg.domain_rand
     if name == "plane_flags_off":         # like oracle/pin_against_reference.py _flags_off
         for f in ("add_lag", "add_dof_lag", "add_imu_lag", "randomize_gains", "randomize_coulomb_friction", "randomize_torque",
@@ -66,7 +70,7 @@ def scenario_cfg(name, num_envs, frame_stack=66):
 
 GOLDEN_SCENARIOS = ["plane_default", "plane_events", "trimesh_heights_push", "plane_extra_terms", "plane_windows",
                     "trimesh_windows", "plane_heading", "plane_no_sw", "plane_flags_off", "plane_flags_mixed",
-                    "plane_heights", "trimesh_plain", "trimesh_no_curriculum"]
+                    "plane_heights", "trimesh_plain", "trimesh_no_curriculum", "plane_ref_actions", "plane_h15"]
 
 
 def gym_calls_of(out):

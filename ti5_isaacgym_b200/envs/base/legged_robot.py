@@ -916,7 +916,7 @@ class LeggedRobot(BaseTask):
         dev = self.device
         plain = ("torques actions last_actions last_last_actions last_dof_vel last_root_vel commands feet_air_time "
                  "feet_height last_feet_z base_quat base_lin_vel base_ang_vel projected_gravity base_euler_xyz "
-                 "feet_euler_xyz ext_forces ext_torques rand_push_force rand_push_torque ref_dof_pos gait_time gait_start "
+                 "feet_euler_xyz ext_forces ext_torques rand_push_force rand_push_torque ref_dof_pos ref_action gait_time gait_start "
                  "torque_multi motor_offsets randomized_p_gains randomized_d_gains randomized_joint_coulomb "
                  "randomized_joint_viscous joint_armatures phase_length_buf rew_buf env_origins env_frictions body_mass "
                  "last_contacts contact_filt time_out_buf").split()
