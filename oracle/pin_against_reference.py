@@ -87,6 +87,25 @@ def _flags_mixed(c):
     dr.push_robots = True
 
 
+def _other_params(c):
+    """Run-time parameters away from t1_cfg's values: decimation, critic frame stack, lag ranges, episode length, gait
+    cycle, action scale, clipping, noise level, tracking sigma."""
+    c.control.decimation = 4
+    c.control.action_scale = 0.4
+    c.env.c_frame_stack = 5
+    c.env.num_privileged_obs = 5 * 73
+    c.env.episode_length_s = 10
+    c.domain_rand.lag_timesteps_range = [1, 8]
+    c.domain_rand.dof_lag_timesteps_range = [0, 5]
+    c.domain_rand.imu_lag_timesteps_range = [2, 4]
+    c.rewards.cycle_time = 0.64
+    c.rewards.tracking_sigma = 4
+    c.rewards.max_contact_force = 300
+    c.normalization.clip_observations = 18.0
+    c.normalization.clip_actions = 1.5
+    c.noise.noise_level = 0.5
+
+
 SCENARIOS = {
     # name: (num_envs, steps, mesh_type, cfg edits, base-contact rate, forced events)
     "plane_default": dict(N=16, steps=28, mesh="plane"),
@@ -134,6 +153,8 @@ SCENARIOS = {
     # a shorter observation history (BASELINE config 5: frame_stack sweep)
     "plane_h15": dict(N=16, steps=20, mesh="plane", contact_rate=0.05, events=True,
                       edit=lambda c: (setattr(c.env, "frame_stack", 15), setattr(c.env, "num_observations", 15 * 47))),
+    # run-time parameters away from t1_cfg's values
+    "plane_params": dict(N=24, steps=24, mesh="plane", contact_rate=0.05, events=False, edit=_other_params),
     "big_plane": dict(N=512, steps=12, mesh="plane", contact_rate=0.03, events=True, golden=False),
     # the reward terms the task defines but t1_cfg leaves at zero scale (t1:894-896, 917-925, 937-940)
     "plane_extra_terms": dict(N=16, steps=12, mesh="plane", contact_rate=0.08, events=True,

@@ -50,6 +50,22 @@ def scenario_cfg(name, num_envs, frame_stack=66):
         cfg.commands.sw_switch = False
     if name == "plane_ref_actions":
         cfg.env.use_ref_actions = True
+    if name == "plane_params":            # like oracle/pin_against_reference.py _other_params
+        c = cfg
+        c.control.decimation = 4
+        c.control.action_scale = 0.4
+        c.env.c_frame_stack = 5
+        c.env.num_privileged_obs = 5 * 73
+        c.env.episode_length_s = 10
+        c.domain_rand.lag_timesteps_range = [1, 8]
+        c.domain_rand.dof_lag_timesteps_range = [0, 5]
+        c.domain_rand.imu_lag_timesteps_range = [2, 4]
+        c.rewards.cycle_time = 0.64
+        c.rewards.tracking_sigma = 4
+        c.rewards.max_contact_force = 300
+        c.normalization.clip_observations = 18.0
+        c.normalization.clip_actions = 1.5
+        c.noise.noise_level = 0.5
     if name == "plane_h15":
         cfg = scenario_cfg("plane_default", num_envs, frame_stack=15)
     dr = cfg.domain_rand
@@ -70,7 +86,7 @@ def scenario_cfg(name, num_envs, frame_stack=66):
 
 GOLDEN_SCENARIOS = ["plane_default", "plane_events", "trimesh_heights_push", "plane_extra_terms", "plane_windows",
                     "trimesh_windows", "plane_heading", "plane_no_sw", "plane_flags_off", "plane_flags_mixed",
-                    "plane_heights", "trimesh_plain", "trimesh_no_curriculum", "plane_ref_actions", "plane_h15"]
+                    "plane_heights", "trimesh_plain", "trimesh_no_curriculum", "plane_ref_actions", "plane_h15", "plane_params"]
 
 
 def gym_calls_of(out):
