@@ -106,6 +106,26 @@ def _other_params(c):
     c.noise.noise_level = 0.5
 
 
+def _points77(c):
+    """An 11 x 7 scan grid: a 150-float privileged frame (not a multiple of four floats)."""
+    c.terrain.measure_heights = True
+    c.terrain.measured_points_x = [-0.5 + 0.1 * i for i in range(11)]
+    c.terrain.measured_points_y = [-0.3 + 0.1 * i for i in range(7)]
+    c.terrain.num_height = 77
+    c.env.num_privileged_obs = 3 * (73 + 77)
+    c.domain_rand.push_robots = True
+
+
+def _gaits4(c):
+    """Four gait slots of the kinds t1_cfg does not schedule, other command ranges and stand threshold."""
+    c.commands.gait = ["walk_sagittal", "rotate", "walk_lateral", "stand"]
+    c.commands.ranges.lin_vel_x = [-0.3, 0.8]
+    c.commands.ranges.lin_vel_y = [-0.2, 0.2]
+    c.commands.ranges.ang_vel_yaw = [-0.7, 0.4]
+    c.commands.stand_com_threshold = 0.1
+    c.commands.max_curriculum = 1.0
+
+
 SCENARIOS = {
     # name: (num_envs, steps, mesh_type, cfg edits, base-contact rate, forced events)
     "plane_default": dict(N=16, steps=28, mesh="plane"),
@@ -155,6 +175,8 @@ SCENARIOS = {
                       edit=lambda c: (setattr(c.env, "frame_stack", 15), setattr(c.env, "num_observations", 15 * 47))),
     # run-time parameters away from t1_cfg's values
     "plane_params": dict(N=24, steps=24, mesh="plane", contact_rate=0.05, events=False, edit=_other_params),
+    "trimesh_points77": dict(N=20, steps=14, mesh="trimesh", contact_rate=0.05, events=True, edit=_points77),
+    "plane_gaits4": dict(N=24, steps=30, mesh="plane", contact_rate=0.05, events=True, edit=_gaits4),
     "big_plane": dict(N=512, steps=12, mesh="plane", contact_rate=0.03, events=True, golden=False),
     # the reward terms the task defines but t1_cfg leaves at zero scale (t1:894-896, 917-925, 937-940)
     "plane_extra_terms": dict(N=16, steps=12, mesh="plane", contact_rate=0.08, events=True,
@@ -187,6 +209,9 @@ def run_scenario(name, spec, write_dir=None, verbose=True):
         env.episode_length_buf[0] = 2398                  # time-out at the 3rd step
         env.episode_length_buf[1] = int(env.gait_time[1, 1]) - 2       # gait switch to "stand"
         env.episode_length_buf[2] = int(env.gait_time[2, 2]) - 3       # and back to walking
+        if env.gait_time.shape[1] > 3:                                 # a fourth gait slot
+            env.episode_length_buf[3] = int(env.gait_time[3, 3]) - 4
+            env.episode_length_buf[4] = int(env.gait_time[4, 1]) - 5
         env.phase_length_buf[:] = env.episode_length_buf
         env.common_step_counter = spec.get("counter", 2397)   # command-curriculum check at step 3, ext-force window
     if spec.get("track_sums"):        # tracking reward above 80 % of its maximum: the curriculum widens lin_vel_x

@@ -161,15 +161,16 @@ def rng_pool_shapes(C, N):
     otherwise ('i', low, high) = integers in [low, high)."""
     D, K = C.num_dof, C.cfg.env.num_single_obs
     dr = C.cfg.domain_rand
+    G = len(C.cfg.commands.gait)                      # gait slots of the schedule (three in t1_cfg)
     return {
         "torque": ((C.decimation, N, D), "u"),        # lr:1071, redrawn every substep (A18)
-        "cmd": ((2, 3, N, 3), "u"),                   # t1:126-177; [0]=callback pass, [1]=pass inside reset_idx
+        "cmd": ((2, G, N, 3), "u"),                   # t1:126-177; [0]=callback pass, [1]=pass inside reset_idx
         "push": ((N, 5), "u"),                        # t1:223-226
         "ext": ((N, 6), "u"),                         # t1:237-241
         "dofs": ((N, D), "u"),                        # lr:1084
         "root_xy": ((N, 2), "u"),                     # lr:1105-1108
         "dr": ((N, len(DR_ROWS), D), "u"),            # lr:735-783
-        "gait_time": ((N, 3), "u"),                   # t1:116
+        "gait_time": ((N, G), "u"),                   # t1:116
         "noise": ((N, K), "u"),                       # t1:472
         "lag_idx": ((N, 3), ("i", 0, 0)),             # lr:608-629 (ranges applied per column by the caller)
         "gait_start": ((N,), ("i", 0, 2)),            # t1:523 (CPU generator in the reference, A25)

@@ -50,6 +50,20 @@ def scenario_cfg(name, num_envs, frame_stack=66):
         cfg.commands.sw_switch = False
     if name == "plane_ref_actions":
         cfg.env.use_ref_actions = True
+    if name == "trimesh_points77":        # _points77
+        cfg.terrain.measure_heights = True
+        cfg.terrain.measured_points_x = [-0.5 + 0.1 * i for i in range(11)]
+        cfg.terrain.measured_points_y = [-0.3 + 0.1 * i for i in range(7)]
+        cfg.terrain.num_height = 77
+        cfg.env.num_privileged_obs = 3 * (73 + 77)
+        cfg.domain_rand.push_robots = True
+    if name == "plane_gaits4":            # _gaits4
+        cfg.commands.gait = ["walk_sagittal", "rotate", "walk_lateral", "stand"]
+        cfg.commands.ranges.lin_vel_x = [-0.3, 0.8]
+        cfg.commands.ranges.lin_vel_y = [-0.2, 0.2]
+        cfg.commands.ranges.ang_vel_yaw = [-0.7, 0.4]
+        cfg.commands.stand_com_threshold = 0.1
+        cfg.commands.max_curriculum = 1.0
     if name == "plane_params":            # like oracle/pin_against_reference.py _other_params
         c = cfg
         c.control.decimation = 4
@@ -86,7 +100,8 @@ def scenario_cfg(name, num_envs, frame_stack=66):
 
 GOLDEN_SCENARIOS = ["plane_default", "plane_events", "trimesh_heights_push", "plane_extra_terms", "plane_windows",
                     "trimesh_windows", "plane_heading", "plane_no_sw", "plane_flags_off", "plane_flags_mixed",
-                    "plane_heights", "trimesh_plain", "trimesh_no_curriculum", "plane_ref_actions", "plane_h15", "plane_params"]
+                    "plane_heights", "trimesh_plain", "trimesh_no_curriculum", "plane_ref_actions", "plane_h15", "plane_params",
+                    "trimesh_points77", "plane_gaits4"]
 
 
 def gym_calls_of(out):
