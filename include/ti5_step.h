@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TI5_ABI_VERSION 8
+#define TI5_ABI_VERSION 9
 
 #define TI5_NUM_DOF 12      /* leg_l1..l6, leg_r1..r6 */
 #define TI5_NUM_BODIES 13   /* base_link + 12 leg links after collapse_fixed_joints */
@@ -69,8 +69,18 @@ enum {
   TI5_F_PLANE = 1 << 20,             /* heights are identically zero on a plane (lr:1564) */
   TI5_F_HEADING_COMMAND = 1 << 21,   /* commands.heading_command: the schedule draws a heading target (column 3), the yaw
                                         rate (column 2) follows the heading error on every step (t1:141-176, 185-188) */
-  TI5_F_NO_SW_SWITCH = 1 << 22       /* commands.sw_switch == False: the gait phase follows episode_length_buf and standing
+  TI5_F_NO_SW_SWITCH = 1 << 22,      /* commands.sw_switch == False: the gait phase follows episode_length_buf and standing
                                         envs keep cycling (t1:89-90) */
+  /* options t1_cfg marks "always False" (t1_cfg:290-312) */
+  TI5_F_LAG_PERSTEP = 1 << 23,       /* randomize_lag_timesteps_perstep: action lag re-drawn every substep (lr:1038-1043);
+                                        unfused substep kernels only (ti5_fused_step refuses) */
+  TI5_F_DOF_LAG_PERSTEP = 1 << 24,   /* randomize_dof_lag_timesteps_perstep (t1:408-413) */
+  TI5_F_IMU_LAG_PERSTEP = 1 << 25,   /* randomize_imu_lag_timesteps_perstep (t1:437-442) */
+  TI5_F_POS_VEL_LAG = 1 << 26,       /* add_dof_pos_vel_lag without add_dof_lag (t1:416-431): joint positions and velocities
+                                        lagged separately; both are read from the DOF ring (set TI5_F_ADD_DOF_LAG with it:
+                                        the ring is pushed, dof_lag_len covers both ranges) */
+  TI5_F_RAND_POS_LAG_STEPS = 1 << 27, TI5_F_RAND_VEL_LAG_STEPS = 1 << 28,   /* randomize_dof_{pos,vel}_lag_timesteps */
+  TI5_F_POS_LAG_PERSTEP = 1 << 29, TI5_F_VEL_LAG_PERSTEP = 1 << 30          /* ..._perstep (t1:417-430) */
 };
 
 /* gait kinds of cfg.commands.gait (t1:138-177) */
@@ -161,6 +171,8 @@ typedef struct Ti5Params {
   double push_duration[TI5_MAX_WINDOWS], add_duration[TI5_MAX_WINDOWS];   /* duration / dt, in steps (double) */
   double cmd_curriculum_max;                       /* commands.max_curriculum */
   double tracking_lin_vel_scale;                   /* reward_scales["tracking_lin_vel"] (double) */
+  /* (appended: the fields above keep the offsets the t1 configuration was tuned with) */
+  int32_t lag_range_pv[2][2];                      /* dof-position / dof-velocity lag index ranges (TI5_F_POS_VEL_LAG) */
 } Ti5Params;
 
 /* ---- device-resident counters and curriculum state (single instance per env object) -------- */
@@ -279,6 +291,10 @@ typedef struct Ti5Buffers {
    * straight over the bus, no copy-engine hop); the `actions_in` of ti5_first_substep may likewise be host-mapped. */
   uint8_t* host_out;
   uint64_t* debug_ts;      /* optional (2, CTAs, 8) globaltimer probes of the two per-env kernels (profiling aid), or NULL */
+  /* the lag options t1_cfg marks "always False" (appended, see Ti5Params) */
+  int32_t* lag_pv;         /* (N,2): dof-position / dof-velocity lag index (TI5_F_POS_VEL_LAG), else NULL */
+  int32_t* last_lag;       /* (2,N,5): the `last_*_lag_timestep` of the per-step re-draws, double-buffered (by substep
+                              parity for the action lag, by step parity for the others); NULL without a *_PERSTEP flag */
 } Ti5Buffers;
 
 /* ---- caller-supplied uniforms of one step (TI5_RNG_POOLS).  All fp32 U[0,1) unless noted --- */
@@ -295,6 +311,9 @@ typedef struct Ti5Rng {
   const int64_t* lag_idx;     /* (N,3)   lr:608-629 integers already in range */
   const int64_t* gait_start;  /* (N)     t1:523 integers in {0,1} */
   const int64_t* terrain_level; /* (N)   lr:1156 integers in [0, max_terrain_level) */
+  const int64_t* lag_idx_pv;  /* (N,2)   lr:639, 646 position / velocity lag at a reset, integers in range */
+  const int64_t* lag_step;    /* (DEC+4, N) per-step re-draws, integers in range: rows 0..DEC-1 the action lag of each
+                                 substep (lr:1039), then DOF, IMU, position, velocity (t1:409, 438, 418, 426) */
 } Ti5Rng;
 
 /* ---- entry points ------------------------------------------------------------------------- */

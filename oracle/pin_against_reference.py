@@ -32,6 +32,8 @@ STATE_KEYS = ("torques actions last_actions last_last_actions last_dof_vel last_
               "randomized_joint_coulomb randomized_joint_viscous joint_armatures lag_buffer dof_lag_buffer "
               "imu_lag_buffer lag_timestep dof_lag_timestep imu_lag_timestep episode_length_buf phase_length_buf "
               "rew_buf reset_buf time_out_buf env_origins").split()
+# state of the options t1_cfg leaves off: compared when the reference allocated it, recorded when the option is on
+OPTIONAL_KEYS = O.OPTIONAL_LAG_STATE
 
 
 def robot_from_env(env):
@@ -55,6 +57,8 @@ def same(a, b):
 def snapshot_state(S, C):
     """All persistent state of an oracle state as a flat dict of tensors."""
     out = {k: getattr(S, k).clone() for k in STATE_KEYS}
+    if C.pos_vel_lag or any(C.perstep.values()):
+        out.update({k: getattr(S, k).clone() for k in OPTIONAL_KEYS})
     out["last_feet_z"] = torch.zeros(S.N, 2) if isinstance(S.last_feet_z, int) else S.last_feet_z.clone()
     out["obs_history"], out["critic_history"] = S.obs_history.clone(), S.critic_history.clone()
     out["episode_sums"] = torch.stack([S.episode_sums[k] for k in C.reward_scales], 0)
@@ -126,6 +130,20 @@ def _gaits4(c):
     c.commands.max_curriculum = 1.0
 
 
+def _perstep(c):
+    """Lag indices re-drawn every substep (actions) / every step (joint state, IMU): lr:1038-1043, t1:408-413, 437-442."""
+    for k in ("lag", "dof_lag", "imu_lag"):
+        setattr(c.domain_rand, f"randomize_{k}_timesteps_perstep", True)
+
+
+def _pos_vel_lag(c):
+    """Separate position / velocity lags instead of the common joint-state lag (lr:425-430, t1:416-431), re-drawn per step."""
+    c.domain_rand.add_dof_lag = False
+    c.domain_rand.add_dof_pos_vel_lag = True
+    c.domain_rand.randomize_dof_pos_lag_timesteps_perstep = True
+    c.domain_rand.randomize_dof_vel_lag_timesteps_perstep = False
+
+
 SCENARIOS = {
     # name: (num_envs, steps, mesh_type, cfg edits, base-contact rate, forced events)
     "plane_default": dict(N=16, steps=28, mesh="plane"),
@@ -177,6 +195,8 @@ SCENARIOS = {
     "plane_params": dict(N=24, steps=24, mesh="plane", contact_rate=0.05, events=False, edit=_other_params),
     "trimesh_points77": dict(N=20, steps=14, mesh="trimesh", contact_rate=0.05, events=True, edit=_points77),
     "plane_gaits4": dict(N=24, steps=30, mesh="plane", contact_rate=0.05, events=True, edit=_gaits4),
+    "plane_lag_perstep": dict(N=24, steps=24, mesh="plane", contact_rate=0.05, events=True, edit=_perstep),
+    "plane_pos_vel_lag": dict(N=24, steps=24, mesh="plane", contact_rate=0.05, events=True, edit=_pos_vel_lag),
     "big_plane": dict(N=512, steps=12, mesh="plane", contact_rate=0.03, events=True, golden=False),
     # the reward terms the task defines but t1_cfg leaves at zero scale (t1:894-896, 917-925, 937-940)
     "plane_extra_terms": dict(N=16, steps=12, mesh="plane", contact_rate=0.08, events=True,
@@ -261,7 +281,7 @@ def run_scenario(name, spec, write_dir=None, verbose=True):
         for key, a, b in (("obs", o_obs, r_obs), ("priv", o_priv, r_priv), ("rew", o_rew, r_rew), ("reset", o_reset, r_reset)):
             if not same(a, b):
                 bad.append(key)
-        for key in STATE_KEYS:
+        for key in list(STATE_KEYS) + [k for k in OPTIONAL_KEYS if hasattr(env, k)]:
             if hasattr(env, key) and not same(getattr(S, key), getattr(env, key)):
                 bad.append(key)
         if not same(S.last_feet_z, env.last_feet_z):

@@ -62,6 +62,10 @@ _RAND_FLOAT_SITES = {
     ("_add_ext_force", 239): ("ext", (2, 3)), ("_add_ext_force", 241): ("ext", (3, 6)),
 }
 _RANDINT_SITES = {("randomize_lag_props", 608): 0, ("randomize_lag_props", 618): 1, ("randomize_lag_props", 628): 2}
+_RANDINT_PV_SITES = {("randomize_lag_props", 639): 0, ("randomize_lag_props", 646): 1}       # position / velocity lag at a reset
+# per-step re-draws over all envs: row of the `lag_step` pool behind the DEC substep rows (DOF, IMU, position, velocity)
+_RANDINT_STEP_SITES = {("compute_observations", 409): 0, ("compute_observations", 438): 1,
+                       ("compute_observations", 418): 2, ("compute_observations", 426): 3}
 
 
 class ReferenceDriver:
@@ -134,6 +138,15 @@ class ReferenceDriver:
         site = (fr[0].f_code.co_name, fr[0].f_lineno)
         if site in _RANDINT_SITES:
             return self.pools["lag_idx"][fr[0].f_locals["env_ids"], _RANDINT_SITES[site]].clone()
+        if site in _RANDINT_PV_SITES:
+            return self.pools["lag_idx_pv"][fr[0].f_locals["env_ids"], _RANDINT_PV_SITES[site]].clone()
+        if site in _RANDINT_STEP_SITES:
+            dec = self.cfg.control.decimation
+            return self.pools["lag_step"][dec + _RANDINT_STEP_SITES[site]].clone()
+        if site == ("_compute_torques", 1039):          # the action lag, re-drawn every substep (lr:1039-1043)
+            k = self.lag_substep
+            self.lag_substep += 1
+            return self.pools["lag_step"][k].clone()
         if site == ("reset_idx", 523):
             return self.pools["gait_start"][fr[0].f_locals["env_ids"]].clone()
         return self._orig["randint"](*args, **kw)
@@ -153,7 +166,7 @@ class ReferenceDriver:
 
     @contextlib.contextmanager
     def pooled_rng(self, pools):
-        self.pools, self.substep = pools, 0
+        self.pools, self.substep, self.lag_substep = pools, 0, 0
         saved = (self.t1_mod.torch_rand_float, self.lr_mod.torch_rand_float)
         self.t1_mod.torch_rand_float = self._rand_float
         self.lr_mod.torch_rand_float = self._rand_float
@@ -171,6 +184,9 @@ class ReferenceDriver:
             return self.env.step(actions.clone())
 
 
+O_OPTIONAL = ("last_lag_timestep last_dof_lag_timestep last_imu_lag_timestep dof_pos_lag_buffer dof_vel_lag_buffer dof_pos_lag_timestep dof_vel_lag_timestep last_dof_pos_lag_timestep last_dof_vel_lag_timestep").split()
+
+
 def adopt_reference_state(S, env):
     """Copy every piece of persistent per-env state of a reference env into an oracle state
     (construction-time random draws included), so both continue from the same point."""
@@ -181,7 +197,7 @@ def adopt_reference_state(S, env):
             "torque_multi motor_offsets randomized_p_gains randomized_d_gains randomized_joint_coulomb "
             "randomized_joint_viscous joint_armatures lag_buffer dof_lag_buffer imu_lag_buffer lag_timestep "
             "dof_lag_timestep imu_lag_timestep episode_length_buf phase_length_buf rew_buf reset_buf "
-            "time_out_buf").split()
+            "time_out_buf " + " ".join(O_OPTIONAL)).split()
     for name in same:
         if hasattr(env, name):          # the reference allocates some buffers only when their option is on (lr:251-349)
             setattr(S, name, getattr(env, name).clone())

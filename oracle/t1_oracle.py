@@ -141,9 +141,11 @@ def make_consts(cfg, sim_dt, robot, device="cpu", terrain=None):
     nv[nc + 3 * D + 3:nc + 3 * D + 6] = ns_.quat * os_.quat
     C.noise_scale_vec = nv
     dr = cfg.domain_rand
-    for flag in ("randomize_lag_timesteps_perstep", "randomize_dof_lag_timesteps_perstep",
-                 "randomize_imu_lag_timesteps_perstep", "add_dof_pos_vel_lag"):
-        assert not getattr(dr, flag), "not exercised by t1_dh_stand (t1_cfg:290-312)"
+    # options t1_cfg marks "always False" (t1_cfg:290-312), restated all the same: per-step re-draws of the lag indices
+    # (lr:1038-1043, t1:408-413, 417-430, 437-442) and separate position / velocity lags (lr:425-430, t1:416-431)
+    C.perstep = {k: bool(getattr(dr, f"randomize_{k}_timesteps_perstep", False) and getattr(dr, f"randomize_{k}_timesteps", False))
+                 for k in ("lag", "dof_lag", "imu_lag", "dof_pos_lag", "dof_vel_lag")}
+    C.pos_vel_lag = bool(getattr(dr, "add_dof_pos_vel_lag", False))
     C.heading_command = bool(cfg.commands.heading_command)
     C.forward_vec = torch.tensor([1., 0., 0.], **f32)                                         # lr:170
     C.custom_origins = cfg.terrain.mesh_type in ("heightfield", "trimesh")                   # lr:1481
@@ -175,7 +177,10 @@ def rng_pool_shapes(C, N):
         "lag_idx": ((N, 3), ("i", 0, 0)),             # lr:608-629 (ranges applied per column by the caller)
         "gait_start": ((N,), ("i", 0, 2)),            # t1:523 (CPU generator in the reference, A25)
         "terrain_level": ((N,), ("i", 0, max(1, getattr(C.cfg.terrain, "num_rows", 1)))),  # lr:1156
-    }
+    } | ({"lag_idx_pv": ((N, 2), ("i", 0, 0))} if C.pos_vel_lag else {}) \
+      | ({"lag_step": ((C.decimation + 4, N), ("i", 0, 0))} if any(C.perstep.values()) else {})
+    # lag_idx_pv: lr:639, 646 (position / velocity lag at a reset); lag_step: per-step re-draws — rows 0 .. DEC-1 the
+    # action lag of each substep (lr:1039), then the DOF, IMU, position and velocity lags of the step (t1:409, 438, 418, 426)
 
 
 def draw_pools(C, N, gen, device="cpu"):
@@ -189,6 +194,14 @@ def draw_pools(C, N, gen, device="cpu"):
             cols = [torch.randint(r[0], r[1] + 1, (N,), generator=gen) for r in
                     (dr.lag_timesteps_range, dr.dof_lag_timesteps_range, dr.imu_lag_timesteps_range)]
             out[name] = torch.stack(cols, 1).to(device)
+        elif name == "lag_idx_pv":
+            cols = [torch.randint(r[0], r[1] + 1, (N,), generator=gen) for r in
+                    (dr.dof_pos_lag_timesteps_range, dr.dof_vel_lag_timesteps_range)]
+            out[name] = torch.stack(cols, 1).to(device)
+        elif name == "lag_step":
+            rows = [dr.lag_timesteps_range] * C.decimation + [dr.dof_lag_timesteps_range, dr.imu_lag_timesteps_range,
+                                                              dr.dof_pos_lag_timesteps_range, dr.dof_vel_lag_timesteps_range]
+            out[name] = torch.stack([torch.randint(r[0], r[1] + 1, (N,), generator=gen) for r in rows], 0).to(device)
         else:
             out[name] = torch.randint(kind[1], kind[2], shape, generator=gen).to(device)
     return out
@@ -253,6 +266,12 @@ def new_state(C, N):
     S.lag_timestep = torch.full((N,), dr.lag_timesteps_range[1], dtype=torch.long, device=dev)
     S.dof_lag_timestep = torch.full((N,), dr.dof_lag_timesteps_range[1], dtype=torch.long, device=dev)
     S.imu_lag_timestep = torch.full((N,), dr.imu_lag_timesteps_range[1], dtype=torch.long, device=dev)
+    S.dof_pos_lag_buffer = z(N, D, dr.dof_pos_lag_timesteps_range[1] + 1)
+    S.dof_vel_lag_buffer = z(N, D, dr.dof_vel_lag_timesteps_range[1] + 1)
+    S.dof_pos_lag_timestep = torch.full((N,), dr.dof_pos_lag_timesteps_range[1], dtype=torch.long, device=dev)
+    S.dof_vel_lag_timestep = torch.full((N,), dr.dof_vel_lag_timesteps_range[1], dtype=torch.long, device=dev)
+    for k in ("lag", "dof_lag", "imu_lag", "dof_pos_lag", "dof_vel_lag"):       # lr:282, 301, 317, 335, 345
+        setattr(S, f"last_{k}_timestep", torch.full((N,), getattr(dr, f"{k}_timesteps_range")[1], dtype=torch.long, device=dev))
     H, CH, K = cfg.env.frame_stack, cfg.env.c_frame_stack, cfg.env.num_single_obs
     P = cfg.env.single_num_privileged_obs + (cfg.terrain.num_height if cfg.terrain.measure_heights else 0)
     S.obs_history = z(H, N, K)          # oldest -> newest (the reference's deque, lr:251-267)
@@ -276,7 +295,18 @@ def sim_views(sim, N, D, NB):
 # ------------------------------------------------------------------------------------------
 
 
-def torque_substep(C, S, sim, actions, u_torque):
+def _redraw_lag(S, kind, draw):
+    """The per-step re-draw of a lag index (lr:1039-1043 and its four copies in t1:408-442): a fresh draw, but never more
+    than one step further back than the last one."""
+    new = draw.clone()
+    last = getattr(S, f"last_{kind}_timestep")
+    cond = new > last + 1
+    new[cond] = last[cond] + 1
+    setattr(S, f"{kind}_timestep", new)
+    setattr(S, f"last_{kind}_timestep", new.clone())
+
+
+def torque_substep(C, S, sim, actions, u_torque, lag_step=None):
     """lr:1019-1074: lagged PD with motor offset, viscous + Coulomb friction, fresh motor
     strength multiplier, clip to the torque limits."""
     dr = C.cfg.domain_rand
@@ -285,6 +315,8 @@ def torque_substep(C, S, sim, actions, u_torque):
     if dr.add_lag:
         S.lag_buffer[:, :, 1:] = S.lag_buffer[:, :, :dr.lag_timesteps_range[1]].clone()
         S.lag_buffer[:, :, 0] = target.clone()
+        if C.perstep["lag"]:                                               # lr:1038-1043
+            _redraw_lag(S, "lag", lag_step)
         target = S.lag_buffer[torch.arange(S.N, device=C.device), :, S.lag_timestep.int()]
     S.lagged_actions_scaled = target
     kp, kd = (S.randomized_p_gains, S.randomized_d_gains) if dr.randomize_gains else (C.p_gains, C.d_gains)
@@ -306,6 +338,11 @@ def lag_push(C, S, sim):
     if dr.add_dof_lag:
         S.dof_lag_buffer[:, :, 1:] = S.dof_lag_buffer[:, :, :dr.dof_lag_timesteps_range[1]].clone()
         S.dof_lag_buffer[:, :, 0] = torch.cat((q, qd), 1)
+    if C.pos_vel_lag:                                                      # lr:425-430
+        S.dof_pos_lag_buffer[:, :, 1:] = S.dof_pos_lag_buffer[:, :, :dr.dof_pos_lag_timesteps_range[1]].clone()
+        S.dof_pos_lag_buffer[:, :, 0] = q.clone()
+        S.dof_vel_lag_buffer[:, :, 1:] = S.dof_vel_lag_buffer[:, :, :dr.dof_vel_lag_timesteps_range[1]].clone()
+        S.dof_vel_lag_buffer[:, :, 0] = qd.clone()
     if dr.add_imu_lag:
         S.base_quat[:] = sim.root_states[:, 3:7]
         S.base_ang_vel[:] = quat_rotate_inverse(S.base_quat, sim.root_states[:, 10:13])
@@ -747,6 +784,16 @@ def reset_envs(C, S, sim, ids, R, terrain=None):
     if dr.add_imu_lag:
         S.imu_lag_buffer[ids, :, :] = 0.0
         S.imu_lag_timestep[ids] = li[:, 2] if dr.randomize_imu_lag_timesteps else dr.imu_lag_timesteps_range[1]
+    if C.pos_vel_lag:                                                      # lr:634-650
+        pv = R["lag_idx_pv"][ids]
+        S.dof_pos_lag_buffer[ids, :, :] = 0.0
+        S.dof_vel_lag_buffer[ids, :, :] = 0.0
+        S.dof_pos_lag_timestep[ids] = pv[:, 0] if dr.randomize_dof_pos_lag_timesteps else dr.dof_pos_lag_timesteps_range[1]
+        S.dof_vel_lag_timestep[ids] = pv[:, 1] if dr.randomize_dof_vel_lag_timesteps else dr.dof_vel_lag_timesteps_range[1]
+    for k, on in (("lag", dr.add_lag), ("dof_lag", dr.add_dof_lag), ("imu_lag", dr.add_imu_lag),
+                  ("dof_pos_lag", C.pos_vel_lag), ("dof_vel_lag", C.pos_vel_lag)):
+        if on and C.perstep[k]:                                            # lr:610-611, 620-621, 630-631, 641-642, 648-649
+            getattr(S, f"last_{k}_timestep")[ids] = getattr(dr, f"{k}_timesteps_range")[1]
     # t1:513-523
     for name in ("last_last_actions", "actions", "last_actions", "last_dof_vel", "last_root_vel", "feet_air_time"):
         getattr(S, name)[ids] = 0.
@@ -785,7 +832,7 @@ def reset_envs(C, S, sim, ids, R, terrain=None):
 # ------------------------------------------------------------------------------------------
 
 
-def compute_observations(C, S, sim, u_noise):
+def compute_observations(C, S, sim, u_noise, lag_step=None):
     cfg, dr, os_ = C.cfg, C.cfg.domain_rand, C.obs_scales
     N, D = S.N, C.num_dof
     q, qd, cf, _ = sim_views(sim, N, D, C.num_bodies)
@@ -805,12 +852,24 @@ def compute_observations(C, S, sim, u_noise):
         S.command_input, (q - C.default_dof_pos) * os_.dof_pos, qd * os_.dof_vel, S.actions, q - S.ref_dof_pos,
         S.base_lin_vel * os_.lin_vel, S.base_ang_vel * os_.ang_vel, S.base_euler_xyz * os_.quat,
         push_f[:, :2], push_t, S.env_frictions, S.body_mass / 30., stance, contact), dim=-1)
+    DEC = C.decimation                                                     # rows of `lag_step` behind the substeps'
     if dr.add_dof_lag:
+        if C.perstep["dof_lag"]:                                           # t1:408-413
+            _redraw_lag(S, "dof_lag", lag_step[DEC])
         S.lagged_dof_pos = S.dof_lag_buffer[ar, :D, S.dof_lag_timestep.int()]
         S.lagged_dof_vel = S.dof_lag_buffer[ar, -D:, S.dof_lag_timestep.int()]
+    elif C.pos_vel_lag:                                                    # t1:416-431
+        if C.perstep["dof_pos_lag"]:
+            _redraw_lag(S, "dof_pos_lag", lag_step[DEC + 2])
+        S.lagged_dof_pos = S.dof_pos_lag_buffer[ar, :, S.dof_pos_lag_timestep.int()]
+        if C.perstep["dof_vel_lag"]:
+            _redraw_lag(S, "dof_vel_lag", lag_step[DEC + 3])
+        S.lagged_dof_vel = S.dof_vel_lag_buffer[ar, :, S.dof_vel_lag_timestep.int()]
     else:
         S.lagged_dof_pos, S.lagged_dof_vel = q, qd
     if dr.add_imu_lag:
+        if C.perstep["imu_lag"]:                                           # t1:437-442
+            _redraw_lag(S, "imu_lag", lag_step[DEC + 1])
         imu = S.imu_lag_buffer[ar, :, S.imu_lag_timestep.int()]
         S.lagged_base_ang_vel, S.lagged_base_euler_xyz = imu[:, :3].clone(), imu[:, -3:].clone()
     else:
@@ -863,7 +922,7 @@ def post_physics(C, S, sim, R, terrain=None, height_samples=None):
     S.reward_terms = compute_reward(C, S, sim)
     S.reset_ids = S.reset_buf.nonzero(as_tuple=False).flatten()
     reset_envs(C, S, sim, S.reset_ids, R, terrain)
-    compute_observations(C, S, sim, R["noise"])
+    compute_observations(C, S, sim, R["noise"], R.get("lag_step"))
     S.last_last_actions[:] = S.last_actions                                # lr:496-499 (live state only)
     S.last_actions[:] = S.actions
     S.last_dof_vel[:] = qd
@@ -877,7 +936,8 @@ def step(C, S, sim, actions, R, terrain=None, height_samples=None, physics=None)
         actions += S.ref_action
     S.actions = torch.clip(actions, -clip_a, clip_a).to(C.device)
     for k in range(C.decimation):
-        S.torques = torque_substep(C, S, sim, S.actions, R["torque"][k]).view(S.torques.shape)
+        S.torques = torque_substep(C, S, sim, S.actions, R["torque"][k],
+                                   R["lag_step"][k] if C.perstep["lag"] else None).view(S.torques.shape)
         if physics is not None:
             physics(k)
         lag_push(C, S, sim)
@@ -922,12 +982,18 @@ _PLAIN_STATE = ("torques actions last_actions last_last_actions last_dof_vel las
                 "rew_buf reset_buf time_out_buf env_origins env_frictions body_mass").split()
 
 
+OPTIONAL_LAG_STATE = ("last_lag_timestep last_dof_lag_timestep last_imu_lag_timestep dof_pos_lag_buffer dof_vel_lag_buffer dof_pos_lag_timestep dof_vel_lag_timestep last_dof_pos_lag_timestep last_dof_vel_lag_timestep").split()
+
+
 def load_state(C, S, state):
     """Adopt a flat state dict (the `state0.*` entries of tests/golden/*.npz)."""
     for k in _PLAIN_STATE:
         setattr(S, k, torch.as_tensor(state[k]).clone().to(C.device))
     if "ref_action" in state:          # fixtures written since env.use_ref_actions is pinned carry it
         S.ref_action = torch.as_tensor(state["ref_action"]).clone().to(C.device)
+    for k in OPTIONAL_LAG_STATE:       # ... and the state of the per-step / position-velocity lag options
+        if k in state:
+            setattr(S, k, torch.as_tensor(state[k]).clone().to(C.device))
     S.last_feet_z = torch.as_tensor(state["last_feet_z"]).clone().to(C.device)
     S.obs_history = torch.as_tensor(state["obs_history"]).clone().to(C.device)
     S.critic_history = torch.as_tensor(state["critic_history"]).clone().to(C.device)

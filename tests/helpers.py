@@ -50,6 +50,14 @@ def scenario_cfg(name, num_envs, frame_stack=66):
         cfg.commands.sw_switch = False
     if name == "plane_ref_actions":
         cfg.env.use_ref_actions = True
+    if name == "plane_lag_perstep":       # _perstep
+        for k in ("lag", "dof_lag", "imu_lag"):
+            setattr(cfg.domain_rand, f"randomize_{k}_timesteps_perstep", True)
+    if name == "plane_pos_vel_lag":       # _pos_vel_lag
+        cfg.domain_rand.add_dof_lag = False
+        cfg.domain_rand.add_dof_pos_vel_lag = True
+        cfg.domain_rand.randomize_dof_pos_lag_timesteps_perstep = True
+        cfg.domain_rand.randomize_dof_vel_lag_timesteps_perstep = False
     if name == "trimesh_points77":        # _points77
         cfg.terrain.measure_heights = True
         cfg.terrain.measured_points_x = [-0.5 + 0.1 * i for i in range(11)]
@@ -101,7 +109,7 @@ def scenario_cfg(name, num_envs, frame_stack=66):
 GOLDEN_SCENARIOS = ["plane_default", "plane_events", "trimesh_heights_push", "plane_extra_terms", "plane_windows",
                     "trimesh_windows", "plane_heading", "plane_no_sw", "plane_flags_off", "plane_flags_mixed",
                     "plane_heights", "trimesh_plain", "trimesh_no_curriculum", "plane_ref_actions", "plane_h15", "plane_params",
-                    "trimesh_points77", "plane_gaits4"]
+                    "trimesh_points77", "plane_gaits4", "plane_lag_perstep", "plane_pos_vel_lag"]
 
 
 def gym_calls_of(out):
@@ -170,6 +178,9 @@ def state_from_oracle(S, C):
             "imu_lag_buffer lag_timestep dof_lag_timestep imu_lag_timestep episode_length_buf phase_length_buf "
             "rew_buf reset_buf time_out_buf env_origins env_frictions body_mass").split()
     out = {k: getattr(S, k).clone() for k in keys}
+    from oracle.t1_oracle import OPTIONAL_LAG_STATE          # state of the lag options t1_cfg leaves off
+    out.update({k: getattr(S, k).clone() for k in OPTIONAL_LAG_STATE})
+    out["ref_action"] = S.ref_action.clone()
     out["last_feet_z"] = torch.zeros(S.N, 2) if isinstance(S.last_feet_z, int) else S.last_feet_z.clone()
     out["obs_history"], out["critic_history"] = S.obs_history.clone(), S.critic_history.clone()
     out["episode_sums"] = torch.stack([S.episode_sums[k] for k in C.reward_scales], 0)

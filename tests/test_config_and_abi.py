@@ -144,9 +144,22 @@ def test_unsupported_options_raise():
     from ti5_isaacgym_b200.envs.base.step_params import build_params
     from ti5_isaacgym_b200.envs.t1.t1_robot import robot_constants
     cfg = DHT1StandCfg()
-    cfg.domain_rand.randomize_lag_timesteps_perstep = True
+    cfg.domain_rand.randomize_joint_friction = True     # its per-joint ranges are commented out in t1_cfg:236-262
     with pytest.raises(NotImplementedError):
         build_params(cfg, 0.001, robot_constants(cfg))
+    from ti5_isaacgym_b200._lib import CONSTS
+    cfg = DHT1StandCfg()                                # the lag options t1_cfg marks "always False" (t1_cfg:290-312)
+    cfg.domain_rand.randomize_lag_timesteps_perstep = True
+    cfg.domain_rand.randomize_imu_lag_timesteps_perstep = True
+    p = build_params(cfg, 0.001, robot_constants(cfg))
+    assert p.flags & CONSTS["TI5_F_LAG_PERSTEP"] and p.flags & CONSTS["TI5_F_IMU_LAG_PERSTEP"]
+    assert not p.flags & CONSTS["TI5_F_DOF_LAG_PERSTEP"] and not p.flags & CONSTS["TI5_F_POS_VEL_LAG"]
+    cfg = DHT1StandCfg()
+    cfg.domain_rand.add_dof_pos_vel_lag = True          # shows only with the common joint-state lag off (t1:407, 416)
+    assert not build_params(cfg, 0.001, robot_constants(cfg)).flags & CONSTS["TI5_F_POS_VEL_LAG"]
+    cfg.domain_rand.add_dof_lag = False
+    p = build_params(cfg, 0.001, robot_constants(cfg))
+    assert p.flags & CONSTS["TI5_F_POS_VEL_LAG"] and p.flags & CONSTS["TI5_F_ADD_DOF_LAG"] and p.dof_lag_len == 26
     cfg = DHT1StandCfg()
     cfg.commands.heading_command = True                 # supported since round 2 (t1:141-176, 185-188)
     p = build_params(cfg, 0.001, robot_constants(cfg))

@@ -179,6 +179,46 @@ def test_fused_step_equals_the_twelve_launch_sequence(N, graph, name, chain):
     assert int(a.sync_from_device().step_index) == int(b.sync_from_device().step_index)
 
 
+@pytest.mark.parametrize("name", ["plane_lag_perstep", "plane_pos_vel_lag"])
+def test_lag_options_in_production_mode(name):
+    """The lag options t1_cfg leaves off with in-kernel Philox draws (parity with the reference is established in pools
+    mode): every lag index stays in its range, a per-step re-draw never looks more than one step further back than the
+    last one (lr:1041-1042, t1:411-412), the indices do move, and the CUDA-graph step equals direct launches."""
+    from ti5_isaacgym_b200.sim.synthetic import synthetic_actions
+    N = 1024
+    torch.manual_seed(0)
+    a, gen = _production_env(N, name, use_cuda_graph=True)
+    torch.manual_seed(0)
+    b, _ = _production_env(N, name, use_cuda_graph=False)
+    a.reset(), b.reset()
+    dr = a.cfg.domain_rand
+    cols = {"lag_timestep": dr.lag_timesteps_range, "imu_lag_timestep": dr.imu_lag_timesteps_range}
+    if name == "plane_pos_vel_lag":
+        cols.update(dof_pos_lag_timestep=dr.dof_pos_lag_timesteps_range, dof_vel_lag_timestep=dr.dof_vel_lag_timesteps_range)
+        perstep = ["dof_pos_lag_timestep"]
+    else:
+        cols.update(dof_lag_timestep=dr.dof_lag_timesteps_range)
+        perstep = ["dof_lag_timestep", "imu_lag_timestep"]       # (the action lag moves ten times per step)
+    prev = {k: getattr(a, k).clone() for k in cols}
+    moved = {k: 0 for k in perstep}
+    for t in range(40):
+        act = synthetic_actions(N, gen, "cuda")
+        oa, pa, ra, da, _ = a.step(act)
+        ob, pb, rb, db, _ = b.step(act.clone())
+        exact(oa, ob, f"{name} step {t}: obs (graph vs direct)"); exact(ra, rb, f"step {t}: rewards"); exact(da, db, f"step {t}: resets")
+        for k, (lo, hi) in cols.items():
+            v = getattr(a, k)
+            exact(v, getattr(b, k), f"step {t}: {k}")
+            assert int(v.min()) >= lo and int(v.max()) <= hi, f"step {t}: {k} outside [{lo}, {hi}]"
+        for k in perstep:
+            v = getattr(a, k)
+            ok = (v <= prev[k] + 1) | da            # a re-spawned env starts over from the range maximum
+            assert bool(ok.all()), f"step {t}: {k} jumped back by more than one step"
+            moved[k] += int((v != prev[k]).sum())
+        prev = {k: getattr(a, k).clone() for k in cols}
+    assert all(m > N for m in moved.values()), moved
+
+
 def test_use_ref_actions_offsets_the_policy_output():
     """t1:360-366 `env.use_ref_actions`: the step runs on actions + ref_action (added in place, as the reference does)."""
     from ti5_isaacgym_b200.sim.synthetic import synthetic_actions

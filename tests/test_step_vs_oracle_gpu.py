@@ -48,6 +48,12 @@ def _build(name, N, device, seed=3, frame_stack=66, counter=2397):
     S.commands[S.episode_length_buf > S.gait_time[:, 2], :3] = -0.5 + r(int((S.episode_length_buf > S.gait_time[:, 2]).sum()), 3)
     if cfg.commands.heading_command:
         S.commands[:, 3] = -3.0 + 6.0 * r(N)                      # heading targets of a schedule in progress
+    if C.pos_vel_lag:
+        S.dof_pos_lag_timestep[:] = torch.randint(7, 26, (N,), generator=gen).to(device)
+        S.dof_vel_lag_timestep[:] = torch.randint(7, 26, (N,), generator=gen).to(device)
+    for kind in ("lag", "dof_lag", "imu_lag", "dof_pos_lag", "dof_vel_lag"):     # a per-step re-draw in progress
+        if C.perstep[kind]:
+            getattr(S, f"last_{kind}_timestep")[:] = getattr(S, f"{kind}_timestep")
     S.env_frictions[:] = 0.2 + 1.1 * r(N, 1)
     S.body_mass[:] = 10 + 5 * r(N, 1)
     S.common_step_counter = counter                               # curriculum check + ext-force window at step 3
@@ -87,6 +93,9 @@ MASS = (1.0, 0.0, 0.04, 0.0, 1.0, 1.0)
     # the optional branches the other way round from t1_cfg (no lags / randomisation / noise / force; fixed lag indices)
     ("plane_flags_off", 1024, 20, "cuda", 66, None), ("plane_flags_mixed", 1024, 20, "cuda", 66, None),
     ("plane_flags_off", 200, 12, "cpu", 66, MASS),
+    # the lag options t1_cfg marks "always False": per-step re-draws of the lag indices, separate position / velocity lags
+    ("plane_lag_perstep", 1024, 30, "cuda", 66, None), ("plane_lag_perstep", 200, 12, "cpu", 66, MASS),
+    ("plane_pos_vel_lag", 1024, 30, "cuda", 66, None), ("plane_pos_vel_lag", 200, 12, "cpu", 66, MASS),
     # BASELINE config 3 at its own size, and the plane step at the sizes where env_block, early mode, the carve-out and
     # the 128-register build switch
     ("trimesh_heights_push", 8192, 5, "cuda", 66, None),
@@ -143,7 +152,20 @@ def test_env_follows_oracle(name, N, steps, where, H, rates, fused=True):
             close(getattr(env, attr), getattr(S, attr), tag + attr)
         exact(env.lag_timestep, S.lag_timestep, tag + "lag_timestep")
         close(env.lag_buffer, S.lag_buffer, tag + "lag_buffer (ring vs shifted array)")
-        close(env.dof_lag_buffer, S.dof_lag_buffer, tag + "dof_lag_buffer")
+        if C.pos_vel_lag:       # separate position / velocity lags: both live in the DOF ring
+            close(env.dof_pos_lag_buffer, S.dof_pos_lag_buffer, tag + "dof_pos_lag_buffer")
+            close(env.dof_vel_lag_buffer, S.dof_vel_lag_buffer, tag + "dof_vel_lag_buffer")
+            exact(env.dof_pos_lag_timestep, S.dof_pos_lag_timestep, tag + "dof_pos_lag_timestep")
+            exact(env.dof_vel_lag_timestep, S.dof_vel_lag_timestep, tag + "dof_vel_lag_timestep")
+        else:
+            close(env.dof_lag_buffer, S.dof_lag_buffer, tag + "dof_lag_buffer")
+            exact(env.dof_lag_timestep, S.dof_lag_timestep, tag + "dof_lag_timestep")
+        exact(env.imu_lag_timestep, S.imu_lag_timestep, tag + "imu_lag_timestep")
+        if any(C.perstep.values()):
+            last = env.last_lag_timesteps()
+            for col, kind in enumerate(("lag", "dof_lag", "imu_lag", "dof_pos_lag", "dof_vel_lag")):
+                if C.perstep[kind] and (col < 3 or C.pos_vel_lag):
+                    exact(last[:, col], getattr(S, f"last_{kind}_timestep"), tag + f"last_{kind}_timestep")
         close(env.imu_lag_buffer, S.imu_lag_buffer, tag + "imu_lag_buffer")
         close(env.root_states, sim.root_states, tag + "root_states")
         close(env.dof_state, sim.dof_state, tag + "dof_state")

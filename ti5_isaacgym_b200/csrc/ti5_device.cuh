@@ -150,7 +150,12 @@ static __device__ __noinline__ void euler_xyz(const float q[4], float e[3]) {
 // (idx, site, step) under the key `seed`; words -> U[0,1) with 24 random bits.
 // ---------------------------------------------------------------------------------------------
 enum RngSite { S_TORQUE = 0, S_CMD = 16, S_PUSH = 24, S_EXT, S_DOFS, S_ROOT, S_DR, S_GAIT_TIME, S_NOISE, S_LAG,
-               S_GAIT_START, S_TERRAIN };
+               S_GAIT_START, S_TERRAIN,
+               S_LAGSTEP };   // per-step lag re-draws and the position / velocity lag draws (idx = env * 32 + slot: 0-15 the
+                              // action lag of substep k, 17-20 DOF / IMU / position / velocity per step, 24-25 reset draws)
+// the options t1_cfg marks "always False": tested together, so the common path pays one uniform branch
+#define TI5_F_LAG_OPTIONS (TI5_F_LAG_PERSTEP | TI5_F_DOF_LAG_PERSTEP | TI5_F_IMU_LAG_PERSTEP | TI5_F_POS_VEL_LAG | \
+                           TI5_F_POS_LAG_PERSTEP | TI5_F_VEL_LAG_PERSTEP)
 
 __device__ __forceinline__ uint4 philox4_inline(uint64_t seed, uint64_t step, uint32_t site, uint32_t idx) {
   uint32_t c0 = idx, c1 = site, c2 = (uint32_t)step, c3 = (uint32_t)(step >> 32);

@@ -85,6 +85,24 @@ struct ObsRng {
       for (int gi = 0; gi < p.num_gaits; ++gi) gait_u[gi] = r.gait_time[(size_t)e * p.num_gaits + gi];
     }
   }
+  // an integer in the lag range of `kind` (0 action, 1 DOF, 2 IMU, 3 position, 4 velocity) from one uniform, like the
+  // reset draws above
+  __device__ __forceinline__ int lag_from_u(int kind, float u) const {
+    const int lo = kind < 3 ? p.lag_range[kind][0] : p.lag_range_pv[kind - 3][0];
+    const int hi = kind < 3 ? p.lag_range[kind][1] : p.lag_range_pv[kind - 3][1];
+    const int v = lo + (int)(u * (float)(hi - lo + 1));
+    return v > hi ? hi : v;
+  }
+  // per-step re-draw of the DOF / IMU / position / velocity lag index (t1:409, 438, 418, 426), before the clamp
+  __device__ __noinline__ int lag_step_draw(int kind, int e, int N) const {
+    if (!philox) return (int)r.lag_step[(size_t)(p.decimation + kind - 1) * N + e];
+    return lag_from_u(kind, philox_u(p.seed, step, S_LAGSTEP, e * 32 + 16 + kind));
+  }
+  // position / velocity lag index of a re-spawned env (lr:639, 646)
+  __device__ __noinline__ int lag_pv_draw(int w, int e) const {
+    if (!philox) return (int)r.lag_idx_pv[(size_t)e * 2 + w];
+    return lag_from_u(3 + w, philox_u(p.seed, step, S_LAGSTEP, e * 32 + 24 + w));
+  }
   __device__ __forceinline__ int64_t terrain_level(int e) const {
     if (!philox) return r.terrain_level[e] % p.max_terrain_level;
     int64_t v = (int64_t)(philox_u(p.seed, step, S_TERRAIN, e) * (float)p.max_terrain_level);
@@ -186,6 +204,7 @@ __device__ __forceinline__ void reset_env_base(const Ti5Params& p, const Ti5Buff
 }
 
 // Schedule (role 1): lag indices, counters, gait start and gait times.
+template <bool LAGOPT>
 __device__ __forceinline__ void reset_env_schedule(const Ti5Params& p, const Ti5Buffers& b, const ObsRng& rng, int es,
                                                    int64_t pushes, const float* pre) {
   int lag[3];
@@ -196,6 +215,20 @@ __device__ __forceinline__ void reset_env_schedule(const Ti5Params& p, const Ti5
   if (p.flags & TI5_F_ADD_LAG) b.lag_timestep[es * 3 + 0] = (p.flags & TI5_F_RAND_LAG_STEPS) ? lag[0] : p.lag_range[0][1];
   if (p.flags & TI5_F_ADD_DOF_LAG) b.lag_timestep[es * 3 + 1] = (p.flags & TI5_F_RAND_DOF_LAG_STEPS) ? lag[1] : p.lag_range[1][1];
   if (p.flags & TI5_F_ADD_IMU_LAG) b.lag_timestep[es * 3 + 2] = (p.flags & TI5_F_RAND_IMU_LAG_STEPS) ? lag[2] : p.lag_range[2][1];
+  if (LAGOPT && (p.flags & TI5_F_LAG_OPTIONS)) {                                 // lr:610-611, 620-621, 630-650
+    if (p.flags & TI5_F_POS_VEL_LAG) {
+      b.lag_pv[es * 2 + 0] = (p.flags & TI5_F_RAND_POS_LAG_STEPS) ? rng.lag_pv_draw(0, es) : p.lag_range_pv[0][1];
+      b.lag_pv[es * 2 + 1] = (p.flags & TI5_F_RAND_VEL_LAG_STEPS) ? rng.lag_pv_draw(1, es) : p.lag_range_pv[1][1];
+    }
+    const int perstep[5] = {TI5_F_LAG_PERSTEP, TI5_F_DOF_LAG_PERSTEP, TI5_F_IMU_LAG_PERSTEP, TI5_F_POS_LAG_PERSTEP,
+                            TI5_F_VEL_LAG_PERSTEP};
+    for (int k = 0; k < 5; ++k)
+      if (p.flags & perstep[k]) {       // `last_*_lag_timestep[env_ids]` = the range maximum, in both copies
+        const int hi = k < 3 ? p.lag_range[k][1] : p.lag_range_pv[k - 3][1];
+        b.last_lag[((size_t)0 * p.num_envs + es) * 5 + k] = hi;
+        b.last_lag[((size_t)1 * p.num_envs + es) * 5 + k] = hi;
+      }
+  }
   b.feet_air_time[es * 2 + 0] = 0.0f; b.feet_air_time[es * 2 + 1] = 0.0f;        // t1:519-523
   b.episode_length_buf[es] = 0;
   b.phase_length_buf[es] = 0;
@@ -225,7 +258,10 @@ constexpr int DRAW_STRIDE = D * 8 + 8 + 1;     // floats per env of the parked r
 // MINB = 2 caps the kernel at 128 registers (122 used, no spills) for large grids, where four CTAs of 128 threads per SM
 // instead of three are worth 10 us per step at 65536 envs; small grids keep the uncapped build (140 registers), which
 // measured 1 us faster there.
-template <int KC, int PC, int MINB>
+// LAGOPT: the lag options t1_cfg marks "always False" (per-step re-draws, separate position / velocity lags) behind a
+// compile-time switch — as run-time branches they cost the t1 configuration 1.2 us per step at 8192 envs (registers and
+// stack of code that never runs).
+template <int KC, int PC, int MINB, bool LAGOPT = false>
 __global__ void __launch_bounds__(256, MINB)
 reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5Buffers b,
                      const __grid_constant__ Ti5Rng r, int phases) {
@@ -454,7 +490,7 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
     }
     probe(b.debug_ts, 1, 6);
   } else if (role == 1 && flagged) {
-    reset_env_schedule(p, b, rng, e, pushes, pre_draws ? s_draw + D * 8 : nullptr);
+    reset_env_schedule<LAGOPT>(p, b, rng, e, pushes, pre_draws ? s_draw + D * 8 : nullptr);
     reset_env_base(p, b, rng, e, s_spawn, org);
   }
   probe(b.debug_ts, 1, 1);
@@ -566,6 +602,12 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
       float* oo = s_obs + lane * Kp;
       float* po = s_priv + lane * Pp;
       auto put = [&](int k, float v) { oo[k] = noisy ? v + oo[k] : v; };       // value + noise (drawn above)
+      // per-step re-draw of a lag index: never more than one step further back than the last one (t1:411-412)
+      auto relag = [&](int kind) {
+        const int draw = rng.lag_step_draw(kind, e, N);
+        const int last = b.last_lag[((size_t)(step & 1) * N + e) * 5 + kind];
+        return draw > last + 1 ? last + 1 : draw;
+      };
 
       if (pA1) {
         // ---------------- obs A1: command input (t1:407-411) -------------------------------------------------
@@ -583,6 +625,11 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
       if (pA3) {
         // ---------------- obs A3: lagged IMU (t1:438-451) ---------------------------------------------------
         float imu[6];
+        if (LAGOPT && (p.flags & TI5_F_IMU_LAG_PERSTEP)) {   // t1:437-442
+          lag_imu = relag(2);
+          b.lag_timestep[e * 3 + 2] = lag_imu;
+          b.last_lag[((size_t)((step + 1) & 1) * N + e) * 5 + 2] = lag_imu;
+        }
         const int64_t ji = (pushes - 1) - lag_imu;
         if (!imu_lag) {
 #pragma unroll
@@ -605,9 +652,31 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
       if (pB1 || pB2) {
         // ---------------- obs B1 / B2: lagged joint positions / velocities; rows pushed before the env's last reset
         // read as zero ----------------------------------------------------------------------------------------
-        const int64_t jj = (pushes - 1) - lag_dof;
+        // the lag of the positions (B1) and of the velocities (B2): the common joint-state lag, unless the options t1_cfg
+        // leaves off are in play — a per-step re-draw (t1:408-413), or separate position / velocity lags (t1:416-431)
+        int lag_q = lag_dof, lag_qd = lag_dof;
+        if (LAGOPT && (p.flags & TI5_F_LAG_OPTIONS)) {
+          const size_t nxt = ((size_t)((step + 1) & 1) * N + e) * 5;
+          if (p.flags & TI5_F_POS_VEL_LAG) {
+            lag_q = b.lag_pv[e * 2 + 0];
+            lag_qd = b.lag_pv[e * 2 + 1];
+            if (pB1 && (p.flags & TI5_F_POS_LAG_PERSTEP)) { lag_q = relag(3); b.lag_pv[e * 2 + 0] = lag_q; b.last_lag[nxt + 3] = lag_q; }
+            if (pB2 && (p.flags & TI5_F_VEL_LAG_PERSTEP)) { lag_qd = relag(4); b.lag_pv[e * 2 + 1] = lag_qd; b.last_lag[nxt + 4] = lag_qd; }
+          } else if (p.flags & TI5_F_DOF_LAG_PERSTEP) {
+            lag_q = lag_qd = relag(1);
+            if (pB1) { b.lag_timestep[e * 3 + 1] = lag_q; b.last_lag[nxt + 1] = lag_q; }
+          }
+        }
+        const int64_t jj = (pushes - 1) - lag_q;
         const bool hit = jj >= stamp && jj >= 0;
         const float* row = hit ? b.dof_ring + ((size_t)ring_slot(jj, p.dof_lag_len) * N + e) * (2 * D) : nullptr;
+        bool hit2 = hit;
+        const float* row2 = row;
+        if (LAGOPT && lag_qd != lag_q) {                       // separate velocity lag only
+          const int64_t jj2 = (pushes - 1) - lag_qd;
+          hit2 = jj2 >= stamp && jj2 >= 0;
+          row2 = hit2 ? b.dof_ring + ((size_t)ring_slot(jj2, p.dof_lag_len) * N + e) * (2 * D) : nullptr;
+        }
         if (pB1) {
           float lq[D];
           if (!dof_lag) {
@@ -627,8 +696,8 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
           if (!dof_lag) {
 #pragma unroll
             for (int i = 0; i < D; ++i) lqd[i] = qd[i];
-          } else if (hit) {
-            load12(row + D, 0, lqd);
+          } else if (hit2) {
+            load12(row2 + D, 0, lqd);
           } else {
 #pragma unroll
             for (int i = 0; i < D; ++i) lqd[i] = 0.0f;
@@ -950,6 +1019,13 @@ extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const 
   TI5_CHECK_ARGS(p->env_block == 32 || p->env_block == 64 || p->env_block == 128);
   TI5_CHECK_ARGS(p->num_single_obs == 47 && p->priv_frame >= 73 && p->num_single_obs <= 64);
   TI5_CHECK_ARGS(p->rng_mode == TI5_RNG_PHILOX || (r && r->cmd && r->dofs && r->dr && r->gait_time && r->noise));
+  {   // the lag options t1_cfg leaves off: their state and (parity mode) their draws
+    const int perstep = TI5_F_LAG_PERSTEP | TI5_F_DOF_LAG_PERSTEP | TI5_F_IMU_LAG_PERSTEP | TI5_F_POS_LAG_PERSTEP | TI5_F_VEL_LAG_PERSTEP;
+    TI5_CHECK_ARGS(!(p->flags & perstep) || b->last_lag);
+    TI5_CHECK_ARGS(!(p->flags & (perstep & ~TI5_F_LAG_PERSTEP)) || p->rng_mode == TI5_RNG_PHILOX || (r && r->lag_step));
+    TI5_CHECK_ARGS(!(p->flags & TI5_F_POS_VEL_LAG) || (b->lag_pv && (p->flags & TI5_F_ADD_DOF_LAG) &&
+                                                        (p->rng_mode == TI5_RNG_PHILOX || (r && r->lag_idx_pv))));
+  }
   Ti5Rng rr = r ? *r : Ti5Rng{};
   const int blocks = (p->num_envs + p->env_block - 1) / p->env_block;
   // warps per 32 envs (2, 4 or 8; TI5_RO_ROLES overrides): eight on the small grids, where the SMs have warp slots to
@@ -975,6 +1051,8 @@ extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const 
   auto kernel = p->priv_frame == 73 ? (big ? reset_observe_kernel<47, 73, 2> : reset_observe_kernel<47, 73, 1>)
                 : p->priv_frame == 260 ? (big ? reset_observe_kernel<47, 260, 2> : reset_observe_kernel<47, 260, 1>)
                                        : (big ? reset_observe_kernel<47, 0, 2> : reset_observe_kernel<47, 0, 1>);
+  if (p->flags & TI5_F_LAG_OPTIONS)       // the rarely used lag options: the generic-width builds carry them
+    kernel = big ? reset_observe_kernel<47, 0, 2, true> : reset_observe_kernel<47, 0, 1, true>;
   if (!ti5_ensure_smem(kernel, smem)) {
     ti5_set_error("ti5_reset_observe: %zu bytes of shared memory per CTA not available", smem);
     return TI5_ECUDA;

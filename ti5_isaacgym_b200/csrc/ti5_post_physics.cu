@@ -1040,6 +1040,8 @@ static int launch_post(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng* r,
   TI5_CHECK_ARGS(p->env_block == 32 || p->env_block == 64 || (!fused && p->env_block == 128));
   TI5_CHECK_ARGS(p->num_gaits >= 0 && p->num_gaits <= TI5_MAX_GAITS);
   TI5_CHECK_ARGS(p->rng_mode == TI5_RNG_PHILOX || (r && r->cmd));
+  // the per-substep re-draw of the action lag (off in t1_cfg) exists in the unfused substep kernels only
+  TI5_CHECK_ARGS(!(fused && (p->flags & TI5_F_LAG_PERSTEP)));
   TI5_CHECK_ARGS((p->term_mask & (1u << T_DOF_VEL_LIMITS)) == 0);   // the reference term reads a cfg field t1 lacks
   TI5_CHECK_ARGS(!(p->flags & TI5_F_ADD_EXT_FORCE) || p->applied_stride >= 3);
   Ti5Rng rr = r ? *r : Ti5Rng{};

@@ -81,11 +81,14 @@ substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5B
 
   // the lagged action row: pushed in an earlier step for most envs (lag > k) and cold in L2 by now — start fetching it
   float4* ring = reinterpret_cast<float4*>(b.act_ring);
-  const int64_t jt = base + k_torque, jj = jt - lag;     // push index now / the one the controller sees
-  const bool need_ring = do_torque && lagged && lag > 0;
-  const bool ring_live = need_ring && jj >= stamp && jj >= 0;   // rows pushed before the env's last reset read as zero (lr:606)
+  const int64_t jt = base + k_torque;                    // push index now
+  int64_t jj = jt - lag;                                 // ... and the one the controller sees
+  bool need_ring = do_torque && lagged && lag > 0;
+  bool ring_live = need_ring && jj >= stamp && jj >= 0;  // rows pushed before the env's last reset read as zero (lr:606)
   const float4* ring_row = ring + (size_t)ring_slot(ring_live ? jj : 0, p.lag_len) * N * 3 + idx;
-  if (ring_live) prefetch_l2(ring_row);
+  // (with the per-substep re-draw of the lag, an option t1_cfg leaves off, the row is only known behind the wait)
+  const bool relag = do_torque && lagged && (p.flags & TI5_F_LAG_PERSTEP);
+  if (ring_live && !relag) prefetch_l2(ring_row);
   // the Philox draw and the IMU arithmetic need nothing from the previous kernel either
   if (do_torque && rt && p.rng_mode == TI5_RNG_PHILOX) u4 = philox_u4(p.seed, (uint64_t)step, S_TORQUE + k_torque, idx);
   float imu_val[4] = {0.f, 0.f, 0.f, 0.f};
@@ -107,6 +110,29 @@ substep_kernel(const __grid_constant__ Ti5Params p, const __grid_constant__ Ti5B
 
   // ---- everything below depends on (or must not overtake) the previous kernel of the step -------------
   chain_wait();
+  if (relag) {
+    // lr:1038-1043: a fresh lag index every substep, never more than one substep further back than the last one.  The
+    // three threads of an env compute the same value from the copy of `last_lag` this substep reads (parity of the
+    // push index); one of them stores the other copy for the next substep.
+    const int lo = p.lag_range[0][0], hi = p.lag_range[0][1];
+    int draw;
+    if (p.rng_mode == TI5_RNG_PHILOX) {
+      draw = lo + (int)(philox_u(p.seed, (uint64_t)step, S_LAGSTEP, e * 32 + k_torque) * (float)(hi - lo + 1));
+      draw = draw > hi ? hi : draw;
+    } else {
+      draw = (int)r.lag_step[(size_t)k_torque * N + e];
+    }
+    const int last = b.last_lag[((size_t)(jt & 1) * N + e) * 5 + 0];
+    lag = draw > last + 1 ? last + 1 : draw;
+    if (gq == 0) {
+      b.lag_timestep[e * 3 + 0] = lag;
+      b.last_lag[((size_t)((jt + 1) & 1) * N + e) * 5 + 0] = lag;
+    }
+    jj = jt - lag;
+    need_ring = lag > 0;
+    ring_live = need_ring && jj >= stamp && jj >= 0;
+    ring_row = ring + (size_t)ring_slot(ring_live ? jj : 0, p.lag_len) * N * 3 + idx;
+  }
   // the one dependent load: the lagged action row (lr:1045)
   float4 t4 = zero4;
   if (ring_live) t4 = *ring_row;
@@ -189,6 +215,7 @@ static int launch_substep(const Ti5Params* p, const Ti5Buffers* b, const Ti5Rng*
   TI5_CHECK_ARGS(p && b && p->num_envs > 0 && k >= 0 && k <= p->decimation && (phases & 3) != 0 && (phases & ~7) == 0);
   TI5_CHECK_ARGS(!(phases & TI5_SUB_TORQUE) || k < p->decimation);
   TI5_CHECK_ARGS(p->decimation <= 16);       // Philox sites S_TORQUE + k must stay below S_CMD
+  TI5_CHECK_ARGS(!(p->flags & TI5_F_LAG_PERSTEP) || (b->last_lag && (p->rng_mode == TI5_RNG_PHILOX || (r && r->lag_step))));
   TI5_CHECK_ARGS(!(phases & TI5_SUB_TORQUE) || p->rng_mode == TI5_RNG_PHILOX || !(p->flags & TI5_F_RAND_TORQUE) ||
                  (r && r->torque));
   Ti5Rng rr = r ? *r : Ti5Rng{};

@@ -261,6 +261,16 @@ class LeggedRobot(BaseTask):
         # kernel-side layout
         self._act_ring, self._dof_ring, self._imu_ring = f32(p.lag_len, N, D), f32(p.dof_lag_len, N, 2 * D), f32(p.imu_lag_len, N, 6)
         self._lag_timestep = torch.zeros(N, 3, dtype=torch.int32, device=dev)
+        # options t1_cfg leaves off: separate joint position / velocity lags, per-step re-draws of the lag indices
+        # (`last_*_lag_timestep`, lr:282-345: the range maximum until the first re-draw; two copies, see ti5_step.h)
+        hi5 = torch.tensor([p.lag_range[k][1] for k in range(3)] + [p.lag_range_pv[k][1] for k in range(2)],
+                           dtype=torch.int32, device=dev)
+        # (allocated at full size only with one of the options on: the t1 configuration keeps its allocation pattern)
+        lag_opts = sum(C[k] for k in ("TI5_F_LAG_PERSTEP", "TI5_F_DOF_LAG_PERSTEP", "TI5_F_IMU_LAG_PERSTEP", "TI5_F_POS_VEL_LAG",
+                                      "TI5_F_POS_LAG_PERSTEP", "TI5_F_VEL_LAG_PERSTEP"))
+        n_opt = N if p.flags & lag_opts else 1
+        self._lag_pv = hi5[3:5].repeat(n_opt, 1).contiguous()
+        self._last_lag = hi5.repeat(2, n_opt, 1).contiguous()
         self._ring_stamp = i64(N)
         self._obs_ring, self._priv_ring = f32(N, 2 * H, K), f32(N, 2 * CH, P)
         nblk = (N + 31) // 32
@@ -334,6 +344,10 @@ class LeggedRobot(BaseTask):
                                               (dr.add_imu_lag, dr.randomize_imu_lag_timesteps, dr.imu_lag_timesteps_range))):
             if on:
                 self._lag_timestep[:, col] = torch.randint(rng[0], rng[1] + 1, (N,), device=dev) if rnd else rng[1]
+        if p.flags & C["TI5_F_POS_VEL_LAG"]:                                  # lr:322-349
+            for col, (rnd, rng) in enumerate(((dr.randomize_dof_pos_lag_timesteps, dr.dof_pos_lag_timesteps_range),
+                                              (dr.randomize_dof_vel_lag_timesteps, dr.dof_vel_lag_timesteps_range))):
+                self._lag_pv[:, col] = torch.randint(rng[0], rng[1] + 1, (N,), device=dev) if rnd else rng[1]
         self.gait_start[:] = torch.randint(0, 2, (N,), device=dev) * 0.5
         if dr.randomize_friction:
             buckets = dr.friction_range[0] + (dr.friction_range[1] - dr.friction_range[0]) * u(256)
@@ -370,6 +384,7 @@ class LeggedRobot(BaseTask):
             coulomb=self.randomized_joint_coulomb, viscous=self.randomized_joint_viscous,
             joint_armatures=self.joint_armatures, act_ring=self._act_ring, dof_ring=self._dof_ring,
             imu_ring=self._imu_ring, lag_timestep=self._lag_timestep, ring_stamp=self._ring_stamp,
+            lag_pv=self._lag_pv, last_lag=self._last_lag,
             last_actions=self.last_actions, last_last_actions=self.last_last_actions, last_dof_vel=self.last_dof_vel,
             last_root_vel=self.last_root_vel, commands=self.commands, episode_length_buf=self._episode_length_buf,
             phase_length_buf=self.phase_length_buf, gait_time=self.gait_time, gait_start=self.gait_start,
@@ -429,6 +444,22 @@ class LeggedRobot(BaseTask):
     def imu_lag_timestep(self):
         return self._lag_timestep[:, 2].long()
 
+    @property
+    def dof_pos_lag_timestep(self):
+        return self._lag_pv[:, 0].long()
+
+    @property
+    def dof_vel_lag_timestep(self):
+        return self._lag_pv[:, 1].long()
+
+    def last_lag_timesteps(self):
+        """The reference's `last_{lag,dof_lag,imu_lag,dof_pos_lag,dof_vel_lag}_timestep` (N,5) as the NEXT re-draw will see
+        them: the action lag's copy is picked by the parity of the substep count, the others' by the step's."""
+        pushes = self._step_index * self._params.decimation
+        out = self._last_lag[(self._step_index + 1) & 1].clone()     # step s + 1 reads the copy step s wrote
+        out[:, 0] = self._last_lag[pushes & 1][:, 0]
+        return out.long()
+
     def _ring_as_shifted(self, ring, length):
         """(len, N, W) slot-major ring -> the reference's (N, W, len) shifted buffer, slot 0 newest."""
         pushes = self._step_index * self._params.decimation
@@ -449,6 +480,17 @@ class LeggedRobot(BaseTask):
     @property
     def imu_lag_buffer(self):
         return self._ring_as_shifted(self._imu_ring, self._params.imu_lag_len)
+
+    @property
+    def dof_pos_lag_buffer(self):
+        """lr:322-326 with `add_dof_pos_vel_lag`: the position half of the DOF ring, cut to the position lag range."""
+        L = self.cfg.domain_rand.dof_pos_lag_timesteps_range[1] + 1
+        return self._ring_as_shifted(self._dof_ring, self._params.dof_lag_len)[:, :self.num_dof, :L]
+
+    @property
+    def dof_vel_lag_buffer(self):
+        L = self.cfg.domain_rand.dof_vel_lag_timesteps_range[1] + 1
+        return self._ring_as_shifted(self._dof_ring, self._params.dof_lag_len)[:, self.num_dof:, :L]
 
     def _history_views(self):
         """The current H-frame / CH-frame windows as (N, H*K) / (N, CH*P) views into the mirrored rings (fresh tensor
@@ -547,7 +589,7 @@ class LeggedRobot(BaseTask):
             t = pools.get(name)
             if t is None:
                 continue
-            want = torch.int64 if name in ("lag_idx", "gait_start", "terrain_level") else torch.float32
+            want = torch.int64 if name in ("lag_idx", "gait_start", "terrain_level", "lag_idx_pv", "lag_step") else torch.float32
             t = t.to(device=self.device, dtype=want).contiguous()
             keep[name] = t
             setattr(r, name, ctypes.c_void_p(t.data_ptr()))
@@ -638,7 +680,9 @@ class LeggedRobot(BaseTask):
         self._launch_post(with_physics, notify=notify)
 
     def _uses_fused_step(self, with_physics=False):
-        return self._fused_step and not with_physics and self._params.env_block <= 64
+        # (the per-substep re-draw of the action lag, off in t1_cfg, exists in the unfused substep kernels only)
+        return (self._fused_step and not with_physics and self._params.env_block <= 64
+                and not self._params.flags & C["TI5_F_LAG_PERSTEP"])
 
     def phase_launchers(self):
         """The kernel families of a fused step as [(name, launch, launches)], for a benchmark that brackets each family
@@ -927,6 +971,14 @@ class LeggedRobot(BaseTask):
         self.reset_buf.copy_(torch.as_tensor(state["reset_buf"]).to(dev).bool())
         for col, name in enumerate(("lag_timestep", "dof_lag_timestep", "imu_lag_timestep")):
             self._lag_timestep[:, col] = torch.as_tensor(state[name]).to(dev).to(torch.int32)
+        lag_opts_on = self._last_lag.shape[1] == N and N > 1 or self._last_lag.shape[1] == N == 1
+        for col, name in enumerate(("dof_pos_lag_timestep", "dof_vel_lag_timestep")):
+            if name in state and lag_opts_on:
+                self._lag_pv[:, col] = torch.as_tensor(state[name]).to(dev).to(torch.int32)
+        for col, name in enumerate(("last_lag_timestep", "last_dof_lag_timestep", "last_imu_lag_timestep",
+                                    "last_dof_pos_lag_timestep", "last_dof_vel_lag_timestep")):
+            if name in state and lag_opts_on:
+                self._last_lag[:, :, col] = torch.as_tensor(state[name]).to(dev).to(torch.int32)
         for i, name in enumerate(self.reward_scales):
             self.episode_sums[name].copy_(torch.as_tensor(state["episode_sums"][i]).to(dev))
         if "terrain_levels" in state:
@@ -947,8 +999,15 @@ class LeggedRobot(BaseTask):
         # lag buffers: age a (slot 0 = newest) was push index pushes-1-a
         pushes = self._step_index * self._params.decimation
         self._ring_stamp.zero_()
+        pos_vel = bool(self._params.flags & C["TI5_F_POS_VEL_LAG"])
         for ring, name in ((self._act_ring, "lag_buffer"), (self._dof_ring, "dof_lag_buffer"), (self._imu_ring, "imu_lag_buffer")):
-            buf = torch.as_tensor(state[name]).to(dev)              # (N, W, len)
+            if pos_vel and name == "dof_lag_buffer":                # the DOF ring holds the position and the velocity lag buffers
+                pb, vb = (torch.as_tensor(state[k]).to(dev) for k in ("dof_pos_lag_buffer", "dof_vel_lag_buffer"))
+                L = ring.shape[0]
+                pad = lambda t: torch.nn.functional.pad(t, (0, L - t.shape[2]))
+                buf = torch.cat((pad(pb), pad(vb)), 1)
+            else:
+                buf = torch.as_tensor(state[name]).to(dev)          # (N, W, len)
             length = buf.shape[2]
             assert pushes >= length
             slots = (pushes - 1 - torch.arange(length, device=dev)) % length

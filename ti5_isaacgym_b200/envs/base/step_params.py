@@ -20,9 +20,8 @@ TERM_NAMES = ("action_smoothness", "base_acc", "base_height", "collision", "defa
 GAIT_KIND = {"stand": C["TI5_GAIT_STAND"], "walk_sagittal": C["TI5_GAIT_WALK_SAGITTAL"],
              "walk_lateral": C["TI5_GAIT_WALK_LATERAL"], "rotate": C["TI5_GAIT_ROTATE"],
              "walk_omnidirectional": C["TI5_GAIT_WALK_OMNI"]}
-UNSUPPORTED_FLAGS = ("randomize_lag_timesteps_perstep", "randomize_dof_lag_timesteps_perstep",
-                     "randomize_imu_lag_timesteps_perstep", "add_dof_pos_vel_lag",
-                     "randomize_joint_friction", "randomize_joint_damping")     # lr:755-773: off in t1_cfg (commented out)
+UNSUPPORTED_FLAGS = ("randomize_joint_friction", "randomize_joint_damping")     # lr:755-773: their per-joint ranges are
+                                                                                # commented out in t1_cfg:236-262
 
 
 def pick_env_block(num_envs, sms=148):
@@ -53,7 +52,11 @@ def build_params(cfg, sim_dt, robot, terrain=None, height_shape=(0, 0), div_mode
     p.priv_frame = cfg.env.single_num_privileged_obs + (cfg.terrain.num_height if measure else 0)
     p.decimation = cfg.control.decimation
     p.lag_len = dr.lag_timesteps_range[1] + 1
-    p.dof_lag_len = dr.dof_lag_timesteps_range[1] + 1
+    # separate position / velocity lags (t1:416-431) only show when the common joint-state lag is off; both read the DOF
+    # ring, which then has to cover both ranges
+    pos_vel = bool(getattr(dr, "add_dof_pos_vel_lag", False)) and not dr.add_dof_lag
+    p.dof_lag_len = (max(dr.dof_pos_lag_timesteps_range[1], dr.dof_vel_lag_timesteps_range[1]) if pos_vel
+                     else dr.dof_lag_timesteps_range[1]) + 1
     p.imu_lag_len = dr.imu_lag_timesteps_range[1] + 1
     custom = cfg.terrain.mesh_type in ("heightfield", "trimesh")
     curriculum = bool(cfg.terrain.curriculum) and custom                     # lr:104-105
@@ -68,7 +71,22 @@ def build_params(cfg, sim_dt, robot, terrain=None, height_shape=(0, 0), div_mode
         "TI5_F_TRIMESH": cfg.terrain.mesh_type == "trimesh", "TI5_F_RAND_LAG_STEPS": dr.randomize_lag_timesteps,
         "TI5_F_RAND_DOF_LAG_STEPS": dr.randomize_dof_lag_timesteps,
         "TI5_F_RAND_IMU_LAG_STEPS": dr.randomize_imu_lag_timesteps, "TI5_F_PLANE": cfg.terrain.mesh_type == "plane",
-        "TI5_F_HEADING_COMMAND": cm.heading_command, "TI5_F_NO_SW_SWITCH": not cm.sw_switch}
+        "TI5_F_HEADING_COMMAND": cm.heading_command, "TI5_F_NO_SW_SWITCH": not cm.sw_switch,
+        # options t1_cfg marks "always False" (a per-step re-draw needs its lag and the randomisation of its index on)
+        "TI5_F_LAG_PERSTEP": dr.add_lag and dr.randomize_lag_timesteps and getattr(dr, "randomize_lag_timesteps_perstep", False),
+        "TI5_F_DOF_LAG_PERSTEP": dr.add_dof_lag and dr.randomize_dof_lag_timesteps
+                                 and getattr(dr, "randomize_dof_lag_timesteps_perstep", False),
+        "TI5_F_IMU_LAG_PERSTEP": dr.add_imu_lag and dr.randomize_imu_lag_timesteps
+                                 and getattr(dr, "randomize_imu_lag_timesteps_perstep", False),
+        "TI5_F_POS_VEL_LAG": pos_vel,
+        "TI5_F_RAND_POS_LAG_STEPS": pos_vel and dr.randomize_dof_pos_lag_timesteps,
+        "TI5_F_RAND_VEL_LAG_STEPS": pos_vel and dr.randomize_dof_vel_lag_timesteps,
+        "TI5_F_POS_LAG_PERSTEP": pos_vel and dr.randomize_dof_pos_lag_timesteps
+                                 and getattr(dr, "randomize_dof_pos_lag_timesteps_perstep", False),
+        "TI5_F_VEL_LAG_PERSTEP": pos_vel and dr.randomize_dof_vel_lag_timesteps
+                                 and getattr(dr, "randomize_dof_vel_lag_timesteps_perstep", False)}
+    if pos_vel:
+        flag_src["TI5_F_ADD_DOF_LAG"] = True          # the DOF ring is pushed (header: TI5_F_POS_VEL_LAG)
     p.flags = sum(C[k] for k, on in flag_src.items() if on)
     if dr.randomize_joint_armature and not dr.randomize_joint_armature_each_joint:
         raise NotImplementedError("randomize_joint_armature without _each_joint is not used by t1_dh_stand")
@@ -92,6 +110,8 @@ def build_params(cfg, sim_dt, robot, terrain=None, height_shape=(0, 0), div_mode
     p.term_body, p.pen_body = robot.termination_contact_indices[0], robot.penalised_contact_indices[0]
     for i, rng in enumerate((dr.lag_timesteps_range, dr.dof_lag_timesteps_range, dr.imu_lag_timesteps_range)):
         p.lag_range[i][0], p.lag_range[i][1] = rng
+    for i, rng in enumerate((dr.dof_pos_lag_timesteps_range, dr.dof_vel_lag_timesteps_range)):
+        p.lag_range_pv[i][0], p.lag_range_pv[i][1] = rng
     # time scales (lr:96-113)
     p.dt = dt
     p.max_episode_length_s = cfg.env.episode_length_s
