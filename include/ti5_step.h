@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TI5_ABI_VERSION 9
+#define TI5_ABI_VERSION 10
 
 #define TI5_NUM_DOF 12      /* leg_l1..l6, leg_r1..r6 */
 #define TI5_NUM_BODIES 13   /* base_link + 12 leg links after collapse_fixed_joints */
@@ -173,7 +173,15 @@ typedef struct Ti5Params {
   double tracking_lin_vel_scale;                   /* reward_scales["tracking_lin_vel"] (double) */
   /* (appended: the fields above keep the offsets the t1 configuration was tuned with) */
   int32_t lag_range_pv[2][2];                      /* dof-position / dof-velocity lag index ranges (TI5_F_POS_VEL_LAG) */
+  int32_t flags2;                                  /* TI5_F2_* (the 31 bits of `flags` are taken) */
+  float joint_friction_w, joint_friction_lo, joint_damping_w, joint_damping_lo;   /* lr:762-773 multiplier ranges */
 } Ti5Params;
+
+/* Ti5Params.flags2 */
+enum {
+  TI5_F2_RAND_JOINT_FRICTION = 1 << 0,   /* randomize_joint_friction (one multiplier per env; lr:762-763, 921-925) */
+  TI5_F2_RAND_JOINT_DAMPING = 1 << 1     /* randomize_joint_damping (lr:772-773, 926-930) */
+};
 
 /* ---- device-resident counters and curriculum state (single instance per env object) -------- */
 typedef struct Ti5Globals {
@@ -295,6 +303,8 @@ typedef struct Ti5Buffers {
   int32_t* lag_pv;         /* (N,2): dof-position / dof-velocity lag index (TI5_F_POS_VEL_LAG), else NULL */
   int32_t* last_lag;       /* (2,N,5): the `last_*_lag_timestep` of the per-step re-draws, double-buffered (by substep
                               parity for the action lag, by step parity for the others); NULL without a *_PERSTEP flag */
+  float* joint_coeffs;     /* (N,2): joint friction / damping multiplier of the env (TI5_F2_RAND_JOINT_*), else NULL; they
+                              go to the simulator in columns 0 / 1 of `dof_props` */
 } Ti5Buffers;
 
 /* ---- caller-supplied uniforms of one step (TI5_RNG_POOLS).  All fp32 U[0,1) unless noted --- */
@@ -312,6 +322,7 @@ typedef struct Ti5Rng {
   const int64_t* gait_start;  /* (N)     t1:523 integers in {0,1} */
   const int64_t* terrain_level; /* (N)   lr:1156 integers in [0, max_terrain_level) */
   const int64_t* lag_idx_pv;  /* (N,2)   lr:639, 646 position / velocity lag at a reset, integers in range */
+  const float* dr_joint;      /* (N,2)   lr:763, 773 joint friction / damping multiplier draws */
   const int64_t* lag_step;    /* (DEC+4, N) per-step re-draws, integers in range: rows 0..DEC-1 the action lag of each
                                  substep (lr:1039), then DOF, IMU, position, velocity (t1:409, 438, 418, 426) */
 } Ti5Rng;

@@ -57,7 +57,7 @@ def same(a, b):
 def snapshot_state(S, C):
     """All persistent state of an oracle state as a flat dict of tensors."""
     out = {k: getattr(S, k).clone() for k in STATE_KEYS}
-    if C.pos_vel_lag or any(C.perstep.values()):
+    if C.pos_vel_lag or any(C.perstep.values()) or any(C.joint_props):
         out.update({k: getattr(S, k).clone() for k in OPTIONAL_KEYS})
     out["last_feet_z"] = torch.zeros(S.N, 2) if isinstance(S.last_feet_z, int) else S.last_feet_z.clone()
     out["obs_history"], out["critic_history"] = S.obs_history.clone(), S.critic_history.clone()
@@ -197,6 +197,10 @@ SCENARIOS = {
     "plane_gaits4": dict(N=24, steps=30, mesh="plane", contact_rate=0.05, events=True, edit=_gaits4),
     "plane_lag_perstep": dict(N=24, steps=24, mesh="plane", contact_rate=0.05, events=True, edit=_perstep),
     "plane_pos_vel_lag": dict(N=24, steps=24, mesh="plane", contact_rate=0.05, events=True, edit=_pos_vel_lag),
+    # joint friction / damping multipliers handed to the simulator with the armatures (lr:755-773, 915-931)
+    "plane_joint_props": dict(N=16, steps=14, mesh="plane", contact_rate=0.08, events=True,
+                              edit=lambda c: (setattr(c.domain_rand, "randomize_joint_friction", True),
+                                              setattr(c.domain_rand, "randomize_joint_damping", True))),
     "big_plane": dict(N=512, steps=12, mesh="plane", contact_rate=0.03, events=True, golden=False),
     # the reward terms the task defines but t1_cfg leaves at zero scale (t1:894-896, 917-925, 937-940)
     "plane_extra_terms": dict(N=16, steps=12, mesh="plane", contact_rate=0.08, events=True,
@@ -274,6 +278,13 @@ def run_scenario(name, spec, write_dir=None, verbose=True):
         props_arm = torch.tensor(np.stack([d["armature"] for _, d in props]) if props else np.zeros((0, 12), np.float32))
         if not (same(props_env, S.reset_ids) and same(props_arm, S.joint_armatures[S.reset_ids])):
             bad.append("dof props")
+        # lr:921-931: friction / damping of the asset times the env's multiplier (the fake gym hands out the asset's values)
+        asset = env.gym.asset.dof_props
+        for fld, on, coeff in (("friction", C.joint_props[0], S.joint_friction_coeffs), ("damping", C.joint_props[1], S.joint_damping_coeffs)):
+            got = torch.tensor(np.stack([d[fld] for _, d in props]) if props else np.zeros((0, 12), np.float32))
+            want = torch.from_numpy(asset[fld].copy()).unsqueeze(0) * (coeff[S.reset_ids] if on else torch.ones(len(S.reset_ids), 1))
+            if not same(got, want.float()):
+                bad.append("dof props " + fld)
         for nm in ("set_dof_state_tensor_indexed", "set_actor_root_state_tensor_indexed"):
             for c in calls:
                 if c[0] == nm and not (same(c[1][1].long(), S.reset_ids) and c[1][2] == len(S.reset_ids)):
@@ -330,6 +341,7 @@ def run_scenario(name, spec, write_dir=None, verbose=True):
             command_ranges=torch.tensor([env.command_ranges[k] for k in ("lin_vel_x", "lin_vel_y", "ang_vel_yaw")],
                                         dtype=torch.float64),
             props_env=props_env, props_armature=props_arm,
+            props_friction_coeff=S.joint_friction_coeffs[S.reset_ids].clone(), props_damping_coeff=S.joint_damping_coeffs[S.reset_ids].clone(),
             # the gym tensor-API calls of this step, in order (lower boundary), as one string
             gym_calls=torch.tensor(list(",".join(c[0] for c in calls).encode()), dtype=torch.uint8)))
     n_resets = sum(int(o["n_reset"]) for o in rec["outputs"])

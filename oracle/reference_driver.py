@@ -46,6 +46,7 @@ _RAND_FLOAT_SITES = {
     ("randomize_dof_props", 746): ("dr", 2), ("randomize_dof_props", 747): ("dr", 3),
     ("randomize_dof_props", 752): ("dr", 4), ("randomize_dof_props", 753): ("dr", 5),
     ("randomize_dof_props", 780): ("dr", 6),
+    ("randomize_dof_props", 763): ("dr_joint", 0), ("randomize_dof_props", 773): ("dr_joint", 1),
     ("_reset_dofs", 1084): ("dofs", None),
     ("_reset_root_states", 1105): ("root_xy", None), ("_reset_root_states", 1108): ("root_xy", None),
     ("_resample_walk_sagittal_command", 147): ("cmd", 0),
@@ -120,6 +121,8 @@ class ReferenceDriver:
         elif name == "dr":
             ids = loc["env_ids"]
             u = P[ids, 6, loc["i"]:loc["i"] + 1] if sel == 6 else P[ids, sel]
+        elif name == "dr_joint":
+            u = P[loc["env_ids"], sel:sel + 1]
         elif name in ("dofs", "root_xy"):
             u = P[loc["env_ids"]]
         elif name == "cmd":
@@ -184,7 +187,7 @@ class ReferenceDriver:
             return self.env.step(actions.clone())
 
 
-O_OPTIONAL = ("last_lag_timestep last_dof_lag_timestep last_imu_lag_timestep dof_pos_lag_buffer dof_vel_lag_buffer dof_pos_lag_timestep dof_vel_lag_timestep last_dof_pos_lag_timestep last_dof_vel_lag_timestep").split()
+O_OPTIONAL = ("last_lag_timestep last_dof_lag_timestep last_imu_lag_timestep dof_pos_lag_buffer dof_vel_lag_buffer dof_pos_lag_timestep dof_vel_lag_timestep last_dof_pos_lag_timestep last_dof_vel_lag_timestep joint_friction_coeffs joint_damping_coeffs").split()
 
 
 def adopt_reference_state(S, env):

@@ -96,6 +96,11 @@ class _Asset:
             lim = j.find("limit")
             for k in ("lower", "upper", "velocity", "effort"):
                 self.dof_props[k][i] = float(lim.get(k))
+            # joint friction / damping: the URDF's <dynamics> where it has one, else a nominal non-zero value, so that the
+            # multipliers of lr:915-931 show in what the reference hands back to the simulator
+            dyn = j.find("dynamics")
+            self.dof_props["friction"][i] = float(dyn.get("friction", 0.0)) if dyn is not None and float(dyn.get("friction", 0.0)) else 0.05 + 0.01 * i
+            self.dof_props["damping"][i] = float(dyn.get("damping", 0.0)) if dyn is not None and float(dyn.get("damping", 0.0)) else 0.5 + 0.1 * i
 
 
 class FakeGym:

@@ -146,6 +146,11 @@ def make_consts(cfg, sim_dt, robot, device="cpu", terrain=None):
     C.perstep = {k: bool(getattr(dr, f"randomize_{k}_timesteps_perstep", False) and getattr(dr, f"randomize_{k}_timesteps", False))
                  for k in ("lag", "dof_lag", "imu_lag", "dof_pos_lag", "dof_vel_lag")}
     C.pos_vel_lag = bool(getattr(dr, "add_dof_pos_vel_lag", False))
+    # joint friction / damping multipliers (lr:755-773, 921-931): one per env; the `_each_joint` variants read per-joint
+    # ranges t1_cfg only has for ten of the twelve joints (the reference raises AttributeError at joint 11)
+    C.joint_props = (bool(getattr(dr, "randomize_joint_friction", False)), bool(getattr(dr, "randomize_joint_damping", False)))
+    assert not (C.joint_props[0] and dr.randomize_joint_friction_each_joint) and \
+        not (C.joint_props[1] and dr.randomize_joint_damping_each_joint), "per-joint ranges exist for ten joints only"
     C.heading_command = bool(cfg.commands.heading_command)
     C.forward_vec = torch.tensor([1., 0., 0.], **f32)                                         # lr:170
     C.custom_origins = cfg.terrain.mesh_type in ("heightfield", "trimesh")                   # lr:1481
@@ -177,7 +182,8 @@ def rng_pool_shapes(C, N):
         "lag_idx": ((N, 3), ("i", 0, 0)),             # lr:608-629 (ranges applied per column by the caller)
         "gait_start": ((N,), ("i", 0, 2)),            # t1:523 (CPU generator in the reference, A25)
         "terrain_level": ((N,), ("i", 0, max(1, getattr(C.cfg.terrain, "num_rows", 1)))),  # lr:1156
-    } | ({"lag_idx_pv": ((N, 2), ("i", 0, 0))} if C.pos_vel_lag else {}) \
+    } | ({"dr_joint": ((N, 2), "u")} if any(C.joint_props) else {}) \
+      | ({"lag_idx_pv": ((N, 2), ("i", 0, 0))} if C.pos_vel_lag else {}) \
       | ({"lag_step": ((C.decimation + 4, N), ("i", 0, 0))} if any(C.perstep.values()) else {})
     # lag_idx_pv: lr:639, 646 (position / velocity lag at a reset); lag_step: per-step re-draws — rows 0 .. DEC-1 the
     # action lag of each substep (lr:1039), then the DOF, IMU, position and velocity lags of the step (t1:409, 438, 418, 426)
@@ -260,6 +266,7 @@ def new_state(C, N):
     S.torque_multi = torch.ones(N, D, device=dev)
     S.motor_offsets, S.randomized_p_gains, S.randomized_d_gains = z(N, D), z(N, D), z(N, D)
     S.randomized_joint_coulomb, S.randomized_joint_viscous, S.joint_armatures = z(N, D), z(N, D), z(N, D)
+    S.joint_friction_coeffs, S.joint_damping_coeffs = torch.ones(N, 1, device=dev), torch.ones(N, 1, device=dev)   # lr:1449-1457
     S.lag_buffer = z(N, D, dr.lag_timesteps_range[1] + 1)
     S.dof_lag_buffer = z(N, 2 * D, dr.dof_lag_timesteps_range[1] + 1)
     S.imu_lag_buffer = z(N, 6, dr.imu_lag_timesteps_range[1] + 1)
@@ -768,6 +775,10 @@ def reset_envs(C, S, sim, ids, R, terrain=None):
     if dr.randomize_coulomb_friction:
         S.randomized_joint_coulomb[ids] = _affine(*dr.joint_coulomb_range, u[:, 4])
         S.randomized_joint_viscous[ids] = _affine(*dr.joint_viscous_range, u[:, 5])
+    if C.joint_props[0]:                                                   # lr:762-763: one multiplier per env
+        S.joint_friction_coeffs[ids] = _affine(*dr.joint_friction_range, R["dr_joint"][ids, 0:1])
+    if C.joint_props[1]:                                                   # lr:772-773
+        S.joint_damping_coeffs[ids] = _affine(*dr.joint_damping_range, R["dr_joint"][ids, 1:2])
     if dr.randomize_joint_armature:
         assert dr.randomize_joint_armature_each_joint
         for j in range(D):
@@ -982,7 +993,7 @@ _PLAIN_STATE = ("torques actions last_actions last_last_actions last_dof_vel las
                 "rew_buf reset_buf time_out_buf env_origins env_frictions body_mass").split()
 
 
-OPTIONAL_LAG_STATE = ("last_lag_timestep last_dof_lag_timestep last_imu_lag_timestep dof_pos_lag_buffer dof_vel_lag_buffer dof_pos_lag_timestep dof_vel_lag_timestep last_dof_pos_lag_timestep last_dof_vel_lag_timestep").split()
+OPTIONAL_LAG_STATE = ("last_lag_timestep last_dof_lag_timestep last_imu_lag_timestep dof_pos_lag_buffer dof_vel_lag_buffer dof_pos_lag_timestep dof_vel_lag_timestep last_dof_pos_lag_timestep last_dof_vel_lag_timestep joint_friction_coeffs joint_damping_coeffs").split()
 
 
 def load_state(C, S, state):

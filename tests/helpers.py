@@ -50,6 +50,9 @@ def scenario_cfg(name, num_envs, frame_stack=66):
         cfg.commands.sw_switch = False
     if name == "plane_ref_actions":
         cfg.env.use_ref_actions = True
+    if name == "plane_joint_props":
+        cfg.domain_rand.randomize_joint_friction = True
+        cfg.domain_rand.randomize_joint_damping = True
     if name == "plane_lag_perstep":       # _perstep
         for k in ("lag", "dof_lag", "imu_lag"):
             setattr(cfg.domain_rand, f"randomize_{k}_timesteps_perstep", True)
@@ -109,7 +112,7 @@ def scenario_cfg(name, num_envs, frame_stack=66):
 GOLDEN_SCENARIOS = ["plane_default", "plane_events", "trimesh_heights_push", "plane_extra_terms", "plane_windows",
                     "trimesh_windows", "plane_heading", "plane_no_sw", "plane_flags_off", "plane_flags_mixed",
                     "plane_heights", "trimesh_plain", "trimesh_no_curriculum", "plane_ref_actions", "plane_h15", "plane_params",
-                    "trimesh_points77", "plane_gaits4", "plane_lag_perstep", "plane_pos_vel_lag"]
+                    "trimesh_points77", "plane_gaits4", "plane_lag_perstep", "plane_pos_vel_lag", "plane_joint_props"]
 
 
 def gym_calls_of(out):

@@ -143,11 +143,14 @@ def test_unsupported_options_raise():
     from ti5_isaacgym_b200.envs import DHT1StandCfg
     from ti5_isaacgym_b200.envs.base.step_params import build_params
     from ti5_isaacgym_b200.envs.t1.t1_robot import robot_constants
+    from ti5_isaacgym_b200._lib import CONSTS
     cfg = DHT1StandCfg()
-    cfg.domain_rand.randomize_joint_friction = True     # its per-joint ranges are commented out in t1_cfg:236-262
+    cfg.domain_rand.randomize_joint_friction = True     # one multiplier per env: supported (lr:762-763)
+    p = build_params(cfg, 0.001, robot_constants(cfg))
+    assert p.flags2 == CONSTS["TI5_F2_RAND_JOINT_FRICTION"] and abs(p.joint_friction_lo - 0.01) < 1e-7
+    cfg.domain_rand.randomize_joint_friction_each_joint = True   # per-joint ranges exist for ten of the twelve joints only
     with pytest.raises(NotImplementedError):
         build_params(cfg, 0.001, robot_constants(cfg))
-    from ti5_isaacgym_b200._lib import CONSTS
     cfg = DHT1StandCfg()                                # the lag options t1_cfg marks "always False" (t1_cfg:290-312)
     cfg.domain_rand.randomize_lag_timesteps_perstep = True
     cfg.domain_rand.randomize_imu_lag_timesteps_perstep = True

@@ -3,6 +3,7 @@ UNMODIFIED reference issued against the fake gym under oracle/shim for the same 
 fixtures by oracle/pin_against_reference.py): names in order, the id lists and counts of the indexed setters, the
 (N, 13, 3) force / torque tensors of apply_rigid_body_force_tensors, the pushed root tensor, and the per-env joint
 property structs of lr:915-939.  Then the sync-free form of the same hand-over (device counts, one property tensor)."""
+import numpy as np
 import pytest
 import torch
 
@@ -90,6 +91,50 @@ def test_sync_free_hand_over_with_device_counts():
         assert bool((props[:len(ids), :, :2] == 1).all())
         seen += len(ids)
     assert seen > 0
+
+
+def test_joint_friction_and_damping_multipliers_reach_the_simulator():
+    """lr:755-773, 915-931 (`randomize_joint_friction` / `randomize_joint_damping`, off in t1_cfg): the multipliers of the
+    re-spawned envs, drawn like the reference draws them (fixture recorded from the unmodified reference), in columns 0 / 1
+    of the dense property tensor, and multiplied into the per-env property structs of an Isaac-Gym-like binding."""
+    from ti5_isaacgym_b200.sim.synthetic import RecordingGym, SyntheticGym
+    name = "plane_joint_props"
+    state0, inputs, outputs, _ = load_golden(name)
+    N = state0["commands"].shape[0]
+    dense, rec = _env(name, N, SyntheticGym), _env(name, N, RecordingGym)
+    for env in (dense, rec):
+        env.load_state(state0)
+    for e in range(N):                       # non-zero joint friction / damping to multiply into
+        rec.gym._dof_props[e]["friction"][:] = 0.05 + 0.01 * np.arange(12)
+        rec.gym._dof_props[e]["damping"][:] = 0.5 + 0.1 * np.arange(12)
+    before = [rec.gym._dof_props[e].copy() for e in range(N)]
+    n_props = 0
+    for t, (inp, out) in enumerate(zip(inputs, outputs)):
+        for env in (dense, rec):
+            set_sim(env, inp)
+            env.set_rng_pools(pools_of(inp))
+        rec.gym.calls.clear()
+        dense.step(inp["actions"].cuda()); rec.step(inp["actions"].cuda())
+        ids = out["reset"].nonzero().flatten()
+        tag = f"{name} step {t}: "
+        close(dense.joint_friction_coeffs[ids], out["props_friction_coeff"], tag + "friction multipliers of the re-spawned envs")
+        close(dense.joint_damping_coeffs[ids], out["props_damping_coeff"], tag + "damping multipliers")
+        if len(ids):
+            _, props, n = dense.gym.dof_props
+            assert int(n) == len(ids)
+            close(props[:len(ids), :, 0], out["props_friction_coeff"].expand(-1, 12), tag + "dense tensor, column 0")
+            close(props[:len(ids), :, 1], out["props_damping_coeff"].expand(-1, 12), tag + "dense tensor, column 1")
+            close(props[:len(ids), :, 2], out["props_armature"], tag + "dense tensor, column 2")
+        structs = [c[1] for c in rec.gym.calls if c[0] == "set_actor_dof_properties"]
+        exact(torch.tensor([e for e, _ in structs], dtype=torch.int64), out["props_env"], tag + "property structs: env order")
+        for r, (e, d) in enumerate(structs):    # the struct the simulator held, times the multiplier (lr:923-930)
+            close(torch.from_numpy(d["friction"].copy()), torch.from_numpy(before[e]["friction"]) * out["props_friction_coeff"][r],
+                  tag + f"env {e}: friction")
+            close(torch.from_numpy(d["damping"].copy()), torch.from_numpy(before[e]["damping"]) * out["props_damping_coeff"][r],
+                  tag + f"env {e}: damping")
+            before[e] = d.copy()
+            n_props += 1
+    assert n_props > 0
 
 
 def test_refresh_actor_dof_props_for_an_explicit_id_list():

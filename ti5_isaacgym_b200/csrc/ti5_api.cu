@@ -100,13 +100,15 @@ __global__ void __launch_bounds__(CB) compact_scatter_kernel(const uint8_t* __re
 // lr:915-939: per-env joint properties of the listed envs, dense, for one hand-over to the simulator
 __global__ void __launch_bounds__(256) gather_dof_props_kernel(const float* __restrict__ armatures, const int32_t* __restrict__ ids,
                                                                const int32_t* __restrict__ count, int capacity, int flags,
-                                                               float* __restrict__ out) {
+                                                               float* __restrict__ out, const float* __restrict__ coeffs,
+                                                               int flags2) {
   const int n = min(*count, capacity);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * D; i += gridDim.x * blockDim.x) {
     const int r = i / D, d = i - r * D;
     float* o = out + (size_t)i * 3;
-    o[0] = 1.0f;                                       // friction multiplier (randomize_joint_friction: off in t1)
-    o[1] = 1.0f;                                       // damping multiplier  (randomize_joint_damping: off in t1)
+    // friction / damping multiplier of the env (randomize_joint_friction / _damping: off in t1_cfg), lr:921-930
+    o[0] = (flags2 & TI5_F2_RAND_JOINT_FRICTION) ? coeffs[(size_t)ids[r] * 2 + 0] : 1.0f;
+    o[1] = (flags2 & TI5_F2_RAND_JOINT_DAMPING) ? coeffs[(size_t)ids[r] * 2 + 1] : 1.0f;
     o[2] = (flags & TI5_F_RAND_ARMATURE) ? armatures[(size_t)ids[r] * D + d] : 0.0f;
   }
 }
@@ -116,8 +118,10 @@ __global__ void __launch_bounds__(256) gather_dof_props_kernel(const float* __re
 extern "C" int ti5_gather_dof_props(const Ti5Params* p, const Ti5Buffers* b, const int32_t* ids, const int32_t* count,
                                     int32_t capacity, float* props_out, void* stream) {
   TI5_CHECK_ARGS(p && b && ids && count && props_out && capacity > 0 && b->joint_armatures);
+  TI5_CHECK_ARGS(p->flags2 == 0 || b->joint_coeffs);
   const int blocks = min((capacity * ti5::D + 255) / 256, ti5_sm_count() * 4);
-  ti5::gather_dof_props_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(b->joint_armatures, ids, count, capacity, p->flags, props_out);
+  ti5::gather_dof_props_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(b->joint_armatures, ids, count, capacity, p->flags, props_out,
+                                                                         b->joint_coeffs, p->flags2);
   return ti5_check_launch("ti5_gather_dof_props");
 }
 

@@ -103,6 +103,10 @@ struct ObsRng {
     if (!philox) return (int)r.lag_idx_pv[(size_t)e * 2 + w];
     return lag_from_u(3 + w, philox_u(p.seed, step, S_LAGSTEP, e * 32 + 24 + w));
   }
+  // uniform of the env's joint friction (w = 0) / damping (w = 1) multiplier (lr:763, 773)
+  __device__ __noinline__ float joint_coeff_u(int w, int e) const {
+    return philox ? philox_u(p.seed, step, S_LAGSTEP, e * 32 + 26 + w) : r.dr_joint[(size_t)e * 2 + w];
+  }
   __device__ __forceinline__ int64_t terrain_level(int e) const {
     if (!philox) return r.terrain_level[e] % p.max_terrain_level;
     int64_t v = (int64_t)(philox_u(p.seed, step, S_TERRAIN, e) * (float)p.max_terrain_level);
@@ -215,6 +219,12 @@ __device__ __forceinline__ void reset_env_schedule(const Ti5Params& p, const Ti5
   if (p.flags & TI5_F_ADD_LAG) b.lag_timestep[es * 3 + 0] = (p.flags & TI5_F_RAND_LAG_STEPS) ? lag[0] : p.lag_range[0][1];
   if (p.flags & TI5_F_ADD_DOF_LAG) b.lag_timestep[es * 3 + 1] = (p.flags & TI5_F_RAND_DOF_LAG_STEPS) ? lag[1] : p.lag_range[1][1];
   if (p.flags & TI5_F_ADD_IMU_LAG) b.lag_timestep[es * 3 + 2] = (p.flags & TI5_F_RAND_IMU_LAG_STEPS) ? lag[2] : p.lag_range[2][1];
+  if (LAGOPT && p.flags2) {                                                      // lr:762-763, 772-773: one multiplier per env
+    if (p.flags2 & TI5_F2_RAND_JOINT_FRICTION)
+      b.joint_coeffs[es * 2 + 0] = affine(p.joint_friction_w, p.joint_friction_lo, rng.joint_coeff_u(0, es));
+    if (p.flags2 & TI5_F2_RAND_JOINT_DAMPING)
+      b.joint_coeffs[es * 2 + 1] = affine(p.joint_damping_w, p.joint_damping_lo, rng.joint_coeff_u(1, es));
+  }
   if (LAGOPT && (p.flags & TI5_F_LAG_OPTIONS)) {                                 // lr:610-611, 620-621, 630-650
     if (p.flags & TI5_F_POS_VEL_LAG) {
       b.lag_pv[es * 2 + 0] = (p.flags & TI5_F_RAND_POS_LAG_STEPS) ? rng.lag_pv_draw(0, es) : p.lag_range_pv[0][1];
@@ -944,8 +954,9 @@ reset_observe_kernel(const __grid_constant__ Ti5Params p, const __grid_constant_
     const float* arm = b.joint_armatures + (size_t)e * D;      // written by this CTA's scatter, before a __syncthreads
 #pragma unroll 1
     for (int d = 0; d < D; ++d) {
-      o[d * 3 + 0] = 1.0f;
-      o[d * 3 + 1] = 1.0f;
+      // (the env's friction / damping multipliers were stored by role 1 of this CTA in front of a __syncthreads)
+      o[d * 3 + 0] = (LAGOPT && (p.flags2 & TI5_F2_RAND_JOINT_FRICTION)) ? b.joint_coeffs[e * 2 + 0] : 1.0f;
+      o[d * 3 + 1] = (LAGOPT && (p.flags2 & TI5_F2_RAND_JOINT_DAMPING)) ? b.joint_coeffs[e * 2 + 1] : 1.0f;
       o[d * 3 + 2] = (p.flags & TI5_F_RAND_ARMATURE) ? arm[d] : 0.0f;
     }
   }
@@ -1051,7 +1062,8 @@ extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const 
   auto kernel = p->priv_frame == 73 ? (big ? reset_observe_kernel<47, 73, 2> : reset_observe_kernel<47, 73, 1>)
                 : p->priv_frame == 260 ? (big ? reset_observe_kernel<47, 260, 2> : reset_observe_kernel<47, 260, 1>)
                                        : (big ? reset_observe_kernel<47, 0, 2> : reset_observe_kernel<47, 0, 1>);
-  if (p->flags & TI5_F_LAG_OPTIONS)       // the rarely used lag options: the generic-width builds carry them
+  TI5_CHECK_ARGS(p->flags2 == 0 || (b->joint_coeffs && (p->rng_mode == TI5_RNG_PHILOX || (r && r->dr_joint))));
+  if ((p->flags & TI5_F_LAG_OPTIONS) || p->flags2)       // the rarely used options: the generic-width builds carry them
     kernel = big ? reset_observe_kernel<47, 0, 2, true> : reset_observe_kernel<47, 0, 1, true>;
   if (!ti5_ensure_smem(kernel, smem)) {
     ti5_set_error("ti5_reset_observe: %zu bytes of shared memory per CTA not available", smem);

@@ -269,6 +269,7 @@ class LeggedRobot(BaseTask):
         lag_opts = sum(C[k] for k in ("TI5_F_LAG_PERSTEP", "TI5_F_DOF_LAG_PERSTEP", "TI5_F_IMU_LAG_PERSTEP", "TI5_F_POS_VEL_LAG",
                                       "TI5_F_POS_LAG_PERSTEP", "TI5_F_VEL_LAG_PERSTEP"))
         n_opt = N if p.flags & lag_opts else 1
+        self._joint_coeffs = torch.ones(N if p.flags2 else 1, 2, dtype=torch.float32, device=dev)      # lr:1449-1457
         self._lag_pv = hi5[3:5].repeat(n_opt, 1).contiguous()
         self._last_lag = hi5.repeat(2, n_opt, 1).contiguous()
         self._ring_stamp = i64(N)
@@ -339,6 +340,10 @@ class LeggedRobot(BaseTask):
         if dr.randomize_joint_armature:
             w, lo = torch.tensor(list(p.armature_w), device=dev), torch.tensor(list(p.armature_lo), device=dev)
             self.joint_armatures[:] = w * u(N, D) + lo
+        if p.flags2 & C["TI5_F2_RAND_JOINT_FRICTION"]:                        # lr:762-763
+            self._joint_coeffs[:, 0] = p.joint_friction_w * u(N) + p.joint_friction_lo
+        if p.flags2 & C["TI5_F2_RAND_JOINT_DAMPING"]:                         # lr:772-773
+            self._joint_coeffs[:, 1] = p.joint_damping_w * u(N) + p.joint_damping_lo
         for col, (on, rnd, rng) in enumerate(((dr.add_lag, dr.randomize_lag_timesteps, dr.lag_timesteps_range),
                                               (dr.add_dof_lag, dr.randomize_dof_lag_timesteps, dr.dof_lag_timesteps_range),
                                               (dr.add_imu_lag, dr.randomize_imu_lag_timesteps, dr.imu_lag_timesteps_range))):
@@ -384,7 +389,7 @@ class LeggedRobot(BaseTask):
             coulomb=self.randomized_joint_coulomb, viscous=self.randomized_joint_viscous,
             joint_armatures=self.joint_armatures, act_ring=self._act_ring, dof_ring=self._dof_ring,
             imu_ring=self._imu_ring, lag_timestep=self._lag_timestep, ring_stamp=self._ring_stamp,
-            lag_pv=self._lag_pv, last_lag=self._last_lag,
+            lag_pv=self._lag_pv, last_lag=self._last_lag, joint_coeffs=self._joint_coeffs,
             last_actions=self.last_actions, last_last_actions=self.last_last_actions, last_dof_vel=self.last_dof_vel,
             last_root_vel=self.last_root_vel, commands=self.commands, episode_length_buf=self._episode_length_buf,
             phase_length_buf=self.phase_length_buf, gait_time=self.gait_time, gait_start=self.gait_start,
@@ -443,6 +448,14 @@ class LeggedRobot(BaseTask):
     @property
     def imu_lag_timestep(self):
         return self._lag_timestep[:, 2].long()
+
+    @property
+    def joint_friction_coeffs(self):
+        return self._joint_coeffs[:, 0:1]
+
+    @property
+    def joint_damping_coeffs(self):
+        return self._joint_coeffs[:, 1:2]
 
     @property
     def dof_pos_lag_timestep(self):
@@ -972,6 +985,10 @@ class LeggedRobot(BaseTask):
         for col, name in enumerate(("lag_timestep", "dof_lag_timestep", "imu_lag_timestep")):
             self._lag_timestep[:, col] = torch.as_tensor(state[name]).to(dev).to(torch.int32)
         lag_opts_on = self._last_lag.shape[1] == N and N > 1 or self._last_lag.shape[1] == N == 1
+        if self._params.flags2:
+            for col, name in enumerate(("joint_friction_coeffs", "joint_damping_coeffs")):
+                if name in state:
+                    self._joint_coeffs[:, col] = torch.as_tensor(state[name]).to(dev).float().view(-1)
         for col, name in enumerate(("dof_pos_lag_timestep", "dof_vel_lag_timestep")):
             if name in state and lag_opts_on:
                 self._lag_pv[:, col] = torch.as_tensor(state[name]).to(dev).to(torch.int32)

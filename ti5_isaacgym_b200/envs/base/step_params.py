@@ -20,8 +20,9 @@ TERM_NAMES = ("action_smoothness", "base_acc", "base_height", "collision", "defa
 GAIT_KIND = {"stand": C["TI5_GAIT_STAND"], "walk_sagittal": C["TI5_GAIT_WALK_SAGITTAL"],
              "walk_lateral": C["TI5_GAIT_WALK_LATERAL"], "rotate": C["TI5_GAIT_ROTATE"],
              "walk_omnidirectional": C["TI5_GAIT_WALK_OMNI"]}
-UNSUPPORTED_FLAGS = ("randomize_joint_friction", "randomize_joint_damping")     # lr:755-773: their per-joint ranges are
-                                                                                # commented out in t1_cfg:236-262
+# lr:755-773 `_each_joint`: t1_cfg has per-joint ranges for ten of the twelve joints only (the reference itself raises
+# AttributeError at joint 11); the one-multiplier-per-env forms are supported
+UNSUPPORTED_FLAGS = ("randomize_joint_friction_each_joint", "randomize_joint_damping_each_joint")
 
 
 def pick_env_block(num_envs, sms=148):
@@ -112,6 +113,10 @@ def build_params(cfg, sim_dt, robot, terrain=None, height_shape=(0, 0), div_mode
         p.lag_range[i][0], p.lag_range[i][1] = rng
     for i, rng in enumerate((dr.dof_pos_lag_timesteps_range, dr.dof_vel_lag_timesteps_range)):
         p.lag_range_pv[i][0], p.lag_range_pv[i][1] = rng
+    p.flags2 = (C["TI5_F2_RAND_JOINT_FRICTION"] if getattr(dr, "randomize_joint_friction", False) else 0) | \
+               (C["TI5_F2_RAND_JOINT_DAMPING"] if getattr(dr, "randomize_joint_damping", False) else 0)
+    p.joint_friction_w, p.joint_friction_lo = dr.joint_friction_range[1] - dr.joint_friction_range[0], dr.joint_friction_range[0]
+    p.joint_damping_w, p.joint_damping_lo = dr.joint_damping_range[1] - dr.joint_damping_range[0], dr.joint_damping_range[0]
     # time scales (lr:96-113)
     p.dt = dt
     p.max_episode_length_s = cfg.env.episode_length_s
