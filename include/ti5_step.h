@@ -175,6 +175,8 @@ typedef struct Ti5Params {
   int32_t lag_range_pv[2][2];                      /* dof-position / dof-velocity lag index ranges (TI5_F_POS_VEL_LAG) */
   int32_t flags2;                                  /* TI5_F2_* (the 31 bits of `flags` are taken) */
   float joint_friction_w, joint_friction_lo, joint_damping_w, joint_damping_lo;   /* lr:762-773 multiplier ranges */
+  int32_t pad_[6];                                 /* sizeof == 1472 = 23 x 64: the structs that follow this one in a kernel's
+                                                      parameter space start on a constant-cache line */
 } Ti5Params;
 
 /* Ti5Params.flags2 */
@@ -305,6 +307,7 @@ typedef struct Ti5Buffers {
                               parity for the action lag, by step parity for the others); NULL without a *_PERSTEP flag */
   float* joint_coeffs;     /* (N,2): joint friction / damping multiplier of the env (TI5_F2_RAND_JOINT_*), else NULL; they
                               go to the simulator in columns 0 / 1 of `dof_props` */
+  uint64_t pad_[6];        /* sizeof == 704 = 11 x 64 (see Ti5Params) */
 } Ti5Buffers;
 
 /* ---- caller-supplied uniforms of one step (TI5_RNG_POOLS).  All fp32 U[0,1) unless noted --- */
