@@ -99,6 +99,7 @@ MASS = (1.0, 0.0, 0.04, 0.0, 1.0, 1.0)
     # BASELINE config 3 at its own size, and the plane step at the sizes where env_block, early mode, the carve-out and
     # the 128-register build switch
     ("trimesh_heights_push", 8192, 5, "cuda", 66, None),
+    ("trimesh_heights_push", 12288, 4, "cuda", 66, None),    # env_block 64 with the heights staged: four roles per env
     ("plane_events", 16384, 4, "cuda", 66, None), ("plane_events", 65536, 3, "cuda", 66, None),
 ])
 def test_env_follows_oracle(name, N, steps, where, H, rates, fused=True):

@@ -1043,7 +1043,11 @@ extern "C" int ti5_reset_observe(const Ti5Params* p, const Ti5Buffers* b, const 
   // spare and the frame-building stretch is bound by the length of one warp's instruction stream; two on large grids
   // (the SMs are full of frame builders there; more warps per env would only take their registers)
   static const int forced_roles = getenv("TI5_RO_ROLES") ? atoi(getenv("TI5_RO_ROLES")) : 0;
-  int nroles = forced_roles ? forced_roles : (p->env_block == 32 ? 8 : 2);
+  // ... and four on large grids WITH measured heights: a tile of 64 envs stages 79 KB there, so only two CTAs fit an SM,
+  // and two roles per env would leave it with eight warps (65536 envs, config 3: this kernel 187 -> 156 us; without the
+  // heights four CTAs of 128 threads fit and four roles measured 5 us slower than two)
+  const bool heights_staged = (p->flags & TI5_F_MEASURE_HEIGHTS) && p->num_height_points > 0;
+  int nroles = forced_roles ? forced_roles : (p->env_block == 32 ? 8 : (p->env_block == 64 && heights_staged) ? 4 : 2);
   while (nroles > 2 && nroles * p->env_block > 256) nroles >>= 1;
   TI5_CHECK_ARGS(nroles == 2 || nroles == 4 || nroles == 8);
   const bool writers = nroles > 2;
