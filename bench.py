@@ -388,8 +388,9 @@ def cuda_arm(args):
         torch.cuda.synchronize()
 
     warm = max(args.warmup, 3)
-    for _ in range(warm):
-        loop.one()
+    # warm-up steps run exactly like the timed ones (flush, event pair, step): with a short warm-up (--warmup 5) the first
+    # timed steps otherwise pay the host's first pass through the event / fill paths inside their brackets
+    loop.timed(warm, flush)
     loop.warm_gae()
     # ---- device-timed region: K steps, L2 flushed (outside the event brackets) between steps ----
     sampler = ClockSampler(local) if rank == 0 else None
